@@ -1,0 +1,42 @@
+"""Deterministic synthetic reduced-energy matrices shared by the golden-vector generator and the tests.
+
+Only +,-,*,/ on IEEE doubles and integer hashing are used, so the matrices are bit-identical on every
+machine/numpy version and need not be stored in the fixtures.
+"""
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+def uniforms(n, key):
+    """n doubles in [0,1) from a counter-based hash; exact (k / 2**53)."""
+    with np.errstate(over='ignore'):
+        ctr = np.arange(n, dtype=np.uint64) + (np.uint64(key) << np.uint64(32))
+        z = _splitmix64(ctr)
+    return (z >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+
+def pseudo_normal(n, key):
+    """Irwin-Hall(12) - 6: mean 0, variance 1, no transcendental functions."""
+    u = uniforms(12 * n, key).reshape(n, 12)
+    return u.sum(axis=1) - 6.0
+
+def energies(model, K, key):
+    if model == 'zeros':
+        return np.zeros((K, K))
+    if model == 'normal':
+        return (2.0 * pseudo_normal(K * K, key)).reshape(K, K)
+    if model == 'ladder':      # harmonic-overlap ladder: low acceptance, neighbour dominated
+        mu = 0.5 * np.arange(K, dtype=np.float64)
+        x = mu + pseudo_normal(K, key)
+        return 0.5 * (x[:, None] - mu[None, :]) ** 2
+    if model == 'flat':        # fine alchemical ladder: high acceptance
+        lam = 1.0 - np.arange(K, dtype=np.float64) / max(K - 1, 1)
+        a = 2.0 * pseudo_normal(K, key)
+        return -600.0 + a[:, None] * lam[None, :]
+    raise ValueError(model)
