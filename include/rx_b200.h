@@ -1,0 +1,162 @@
+/*
+ * rx_b200.h -- C ABI of librx_b200.so, the B200-native replica-exchange engine.
+ *
+ * This is the drop-in boundary for the hot path of choderalab/openmmtools'
+ * multistate.ReplicaExchangeSampler (mix -> propagate -> energies; reference:
+ * openmmtools/multistate/multistatesampler.py:766-804).  The reference has no native/FFI boundary for this
+ * path (it is Python over OpenMM); its extension points are the three sampler hooks and the MCMCMove.apply
+ * interface.  Each entry point below names the reference code it replaces; the
+ * Python-side binding a maintainer would add is shown in INTEGRATION.md and shipped in
+ * openmmtools_b200/_engine.py.
+ *
+ * Conventions: C linkage, POD structs, caller-owned host buffers (C-contiguous), md units
+ * (nm, ps, amu, kJ/mol, K).  Every call returns 0 on success or a negative rx_status; the message is
+ * available from rx_last_error().  No exceptions cross the ABI.  One engine = one GPU = one host thread;
+ * calls are not re-entrant.  Every call synchronises with the device before returning unless noted.
+ */
+#ifndef RX_B200_H
+#define RX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RX_ABI_VERSION 1
+#if defined(__GNUC__)
+#define RX_API __attribute__((visibility("default")))
+#else
+#define RX_API
+#endif
+
+typedef struct rx_engine rx_engine;
+
+enum rx_status {
+    RX_OK = 0,
+    RX_ERR_INVALID = -1,     /* bad argument / call order          -> ValueError / RuntimeError        */
+    RX_ERR_CUDA = -2,        /* CUDA runtime failure               -> RuntimeError                     */
+    RX_ERR_NAN = -3,         /* NaN positions/energies             -> SimulationNaNError / IntegratorMoveError */
+    RX_ERR_UNSUPPORTED = -4, /* feature outside the hot path       -> NotImplementedError              */
+    RX_ERR_COMM = -5,        /* NCCL failure                       -> RuntimeError                     */
+    RX_ERR_CAPACITY = -6     /* an internal list overflowed        -> RuntimeError                     */
+};
+
+enum rx_system_kind {
+    RX_SYSTEM_NONE = 0,     /* mixing only: energies are supplied with rx_set_energies                */
+    RX_SYSTEM_LJ_ALCH = 1,  /* testsystems.LennardJonesFluid (testsystems.py:1872-2030) through
+                               alchemy.AbsoluteAlchemicalFactory (alchemy.py:1539-2038): switched LJ +
+                               soft-core sterics, cubic periodic box                                   */
+    RX_SYSTEM_HARMONIC = 2  /* testsystems.HarmonicOscillator (testsystems.py:761-788), per-state K/x0/U0 */
+};
+
+typedef struct {
+    int32_t abi_version;      /* RX_ABI_VERSION */
+    int32_t system_kind;      /* rx_system_kind */
+    int32_t n_replicas;       /* K, global */
+    int32_t n_states;         /* M (== K for ReplicaExchangeSampler) */
+    int32_t n_atoms;          /* N */
+    int32_t device;           /* CUDA ordinal */
+    int32_t rank;             /* replica shard owner: this engine owns replicas [rank*K/world, (rank+1)*K/world) */
+    int32_t world_size;       /* 1 = single GPU */
+    double box[3];            /* cubic/rectangular periodic box edge lengths (LJ) */
+    double r_cutoff;          /* NonbondedForce cutoff (testsystems.py:1981)          */
+    double r_switch;          /* switching distance (testsystems.py:1989)             */
+    int32_t use_switch;       /* 1: OpenMM switching function on [r_switch, r_cutoff] */
+    int32_t annihilate_sterics; /* AlchemicalRegion.annihilate_sterics (alchemy.py:423) */
+    double softcore_alpha, softcore_a, softcore_b, softcore_c; /* alchemy.py:424 */
+} rx_config;
+
+/* One thermodynamic state (states.ThermodynamicState + alchemy.AlchemicalState / HO parameters). */
+typedef struct {
+    double temperature;      /* K; beta = 1/(kB*T), kB = 8.31446261815324e-3 kJ/mol/K (constants.py:7)  */
+    double lambda_sterics;   /* AlchemicalState.lambda_sterics (alchemy.py:207-225)                       */
+    double energy_offset;    /* kJ/mol added to U in this state (dispersion corrections, U0)              */
+    double ho_K;             /* kJ/mol/nm^2 */
+    double ho_x0[3];         /* nm */
+} rx_state_params;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+/* Replaces: MultiStateSampler.create/_pre_write_create (multistatesampler.py:537-609,836-926) +
+ * ContextCache.get_context (cache.py:378-461): allocates the resident device state once.               */
+RX_API int rx_create(const rx_config *cfg, rx_engine **out);
+RX_API void rx_destroy(rx_engine *h);
+/* h may be NULL to read the error of a failed rx_create. Pointer valid until the next call. */
+RX_API const char *rx_last_error(const rx_engine *h);
+RX_API int rx_abi_version(void);
+
+/* ---- static tables -------------------------------------------------------------------------------- */
+/* per-atom sigma (nm), epsilon (kJ/mol), mass (amu), alchemical mask; for RX_SYSTEM_HARMONIC only mass. */
+RX_API int rx_set_particles(rx_engine *h, const double *sigma, const double *epsilon, const double *mass,
+                     const uint8_t *alchemical_mask);
+RX_API int rx_set_states(rx_engine *h, const rx_state_params *states /* [n_states] */);
+/* LangevinSplittingDynamicsMove parameters (mcmc.py:1280-1291) / LangevinIntegrator (integrators.py:1071-1158):
+ * timestep (ps), collision_rate (1/ps), n_steps, splitting with the spaces removed, e.g. "VRORV".        */
+RX_API int rx_set_integrator(rx_engine *h, double timestep, double collision_rate, int32_t n_steps,
+                      const char *splitting);
+
+/* ---- replica state I/O (SamplerState.apply_to_context / update_from_context, states.py:2215-2279) -- */
+/* xyz: [count][N][3] doubles, global replica indices; replicas not owned by this engine are skipped.    */
+RX_API int rx_set_positions(rx_engine *h, int32_t first, int32_t count, const double *xyz);
+RX_API int rx_set_velocities(rx_engine *h, int32_t first, int32_t count, const double *xyz);
+RX_API int rx_get_positions(rx_engine *h, int32_t first, int32_t count, double *xyz);
+RX_API int rx_get_velocities(rx_engine *h, int32_t first, int32_t count, double *xyz);
+/* potential (kJ/mol, in the replica's current state) and kinetic energy after the last propagate.       */
+RX_API int rx_get_replica_energies(rx_engine *h, double *potential /*[K] or NULL*/, double *kinetic /*[K] or NULL*/);
+/* context.setVelocitiesToTemperature (mcmc.py:711): v = sqrt(kB T/m) N(0,1) for every owned replica.     */
+RX_API int rx_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream);
+
+/* replica -> state map (MultiStateSampler._replica_thermodynamic_states, multistatesampler.py:895)       */
+RX_API int rx_set_replica_states(rx_engine *h, const int64_t *states /*[K]*/);
+RX_API int rx_get_replica_states(rx_engine *h, int64_t *states /*[K]*/);
+
+/* ---- the three phases ----------------------------------------------------------------------------- */
+/* Replaces MultiStateSampler._propagate_replicas (multistatesampler.py:1287-1337) ->
+ * BaseIntegratorMove.apply (mcmc.py:668-776) -> integrator.step(n_steps) (mcmc.py:719).
+ * Noise is Philox4x32-10 keyed by (seed; iteration, global replica, atom, step), so trajectories do not
+ * depend on the number of GPUs.  nan_flags[K] (may be NULL) gets 1 for replicas whose state went NaN.    */
+RX_API int rx_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int32_t reassign_velocities,
+                 int32_t *nan_flags);
+
+/* Replaces MultiStateSampler._compute_energies (multistatesampler.py:1436-1494) ->
+ * ThermodynamicState.reduced_potential_at_states (states.py:911-992).  Fills the device-resident
+ * u[K][M]; with world_size > 1 the rows are all-gathered over NCCL.  u_out (may be NULL): [K][M].        */
+RX_API int rx_compute_energies(rx_engine *h, double *u_out);
+RX_API int rx_set_energies(rx_engine *h, const double *u /*[K][M]*/);
+RX_API int rx_get_energies(rx_engine *h, double *u /*[K][M]*/);
+
+/* Replaces ReplicaExchangeSampler._mix_replicas (replicaexchange.py:255-292).
+ * swap-all: bit-exact restatement of _mix_all_replicas_numba (replicaexchange.py:294-349) on the numba
+ * MT19937 stream `RX_STREAM_NUMBA`; swap-neighbors: _mix_neighboring_replicas (:366-380) on the numpy
+ * RandomState stream `RX_STREAM_NUMPY`.  Count matrices are zeroed by the call (as :261-262 does) and
+ * returned if the pointers are non-NULL ([M][M] int64).                                                   */
+enum rx_rng_stream { RX_STREAM_NUMBA = 0, RX_STREAM_NUMPY = 1 };
+RX_API int rx_mix_seed(rx_engine *h, int32_t stream, uint32_t seed);         /* np.random.seed(seed) semantics */
+RX_API int rx_mix_swap_all(rx_engine *h, int64_t nswap_attempts, int64_t *states_out /*[K] or NULL*/,
+                    int64_t *n_accepted /*[M][M] or NULL*/, int64_t *n_proposed /*[M][M] or NULL*/);
+RX_API int rx_mix_swap_neighbors(rx_engine *h, int64_t *states_out, int64_t *n_accepted, int64_t *n_proposed);
+RX_API int rx_get_mix_counts(rx_engine *h, int64_t *n_accepted, int64_t *n_proposed);
+/* MT words consumed so far on a stream (for checkpoints: state = seed + position). */
+RX_API int rx_mix_stream_position(rx_engine *h, int32_t stream, uint64_t *words_consumed);
+
+/* Fused hot loop: n_iterations x (mix -> propagate -> energies), multistatesampler.py:776-782, with no host
+ * round trip in between.  mixing: 0 none, 1 swap-all (nswap = K^3), 2 swap-neighbors.                     */
+RX_API int rx_run_iterations(rx_engine *h, int32_t n_iterations, int32_t mixing, uint64_t seed,
+                      uint64_t first_iteration, int32_t reassign_velocities);
+
+/* Device-side phase timings (CUDA events) of the last rx_run_iterations / phase calls, in ms:
+ * [0] mix, [1] propagate, [2] energies (incl. allgather), [3] rng-stream generation, accumulated;
+ * counts[i] = number of launches of my kernels in phase i.                                                */
+RX_API int rx_get_phase_times(rx_engine *h, double ms[4], int64_t counts[4], int32_t reset);
+
+/* ---- multi-GPU ------------------------------------------------------------------------------------ */
+/* NCCL is loaded with dlopen(nccl_library_path).  Rank 0 creates an id (rx_comm_unique_id), the host code
+ * distributes its bytes (torch.distributed / MPI / a file), every rank calls rx_comm_init.  Replaces
+ * mpiplus.distribute(..., send_results_to=0) (multistatesampler.py:1296,1448).                             */
+RX_API int rx_comm_unique_id(const char *nccl_library_path, void *id_out /*128 bytes*/);
+RX_API int rx_comm_init(rx_engine *h, const char *nccl_library_path, const void *unique_id /*128 bytes*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RX_B200_H */

@@ -1,0 +1,214 @@
+"""Thin Python handle over the C-ABI engine (one engine = one GPU = one shard of the replicas).
+
+This is the binding the reference-side hooks call:
+  ReplicaExchangeSampler._mix_replicas       -> Engine.mix_swap_all / mix_swap_neighbors
+  MultiStateSampler._propagate_replicas      -> Engine.propagate
+  MultiStateSampler._compute_energies        -> Engine.compute_energies
+(/root/reference/openmmtools/multistate/multistatesampler.py:1287,1436; replicaexchange.py:255)
+"""
+import ctypes as C
+import numpy as np
+from . import _lib
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__('[rx %d] %s' % (code, message))
+        self.code = code
+        self.message = message
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError('expected array of shape %s, got %s' % (shape, a.shape))
+    return a
+
+
+class Engine:
+    def __init__(self, system_kind, n_replicas, n_states, n_atoms=0, device=0, rank=0, world_size=1,
+                 box=(1.0, 1.0, 1.0), r_cutoff=0.0, r_switch=0.0, use_switch=False, annihilate_sterics=False,
+                 softcore_alpha=0.5, softcore_a=1.0, softcore_b=1.0, softcore_c=6.0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.K, self.M, self.N = int(n_replicas), int(n_states), int(n_atoms)
+        self.rank, self.world_size = int(rank), int(world_size)
+        cfg = _lib.RxConfig(_lib.RX_ABI_VERSION, system_kind, self.K, self.M, self.N, device, rank, world_size,
+                            (C.c_double * 3)(*[float(b) for b in box]), float(r_cutoff), float(r_switch),
+                            int(bool(use_switch)), int(bool(annihilate_sterics)), float(softcore_alpha),
+                            float(softcore_a), float(softcore_b), float(softcore_c))
+        rc = self._lib.rx_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.rx_last_error(None).decode()
+            self._h = None
+            raise EngineError(rc, msg)
+        self.k0 = (self.rank * self.K) // self.world_size
+        self.k1 = ((self.rank + 1) * self.K) // self.world_size
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(rc, self._lib.rx_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.rx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- tables
+    def set_particles(self, sigma, epsilon, mass, alchemical_mask=None):
+        mass = _c64(mass, (self.N,))
+        sigma = None if sigma is None else _c64(sigma, (self.N,))
+        epsilon = None if epsilon is None else _c64(epsilon, (self.N,))
+        mask = None if alchemical_mask is None else np.ascontiguousarray(alchemical_mask, dtype=np.uint8)
+        self._check(self._lib.rx_set_particles(self._h, _ptr(sigma), _ptr(epsilon), _ptr(mass), _ptr(mask)))
+
+    def set_states(self, temperature, lambda_sterics=None, energy_offset=None, ho_K=None, ho_x0=None):
+        M = self.M
+        arr = (_lib.RxStateParams * M)()
+        for l in range(M):
+            arr[l].temperature = float(temperature[l])
+            arr[l].lambda_sterics = 1.0 if lambda_sterics is None else float(lambda_sterics[l])
+            arr[l].energy_offset = 0.0 if energy_offset is None else float(energy_offset[l])
+            arr[l].ho_K = 0.0 if ho_K is None else float(ho_K[l])
+            x0 = (0.0, 0.0, 0.0) if ho_x0 is None else ho_x0[l]
+            for q in range(3):
+                arr[l].ho_x0[q] = float(x0[q])
+        self._check(self._lib.rx_set_states(self._h, C.cast(arr, C.c_void_p)))
+
+    def set_integrator(self, timestep, collision_rate, n_steps, splitting='V R O R V'):
+        self._check(self._lib.rx_set_integrator(self._h, float(timestep), float(collision_rate), int(n_steps),
+                                                splitting.replace(' ', '').encode()))
+
+    # -- replica state
+    def set_positions(self, xyz, first=0):
+        xyz = _c64(xyz)
+        self._check(self._lib.rx_set_positions(self._h, first, xyz.shape[0], _ptr(xyz)))
+
+    def set_velocities(self, xyz, first=0):
+        xyz = _c64(xyz)
+        self._check(self._lib.rx_set_velocities(self._h, first, xyz.shape[0], _ptr(xyz)))
+
+    def get_positions(self, first=None, count=None):
+        first = self.k0 if first is None else first
+        count = (self.k1 - first) if count is None else count
+        out = np.zeros((count, self.N, 3))
+        self._check(self._lib.rx_get_positions(self._h, first, count, _ptr(out)))
+        return out
+
+    def get_velocities(self, first=None, count=None):
+        first = self.k0 if first is None else first
+        count = (self.k1 - first) if count is None else count
+        out = np.zeros((count, self.N, 3))
+        self._check(self._lib.rx_get_velocities(self._h, first, count, _ptr(out)))
+        return out
+
+    def get_replica_energies(self):
+        pot, kin = np.zeros(self.K), np.zeros(self.K)
+        self._check(self._lib.rx_get_replica_energies(self._h, _ptr(pot), _ptr(kin)))
+        return pot, kin
+
+    def randomize_velocities(self, seed, stream=0):
+        self._check(self._lib.rx_randomize_velocities(self._h, int(seed), int(stream)))
+
+    def set_replica_states(self, states):
+        s = np.ascontiguousarray(states, dtype=np.int64)
+        if s.shape != (self.K,):
+            raise ValueError('expected %d replica states' % self.K)
+        self._check(self._lib.rx_set_replica_states(self._h, _ptr(s)))
+
+    def get_replica_states(self):
+        s = np.zeros(self.K, np.int64)
+        self._check(self._lib.rx_get_replica_states(self._h, _ptr(s)))
+        return s
+
+    # -- phases
+    def propagate(self, seed, iteration, reassign_velocities=False):
+        """Returns the per-replica NaN flags; raises EngineError(RX_ERR_NAN) if any is set."""
+        flags = np.zeros(self.K, np.int32)
+        rc = self._lib.rx_propagate(self._h, int(seed), int(iteration), int(bool(reassign_velocities)), _ptr(flags))
+        if rc == _lib.RX_ERR_NAN:
+            e = EngineError(rc, self._lib.rx_last_error(self._h).decode())
+            e.nan_flags = flags
+            raise e
+        self._check(rc)
+        return flags
+
+    def compute_energies(self, fetch=True):
+        u = np.zeros((self.K, self.M)) if fetch else None
+        self._check(self._lib.rx_compute_energies(self._h, _ptr(u)))
+        return u
+
+    def set_energies(self, u):
+        u = _c64(u, (self.K, self.M))
+        self._check(self._lib.rx_set_energies(self._h, _ptr(u)))
+
+    def get_energies(self):
+        u = np.zeros((self.K, self.M))
+        self._check(self._lib.rx_get_energies(self._h, _ptr(u)))
+        return u
+
+    def mix_seed(self, seed, stream=_lib.RX_STREAM_NUMBA):
+        self._check(self._lib.rx_mix_seed(self._h, stream, int(seed) & 0xFFFFFFFF))
+
+    def mix_swap_all(self, nswap_attempts=None, fetch=True):
+        n = self.K ** 3 if nswap_attempts is None else int(nswap_attempts)
+        if not fetch:
+            self._check(self._lib.rx_mix_swap_all(self._h, n, None, None, None))
+            return None
+        st = np.zeros(self.K, np.int64)
+        nacc = np.zeros((self.M, self.M), np.int64); nprop = np.zeros((self.M, self.M), np.int64)
+        self._check(self._lib.rx_mix_swap_all(self._h, n, _ptr(st), _ptr(nacc), _ptr(nprop)))
+        return st, nacc, nprop
+
+    def mix_swap_neighbors(self):
+        st = np.zeros(self.K, np.int64)
+        nacc = np.zeros((self.M, self.M), np.int64); nprop = np.zeros((self.M, self.M), np.int64)
+        self._check(self._lib.rx_mix_swap_neighbors(self._h, _ptr(st), _ptr(nacc), _ptr(nprop)))
+        return st, nacc, nprop
+
+    def get_mix_counts(self):
+        nacc = np.zeros((self.M, self.M), np.int64); nprop = np.zeros((self.M, self.M), np.int64)
+        self._check(self._lib.rx_get_mix_counts(self._h, _ptr(nacc), _ptr(nprop)))
+        return nacc, nprop
+
+    def mix_stream_position(self, stream=_lib.RX_STREAM_NUMBA):
+        v = C.c_uint64()
+        self._check(self._lib.rx_mix_stream_position(self._h, stream, C.byref(v)))
+        return v.value
+
+    def run_iterations(self, n, mixing, seed, first_iteration, reassign_velocities=False):
+        """mixing: None | 'swap-all' | 'swap-neighbors' (replicaexchange.py:223)."""
+        code = {None: 0, 'swap-all': 1, 'swap-neighbors': 2}[mixing]
+        self._check(self._lib.rx_run_iterations(self._h, int(n), code, int(seed), int(first_iteration),
+                                                int(bool(reassign_velocities))))
+
+    def phase_times(self, reset=False):
+        ms = np.zeros(4); cnt = np.zeros(4, np.int64)
+        self._check(self._lib.rx_get_phase_times(self._h, _ptr(ms), _ptr(cnt), int(reset)))
+        return dict(mix_ms=ms[0], propagate_ms=ms[1], energies_ms=ms[2], rng_ms=ms[3],
+                    launches=int(cnt.sum()), launches_by_phase=cnt.tolist())
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id(nccl_path=None):
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        rc = lib.rx_comm_unique_id((nccl_path or _lib.find_nccl()).encode(), buf)
+        if rc != 0:
+            raise EngineError(rc, lib.rx_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, nccl_path=None):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.rx_comm_init(self._h, (nccl_path or _lib.find_nccl()).encode(), buf))

@@ -1,0 +1,506 @@
+// rx_api.cu -- the C ABI of librx_b200.so (include/rx_b200.h): lifecycle, tables, replica I/O, phase calls,
+// the fused iteration loop, NCCL (dlopen) energy-row all-gather.
+#include "rx_internal.cuh"
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+thread_local std::string g_rx_create_error;
+
+extern "C" int rx_abi_version(void) { return RX_ABI_VERSION; }
+
+extern "C" const char *rx_last_error(const rx_engine *h) { return h ? h->err.c_str() : g_rx_create_error.c_str(); }
+
+#define CREATE_FAIL(code, msg)       \
+    do {                             \
+        g_rx_create_error = (msg);   \
+        if (h) rx_destroy(h);        \
+        return (code);               \
+    } while (0)
+#define CREATE_CUDA(call)                                                                 \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) CREATE_FAIL(RX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" int rx_create(const rx_config *cfg, rx_engine **out) {
+    rx_engine *h = nullptr;
+    if (!cfg || !out) CREATE_FAIL(RX_ERR_INVALID, "rx_create: null argument");
+    if (cfg->abi_version != RX_ABI_VERSION) CREATE_FAIL(RX_ERR_INVALID, "rx_create: ABI version mismatch");
+    if (cfg->n_replicas < 1 || cfg->n_states < 1) CREATE_FAIL(RX_ERR_INVALID, "rx_create: n_replicas and n_states must be >= 1");
+    if (cfg->system_kind < RX_SYSTEM_NONE || cfg->system_kind > RX_SYSTEM_HARMONIC) CREATE_FAIL(RX_ERR_INVALID, "rx_create: unknown system_kind");
+    if (cfg->system_kind != RX_SYSTEM_NONE && cfg->n_atoms < 1) CREATE_FAIL(RX_ERR_INVALID, "rx_create: n_atoms must be >= 1");
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) CREATE_FAIL(RX_ERR_INVALID, "rx_create: bad rank/world_size");
+    if (cfg->system_kind == RX_SYSTEM_LJ_ALCH) {
+        for (int d = 0; d < 3; d++)
+            if (!(cfg->box[d] > 0) || cfg->r_cutoff > 0.5 * cfg->box[d])
+                CREATE_FAIL(RX_ERR_INVALID, "rx_create: cutoff must not exceed half the box edge (minimum image)");
+        if (!(cfg->r_cutoff > 0)) CREATE_FAIL(RX_ERR_INVALID, "rx_create: r_cutoff must be > 0");
+        if (cfg->use_switch && !(cfg->r_switch >= 0 && cfg->r_switch < cfg->r_cutoff))
+            CREATE_FAIL(RX_ERR_INVALID, "rx_create: need 0 <= r_switch < r_cutoff");
+        if (!(cfg->softcore_c > 0)) CREATE_FAIL(RX_ERR_INVALID, "rx_create: softcore_c must be > 0");
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) CREATE_FAIL(RX_ERR_CUDA, std::string("rx_create: no CUDA device available (") + cudaGetErrorString(e) + "); this engine has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) CREATE_FAIL(RX_ERR_INVALID, "rx_create: device ordinal out of range");
+    CREATE_CUDA(cudaSetDevice(cfg->device));
+    h = new rx_engine();
+    h->cfg = *cfg;
+    const int K = cfg->n_replicas, M = cfg->n_states, N = cfg->n_atoms, W = cfg->world_size, R = cfg->rank;
+    h->k0 = (int)(((long long)R * K) / W);
+    h->kloc = (int)(((long long)(R + 1) * K) / W) - h->k0;
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream_rng, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CREATE_CUDA(cudaEventCreate(&h->ev[i]));
+    CREATE_CUDA(cudaMalloc(&h->d_perm, sizeof(int) * K));
+    CREATE_CUDA(cudaMalloc(&h->d_u, sizeof(double) * (size_t)K * M));
+    CREATE_CUDA(cudaMemset(h->d_u, 0, sizeof(double) * (size_t)K * M));
+    CREATE_CUDA(cudaMalloc(&h->d_nacc, sizeof(unsigned long long) * (size_t)M * M));
+    CREATE_CUDA(cudaMalloc(&h->d_nprop, sizeof(unsigned long long) * (size_t)M * M));
+    CREATE_CUDA(cudaMemset(h->d_nacc, 0, sizeof(unsigned long long) * (size_t)M * M));
+    CREATE_CUDA(cudaMemset(h->d_nprop, 0, sizeof(unsigned long long) * (size_t)M * M));
+    CREATE_CUDA(cudaMalloc(&h->d_pot, sizeof(double) * K));
+    CREATE_CUDA(cudaMalloc(&h->d_kin, sizeof(double) * K));
+    CREATE_CUDA(cudaMemset(h->d_pot, 0, sizeof(double) * K));
+    CREATE_CUDA(cudaMemset(h->d_kin, 0, sizeof(double) * K));
+    CREATE_CUDA(cudaMalloc(&h->d_nan, sizeof(int) * K));
+    CREATE_CUDA(cudaMemset(h->d_nan, 0, sizeof(int) * K));
+    CREATE_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
+    CREATE_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+    CREATE_CUDA(cudaMalloc(&h->d_ctl, sizeof(MixCtl)));
+    CREATE_CUDA(cudaMalloc(&h->d_states, sizeof(StateDev) * M));
+    {
+        std::vector<int> perm(K);
+        for (int k = 0; k < K; k++) perm[k] = k % M;
+        CREATE_CUDA(cudaMemcpy(h->d_perm, perm.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+    }
+    if (cfg->system_kind != RX_SYSTEM_NONE) {
+        const size_t n = (size_t)(h->kloc > 0 ? h->kloc : 1) * N;
+        CREATE_CUDA(cudaMalloc(&h->d_pos, sizeof(float4) * n));
+        CREATE_CUDA(cudaMalloc(&h->d_vel, sizeof(float4) * n));
+        CREATE_CUDA(cudaMemset(h->d_pos, 0, sizeof(float4) * n));
+        CREATE_CUDA(cudaMemset(h->d_vel, 0, sizeof(float4) * n));
+        CREATE_CUDA(cudaMalloc(&h->d_io, sizeof(double) * 3 * n));
+        CREATE_CUDA(cudaMalloc(&h->d_atom, sizeof(float4) * N));
+        CREATE_CUDA(cudaMalloc(&h->d_atom_d, sizeof(double4) * N));
+        CREATE_CUDA(cudaMalloc(&h->d_alch_list, sizeof(int) * N));
+    }
+    *out = h;
+    return RX_OK;
+}
+
+extern "C" void rx_destroy(rx_engine *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->nccl_comm && h->nccl_lib) {
+        typedef int (*destroy_t)(void *);
+        destroy_t f = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");
+        if (f) f(h->nccl_comm);
+    }
+    rxi_mix_free(h);
+    cudaFree(h->d_atom); cudaFree(h->d_atom_d); cudaFree(h->d_alch_list); cudaFree(h->d_states);
+    cudaFree(h->d_pos); cudaFree(h->d_vel); cudaFree(h->d_io); cudaFree(h->d_perm); cudaFree(h->d_u);
+    cudaFree(h->d_nacc); cudaFree(h->d_nprop); cudaFree(h->d_pot); cudaFree(h->d_kin); cudaFree(h->d_nan);
+    cudaFree(h->d_err); cudaFree(h->d_pairs);
+    for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream_rng) cudaStreamDestroy(h->stream_rng);
+    delete h;
+}
+
+#define ENTER(h)                                  \
+    if (!(h)) return RX_ERR_INVALID;              \
+    (h)->err.clear();                             \
+    RX_CHECK_CUDA(h, cudaSetDevice((h)->cfg.device))
+
+extern "C" int rx_set_particles(rx_engine *h, const double *sigma, const double *epsilon, const double *mass,
+                                const uint8_t *alch) {
+    ENTER(h);
+    if (h->cfg.system_kind == RX_SYSTEM_NONE) RX_FAIL(h, RX_ERR_INVALID, "rx_set_particles: engine has no particle system");
+    if (!mass) RX_FAIL(h, RX_ERR_INVALID, "rx_set_particles: mass is required");
+    const int N = h->cfg.n_atoms;
+    const bool lj = h->cfg.system_kind == RX_SYSTEM_LJ_ALCH;
+    if (lj && (!sigma || !epsilon)) RX_FAIL(h, RX_ERR_INVALID, "rx_set_particles: sigma and epsilon are required");
+    std::vector<float4> a(N);
+    std::vector<double4> ad(N);
+    std::vector<int> al;
+    for (int i = 0; i < N; i++) {
+        const double s = lj ? sigma[i] : 1.0, e = lj ? epsilon[i] : 0.0, m = mass[i];
+        const bool isal = lj && alch && alch[i];
+        if (!(m > 0)) RX_FAIL(h, RX_ERR_INVALID, "rx_set_particles: masses must be > 0");
+        if (lj && (!(s > 0) || e < 0)) RX_FAIL(h, RX_ERR_INVALID, "rx_set_particles: need sigma > 0 and epsilon >= 0");
+        a[i] = make_float4((float)s, (float)sqrt(e), (float)(1.0 / m), isal ? 1.f : 0.f);
+        ad[i] = make_double4(s, e, m, isal ? 1.0 : 0.0);
+        if (isal) al.push_back(i);
+    }
+    h->n_alch = (int)al.size();
+    RX_CHECK_CUDA(h, cudaMemcpy(h->d_atom, a.data(), sizeof(float4) * N, cudaMemcpyHostToDevice));
+    RX_CHECK_CUDA(h, cudaMemcpy(h->d_atom_d, ad.data(), sizeof(double4) * N, cudaMemcpyHostToDevice));
+    if (h->n_alch) RX_CHECK_CUDA(h, cudaMemcpy(h->d_alch_list, al.data(), sizeof(int) * h->n_alch, cudaMemcpyHostToDevice));
+    // scratch for the lambda-controlled pair list of each owned replica
+    long long cap = (long long)h->n_alch * (N - 1);
+    if (cap > (1 << 18)) cap = 1 << 18;
+    if (cap < 1) cap = 1;
+    cudaFree(h->d_pairs);
+    h->d_pairs = nullptr;
+    h->pair_cap = (int)cap;
+    RX_CHECK_CUDA(h, cudaMalloc(&h->d_pairs, sizeof(double2) * (size_t)cap * (h->kloc > 0 ? h->kloc : 1)));
+    h->have_particles = true;
+    return RX_OK;
+}
+
+extern "C" int rx_set_states(rx_engine *h, const rx_state_params *s) {
+    ENTER(h);
+    if (!s) RX_FAIL(h, RX_ERR_INVALID, "rx_set_states: null");
+    const int M = h->cfg.n_states;
+    h->h_states.resize(M);
+    for (int l = 0; l < M; l++) {
+        if (!(s[l].temperature > 0)) RX_FAIL(h, RX_ERR_INVALID, "rx_set_states: temperature must be > 0");
+        if (h->cfg.system_kind == RX_SYSTEM_LJ_ALCH && !(s[l].lambda_sterics >= 0.0 && s[l].lambda_sterics <= 1.0))
+            RX_FAIL(h, RX_ERR_INVALID, "rx_set_states: lambda_sterics must be in [0, 1]");
+        StateDev &d = h->h_states[l];
+        d.kT = RX_KB * s[l].temperature;
+        d.beta = 1.0 / d.kT;
+        d.lambda = s[l].lambda_sterics;
+        d.la = pow(s[l].lambda_sterics, h->cfg.softcore_a);
+        d.ob = h->cfg.softcore_alpha * pow(1.0 - s[l].lambda_sterics, h->cfg.softcore_b);
+        d.offset = s[l].energy_offset;
+        d.ho_K = s[l].ho_K;
+        for (int q = 0; q < 3; q++) d.ho_x0[q] = s[l].ho_x0[q];
+    }
+    RX_CHECK_CUDA(h, cudaMemcpy(h->d_states, h->h_states.data(), sizeof(StateDev) * M, cudaMemcpyHostToDevice));
+    h->have_states = true;
+    return RX_OK;
+}
+
+extern "C" int rx_set_integrator(rx_engine *h, double timestep, double collision_rate, int32_t n_steps,
+                                 const char *splitting) {
+    ENTER(h);
+    if (!(timestep > 0) || collision_rate < 0 || n_steps < 0) RX_FAIL(h, RX_ERR_INVALID, "rx_set_integrator: bad timestep/collision_rate/n_steps");
+    if (!splitting) RX_FAIL(h, RX_ERR_INVALID, "rx_set_integrator: null splitting");
+    const size_t n = strlen(splitting);
+    if (n == 0 || n >= RX_MAX_PROGRAM) RX_FAIL(h, RX_ERR_INVALID, "rx_set_integrator: splitting must have 1..31 substeps");
+    bool hasV = false, hasR = false, hasO = false;
+    for (size_t i = 0; i < n; i++) {
+        const char c = splitting[i];
+        if (c == 'V') hasV = true; else if (c == 'R') hasR = true; else if (c == 'O') hasO = true;
+        else RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_set_integrator: only R, V and O substeps are supported (no force groups / Metropolization)");
+    }
+    if (!(hasV && hasR && hasO)) RX_FAIL(h, RX_ERR_INVALID, "rx_set_integrator: splitting must contain R, V and O (integrators.py:1360-1363)");
+    h->dt = timestep; h->gamma = collision_rate; h->n_steps = n_steps;
+    memset(h->program, 0, sizeof(h->program));
+    memcpy(h->program, splitting, n);
+    h->have_integrator = true;
+    return RX_OK;
+}
+
+static int local_range(rx_engine *h, int first, int count, int *lo, int *n, int *skip) {
+    const int K = h->cfg.n_replicas;
+    if (first < 0 || count < 0 || first + count > K) RX_FAIL(h, RX_ERR_INVALID, "replica range out of bounds");
+    int a = first > h->k0 ? first : h->k0;
+    int b = (first + count) < (h->k0 + h->kloc) ? (first + count) : (h->k0 + h->kloc);
+    if (b < a) b = a;
+    *lo = a - h->k0; *n = b - a; *skip = a - first;
+    return RX_OK;
+}
+
+static int set_xyz(rx_engine *h, float4 *dst, int first, int count, const double *xyz, const char *what) {
+    if (h->cfg.system_kind == RX_SYSTEM_NONE) RX_FAIL(h, RX_ERR_INVALID, "engine has no particle system");
+    if (!xyz) RX_FAIL(h, RX_ERR_INVALID, std::string(what) + ": null buffer");
+    int lo, n, skip;
+    int rc = local_range(h, first, count, &lo, &n, &skip);
+    if (rc) return rc;
+    return rxi_convert_in(h, dst, lo, n, xyz + (size_t)skip * h->cfg.n_atoms * 3, false);
+}
+static int get_xyz(rx_engine *h, const float4 *src, int first, int count, double *xyz, bool wrap, const char *what) {
+    if (h->cfg.system_kind == RX_SYSTEM_NONE) RX_FAIL(h, RX_ERR_INVALID, "engine has no particle system");
+    if (!xyz) RX_FAIL(h, RX_ERR_INVALID, std::string(what) + ": null buffer");
+    int lo, n, skip;
+    int rc = local_range(h, first, count, &lo, &n, &skip);
+    if (rc) return rc;
+    return rxi_convert_out(h, src, lo, n, xyz + (size_t)skip * h->cfg.n_atoms * 3, wrap);
+}
+
+extern "C" int rx_set_positions(rx_engine *h, int32_t first, int32_t count, const double *xyz) {
+    ENTER(h);
+    return set_xyz(h, h->d_pos, first, count, xyz, "rx_set_positions");
+}
+extern "C" int rx_set_velocities(rx_engine *h, int32_t first, int32_t count, const double *xyz) {
+    ENTER(h);
+    return set_xyz(h, h->d_vel, first, count, xyz, "rx_set_velocities");
+}
+extern "C" int rx_get_positions(rx_engine *h, int32_t first, int32_t count, double *xyz) {
+    ENTER(h);
+    return get_xyz(h, h->d_pos, first, count, xyz, h->cfg.system_kind == RX_SYSTEM_LJ_ALCH, "rx_get_positions");
+}
+extern "C" int rx_get_velocities(rx_engine *h, int32_t first, int32_t count, double *xyz) {
+    ENTER(h);
+    return get_xyz(h, h->d_vel, first, count, xyz, false, "rx_get_velocities");
+}
+
+extern "C" int rx_get_replica_energies(rx_engine *h, double *potential, double *kinetic) {
+    ENTER(h);
+    const int K = h->cfg.n_replicas;
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (potential) RX_CHECK_CUDA(h, cudaMemcpy(potential, h->d_pot, sizeof(double) * K, cudaMemcpyDeviceToHost));
+    if (kinetic) RX_CHECK_CUDA(h, cudaMemcpy(kinetic, h->d_kin, sizeof(double) * K, cudaMemcpyDeviceToHost));
+    return RX_OK;
+}
+
+extern "C" int rx_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream) {
+    ENTER(h);
+    if (!h->have_particles || !h->have_states) RX_FAIL(h, RX_ERR_INVALID, "rx_randomize_velocities: set particles and states first");
+    return rxi_randomize_velocities(h, seed, stream);
+}
+
+extern "C" int rx_set_replica_states(rx_engine *h, const int64_t *states) {
+    ENTER(h);
+    const int K = h->cfg.n_replicas, M = h->cfg.n_states;
+    std::vector<int> p(K);
+    for (int k = 0; k < K; k++) {
+        if (states[k] < 0 || states[k] >= M) RX_FAIL(h, RX_ERR_INVALID, "rx_set_replica_states: state index out of range");
+        p[k] = (int)states[k];
+    }
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    RX_CHECK_CUDA(h, cudaMemcpy(h->d_perm, p.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+    return RX_OK;
+}
+extern "C" int rx_get_replica_states(rx_engine *h, int64_t *states) {
+    ENTER(h);
+    const int K = h->cfg.n_replicas;
+    std::vector<int> p(K);
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    RX_CHECK_CUDA(h, cudaMemcpy(p.data(), h->d_perm, sizeof(int) * K, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < K; k++) states[k] = p[k];
+    return RX_OK;
+}
+
+static int check_ready(rx_engine *h, const char *who) {
+    if (h->cfg.system_kind == RX_SYSTEM_NONE) RX_FAIL(h, RX_ERR_INVALID, std::string(who) + ": engine has no particle system");
+    if (!h->have_particles || !h->have_states) RX_FAIL(h, RX_ERR_INVALID, std::string(who) + ": rx_set_particles and rx_set_states must be called first");
+    return RX_OK;
+}
+
+static int check_device_error(rx_engine *h) {
+    int e = 0;
+    RX_CHECK_CUDA(h, cudaMemcpy(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) {
+        cudaMemset(h->d_err, 0, sizeof(int));
+        RX_FAIL(h, e, e == RX_ERR_CAPACITY ? "lambda-controlled pair list overflowed its capacity" : "device-side error");
+    }
+    return RX_OK;
+}
+
+extern "C" int rx_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int32_t reassign, int32_t *nan_flags) {
+    ENTER(h);
+    int rc = check_ready(h, "rx_propagate");
+    if (rc) return rc;
+    if (!h->have_integrator) RX_FAIL(h, RX_ERR_INVALID, "rx_propagate: rx_set_integrator must be called first");
+    PhaseTimer T(h, 1);
+    int launches = 0;
+    rc = rxi_propagate(h, seed, iteration, reassign, &launches);
+    if (rc) return rc;
+    T.stop(launches);
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    T.accumulate();
+    const int K = h->cfg.n_replicas;
+    std::vector<int> f(K, 0);
+    RX_CHECK_CUDA(h, cudaMemcpy(f.data(), h->d_nan, sizeof(int) * K, cudaMemcpyDeviceToHost));
+    int any = 0;
+    for (int k = 0; k < K; k++) {
+        const bool mine = k >= h->k0 && k < h->k0 + h->kloc;
+        const int v = mine ? f[k] : 0;
+        if (nan_flags) nan_flags[k] = v;
+        any |= v;
+    }
+    if (any) RX_FAIL(h, RX_ERR_NAN, "rx_propagate: NaN encountered in positions, velocities or potential energy");
+    return RX_OK;
+}
+
+extern "C" int rx_compute_energies(rx_engine *h, double *u_out) {
+    ENTER(h);
+    int rc = check_ready(h, "rx_compute_energies");
+    if (rc) return rc;
+    PhaseTimer T(h, 2);
+    int launches = 0;
+    rc = rxi_compute_energy_rows(h, &launches);
+    if (rc) return rc;
+    rc = rxi_allgather_energies(h);
+    if (rc) return rc;
+    T.stop(launches);
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    T.accumulate();
+    rc = check_device_error(h);
+    if (rc) return rc;
+    if (u_out) RX_CHECK_CUDA(h, cudaMemcpy(u_out, h->d_u, sizeof(double) * (size_t)h->cfg.n_replicas * h->cfg.n_states, cudaMemcpyDeviceToHost));
+    return RX_OK;
+}
+
+extern "C" int rx_set_energies(rx_engine *h, const double *u) {
+    ENTER(h);
+    if (!u) RX_FAIL(h, RX_ERR_INVALID, "rx_set_energies: null");
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    RX_CHECK_CUDA(h, cudaMemcpy(h->d_u, u, sizeof(double) * (size_t)h->cfg.n_replicas * h->cfg.n_states, cudaMemcpyHostToDevice));
+    return RX_OK;
+}
+extern "C" int rx_get_energies(rx_engine *h, double *u) {
+    ENTER(h);
+    if (!u) RX_FAIL(h, RX_ERR_INVALID, "rx_get_energies: null");
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    RX_CHECK_CUDA(h, cudaMemcpy(u, h->d_u, sizeof(double) * (size_t)h->cfg.n_replicas * h->cfg.n_states, cudaMemcpyDeviceToHost));
+    return RX_OK;
+}
+
+extern "C" int rx_mix_seed(rx_engine *h, int32_t stream, uint32_t seed) {
+    ENTER(h);
+    return rxi_mix_seed(h, stream, seed);
+}
+
+static int fetch_mix_results(rx_engine *h, int64_t *states_out, int64_t *nacc, int64_t *nprop) {
+    const size_t mm = (size_t)h->cfg.n_states * h->cfg.n_states;
+    if (states_out) { int rc = rx_get_replica_states(h, states_out); if (rc) return rc; }
+    if (nacc) RX_CHECK_CUDA(h, cudaMemcpy(nacc, h->d_nacc, sizeof(int64_t) * mm, cudaMemcpyDeviceToHost));
+    if (nprop) RX_CHECK_CUDA(h, cudaMemcpy(nprop, h->d_nprop, sizeof(int64_t) * mm, cudaMemcpyDeviceToHost));
+    return RX_OK;
+}
+
+extern "C" int rx_mix_swap_all(rx_engine *h, int64_t nswap, int64_t *states_out, int64_t *nacc, int64_t *nprop) {
+    ENTER(h);
+    if (nswap < 0) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_swap_all: nswap_attempts must be >= 0");
+    PhaseTimer T(h, 0);
+    int launches = 0;
+    int rc = rxi_mix_swap_all(h, nswap, &launches);
+    if (rc) return rc;
+    T.stop(launches);
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    T.accumulate();
+    return fetch_mix_results(h, states_out, nacc, nprop);
+}
+
+extern "C" int rx_mix_swap_neighbors(rx_engine *h, int64_t *states_out, int64_t *nacc, int64_t *nprop) {
+    ENTER(h);
+    PhaseTimer T(h, 0);
+    int launches = 0;
+    int rc = rxi_mix_swap_neighbors(h, &launches);
+    if (rc) return rc;
+    T.stop(launches);
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    T.accumulate();
+    return fetch_mix_results(h, states_out, nacc, nprop);
+}
+
+extern "C" int rx_get_mix_counts(rx_engine *h, int64_t *nacc, int64_t *nprop) {
+    ENTER(h);
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return fetch_mix_results(h, nullptr, nacc, nprop);
+}
+
+extern "C" int rx_mix_stream_position(rx_engine *h, int32_t stream, uint64_t *words) {
+    ENTER(h);
+    if (stream < 0 || stream > 1 || !words) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_stream_position: bad arguments");
+    *words = h->streams[stream].consumed;
+    return RX_OK;
+}
+
+extern "C" int rx_run_iterations(rx_engine *h, int32_t n_iterations, int32_t mixing, uint64_t seed,
+                                 uint64_t first_iteration, int32_t reassign) {
+    ENTER(h);
+    int rc = check_ready(h, "rx_run_iterations");
+    if (rc) return rc;
+    if (!h->have_integrator) RX_FAIL(h, RX_ERR_INVALID, "rx_run_iterations: rx_set_integrator must be called first");
+    if (mixing < 0 || mixing > 2) RX_FAIL(h, RX_ERR_INVALID, "rx_run_iterations: mixing must be 0, 1 or 2");
+    const long long K = h->cfg.n_replicas;
+    for (int it = 0; it < n_iterations; it++) {
+        // multistatesampler.py:776-782: mix (with the previous iteration's energies) -> propagate -> energies
+        int lm = 0, lp = 0, le = 0;
+        PhaseTimer Tm(h, 0);
+        if (mixing == 1) rc = rxi_mix_swap_all(h, K * K * K, &lm);
+        else if (mixing == 2) rc = rxi_mix_swap_neighbors(h, &lm);
+        if (rc) return rc;
+        Tm.stop(lm);
+        PhaseTimer Tp(h, 1);
+        rc = rxi_propagate(h, seed, first_iteration + it, reassign, &lp);
+        if (rc) return rc;
+        Tp.stop(lp);
+        PhaseTimer Te(h, 2);
+        rc = rxi_compute_energy_rows(h, &le);
+        if (rc) return rc;
+        rc = rxi_allgather_energies(h);
+        if (rc) return rc;
+        Te.stop(le);
+        RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+        Tm.accumulate(); Tp.accumulate(); Te.accumulate();
+    }
+    rc = check_device_error(h);
+    if (rc) return rc;
+    std::vector<int> f(K, 0);
+    RX_CHECK_CUDA(h, cudaMemcpy(f.data(), h->d_nan, sizeof(int) * K, cudaMemcpyDeviceToHost));
+    for (int k = h->k0; k < h->k0 + h->kloc; k++)
+        if (f[k]) RX_FAIL(h, RX_ERR_NAN, "rx_run_iterations: NaN encountered in a replica");
+    return RX_OK;
+}
+
+extern "C" int rx_get_phase_times(rx_engine *h, double ms[4], int64_t counts[4], int32_t reset) {
+    ENTER(h);
+    for (int i = 0; i < 4; i++) {
+        if (ms) ms[i] = h->phase_ms[i];
+        if (counts) counts[i] = h->phase_launches[i];
+        if (reset) { h->phase_ms[i] = 0; h->phase_launches[i] = 0; }
+    }
+    return RX_OK;
+}
+
+// ---- NCCL through dlopen: the single-GPU path has no NCCL dependency -------------------------------
+typedef struct { char internal[128]; } rx_nccl_id;
+typedef int (*nccl_get_id_t)(rx_nccl_id *);
+typedef int (*nccl_init_rank_t)(void **, int, rx_nccl_id, int);
+typedef int (*nccl_allgather_t)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef const char *(*nccl_errstr_t)(int);
+#define RX_NCCL_FLOAT64 8 /* ncclFloat64 / ncclDouble in nccl.h's ncclDataType_t */
+
+extern "C" int rx_comm_unique_id(const char *path, void *id_out) {
+    if (!path || !id_out) { g_rx_create_error = "rx_comm_unique_id: null argument"; return RX_ERR_INVALID; }
+    void *lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { g_rx_create_error = std::string("dlopen failed: ") + dlerror(); return RX_ERR_COMM; }
+    nccl_get_id_t f = (nccl_get_id_t)dlsym(lib, "ncclGetUniqueId");
+    if (!f) { g_rx_create_error = "ncclGetUniqueId not found"; return RX_ERR_COMM; }
+    rx_nccl_id id;
+    int r = f(&id);
+    if (r != 0) { g_rx_create_error = "ncclGetUniqueId failed"; return RX_ERR_COMM; }
+    memcpy(id_out, &id, sizeof(id));
+    return RX_OK;
+}
+
+extern "C" int rx_comm_init(rx_engine *h, const char *path, const void *unique_id) {
+    ENTER(h);
+    if (h->cfg.world_size == 1) return RX_OK;
+    if (!path || !unique_id) RX_FAIL(h, RX_ERR_INVALID, "rx_comm_init: null argument");
+    h->nccl_lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h->nccl_lib) RX_FAIL(h, RX_ERR_COMM, std::string("dlopen failed: ") + dlerror());
+    nccl_init_rank_t f = (nccl_init_rank_t)dlsym(h->nccl_lib, "ncclCommInitRank");
+    if (!f) RX_FAIL(h, RX_ERR_COMM, "ncclCommInitRank not found");
+    rx_nccl_id id;
+    memcpy(&id, unique_id, sizeof(id));
+    int r = f(&h->nccl_comm, h->cfg.world_size, id, h->cfg.rank);
+    if (r != 0) {
+        nccl_errstr_t es = (nccl_errstr_t)dlsym(h->nccl_lib, "ncclGetErrorString");
+        RX_FAIL(h, RX_ERR_COMM, std::string("ncclCommInitRank failed: ") + (es ? es(r) : "?"));
+    }
+    if ((h->cfg.n_replicas % h->cfg.world_size) != 0) RX_FAIL(h, RX_ERR_INVALID, "rx_comm_init: n_replicas must be divisible by world_size");
+    return RX_OK;
+}
+
+int rxi_allgather_energies(rx_engine *h) {
+    if (h->cfg.world_size == 1) return RX_OK;
+    if (!h->nccl_comm) RX_FAIL(h, RX_ERR_COMM, "world_size > 1 but rx_comm_init has not been called");
+    nccl_allgather_t f = (nccl_allgather_t)dlsym(h->nccl_lib, "ncclAllGather");
+    if (!f) RX_FAIL(h, RX_ERR_COMM, "ncclAllGather not found");
+    const size_t cnt = (size_t)h->kloc * h->cfg.n_states;
+    // in place: each rank's rows already sit at their final offset in d_u
+    int r = f(h->d_u + (size_t)h->k0 * h->cfg.n_states, h->d_u, cnt, RX_NCCL_FLOAT64, h->nccl_comm, h->stream);
+    if (r != 0) RX_FAIL(h, RX_ERR_COMM, "ncclAllGather failed");
+    return RX_OK;
+}

@@ -1,0 +1,466 @@
+// rx_dynamics.cu -- propagation (Langevin splitting dynamics) and the reduced-potential matrix.
+//
+// k_propagate   replaces MultiStateSampler._propagate_replicas (multistatesampler.py:1287-1337) ->
+//               BaseIntegratorMove.apply (mcmc.py:668-776) -> LangevinIntegrator V/R/O substeps
+//               (integrators.py:1404-1460): one CTA per replica, the replica lives in shared memory and
+//               registers for all n_steps, one force evaluation per step (CustomIntegrator's lazy `f`).
+// k_energy_rows replaces MultiStateSampler._compute_replica_energies (multistatesampler.py:1458-1494) ->
+//               ThermodynamicState.reduced_potential_at_states (states.py:911-992): like the reference it
+//               evaluates the lambda-independent groups once per configuration and only the
+//               lambda-controlled pairs once per state (states.py:3649-3691).  All double precision.
+// Energy function: alchemy/alchemy.py:1379-1388 (soft-core sterics), :1723-1750 / :1903-1919 (which pairs go
+// to which force), testsystems.py:1956-1997 (switched LJ, cutoff-periodic).
+#include "rx_internal.cuh"
+#include <math.h>
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator: noise is a pure function of (seed, iteration, replica, atom, step)
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                                       uint32_t k0, uint32_t k1) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    uint32_t c0 = ctr.x, c1 = ctr.y, c2 = ctr.z, c3 = ctr.w, k0 = key.x, k1 = key.y;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// three standard normals from one Philox block (Box-Muller on words 0,1 and 2,3)
+__device__ __forceinline__ float3 philox_normal3(uint4 r) {
+    const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u4 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+    float s1, c1, s2, c2;
+    sincospif(2.0f * u2, &s1, &c1);
+    sincospif(2.0f * u4, &s2, &c2);
+    (void)s2;
+    return make_float3(ra * c1, ra * s1, rb * c2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct DynParams {
+    int N, kind;
+    float Lx, Ly, Lz, iLx, iLy, iLz;
+    float rc2, rs2, rs, inv_w;  // cutoff^2, switch^2, switch, 1/(rc-rs)
+    int use_switch, annihilate, c_is_6;
+    float sc_c;                 // softcore_c
+    float dt, a, b;             // timestep, O-step coefficients exp(-gamma h), sqrt(1-exp(-2 gamma h))
+    int n_steps, n_prog, nV, nR, nO;
+    char prog[RX_MAX_PROGRAM];
+};
+
+struct PairLam { float la, ob; };
+
+// Pair interaction in float: returns -dU/dr / r (so f_i += ret * (xi - xj)) and optionally the energy.
+template <bool ENERGY>
+__device__ __forceinline__ float lj_pair_f(const DynParams &p, float r2, float sig, float eps, bool softcore,
+                                           PairLam lam, float &energy) {
+    float e, fr;  // energy, -dU/dr / r
+    const float inv_r2 = 1.0f / r2;
+    if (!softcore) {
+        const float s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
+        e = 4.0f * eps * (s6 * s6 - s6);
+        fr = 4.0f * eps * (12.0f * s6 * s6 - 6.0f * s6) * inv_r2;
+    } else {
+        const float q = r2 / (sig * sig);
+        float rsc, x;
+        if (p.c_is_6) { rsc = q * q * q; x = 1.0f / (lam.ob + rsc); }
+        else { rsc = powf(q, 0.5f * p.sc_c); x = powf(lam.ob + rsc, -6.0f / p.sc_c); }
+        const float D = lam.ob + rsc;
+        e = lam.la * 4.0f * eps * x * (x - 1.0f);
+        fr = lam.la * 4.0f * eps * (2.0f * x - 1.0f) * 6.0f * x * rsc / (D * r2);
+    }
+    if (p.use_switch && r2 > p.rs2) {
+        const float r = sqrtf(r2);
+        const float t = (r - p.rs) * p.inv_w;
+        const float S = 1.0f + t * t * t * (-10.0f + t * (15.0f - 6.0f * t));
+        const float dS = t * t * (-30.0f + t * (60.0f - 30.0f * t)) * p.inv_w;
+        fr = fr * S - e * dS / r;
+        e *= S;
+    }
+    if (ENERGY) energy = e;
+    return fr;
+}
+
+__device__ __forceinline__ double block_reduce_sum(double v, double *s_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) s_red[w] = v;
+    __syncthreads();
+    double t = 0;
+    if (threadIdx.x == 0) for (int q = 0; q < nw; q++) t += s_red[q];  // fixed order: deterministic
+    return t;  // valid on thread 0
+}
+
+// One CTA per owned replica; thread t owns atom t (N <= 1024).
+__global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *__restrict__ atom,
+                                                    const StateDev *__restrict__ states, const int *__restrict__ perm,
+                                                    float4 *__restrict__ pos, float4 *__restrict__ vel, int k0,
+                                                    uint2 key, uint32_t iteration, int reassign,
+                                                    double *__restrict__ pot, double *__restrict__ kin,
+                                                    int *__restrict__ nan_flag) {
+    extern __shared__ float4 s_dyn[];
+    float4 *s_pos = s_dyn;                         // [N] xyz, w = sigma
+    float2 *s_par = (float2 *)(s_dyn + p.N);       // [N] (sqrt_eps, alch)
+    __shared__ double s_red[32];
+    const int r = blockIdx.x, k = k0 + r, t = threadIdx.x;
+    const bool active = t < p.N;
+    const StateDev st = states[perm[k]];
+    const PairLam lam = {(float)st.la, (float)st.ob};
+    float4 a4 = active ? atom[t] : make_float4(1.f, 0.f, 1.f, 0.f);
+    const float sig_i = a4.x, se_i = a4.y, inv_m = a4.z;
+    const bool alch_i = a4.w != 0.f;
+    float4 x4 = active ? pos[(size_t)r * p.N + t] : make_float4(0, 0, 0, 0);
+    float4 v4 = active ? vel[(size_t)r * p.N + t] : make_float4(0, 0, 0, 0);
+    float x = x4.x, y = x4.y, z = x4.z, vx = v4.x, vy = v4.y, vz = v4.z;
+    const float sigma_v = sqrtf((float)st.kT * inv_m);  // sqrt(kT/m), integrators.py:1314
+    if (reassign && active) {  // context.setVelocitiesToTemperature, mcmc.py:711
+        const float3 g = philox_normal3(philox4x32_10(make_uint4(t, 0x80000000u, k, iteration), key));
+        vx = sigma_v * g.x; vy = sigma_v * g.y; vz = sigma_v * g.z;
+    }
+    if (active) { s_pos[t] = make_float4(x, y, z, sig_i); s_par[t] = make_float2(se_i, alch_i ? 1.f : 0.f); }
+    __syncthreads();
+    float fx = 0, fy = 0, fz = 0;
+    bool f_valid = false;
+    const float hx0 = (float)st.ho_x0[0], hx1 = (float)st.ho_x0[1], hx2 = (float)st.ho_x0[2], hK = (float)st.ho_K;
+
+    auto compute_forces = [&](bool want_energy, float &e_out) {
+        float ax = 0, ay = 0, az = 0, en = 0;
+        if (p.kind == RX_SYSTEM_HARMONIC) {
+            ax = -hK * (x - hx0); ay = -hK * (y - hx1); az = -hK * (z - hx2);
+            if (want_energy) en = 0.5f * hK * ((x - hx0) * (x - hx0) + (y - hx1) * (y - hx1) + (z - hx2) * (z - hx2));
+        } else if (active) {
+            for (int j = 0; j < p.N; j++) {
+                const float4 pj = s_pos[j];
+                const float2 qj = s_par[j];
+                float dx = x - pj.x, dy = y - pj.y, dz = z - pj.z;
+                dx -= p.Lx * rintf(dx * p.iLx); dy -= p.Ly * rintf(dy * p.iLy); dz -= p.Lz * rintf(dz * p.iLz);
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 < p.rc2 && j != t) {
+                    const bool alch_j = qj.y != 0.f;
+                    const bool soft = (alch_i != alch_j) || (alch_i && alch_j && p.annihilate);
+                    float e;
+                    const float fr = want_energy ? lj_pair_f<true>(p, r2, 0.5f * (sig_i + pj.w), se_i * qj.x, soft, lam, e)
+                                                 : lj_pair_f<false>(p, r2, 0.5f * (sig_i + pj.w), se_i * qj.x, soft, lam, e);
+                    ax += fr * dx; ay += fr * dy; az += fr * dz;
+                    if (want_energy) en += 0.5f * e;
+                }
+            }
+        }
+        fx = ax; fy = ay; fz = az;
+        e_out = en;
+    };
+
+    uint32_t ocount = 0;
+    float dummy;
+    for (int s = 0; s < p.n_steps; s++) {
+        for (int q = 0; q < p.n_prog; q++) {
+            const char op = p.prog[q];
+            if (op == 'V') {
+                if (!f_valid) { compute_forces(false, dummy); f_valid = true; }
+                const float h = p.dt / (float)p.nV;
+                vx += h * fx * inv_m; vy += h * fy * inv_m; vz += h * fz * inv_m;
+            } else if (op == 'R') {
+                const float h = p.dt / (float)p.nR;
+                x += h * vx; y += h * vy; z += h * vz;
+                if (p.kind != RX_SYSTEM_HARMONIC) {
+                    __syncthreads();  // everyone finished reading the old positions
+                    if (active) s_pos[t] = make_float4(x, y, z, sig_i);
+                    __syncthreads();
+                }
+                f_valid = false;
+            } else {  // 'O'
+                const float3 g = philox_normal3(philox4x32_10(make_uint4(t, ocount, k, iteration), key));
+                ocount++;
+                vx = p.a * vx + p.b * sigma_v * g.x;
+                vy = p.a * vy + p.b * sigma_v * g.y;
+                vz = p.a * vz + p.b * sigma_v * g.z;
+            }
+        }
+    }
+    // potential (in the replica's current state) and kinetic energy, SamplerState.potential_energy/kinetic_energy
+    float e_i = 0;
+    compute_forces(true, e_i);
+    double ke_i = active ? 0.5 * (double)(vx * vx + vy * vy + vz * vz) / (double)inv_m : 0.0;
+    const double U = block_reduce_sum(active ? (double)e_i : 0.0, s_red);
+    const double KE = block_reduce_sum(ke_i, s_red);
+    const bool bad = active && !(isfinite(x) && isfinite(y) && isfinite(z) && isfinite(vx) && isfinite(vy) && isfinite(vz));
+    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+    if (t == 0) {
+        pot[k] = U + st.offset;
+        kin[k] = KE;
+        nan_flag[k] = (any_bad || !isfinite(U)) ? 1 : 0;
+    }
+    if (active) {
+        if (p.kind != RX_SYSTEM_HARMONIC) {  // getState(enforcePeriodicBox=True), mcmc.py:731
+            x -= p.Lx * floorf(x * p.iLx); y -= p.Ly * floorf(y * p.iLy); z -= p.Lz * floorf(z * p.iLz);
+        }
+        pos[(size_t)r * p.N + t] = make_float4(x, y, z, 0.f);
+        vel[(size_t)r * p.N + t] = make_float4(vx, vy, vz, 0.f);
+    }
+}
+
+__global__ void k_randomize_velocities(int N, const float4 *__restrict__ atom, const StateDev *__restrict__ states,
+                                       const int *__restrict__ perm, float4 *__restrict__ vel, int k0, uint2 key,
+                                       uint32_t stream_id) {
+    const int r = blockIdx.x, k = k0 + r;
+    const StateDev st = states[perm[k]];
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        const float sv = sqrtf((float)st.kT * atom[t].z);
+        const float3 g = philox_normal3(philox4x32_10(make_uint4(t, 0xC0000000u, k, stream_id), key));
+        vel[(size_t)r * N + t] = make_float4(sv * g.x, sv * g.y, sv * g.z, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Energy rows, double precision.
+// ---------------------------------------------------------------------------------------------------
+struct EnParams {
+    int N, M, kind, n_alch;
+    double Lx, Ly, Lz;
+    double rc2, rs, rc, inv_w;
+    int use_switch, annihilate, c_is_6;
+    double sc_c;
+    int pair_cap;
+};
+
+__device__ __forceinline__ double min_image_d(double d, double L) { return d - L * rint(d / L); }
+__device__ __forceinline__ double switch_d(const EnParams &p, double r) {
+    if (!p.use_switch || r <= p.rs) return 1.0;
+    const double t = (r - p.rs) * p.inv_w;
+    return 1.0 + t * t * t * (-10.0 + t * (15.0 - 6.0 * t));
+}
+
+__global__ void __launch_bounds__(512) k_energy_rows(EnParams p, const double4 *__restrict__ atom_d,
+                                                     const int *__restrict__ alch_list,
+                                                     const StateDev *__restrict__ states,
+                                                     const float4 *__restrict__ pos, int k0, double2 *__restrict__ pairs,
+                                                     double *__restrict__ u, int *__restrict__ err) {
+    extern __shared__ double s_en[];
+    double *sx = s_en, *sy = s_en + p.N, *sz = s_en + 2 * p.N;
+    __shared__ double s_red[32];
+    __shared__ int s_scan[32];
+    __shared__ double s_U0;
+    __shared__ int s_npairs;
+    const int r = blockIdx.x, k = k0 + r, t = threadIdx.x, nt = blockDim.x;
+    for (int q = t; q < p.N; q += nt) {
+        const float4 x4 = pos[(size_t)r * p.N + q];
+        sx[q] = (double)x4.x; sy[q] = (double)x4.y; sz[q] = (double)x4.z;
+    }
+    __syncthreads();
+    double U0 = 0.0;
+    if (p.kind == RX_SYSTEM_HARMONIC) {
+        // u[k,l] = beta_l (sum_i K_l/2 |x_i - x0_l|^2 + offset_l)
+        for (int l = t; l < p.M; l += nt) {
+            const StateDev st = states[l];
+            double U = 0;
+            for (int i = 0; i < p.N; i++) {
+                const double dx = sx[i] - st.ho_x0[0], dy = sy[i] - st.ho_x0[1], dz = sz[i] - st.ho_x0[2];
+                U += 0.5 * st.ho_K * (dx * dx + dy * dy + dz * dz);
+            }
+            u[(size_t)k * p.M + l] = st.beta * (U + st.offset);
+        }
+        return;
+    }
+    // ---- phase 1: lambda-independent pairs (E-E, and A-A when not annihilating), half shell: i with i+1..i+N/2
+    const int half = p.N / 2;
+    for (int i = t; i < p.N; i += nt) {
+        const double4 ai = atom_d[i];
+        const bool alch_i = ai.w != 0.0;
+        for (int d = 1; d <= half; d++) {
+            if ((p.N % 2 == 0) && d == half && i >= half) break;  // the antipodal pair is counted once
+            int j = i + d; if (j >= p.N) j -= p.N;
+            const double4 aj = atom_d[j];
+            const bool alch_j = aj.w != 0.0;
+            const bool soft = (alch_i != alch_j) || (alch_i && alch_j && p.annihilate);
+            if (soft) continue;
+            const double dx = min_image_d(sx[i] - sx[j], p.Lx), dy = min_image_d(sy[i] - sy[j], p.Ly),
+                         dz = min_image_d(sz[i] - sz[j], p.Lz);
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 >= p.rc2) continue;
+            const double sig = 0.5 * (ai.x + aj.x), eps = sqrt(ai.y * aj.y);
+            const double s2 = sig * sig / r2, s6 = s2 * s2 * s2;
+            U0 += 4.0 * eps * (s6 * s6 - s6) * switch_d(p, sqrt(r2));
+        }
+    }
+    const double U0_tot = block_reduce_sum(U0, s_red);
+    if (t == 0) s_U0 = U0_tot;
+    // ---- phase 2: lambda-controlled pairs (alchemical atom a) x (atom j), deterministic order by a stable scan
+    double2 *my_pairs = pairs + (size_t)r * p.pair_cap;
+    int total = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        int cnt = 0, base = 0;
+        if (pass == 1) {
+            // exclusive scan of per-thread counts (warp shuffle + warp totals)
+            const int lane = t & 31, w = t >> 5, nw = (nt + 31) >> 5;
+            int incl = total;  // `total` holds this thread's count from pass 0
+            for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+            if (lane == 31) s_scan[w] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int q = 0; q < w; q++) woff += s_scan[q];
+            base = woff + incl - total;
+            if (t == nt - 1) s_npairs = base + total;
+            (void)nw;
+        }
+        for (int ai_ = 0; ai_ < p.n_alch; ai_++) {
+            const int a = alch_list[ai_];
+            const double4 pa = atom_d[a];
+            for (int j = t; j < p.N; j += nt) {
+                if (j == a) continue;
+                const double4 pj = atom_d[j];
+                const bool alch_j = pj.w != 0.0;
+                if (alch_j && (!p.annihilate || j < a)) continue;  // A-A: only when annihilating, counted once
+                const double dx = min_image_d(sx[a] - sx[j], p.Lx), dy = min_image_d(sy[a] - sy[j], p.Ly),
+                             dz = min_image_d(sz[a] - sz[j], p.Lz);
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 >= p.rc2) continue;
+                if (pass == 1) {
+                    const int slot = base + cnt;
+                    if (slot < p.pair_cap) {
+                        const double sig = 0.5 * (pa.x + pj.x), eps = sqrt(pa.y * pj.y);
+                        const double q = r2 / (sig * sig);
+                        const double rsc = p.c_is_6 ? q * q * q : pow(q, 0.5 * p.sc_c);
+                        my_pairs[slot] = make_double2(rsc, 4.0 * eps * switch_d(p, sqrt(r2)));
+                    }
+                }
+                cnt++;
+            }
+        }
+        if (pass == 0) total = cnt;
+    }
+    __syncthreads();
+    int npairs = s_npairs;
+    if (npairs > p.pair_cap) { if (t == 0) atomicExch(err, RX_ERR_CAPACITY); npairs = p.pair_cap; }
+    // ---- phase 3: one state per thread, pairs summed in list order
+    const double U0s = s_U0;
+    for (int l = t; l < p.M; l += nt) {
+        const StateDev st = states[l];
+        double Ua = 0.0;
+        for (int q = 0; q < npairs; q++) {
+            const double2 pr = my_pairs[q];
+            const double D = st.ob + pr.x;
+            const double x = p.c_is_6 ? 1.0 / D : pow(D, -6.0 / p.sc_c);
+            Ua += st.la * pr.y * x * (x - 1.0);
+        }
+        u[(size_t)k * p.M + l] = st.beta * (U0s + Ua + st.offset);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host <-> device conversions at the boundary (double xyz <-> float4)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_pack(const double *__restrict__ in, float4 *__restrict__ out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4((float)in[3 * i], (float)in[3 * i + 1], (float)in[3 * i + 2], 0.f);
+}
+__global__ void k_unpack(const float4 *__restrict__ in, double *__restrict__ out, long long n, int wrap, double Lx,
+                         double Ly, double Lz) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = in[i];
+    double x = v.x, y = v.y, z = v.z;
+    if (wrap) { x -= Lx * floor(x / Lx); y -= Ly * floor(y / Ly); z -= Lz * floor(z / Lz); }
+    out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+}
+
+int rxi_convert_in(rx_engine *h, float4 *dst, int first_local, int count, const double *host_xyz, bool) {
+    const long long n = (long long)count * h->cfg.n_atoms;
+    if (n == 0) return RX_OK;
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_io, host_xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_io, dst + (size_t)first_local * h->cfg.n_atoms, n);
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RX_OK;
+}
+
+int rxi_convert_out(rx_engine *h, const float4 *src, int first_local, int count, double *host_xyz, bool wrap) {
+    const long long n = (long long)count * h->cfg.n_atoms;
+    if (n == 0) return RX_OK;
+    k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(src + (size_t)first_local * h->cfg.n_atoms, h->d_io, n,
+                                                                 wrap ? 1 : 0, h->cfg.box[0], h->cfg.box[1], h->cfg.box[2]);
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(host_xyz, h->d_io, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int fill_dyn(rx_engine *h, DynParams &p) {
+    const rx_config &c = h->cfg;
+    memset(&p, 0, sizeof(p));
+    p.N = c.n_atoms; p.kind = c.system_kind;
+    p.Lx = (float)c.box[0]; p.Ly = (float)c.box[1]; p.Lz = (float)c.box[2];
+    p.iLx = (float)(1.0 / c.box[0]); p.iLy = (float)(1.0 / c.box[1]); p.iLz = (float)(1.0 / c.box[2]);
+    p.rc2 = (float)(c.r_cutoff * c.r_cutoff); p.rs2 = (float)(c.r_switch * c.r_switch); p.rs = (float)c.r_switch;
+    p.inv_w = (float)(1.0 / (c.r_cutoff - c.r_switch));
+    p.use_switch = c.use_switch; p.annihilate = c.annihilate_sterics;
+    p.c_is_6 = (c.softcore_c == 6.0); p.sc_c = (float)c.softcore_c;
+    p.dt = (float)h->dt; p.n_steps = h->n_steps;
+    int nV = 0, nR = 0, nO = 0, n = 0;
+    for (const char *q = h->program; *q; q++, n++) { if (*q == 'V') nV++; else if (*q == 'R') nR++; else nO++; p.prog[n] = *q; }
+    p.n_prog = n; p.nV = nV; p.nR = nR; p.nO = nO;
+    const double hO = h->dt / (nO > 0 ? nO : 1);   // integrators.py:1141-1146
+    p.a = (float)exp(-h->gamma * hO);
+    p.b = (float)sqrt(1.0 - exp(-2.0 * h->gamma * hO));
+    return RX_OK;
+}
+
+int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches) {
+    if (h->kloc == 0) return RX_OK;
+    DynParams p;
+    fill_dyn(h, p);
+    const int N = h->cfg.n_atoms;
+    if (N > 1024) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: more than 1024 atoms per replica is not supported yet");
+    const int threads = ((N + 31) / 32) * 32;
+    const size_t smem = (size_t)N * (sizeof(float4) + sizeof(float2));
+    if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
+    k_propagate<<<h->kloc, threads, smem, h->stream>>>(p, h->d_atom, h->d_states, h->d_perm, h->d_pos, h->d_vel, h->k0, key,
+                                                      (uint32_t)iteration, reassign, h->d_pot, h->d_kin, h->d_nan);
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    (*launches)++;
+    return RX_OK;
+}
+
+int rxi_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream_id) {
+    if (h->kloc == 0) return RX_OK;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    k_randomize_velocities<<<h->kloc, 256, 0, h->stream>>>(h->cfg.n_atoms, h->d_atom, h->d_states, h->d_perm, h->d_vel, h->k0,
+                                                           key, (uint32_t)stream_id);
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RX_OK;
+}
+
+int rxi_compute_energy_rows(rx_engine *h, int *launches) {
+    if (h->kloc == 0) return RX_OK;
+    const rx_config &c = h->cfg;
+    EnParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = c.n_atoms; p.M = c.n_states; p.kind = c.system_kind; p.n_alch = h->n_alch;
+    p.Lx = c.box[0]; p.Ly = c.box[1]; p.Lz = c.box[2];
+    p.rc2 = c.r_cutoff * c.r_cutoff; p.rs = c.r_switch; p.rc = c.r_cutoff;
+    p.inv_w = 1.0 / (c.r_cutoff - c.r_switch);
+    p.use_switch = c.use_switch; p.annihilate = c.annihilate_sterics;
+    p.c_is_6 = (c.softcore_c == 6.0); p.sc_c = c.softcore_c;
+    p.pair_cap = h->pair_cap;
+    const size_t smem = (size_t)3 * c.n_atoms * sizeof(double);
+    if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_energy_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_energy_rows<<<h->kloc, 512, smem, h->stream>>>(p, h->d_atom_d, h->d_alch_list, h->d_states, h->d_pos, h->k0,
+                                                    (double2 *)h->d_pairs, h->d_u, h->d_err);
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    (*launches)++;
+    return RX_OK;
+}

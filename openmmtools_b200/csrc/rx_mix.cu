@@ -1,0 +1,484 @@
+// rx_mix.cu -- replica mixing (Gibbs / Metropolis state swaps) on the device.
+//
+// Replaces ReplicaExchangeSampler._mix_replicas (openmmtools/multistate/replicaexchange.py:255-292):
+//   swap-all       _mix_all_replicas_numba  (replicaexchange.py:294-349)  -> k_mix_walk_pow2 / k_mix_walk_serial
+//   swap-neighbors _mix_neighboring_replicas (replicaexchange.py:366-406) -> k_mix_neighbors
+// The results are bit-identical to the reference for the same MT19937 state: the random stream is numba's
+// (numba/_random.c:37-73; randint = low bit_length(K-1) bits of one word with rejection, rand = 53-bit double
+// from two words), reproduced on the device by k_mt_generate.
+//
+// Design (see DESIGN.md "mixing"): the K^3-long chain is data dependent (an attempt draws rand() only when
+// log_p < 0), but the stream itself is state independent.  For power-of-two K every attempt starts on an
+// even word ("slot"), so a parallel pre-pass turns the stream into slot records (i, j, log U, overlap mask)
+// and ONE warp then walks the chain speculatively: 32 lanes evaluate 32 consecutive slots under the current
+// permutation, the visited-slot chain is resolved with a carry-propagation bit trick, and the longest prefix
+// in which no visited slot touches a replica swapped earlier in the same window is committed.
+#include "rx_internal.cuh"
+#include <math.h>
+#include <stdio.h>
+
+// ------------------------------------------------------------------------------------------------------
+// MT19937 generation: x[n+624] = x[n+397] ^ twist(x[n], x[n+1]); 227 words are independent per step and
+// a thread's second consecutive step only needs its own previous output, so there is one barrier per 454
+// words.  `window` holds the last 624 raw words and is advanced by exactly n.
+// ------------------------------------------------------------------------------------------------------
+#define MT_RING 2048
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__global__ void __launch_bounds__(256) k_mt_generate(uint32_t *__restrict__ window, uint32_t *__restrict__ out,
+                                                     long long n) {
+    __shared__ uint32_t buf[MT_RING];
+    const int t = threadIdx.x;
+    for (int q = t; q < 624; q += 256) buf[q] = window[q];
+    __syncthreads();
+    long long produced = 0;
+    unsigned base = 0;
+    while (produced < n) {
+        if (t < 227) {
+            uint32_t a = buf[(base + t) & (MT_RING - 1)], b = buf[(base + t + 1) & (MT_RING - 1)];
+            uint32_t c = buf[(base + t + 397) & (MT_RING - 1)];
+            uint32_t x = mt_twist(a, b, c);
+            buf[(base + t + 624) & (MT_RING - 1)] = x;
+            if (produced + t < n) out[produced + t] = mt_temper(x);
+            // second step: x[n+227+t+624] needs x[n+227+t], x[n+228+t] (old) and this thread's x[n+624+t]
+            a = buf[(base + 227 + t) & (MT_RING - 1)];
+            b = buf[(base + 228 + t) & (MT_RING - 1)];
+            uint32_t x2 = mt_twist(a, b, x);
+            buf[(base + 227 + t + 624) & (MT_RING - 1)] = x2;
+            if (produced + 227 + t < n) out[produced + 227 + t] = mt_temper(x2);
+        }
+        __syncthreads();
+        produced += 454;
+        base += 454;
+    }
+    // ring position of x_{n0 + n}: base - (produced - n)
+    unsigned w0 = base - (unsigned)(produced - n);
+    __syncthreads();
+    uint32_t keep[3];
+    for (int q = t, m = 0; q < 624; q += 256, m++) keep[m] = buf[(w0 + q) & (MT_RING - 1)];
+    for (int q = t, m = 0; q < 624; q += 256, m++) window[q] = keep[m];
+}
+
+__global__ void k_copy_words(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = src[i];
+}
+
+// numba/numpy double from two words: ((a >> 5) * 2^26 + (b >> 6)) / 2^53
+__device__ __forceinline__ double mt_double(uint32_t w0, uint32_t w1) {
+    return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// log_p exactly as the reference evaluates it: -(e_ij + e_ji) + e_ii + e_jj, left to right, no contraction.
+__device__ __forceinline__ double swap_logp(double e_ij, double e_ji, double e_ii, double e_jj) {
+    return __dadd_rn(__dadd_rn(-__dadd_rn(e_ij, e_ji), e_ii), e_jj);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Slot records (state independent, fully parallel).
+// ------------------------------------------------------------------------------------------------------
+#define LOGU_ZERO (-745.5)  /* stands in for log(0): exp(x) == 0 <=> x < -745.13 */
+
+__global__ void __launch_bounds__(256) k_slots_build(const uint32_t *__restrict__ words, long long nslots,
+                                                     uint32_t mask, SlotRec *__restrict__ rec) {
+    __shared__ uint32_t s_ij[256 + 32];
+    long long s0 = (long long)blockIdx.x * 256;
+    int t = threadIdx.x;
+    // tile: slots s0-32 .. s0+255
+    for (int q = t; q < 256 + 32; q += 256) {
+        long long s = s0 - 32 + q;
+        uint32_t ij = 0xffffffffu;
+        if (s >= 0 && s < nslots) ij = (words[2 * s] & mask) | ((words[2 * s + 1] & mask) << 16);
+        s_ij[q] = ij;
+    }
+    __syncthreads();
+    long long s = s0 + t;
+    if (s >= nslots) return;
+    uint32_t w0 = words[2 * s], w1 = words[2 * s + 1];
+    uint32_t ij = s_ij[t + 32];
+    uint32_t i = ij & 0xffffu, j = ij >> 16;
+    uint32_t bm = 0;
+#pragma unroll
+    for (int b = 0; b < 31; b++) {
+        uint32_t o = s_ij[t + 32 - 1 - b];
+        uint32_t oi = o & 0xffffu, oj = o >> 16;
+        bool hit = (o != 0xffffffffu) && (oi == i || oi == j || oj == i || oj == j);
+        bm |= (hit ? 1u : 0u) << b;
+    }
+    double U = mt_double(w0, w1);
+    SlotRec r;
+    r.ij = ij;
+    r.backmask = bm;
+    r.logU = (U == 0.0) ? LOGU_ZERO : log(U);
+    rec[s] = r;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The speculative chain walker (one warp).  K must be a power of two <= 65536.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict__ rec, const uint32_t *__restrict__ words,
+                                                      long long nslots, const double *__restrict__ u, int K, int M,
+                                                      int *__restrict__ perm_g, unsigned long long *__restrict__ nacc,
+                                                      unsigned long long *__restrict__ nprop, MixCtl *ctl) {
+    extern __shared__ int s_perm[];
+    const int lane = threadIdx.x;
+    for (int q = lane; q < K; q += 32) s_perm[q] = perm_g[q];
+    __syncwarp();
+    long long h = ctl->head;
+    long long remaining = ctl->remaining;
+    int rounds = 0;
+    long long slow = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    while (remaining > 0 && h + 33 <= nslots) {
+        rounds++;
+        const SlotRec r = rec[h + lane];
+        const double logU_next = rec[h + lane + 1].logU;  // the uniform an attempt at this slot would draw
+        const int i = r.ij & 0xffffu, j = r.ij >> 16;
+        const int si = s_perm[i], sj = s_perm[j];
+        const double e_ij = u[(size_t)i * M + sj], e_ji = u[(size_t)j * M + si];
+        const double e_ii = u[(size_t)i * M + si], e_jj = u[(size_t)j * M + sj];
+        const double logp = swap_logp(e_ij, e_ji, e_ii, e_jj);
+        const bool ge0 = logp >= 0.0;
+        bool acc = ge0;
+        if (!ge0) {
+            const double d = logp - logU_next;
+            if (d > 1e-9) acc = true;
+            else if (d < -1e-9) acc = false;
+            else {  // too close to call in the log domain: do exactly what the reference does
+                const long long s1 = h + lane + 1;
+                const double U = mt_double(words[2 * s1], words[2 * s1 + 1]);
+                acc = U < exp(logp);
+                slow++;
+            }
+        }
+        const unsigned G = __ballot_sync(0xffffffffu, ge0);
+        const unsigned A = __ballot_sync(0xffffffffu, acc);
+        const unsigned E = __ballot_sync(0xffffffffu, i == j);
+        // Visited chain: from a visited slot s the next attempt starts at s+1 if log_p >= 0 (no uniform drawn)
+        // else at s+2.  skip[s+1] = NG[s] & ~skip[s]: inside a run of NG ones the skip flag alternates, so
+        // skip[s] = parity of (s - run start); runs are split by start parity with an add-carry.
+        const unsigned long long X = (unsigned long long)(~G);
+        const unsigned long long starts = X & ~(X << 1);
+        const unsigned long long SE = starts & 0x5555555555555555ull, SO = starts & 0xAAAAAAAAAAAAAAAAull;
+        const unsigned long long DE = ((X + SE) ^ X) & ~SE, DO = ((X + SO) ^ X) & ~SO;
+        const unsigned long long skip = (DE & 0xAAAAAAAAAAAAAAAAull) | (DO & 0x5555555555555555ull);
+        const unsigned V = ~(unsigned)skip;
+        const unsigned skip32 = (unsigned)(skip >> 32) & 1u;
+        const unsigned VA = V & A & ~E;  // visited, accepted, really changing the permutation
+        // lane t is stale if an earlier visited state-changing swap in this window shares a replica with it
+        const unsigned earlier = lane ? (__brev(VA) >> (32 - lane)) : 0u;
+        const bool stale = (earlier & r.backmask) != 0u;
+        const unsigned C = __ballot_sync(0xffffffffu, stale) & V;
+        const int first = C ? (__ffs(C) - 1) : 32;
+        unsigned cm = V & (first == 32 ? 0xffffffffu : ((1u << first) - 1u));
+        int n = __popc(cm);
+        long long advance;
+        if ((long long)n > remaining) {
+            const int pos = __fns(cm, 0, (int)remaining + 1);  // the first visited lane we must NOT run
+            cm &= (1u << pos) - 1u;
+            n = (int)remaining;
+            advance = pos;
+        } else if (first < 32) {
+            advance = first;
+        } else {
+            advance = 32 + skip32;
+        }
+        if ((cm >> lane) & 1u) {
+            atomicAdd(&nprop[(size_t)si * M + sj], 1ull);
+            atomicAdd(&nprop[(size_t)sj * M + si], 1ull);
+            if (acc) {
+                atomicAdd(&nacc[(size_t)si * M + sj], 1ull);
+                atomicAdd(&nacc[(size_t)sj * M + si], 1ull);
+                s_perm[i] = sj;
+                s_perm[j] = si;
+            }
+        }
+        (void)lt_mask;
+        h += advance;
+        remaining -= n;
+        __syncwarp();
+    }
+    for (int q = lane; q < K; q += 32) perm_g[q] = s_perm[q];
+    slow = __reduce_add_sync(0xffffffffu, (unsigned)slow);
+    if (lane == 0) {
+        ctl->head = h;
+        ctl->remaining = remaining;
+        ctl->status = remaining > 0 ? 1 : 0;
+        ctl->rounds += rounds;
+        ctl->slow_exp += slow;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Plain serial walker for any K (rejection sampling makes the slot structure state dependent).
+// head counts WORDS here.  An attempt that would run out of words is rolled back.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_mix_walk_serial(const uint32_t *__restrict__ words, long long nwords,
+                                                        const double *__restrict__ u, int K, int M, int *perm_g,
+                                                        unsigned long long *nacc, unsigned long long *nprop,
+                                                        MixCtl *ctl) {
+    extern __shared__ int s_perm[];
+    const int lane = threadIdx.x;
+    for (int q = lane; q < K; q += 32) s_perm[q] = perm_g[q];
+    __syncwarp();
+    if (lane == 0) {
+        long long p = ctl->head, remaining = ctl->remaining;
+        int nbits = 0;
+        for (unsigned m = (unsigned)(K - 1); m; m >>= 1) nbits++;
+        const uint32_t mask = nbits ? (0xffffffffu >> (32 - nbits)) : 0u;
+        while (remaining > 0) {
+            long long q = p;
+            int i = 0, j = 0;
+            bool ok = true;
+            if (K > 1) {
+                for (;;) { if (q >= nwords) { ok = false; break; } uint32_t r = words[q++] & mask; if ((int)r < K) { i = r; break; } }
+                if (ok) for (;;) { if (q >= nwords) { ok = false; break; } uint32_t r = words[q++] & mask; if ((int)r < K) { j = r; break; } }
+            }
+            if (!ok) break;
+            const int si = s_perm[i], sj = s_perm[j];
+            const double logp = swap_logp(u[(size_t)i * M + sj], u[(size_t)j * M + si], u[(size_t)i * M + si],
+                                          u[(size_t)j * M + sj]);
+            bool acc = logp >= 0.0;
+            if (!acc) {
+                if (q + 2 > nwords) break;
+                const double U = mt_double(words[q], words[q + 1]);
+                q += 2;
+                acc = U < exp(logp);
+            }
+            nprop[(size_t)si * M + sj] += 1;
+            nprop[(size_t)sj * M + si] += 1;
+            if (acc) {
+                s_perm[i] = sj;
+                s_perm[j] = si;
+                nacc[(size_t)si * M + sj] += 1;
+                nacc[(size_t)sj * M + si] += 1;
+            }
+            p = q;
+            remaining--;
+        }
+        ctl->head = p;
+        ctl->remaining = remaining;
+        ctl->status = remaining > 0 ? 1 : 0;
+    }
+    __syncwarp();
+    for (int q = lane; q < K; q += 32) perm_g[q] = s_perm[q];
+}
+
+// swap-neighbors (replicaexchange.py:366-406) on numpy's RandomState stream: offset = randint(2) is one
+// masked word; each state pair (s, s+1) is attempted once; rand() (two words) only when log_p < 0.
+__global__ void __launch_bounds__(32) k_mix_neighbors(const uint32_t *__restrict__ words, long long nwords,
+                                                      const double *__restrict__ u, int K, int M, int *perm_g,
+                                                      unsigned long long *nacc, unsigned long long *nprop,
+                                                      MixCtl *ctl) {
+    extern __shared__ int s_mem[];
+    int *s_perm = s_mem, *s_inv = s_mem + K;
+    const int lane = threadIdx.x;
+    for (int q = lane; q < K; q += 32) { int s = perm_g[q]; s_perm[q] = s; if (s >= 0 && s < K) s_inv[s] = q; }
+    __syncwarp();
+    if (lane == 0) {
+        long long p = 0;
+        const int offset = (int)(words[p++] & 1u);
+        for (int s = offset; s < K - 1; s += 2) {
+            const int i = s_inv[s], j = s_inv[s + 1];
+            const int si = s, sj = s + 1;
+            const double logp = swap_logp(u[(size_t)i * M + sj], u[(size_t)j * M + si], u[(size_t)i * M + si],
+                                          u[(size_t)j * M + sj]);
+            bool acc = logp >= 0.0;
+            if (!acc) {
+                const double U = mt_double(words[p], words[p + 1]);
+                p += 2;
+                acc = U < exp(logp);
+            }
+            nprop[(size_t)si * M + sj] += 1;
+            nprop[(size_t)sj * M + si] += 1;
+            if (acc) {
+                s_perm[i] = sj; s_perm[j] = si;
+                s_inv[sj] = i; s_inv[si] = j;
+                nacc[(size_t)si * M + sj] += 1;
+                nacc[(size_t)sj * M + si] += 1;
+            }
+        }
+        ctl->head = p;
+        ctl->remaining = 0;
+        ctl->status = 0;
+    }
+    __syncwarp();
+    for (int q = lane; q < K; q += 32) perm_g[q] = s_perm[q];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Host side: stream management
+// ------------------------------------------------------------------------------------------------------
+static int stream_reserve(rx_engine *h, MTStream &S, size_t cap) {
+    if (cap <= S.cap) return RX_OK;
+    uint32_t *a = nullptr, *b = nullptr;
+    RX_CHECK_CUDA(h, cudaMalloc(&a, cap * sizeof(uint32_t)));
+    RX_CHECK_CUDA(h, cudaMalloc(&b, cap * sizeof(uint32_t)));
+    if (S.avail) RX_CHECK_CUDA(h, cudaMemcpyAsync(a, S.d_words, S.avail * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(S.d_words);
+    cudaFree(S.d_words_alt);
+    S.d_words = a;
+    S.d_words_alt = b;
+    S.cap = cap;
+    return RX_OK;
+}
+
+// make at least `need` unconsumed words available
+static int stream_fill(rx_engine *h, MTStream &S, size_t need, int *launches) {
+    if (S.avail >= need) return RX_OK;
+    int rc = stream_reserve(h, S, need);
+    if (rc) return rc;
+    long long n = (long long)(need - S.avail);
+    k_mt_generate<<<1, 256, 0, h->stream>>>(S.d_window, S.d_words + S.avail, n);
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    S.avail = need;
+    (*launches)++;
+    return RX_OK;
+}
+
+static int stream_consume(rx_engine *h, MTStream &S, size_t c, int *launches) {
+    if (c > S.avail) RX_FAIL(h, RX_ERR_INVALID, "internal: consumed more words than available");
+    size_t left = S.avail - c;
+    if (left && c) {
+        k_copy_words<<<(unsigned)((left + 1023) / 1024 > 1184 ? 1184 : (left + 1023) / 1024), 1024, 0, h->stream>>>(
+            S.d_words + c, S.d_words_alt, (long long)left);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        std::swap(S.d_words, S.d_words_alt);
+        (*launches)++;
+    }
+    S.avail = left;
+    S.consumed += c;
+    return RX_OK;
+}
+
+int rxi_mix_seed(rx_engine *h, int stream, uint32_t seed) {
+    if (stream < 0 || stream > 1) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_seed: stream must be 0 (numba) or 1 (numpy)");
+    MTStream &S = h->streams[stream];
+    uint32_t mt[624];
+    mt[0] = seed;  // init_genrand, numba/_random.c:59-73
+    for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    if (!S.d_window) RX_CHECK_CUDA(h, cudaMalloc(&S.d_window, 624 * sizeof(uint32_t)));
+    RX_CHECK_CUDA(h, cudaMemcpy(S.d_window, mt, sizeof(mt), cudaMemcpyHostToDevice));
+    S.avail = 0;
+    S.consumed = 0;
+    S.seeded = true;
+    return RX_OK;
+}
+
+static inline bool is_pow2(int k) { return k >= 2 && (k & (k - 1)) == 0; }
+
+int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
+    MTStream &S = h->streams[RX_STREAM_NUMBA];
+    if (!S.seeded) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_swap_all: the numba MT19937 stream has not been seeded (rx_mix_seed)");
+    const int K = h->cfg.n_replicas, M = h->cfg.n_states;
+    if (K != M) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_swap_all: requires n_replicas == n_states");
+    const size_t mm = (size_t)M * M * sizeof(unsigned long long);
+    RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_nacc, 0, mm, h->stream));
+    RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_nprop, 0, mm, h->stream));
+    if (nswap <= 0) return RX_OK;
+    if (K == 1) {  // randint(1) draws nothing, log_p == 0: every attempt is an accepted no-op
+        unsigned long long two_n = 2ull * (unsigned long long)nswap;
+        RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_nacc, &two_n, 8, cudaMemcpyHostToDevice, h->stream));
+        RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_nprop, &two_n, 8, cudaMemcpyHostToDevice, h->stream));
+        RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+        return RX_OK;
+    }
+    const bool fast = is_pow2(K) && K <= 65536;
+    const size_t smem = (size_t)K * sizeof(int);
+    if (smem > 48 * 1024) {
+        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    long long remaining = nswap;
+    const size_t chunk_words = (size_t)1 << 26;  // 64 Mi words per pass
+    while (remaining > 0) {
+        size_t need = fast ? (size_t)(4 * remaining + 160) : (size_t)(8 * remaining + 512);
+        if (need > chunk_words) need = chunk_words;
+        if (need < 512) need = 512;
+        int rc = stream_fill(h, S, need, launches);
+        if (rc) return rc;
+        MixCtl ctl = {0, remaining, 0, 0, 0};
+        RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->stream));
+        size_t consumed_words;
+        if (fast) {
+            long long nslots = (long long)(S.avail / 2);
+            if ((size_t)nslots > h->slots_cap) {
+                cudaFree(h->d_slots);
+                h->d_slots = nullptr;
+                h->slots_cap = 0;
+                RX_CHECK_CUDA(h, cudaMalloc(&h->d_slots, (size_t)nslots * sizeof(SlotRec)));
+                h->slots_cap = (size_t)nslots;
+            }
+            k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(S.d_words, nslots, (uint32_t)(K - 1), h->d_slots);
+            RX_CHECK_CUDA(h, cudaGetLastError());
+            k_mix_walk_pow2<<<1, 32, smem, h->stream>>>(h->d_slots, S.d_words, nslots, h->d_u, K, M, h->d_perm, h->d_nacc,
+                                                      h->d_nprop, h->d_ctl);
+            RX_CHECK_CUDA(h, cudaGetLastError());
+            *launches += 2;
+            RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+            RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+            consumed_words = (size_t)(2 * ctl.head);
+        } else {
+            k_mix_walk_serial<<<1, 32, smem, h->stream>>>(S.d_words, (long long)S.avail, h->d_u, K, M, h->d_perm, h->d_nacc,
+                                                        h->d_nprop, h->d_ctl);
+            RX_CHECK_CUDA(h, cudaGetLastError());
+            *launches += 1;
+            RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+            RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+            consumed_words = (size_t)ctl.head;
+        }
+        if (ctl.remaining == remaining && consumed_words == 0 && need >= chunk_words)
+            RX_FAIL(h, RX_ERR_INVALID, "internal: mixing made no progress");
+        remaining = ctl.remaining;
+        rc = stream_consume(h, S, consumed_words, launches);
+        if (rc) return rc;
+    }
+    return RX_OK;
+}
+
+int rxi_mix_swap_neighbors(rx_engine *h, int *launches) {
+    MTStream &S = h->streams[RX_STREAM_NUMPY];
+    if (!S.seeded) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_swap_neighbors: the numpy MT19937 stream has not been seeded (rx_mix_seed)");
+    const int K = h->cfg.n_replicas, M = h->cfg.n_states;
+    if (K != M) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_swap_neighbors: requires n_replicas == n_states");
+    const size_t mm = (size_t)M * M * sizeof(unsigned long long);
+    RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_nacc, 0, mm, h->stream));
+    RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_nprop, 0, mm, h->stream));
+    int rc = stream_fill(h, S, (size_t)K + 64, launches);
+    if (rc) return rc;
+    const size_t smem = 2 * (size_t)K * sizeof(int);
+    if (smem > 48 * 1024)
+        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_neighbors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MixCtl ctl = {0, 0, 0, 0, 0};
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->stream));
+    k_mix_neighbors<<<1, 32, smem, h->stream>>>(S.d_words, (long long)S.avail, h->d_u, K, M, h->d_perm, h->d_nacc, h->d_nprop,
+                                              h->d_ctl);
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    (*launches)++;
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return stream_consume(h, S, (size_t)ctl.head, launches);
+}
+
+void rxi_mix_free(rx_engine *h) {
+    for (int s = 0; s < 2; s++) {
+        cudaFree(h->streams[s].d_window);
+        cudaFree(h->streams[s].d_words);
+        cudaFree(h->streams[s].d_words_alt);
+    }
+    cudaFree(h->d_slots);
+    cudaFree(h->d_ctl);
+}

@@ -1,0 +1,93 @@
+"""GPU mixing kernels (through the C ABI) against the golden vectors of the real reference and, at full
+size, against the pinned CPU oracle.  Bit-exact: permutation and both count matrices."""
+import os
+import numpy as np
+import pytest
+from energy_models import energies
+from helpers import gpu_engine
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'mixing_golden.npz'))
+
+
+def digest(mat):
+    m = mat.astype(np.uint64).ravel()
+    w = (np.arange(m.size, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1))
+    return np.array([m.sum(), (m * m).sum(), (m * w).sum()], dtype=np.uint64)
+
+
+def check_counts(key, mat):
+    if mat.shape[0] >= 100:
+        assert np.array_equal(G[key + '_digest'], digest(mat)), key
+    else:
+        assert np.array_equal(G[key], mat), key
+
+
+def parse(tag):
+    _, K, s, model = tag.split('_')
+    return int(K[1:]), int(s[1:]), model
+
+
+@pytest.mark.parametrize('tag', [str(t) for t in G['all_cases']])
+def test_swap_all_golden(tag):
+    K, seed, model = parse(tag)
+    u = energies(model, K, K * 1000 + (seed % 1000))
+    e = gpu_engine(0, K, K)
+    e.set_energies(u)
+    e.set_replica_states(np.arange(K))
+    e.mix_seed(seed, 0)
+    for call, nswap in ((1, K ** 3), (2, K ** 3), (3, 777)):
+        st, nacc, nprop = e.mix_swap_all(nswap)
+        assert np.array_equal(st, G[f'{tag}_perm{call}']), (tag, call)
+        check_counts(f'{tag}_nacc{call}', nacc)
+        check_counts(f'{tag}_nprop{call}', nprop)
+    e.close()
+
+
+@pytest.mark.parametrize('tag', [str(t) for t in G['nbr_cases']])
+def test_swap_neighbors_golden(tag):
+    K, seed, model = parse(tag)
+    u = energies(model, K, K * 77 + seed % 1000)
+    e = gpu_engine(0, K, K)
+    e.set_energies(u)
+    e.set_replica_states(np.arange(K))
+    e.mix_seed(seed, 1)
+    for it in range(6):
+        st, nacc, nprop = e.mix_swap_neighbors()
+        assert np.array_equal(st, G[f'{tag}_perms'][it]), (tag, it)
+    check_counts(f'{tag}_nacc_last', nacc)
+    check_counts(f'{tag}_nprop_last', nprop)
+    e.close()
+
+
+@pytest.mark.parametrize('K,model,seed', [(256, 'flat', 5), (256, 'normal', 6), (256, 'zeros', 7), (512, 'ladder', 8),
+                                          (1, 'zeros', 1), (96, 'flat', 9)])
+def test_swap_all_full_size_vs_oracle(K, model, seed):
+    """BASELINE.json sizes (K=256: 16.7M attempts) and beyond, three consecutive iterations, against the CPU
+    oracle that test_oracle_mixing.py pins to the reference."""
+    from oracle import oracle
+    u = energies(model, K, 4242 + K)
+    e = gpu_engine(0, K, K)
+    e.set_energies(u)
+    e.set_replica_states(np.arange(K))
+    e.mix_seed(seed, 0)
+    mt = oracle.MT(seed)
+    st_o = np.arange(K, dtype=np.int64)
+    nswap = K ** 3 if K <= 256 else 3_000_000
+    for it in range(2):
+        st, nacc, nprop = e.mix_swap_all(nswap)
+        na = np.zeros((K, K), np.int64); npr = np.zeros((K, K), np.int64)
+        oracle.mix_swap_all(mt, nswap, st_o, u, na, npr)
+        assert np.array_equal(st, st_o)
+        assert np.array_equal(nacc, na) and np.array_equal(nprop, npr)
+        assert nprop.sum() == 2 * nswap
+        assert sorted(st) == list(range(K))
+    e.close()
+
+
+def test_unseeded_stream_is_an_error():
+    from openmmtools_b200._engine import EngineError
+    e = gpu_engine(0, 4, 4)
+    with pytest.raises(EngineError):
+        e.mix_swap_all(10)
+    e.close()

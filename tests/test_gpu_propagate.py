@@ -1,0 +1,107 @@
+"""k_propagate (float32 state, one CTA per replica) against the double-precision oracle integrator fed with the
+same Philox noise.  Dynamics cannot be compared with OpenMM bit for bit (its Gaussian stream is internal), so
+parity is: identical update rule on identical inputs and noise, to float32 accuracy."""
+import numpy as np
+import pytest
+from helpers import lj_setup, oracle_system, gpu_engine, KB, device_noise, device_reassign_noise
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(s, K, M, lambdas, temps, dt, gamma, n_steps, splitting):
+    e = gpu_engine(1, K, M, s['N'], box=(s['L'],) * 3, r_cutoff=s['rc'], r_switch=s['rs'], use_switch=True)
+    e.set_particles(s['sigma'], s['eps'], s['mass'], s['alch'])
+    e.set_states(temps, lambdas)
+    e.set_integrator(dt, gamma, n_steps, splitting)
+    return e
+
+
+@pytest.mark.parametrize('splitting,n_steps', [('V R O R V', 1), ('V R O R V', 8), ('O V R V O', 4), ('R V O', 3),
+                                               ('V R R O R R V', 2)])
+def test_steps_match_oracle_with_same_noise(splitting, n_steps):
+    N, K, M = 256, 4, 4
+    s = lj_setup(N=N, n_alch=6, seed=11)
+    lambdas = np.array([1.0, 0.6, 0.3, 0.0]); temps = np.array([300.0, 310.0, 320.0, 330.0])
+    dt, gamma = 0.002, 10.0
+    e = make_engine(s, K, M, lambdas, temps, dt, gamma, n_steps, splitting)
+    rng = np.random.default_rng(2)
+    x0 = np.stack([s['x']] * K)
+    v0 = rng.normal(scale=0.25, size=(K, N, 3)).astype(np.float32).astype(np.float64)
+    e.set_positions(x0); e.set_velocities(v0)
+    states = np.array([2, 0, 3, 1])
+    e.set_replica_states(states)
+    seed, iteration = 0x1234567890ABCDEF, 7
+    e.propagate(seed, iteration)
+    xg = e.get_positions(); vg = e.get_velocities()
+    pot, kin = e.get_replica_energies()
+    osys = oracle_system(s)
+    prog = splitting.replace(' ', '')
+    nO = prog.count('O')
+    for k in range(K):
+        x = x0[k].copy(); v = v0[k].copy()
+        noise = device_noise(seed, iteration, k, N, n_steps * nO)
+        U = osys.langevin(x, v, noise, lambdas[states[k]], KB * temps[states[k]], dt, gamma, n_steps, prog)
+        xw = x - s['L'] * np.floor(x / s['L'])
+        d = xg[k] - xw
+        d -= s['L'] * np.round(d / s['L'])
+        assert np.abs(d).max() < 2e-5, (k, np.abs(d).max())
+        assert np.abs(vg[k] - v).max() < 2e-4, (k, np.abs(vg[k] - v).max())
+        assert abs(pot[k] - U) < 1e-3 * max(1.0, abs(U)), (pot[k], U)
+        ke = 0.5 * (s['mass'][:, None] * v * v).sum()
+        assert abs(kin[k] - ke) < 1e-4 * ke
+    e.close()
+
+
+def test_reassign_velocities_uses_maxwell_boltzmann():
+    N, K, M = 512, 8, 8
+    s = lj_setup(N=N, n_alch=10, seed=12)
+    temps = np.linspace(250, 400, M); lambdas = np.ones(M)
+    e = make_engine(s, K, M, lambdas, temps, 0.001, 10.0, 0, 'V R O R V')
+    e.set_positions(np.stack([s['x']] * K))
+    e.set_replica_states(np.arange(K))
+    e.propagate(99, 3, reassign_velocities=True)
+    v = e.get_velocities()
+    for k in range(K):
+        g = device_reassign_noise(99, 3, k, N)
+        ref = np.sqrt(KB * temps[k] / s['mass'][0]) * g
+        assert np.abs(v[k] - ref).max() < 1e-5
+        T_kin = (s['mass'][:, None] * v[k] ** 2).sum() / (3 * N * KB)
+        assert abs(T_kin / temps[k] - 1) < 0.15
+    e.close()
+
+
+def test_harmonic_oscillator_steps():
+    from oracle import oracle
+    N, K, M = 1, 3, 3
+    e = gpu_engine(2, K, M, N)
+    mass = np.array([39.948])
+    e.set_particles(None, None, mass, None)
+    Ks = np.array([100.0, 200.0, 400.0]) * 4.184 * 100
+    x0s = np.array([[0.0, 0, 0], [0.1, 0, 0], [0.0, -0.1, 0.05]])
+    temps = np.array([300.0, 310.0, 320.0])
+    e.set_states(temps, None, np.array([0.0, 1.0, 2.0]), Ks, x0s)
+    n_steps, dt, gamma = 50, 0.001, 10.0
+    e.set_integrator(dt, gamma, n_steps, 'V R O R V')
+    x0 = np.array([[[0.01, 0.02, -0.01]], [[0.1, 0.0, 0.0]], [[0.0, 0.0, 0.0]]])
+    v0 = np.array([[[0.1, -0.2, 0.3]], [[0.0, 0.1, 0.0]], [[0.2, 0.2, 0.2]]])
+    e.set_positions(x0); e.set_velocities(v0)
+    e.set_replica_states(np.array([1, 2, 0]))
+    e.propagate(5, 0)
+    xg, vg = e.get_positions(), e.get_velocities()
+    pot, kin = e.get_replica_energies()
+    st = [1, 2, 0]
+    for k in range(K):
+        x = x0[k].astype(np.float32).astype(np.float64); v = v0[k].astype(np.float32).astype(np.float64)
+        noise = device_noise(5, 0, k, N, n_steps)
+        U = oracle.ho_langevin(x, v, mass, noise, Ks[st[k]], x0s[st[k]], [0.0, 1.0, 2.0][st[k]], KB * temps[st[k]], dt,
+                               gamma, n_steps)
+        assert np.abs(xg[k] - x).max() < 1e-5
+        assert np.abs(vg[k] - v).max() < 1e-4
+        assert abs(pot[k] - U) < 1e-4 * max(1, abs(U))
+    # energies: u[k,l] = beta_l (K_l/2 |x-x0_l|^2 + U0_l)
+    u = e.compute_energies()
+    for k in range(K):
+        for l in range(M):
+            ref = (0.5 * Ks[l] * ((xg[k][0] - x0s[l]) ** 2).sum() + [0.0, 1.0, 2.0][l]) / (KB * temps[l])
+            assert abs(u[k, l] - ref) < 1e-5 * max(1, abs(ref))
+    e.close()
