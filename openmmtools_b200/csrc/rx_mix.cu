@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict_
     long long remaining = ctl->remaining;
     int rounds = 0;
     long long slow = 0;
-    const unsigned lt_mask = (1u << lane) - 1u;
     while (remaining > 0 && h + 33 <= nslots) {
         rounds++;
         const SlotRec r = rec[h + lane];
@@ -186,7 +185,9 @@ __global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict_
         int n = __popc(cm);
         long long advance;
         if ((long long)n > remaining) {
-            const int pos = __fns(cm, 0, (int)remaining + 1);  // the first visited lane we must NOT run
+            int pos = 0;  // the first visited lane we must NOT run: the (remaining+1)-th set bit of cm
+            for (int cnt = 0; pos < 32; pos++)
+                if ((cm >> pos) & 1u) { if (cnt == (int)remaining) break; cnt++; }
             cm &= (1u << pos) - 1u;
             n = (int)remaining;
             advance = pos;
@@ -201,11 +202,12 @@ __global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict_
             if (acc) {
                 atomicAdd(&nacc[(size_t)si * M + sj], 1ull);
                 atomicAdd(&nacc[(size_t)sj * M + si], 1ull);
-                s_perm[i] = sj;
-                s_perm[j] = si;
+                if (i != j) {  // an i == j lane must not write: a later committed lane may swap this replica
+                    s_perm[i] = sj;
+                    s_perm[j] = si;
+                }
             }
         }
-        (void)lt_mask;
         h += advance;
         remaining -= n;
         __syncwarp();
