@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- replica-exchange iterations/second on the 256-replica alchemical Lennard-Jones fluid.
+
+Workload (BASELINE.json metric): LennardJonesFluid(512) made alchemical with
+AbsoluteAlchemicalFactory (atoms 0-9, annihilate_sterics=False, disable_alchemical_dispersion_correction=True),
+K = M = 256 states lambda_l = 1 - l/(K-1) at 300 K, LangevinSplittingDynamicsMove("V R O R V", 1 fs, 10/ps,
+500 steps), swap-all mixing (K^3 = 16 777 216 attempts).  One "step" = one iteration = mix -> propagate ->
+energies (multistatesampler.py:776-782).  Strong scaling: the 256 replicas are sharded over --gpus ranks.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...        (the CPU arm: the oracle port of the reference's path, all host cores)
+
+`value`   : device-resident loop (rx_run_iterations), CUDA events on the engine's stream, max over ranks.
+`e2e`     : the same iterations through the public API (ReplicaExchangeSampler.run with host_resident_states=True):
+            every iteration pushes all positions+velocities from (pinned-staged) host memory, and pulls them, the
+            energy matrix, the permutation and the swap statistics back.
+torch.distributed (gloo) is plumbing only: barrier, max-reduction of the timings, broadcast of the NCCL id.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KB = 8.31446261815324e-3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--replicas', type=int, default=256)
+    ap.add_argument('--atoms', type=int, default=512)
+    ap.add_argument('--md-steps', type=int, default=500)
+    ap.add_argument('--mixing', default='swap-all', choices=['swap-all', 'swap-neighbors', 'none'])
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def build_workload(K, N):
+    from openmmtools_b200 import testsystems, alchemy, states, unit
+    fluid = testsystems.LennardJonesFluid(nparticles=N)
+    factory = alchemy.AbsoluteAlchemicalFactory(disable_alchemical_dispersion_correction=True)
+    region = alchemy.AlchemicalRegion(alchemical_atoms=range(10), annihilate_sterics=False)
+    asys = factory.create_alchemical_system(fluid.system, region)
+    lambdas = [1.0 - l / (K - 1) for l in range(K)]
+    protocol = {'lambda_sterics': lambdas, 'lambda_electrostatics': lambdas}
+    tstates = states.create_thermodynamic_state_protocol(
+        asys, protocol, constants={'temperature': 300.0 * unit.kelvin},
+        composable_states=alchemy.AlchemicalState.from_system(asys))
+    sstate = states.SamplerState(fluid.positions, box_vectors=asys.getDefaultPeriodicBoxVectors())
+    return fluid, asys, tstates, sstate, lambdas
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.p = None
+        self.path = '/tmp/rx_clocks_%d.csv' % os.getpid()
+        try:
+            self.f = open(self.path, 'w')
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(device), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                   'samples': len(sm)}
+        return out
+
+
+class Dist:
+    def __init__(self, world):
+        self.world = world
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            os.environ.setdefault('MASTER_PORT', '29511')
+            dist.init_process_group('gloo', rank=self.rank, world_size=world)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max(self, v):
+        if not self.dist:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum(self, v):
+        if not self.dist:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t[0])
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_arm(args, steps, warmup, full_line):
+    """The reference's CPU path restated (oracle/rx_oracle.c): numba-identical mixing (single thread, it is a
+    serial chain), Verlet-list Langevin propagation and the energy matrix with OpenMP over replicas on all host
+    cores.  One step = one full iteration of the same workload."""
+    from oracle import oracle
+    K, N = args.replicas, args.atoms
+    fluid, asys, tstates, sstate, lambdas = build_workload(K, N)
+    L = asys.box_vectors[0, 0]
+    osys = oracle.LJSystem(asys.sigma, asys.epsilon, asys.masses, asys.alchemical_mask(), (L, L, L), asys.cutoff,
+                           asys.switching_distance, use_switch=True)
+    threads = oracle.max_threads()
+    rng = np.random.default_rng(2024)
+    x = np.stack([np.asarray(sstate._positions)] * K)
+    v = rng.normal(scale=np.sqrt(KB * 300.0 / asys.masses[0]), size=x.shape)
+    lam = np.array(lambdas); betas = np.full(K, 1.0 / (KB * 300.0)); kTs = np.full(K, KB * 300.0)
+    perm = np.arange(K, dtype=np.int64)
+    mt = oracle.MT(1234)
+    u = osys.energy_matrix(x, lam, betas, None, threads)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.time()
+        nacc = np.zeros((K, K), np.int64); nprop = np.zeros((K, K), np.int64)
+        if args.mixing == 'swap-all':
+            oracle.mix_swap_all(mt, K ** 3, perm, u, nacc, nprop)
+        elif args.mixing == 'swap-neighbors':
+            oracle.mix_swap_neighbors(mt, perm, u, nacc, nprop)
+        t1 = time.time()
+        osys.propagate_replicas(x, v, lam[perm], kTs, 0.001, 10.0, args.md_steps, 7 + it, threads)
+        t2 = time.time()
+        u = osys.energy_matrix(x, lam, betas, None, threads)
+        t3 = time.time()
+        if it >= warmup:
+            times.append((t3 - t0, t1 - t0, t2 - t1, t3 - t2))
+    tt = np.array(times)
+    mean = tt[:, 0].mean()
+    base = {'value': 1.0 / mean, 'unit': 'iterations/s', 'cores': threads, 'kind': 'port',
+            'sample': '%d full iterations (K=%d, N=%d, %d BAOAB steps, %s): mixing single-threaded (serial chain), '
+                      'propagation+energies OpenMP over replicas on %d threads; oracle/rx_oracle.c (OpenMM itself is '
+                      'not installable here)' % (steps, K, N, args.md_steps, args.mixing, threads),
+            'phases_ms': {'mix': 1e3 * tt[:, 1].mean(), 'propagate': 1e3 * tt[:, 2].mean(), 'energies': 1e3 * tt[:, 3].mean()}}
+    if not full_line:
+        return base
+    line = {'impl': 'reference', 'metric': 'replica-exchange iterations/sec, 256-replica alchemical LJ fluid',
+            'value': 1.0 / mean, 'unit': 'iterations/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': 1e3 * mean, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args), 'cpu_baseline': base,
+            'e2e': {'value': 1.0 / mean, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    return line
+
+
+def workload_config(args):
+    return {'workload': 'configs[2]: alchemical LennardJonesFluid(%d), %d lambda-replicas, %d BAOAB steps/iter, %s'
+                        % (args.atoms, args.replicas, args.md_steps, args.mixing),
+            'replicas': args.replicas, 'atoms': args.atoms, 'md_steps': args.md_steps, 'mixing': args.mixing,
+            'parallelism': 'replica-sharded x%d, NCCL allgather of energy rows, replicated mixing' % args.gpus,
+            'l2': 'no explicit flush: each iteration streams ~0.8 GB of RNG words + slot records (> 126 MB L2); the '
+                  '4 MB replica state is the resident working set by design'}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        line = cpu_arm(args, args.steps, max(args.warmup, 0), True)
+        print(json.dumps(line))
+        return 0
+
+    if world != args.gpus and world > 1:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
+    dist = Dist(world)
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    K, N = args.replicas, args.atoms
+    from openmmtools_b200 import multistate, mcmc, unit, _lib
+    from openmmtools_b200._dist import TorchCommunicator
+    fluid, asys, tstates, sstate, lambdas = build_workload(K, N)
+    mixing = None if args.mixing == 'none' else args.mixing
+    move = mcmc.LangevinSplittingDynamicsMove(timestep=1.0 * unit.femtosecond, collision_rate=10.0 / unit.picosecond,
+                                              n_steps=args.md_steps, reassign_velocities=False, splitting='V R O R V')
+    comm = TorchCommunicator() if world > 1 else None
+    os.environ['LOCAL_RANK'] = str(local_rank)
+    sampler = multistate.ReplicaExchangeSampler(mcmc_moves=move, number_of_iterations=10 ** 9, replica_mixing_scheme=mixing,
+                                                seed=1234, communicator=comm)
+    sampler.create(tstates, [sstate], storage=None)
+    eng = sampler._engine
+    # iteration 0 energies, as run() does
+    sampler._compute_energies()
+
+    # ---------------- device-resident loop
+    eng.run_iterations(args.warmup, mixing, sampler._seed, 1)
+    eng.phase_times(reset=True)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    dist.barrier()
+    eng.timer_mark(0)
+    t0 = time.time()
+    eng.run_iterations(args.steps, mixing, sampler._seed, 1 + args.warmup)
+    eng.timer_mark(1)
+    ms_dev = eng.timer_elapsed_ms()
+    wall = time.time() - t0
+    dist.barrier()
+    ms = dist.max(ms_dev)
+    ck = clocks.stop() if clocks else None
+    pt = eng.phase_times()
+    mstats = eng.mix_stats()
+    launches = dist.sum(pt['launches'])
+    value = args.steps / (ms * 1e-3)
+
+    # roofline of k_propagate (the HBM-streaming kernel of SURVEY.md 8d): algorithmic bytes per launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    kloc = eng.k1 - eng.k0
+    b_prop = kloc * N * args.md_steps * 64.0
+    t_prop = pt['propagate_ms'] / max(args.steps, 1) * 1e-3
+    ach = b_prop / t_prop / 1e9 if t_prop > 0 else 0.0
+    b_iter = K * N * args.md_steps * 64.0 / world + K * N * 16.0 / world + 2 * K * K * 8.0 + K * 8.0
+    roof = {'kernel': 'k_propagate', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+            'frac': ach / peak, 'traffic': None,
+            'peak_source': 'MEASURED_PEAKS.json (of measured)' if peaks else 'fallback 6650 GB/s',
+            'algorithmic_bytes_per_launch': b_prop,
+            'whole_iteration': {'bytes': b_iter, 'achieved': b_iter / (ms * 1e-3 / args.steps) / 1e9,
+                                'frac': b_iter / (ms * 1e-3 / args.steps) / 1e9 / peak},
+            'note': 'wall-clock is dominated by the exact swap-all mixing chain (serial dependency, latency bound), '
+                    'not by HBM traffic; see phases_ms'}
+
+    # ---------------- end to end through the public API with host-resident sampler states
+    e2e = None
+    if not args.no_e2e:
+        sampler.host_resident_states = True
+        sampler._states_stale = True
+        sampler._sync_sampler_states()
+        sampler._iteration = 1 + args.warmup + args.steps
+        n_e2e = max(2, min(args.steps, 5))
+        sampler.run(1)      # warm the host path
+        dist.barrier()
+        t0 = time.time()
+        sampler.run(n_e2e)
+        dt = time.time() - t0
+        dist.barrier()
+        dt = dist.max(dt)
+        h2d = kloc * N * 3 * 8 * 2
+        d2h = kloc * N * 3 * 8 * 2 + K * K * 8 + K * 8 + 2 * K * K * 8 + 2 * K * 8
+        e2e = {'value': n_e2e / dt, 'unit': 'iterations/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+               'iterations': n_e2e, 'api': 'ReplicaExchangeSampler.run(host_resident_states=True)'}
+
+    if rank != 0:
+        return 0
+    line = {'metric': 'replica-exchange iterations/sec, 256-replica alchemical LJ fluid',
+            'value': value, 'unit': 'iterations/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32 dynamics, f64 energies and mixing', 'data': 'synthetic',
+            'config': workload_config(args), 'roofline': roof,
+            'phases_ms': {'mix': pt['mix_ms'] / args.steps, 'propagate': pt['propagate_ms'] / args.steps,
+                          'energies_incl_allgather': pt['energies_ms'] / args.steps},
+            'mixing_stats': mstats, 'clocks': ck, 'e2e': e2e, 'gpu_launches': int(launches),
+            'host_wall_ms_per_step': 1e3 * wall / args.steps}
+    if not args.no_cpu_baseline:
+        try:
+            line['cpu_baseline'] = cpu_arm(args, 2, 1, False)
+        except Exception as e:   # the oracle is test infrastructure; never fail the GPU number because of it
+            line['cpu_baseline'] = {'error': repr(e)}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -149,6 +149,14 @@ RX_API int rx_run_iterations(rx_engine *h, int32_t n_iterations, int32_t mixing,
  * counts[i] = number of launches of my kernels in phase i.                                                */
 RX_API int rx_get_phase_times(rx_engine *h, double ms[4], int64_t counts[4], int32_t reset);
 
+/* CUDA-event stopwatch on the engine's stream: rx_timer_mark(h, 0|1) records an event (asynchronously);
+ * rx_timer_elapsed synchronises and returns the device time between mark 0 and mark 1 in ms.                 */
+RX_API int rx_timer_mark(rx_engine *h, int32_t which);
+RX_API int rx_timer_elapsed(rx_engine *h, double *ms);
+/* Mixing-kernel statistics of the last swap-all call: [0] speculation rounds, [1] exact-exp fallbacks,
+ * [2] passes, [3] MT words consumed.                                                                          */
+RX_API int rx_get_mix_stats(rx_engine *h, int64_t out[4]);
+
 /* ---- multi-GPU ------------------------------------------------------------------------------------ */
 /* NCCL is loaded with dlopen(nccl_library_path).  Rank 0 creates an id (rx_comm_unique_id), the host code
  * distributes its bytes (torch.distributed / MPI / a file), every rank calls rx_comm_init.  Replaces

@@ -199,6 +199,19 @@ class Engine:
         return dict(mix_ms=ms[0], propagate_ms=ms[1], energies_ms=ms[2], rng_ms=ms[3],
                     launches=int(cnt.sum()), launches_by_phase=cnt.tolist())
 
+    def timer_mark(self, which):
+        self._check(self._lib.rx_timer_mark(self._h, int(which)))
+
+    def timer_elapsed_ms(self):
+        v = C.c_double()
+        self._check(self._lib.rx_timer_elapsed(self._h, C.byref(v)))
+        return v.value
+
+    def mix_stats(self):
+        out = np.zeros(4, np.int64)
+        self._check(self._lib.rx_get_mix_stats(self._h, _ptr(out)))
+        return dict(rounds=int(out[0]), exact_exp=int(out[1]), passes=int(out[2]), words=int(out[3]))
+
     # -- multi-GPU
     @staticmethod
     def comm_unique_id(nccl_path=None):

@@ -21,7 +21,7 @@ SYMBOLS = [
     'rx_get_replica_energies', 'rx_randomize_velocities', 'rx_set_replica_states', 'rx_get_replica_states',
     'rx_propagate', 'rx_compute_energies', 'rx_set_energies', 'rx_get_energies', 'rx_mix_seed',
     'rx_mix_swap_all', 'rx_mix_swap_neighbors', 'rx_get_mix_counts', 'rx_mix_stream_position',
-    'rx_run_iterations', 'rx_get_phase_times', 'rx_comm_unique_id', 'rx_comm_init',
+    'rx_run_iterations', 'rx_get_phase_times', 'rx_timer_mark', 'rx_timer_elapsed', 'rx_get_mix_stats', 'rx_comm_unique_id', 'rx_comm_init',
 ]
 
 
@@ -78,6 +78,9 @@ def load():
     lib.rx_mix_stream_position.argtypes = [vp, i32, C.POINTER(u64)]
     lib.rx_run_iterations.argtypes = [vp, i32, i32, u64, u64, i32]
     lib.rx_get_phase_times.argtypes = [vp, vp, vp, i32]
+    lib.rx_timer_mark.argtypes = [vp, i32]
+    lib.rx_timer_elapsed.argtypes = [vp, C.POINTER(dbl)]
+    lib.rx_get_mix_stats.argtypes = [vp, vp]
     lib.rx_comm_unique_id.argtypes = [C.c_char_p, vp]
     lib.rx_comm_init.argtypes = [vp, C.c_char_p, vp]
     if lib.rx_abi_version() != RX_ABI_VERSION:

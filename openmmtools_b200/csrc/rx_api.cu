@@ -54,6 +54,7 @@ extern "C" int rx_create(const rx_config *cfg, rx_engine **out) {
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream_rng, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) CREATE_CUDA(cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&h->ev_user[i]));
     CREATE_CUDA(cudaMalloc(&h->d_perm, sizeof(int) * K));
     CREATE_CUDA(cudaMalloc(&h->d_u, sizeof(double) * (size_t)K * M));
     CREATE_CUDA(cudaMemset(h->d_u, 0, sizeof(double) * (size_t)K * M));
@@ -83,6 +84,7 @@ extern "C" int rx_create(const rx_config *cfg, rx_engine **out) {
         CREATE_CUDA(cudaMemset(h->d_pos, 0, sizeof(float4) * n));
         CREATE_CUDA(cudaMemset(h->d_vel, 0, sizeof(float4) * n));
         CREATE_CUDA(cudaMalloc(&h->d_io, sizeof(double) * 3 * n));
+        CREATE_CUDA(cudaHostAlloc(&h->h_io, sizeof(double) * 3 * n, cudaHostAllocDefault));
         CREATE_CUDA(cudaMalloc(&h->d_atom, sizeof(float4) * N));
         CREATE_CUDA(cudaMalloc(&h->d_atom_d, sizeof(double4) * N));
         CREATE_CUDA(cudaMalloc(&h->d_alch_list, sizeof(int) * N));
@@ -106,6 +108,8 @@ extern "C" void rx_destroy(rx_engine *h) {
     cudaFree(h->d_nacc); cudaFree(h->d_nprop); cudaFree(h->d_pot); cudaFree(h->d_kin); cudaFree(h->d_nan);
     cudaFree(h->d_err); cudaFree(h->d_pairs);
     for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; i++) if (h->ev_user[i]) cudaEventDestroy(h->ev_user[i]);
+    if (h->h_io) cudaFreeHost(h->h_io);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_rng) cudaStreamDestroy(h->stream_rng);
     delete h;
@@ -450,6 +454,27 @@ extern "C" int rx_get_phase_times(rx_engine *h, double ms[4], int64_t counts[4],
         if (counts) counts[i] = h->phase_launches[i];
         if (reset) { h->phase_ms[i] = 0; h->phase_launches[i] = 0; }
     }
+    return RX_OK;
+}
+
+extern "C" int rx_timer_mark(rx_engine *h, int32_t which) {
+    ENTER(h);
+    if (which < 0 || which > 1) RX_FAIL(h, RX_ERR_INVALID, "rx_timer_mark: which must be 0 or 1");
+    RX_CHECK_CUDA(h, cudaEventRecord(h->ev_user[which], h->stream));
+    return RX_OK;
+}
+extern "C" int rx_timer_elapsed(rx_engine *h, double *ms) {
+    ENTER(h);
+    if (!ms) RX_FAIL(h, RX_ERR_INVALID, "rx_timer_elapsed: null");
+    RX_CHECK_CUDA(h, cudaEventSynchronize(h->ev_user[1]));
+    float f = 0;
+    RX_CHECK_CUDA(h, cudaEventElapsedTime(&f, h->ev_user[0], h->ev_user[1]));
+    *ms = f;
+    return RX_OK;
+}
+extern "C" int rx_get_mix_stats(rx_engine *h, int64_t out[4]) {
+    ENTER(h);
+    for (int i = 0; i < 4; i++) out[i] = h->mix_stats[i];
     return RX_OK;
 }
 

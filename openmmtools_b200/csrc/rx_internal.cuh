@@ -51,6 +51,8 @@ struct rx_engine {
     int k0 = 0, kloc = 0;  // owned replicas [k0, k0+kloc)
     cudaStream_t stream = nullptr, stream_rng = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_user[2] = {};
+    long long mix_stats[4] = {0, 0, 0, 0};
     // particles
     float4 *d_atom = nullptr;     // (sigma, sqrt_eps, inv_mass, alch ? 1 : 0)
     double4 *d_atom_d = nullptr;  // (sigma, eps, mass, alch)
@@ -62,6 +64,7 @@ struct rx_engine {
     // replica state
     float4 *d_pos = nullptr, *d_vel = nullptr;  // [kloc][N]
     double *d_io = nullptr;                     // staging for set/get: [kloc][N][3]
+    double *h_io = nullptr;                     // pinned host staging of the same size
     int *d_perm = nullptr;                      // [K] replica -> state
     double *d_u = nullptr;                      // [K][M]
     unsigned long long *d_nacc = nullptr, *d_nprop = nullptr;  // [M][M]

@@ -405,6 +405,8 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     long long remaining = nswap;
+    h->mix_stats[0] = h->mix_stats[1] = h->mix_stats[2] = 0;
+    const uint64_t consumed0 = S.consumed;
     const size_t chunk_words = (size_t)1 << 26;  // 64 Mi words per pass
     while (remaining > 0) {
         size_t need = fast ? (size_t)(4 * remaining + 160) : (size_t)(8 * remaining + 512);
@@ -445,9 +447,13 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         if (ctl.remaining == remaining && consumed_words == 0 && need >= chunk_words)
             RX_FAIL(h, RX_ERR_INVALID, "internal: mixing made no progress");
         remaining = ctl.remaining;
+        h->mix_stats[0] += ctl.rounds;
+        h->mix_stats[1] += ctl.slow_exp;
+        h->mix_stats[2] += 1;
         rc = stream_consume(h, S, consumed_words, launches);
         if (rc) return rc;
     }
+    h->mix_stats[3] = (long long)(S.consumed - consumed0);
     return RX_OK;
 }
 

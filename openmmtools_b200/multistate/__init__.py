@@ -1,0 +1,4 @@
+"""multistate samplers on the B200 engine (mirrors openmmtools.multistate for the replica-exchange path)."""
+from .multistatesampler import MultiStateSampler
+from .replicaexchange import ReplicaExchangeSampler
+from .utils import SimulationNaNError

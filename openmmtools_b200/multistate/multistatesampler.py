@@ -1,0 +1,427 @@
+"""MultiStateSampler: K replicas x M thermodynamic states on one (or several) B200s.
+
+Mirrors /root/reference/openmmtools/multistate/multistatesampler.py for the hot path: ``create`` (:537-609,
+836-926), ``run`` (:724-804), ``extend`` (:806), ``equilibrate`` (:649-720) and the three hooks
+``_mix_replicas`` (:1500-1517), ``_propagate_replicas`` (:1287-1337), ``_compute_energies`` (:1436-1494).
+
+What is different by design: the replicas are resident on the GPU (float4 positions/velocities for all K
+replicas, the K x M energy matrix, the replica->state map, the swap statistics), the three phases are three
+kernel launches, and ``sampler_states`` are materialised on the host only when asked for (or every iteration with
+``host_resident_states=True``, which reproduces the reference's per-iteration host round trip).  Storage
+(NetCDF reporter), online MBAR analysis and minimisation are outside the hot path.
+
+Multi-GPU: one process per GPU (torchrun style: RANK / WORLD_SIZE / LOCAL_RANK); replicas are sharded in contiguous
+blocks, energy rows are all-gathered with NCCL, mixing is replicated from identical generator state.
+"""
+import collections
+import copy
+import logging
+import os
+import time
+import numpy as np
+from .. import unit, mcmc, states, _backend, _lib
+from .._engine import EngineError
+from ..cache import ContextCache
+from .utils import SimulationNaNError
+
+logger = logging.getLogger(__name__)
+
+
+class MultiStateSampler:
+    """Base class for samplers of multiple thermodynamic states (multistatesampler.py:63)."""
+
+    _TITLE_TEMPLATE = ('Multi-state sampler simulation created using MultiStateSampler class '
+                       'of openmmtools_b200.multistate on {}')
+    Status = collections.namedtuple('Status', ['iteration', 'target_error', 'is_completed'])
+    _global_citation_silence = False
+
+    def __init__(self, mcmc_moves=None, number_of_iterations=1, online_analysis_interval=200,
+                 online_analysis_target_error=0.0, online_analysis_minimum_iterations=200, locality=None,
+                 host_resident_states=False, seed=None, communicator=None):
+        if locality is not None:
+            raise NotImplementedError('locality (neighbourhood-restricted energies) is not provided yet')
+        # default move as the reference (multistatesampler.py:222-227)
+        if mcmc_moves is None:
+            self._mcmc_moves = mcmc.LangevinDynamicsMove(timestep=2.0 * unit.femtosecond,
+                                                         collision_rate=5.0 / unit.picosecond, n_steps=500,
+                                                         reassign_velocities=True, n_restart_attempts=6)
+        else:
+            self._mcmc_moves = copy.deepcopy(mcmc_moves)
+        self._thermodynamic_states = None
+        self._unsampled_states = None
+        self._sampler_states = None
+        self._replica_thermodynamic_states = None
+        self._iteration = None
+        self._energy_thermodynamic_states = None
+        self._neighborhoods = None
+        self._energy_unsampled_states = None
+        self._n_accepted_matrix = None
+        self._n_proposed_matrix = None
+        self._metadata = None
+        self._timing_data = dict()
+        self._have_displayed_citations_before = False
+        self.number_of_iterations = number_of_iterations
+        self.online_analysis_interval = online_analysis_interval
+        self.online_analysis_target_error = online_analysis_target_error
+        self.online_analysis_minimum_iterations = online_analysis_minimum_iterations
+        self.locality = locality
+        self.host_resident_states = host_resident_states
+        self.energy_context_cache = ContextCache()
+        self.sampler_context_cache = ContextCache()
+        self._engine = None
+        self._states_stale = False     # host copies of sampler states are behind the device
+        self._seed = seed
+        self._communicator = communicator
+        self._rank = int(os.environ.get('RANK', '0')) if communicator is None else communicator.rank
+        self._world_size = int(os.environ.get('WORLD_SIZE', '1')) if communicator is None else communicator.world_size
+
+    # ------------------------------------------------------------------ properties (multistatesampler.py:365-535)
+    @property
+    def n_states(self):
+        return None if self._thermodynamic_states is None else len(self._thermodynamic_states)
+
+    @property
+    def n_replicas(self):
+        return None if self._sampler_states is None else len(self._sampler_states)
+
+    @property
+    def iteration(self):
+        return self._iteration
+
+    @property
+    def mcmc_moves(self):
+        return copy.deepcopy(self._mcmc_moves)
+
+    @mcmc_moves.setter
+    def mcmc_moves(self, new_value):
+        if self._thermodynamic_states is not None:
+            raise RuntimeError('Cannot modify MCMC move after initialization (create()).')
+        self._mcmc_moves = copy.deepcopy(new_value)
+
+    @property
+    def sampler_states(self):
+        """Deep copies of the sampler states (multistatesampler.py:410-429); pulls them from the GPU if needed."""
+        self._sync_sampler_states()
+        return copy.deepcopy(self._sampler_states)
+
+    @sampler_states.setter
+    def sampler_states(self, value):
+        if self._iteration != 0:
+            raise RuntimeError('Sampler states can be assigned only between create() and run().')
+        if len(value) != self.n_replicas:
+            raise ValueError('Passed {} sampler states for {} replicas'.format(len(value), self.n_replicas))
+        self._sampler_states = copy.deepcopy(value)
+        self._upload_sampler_states()
+
+    @property
+    def is_periodic(self):
+        if self._thermodynamic_states is None:
+            return None
+        return self._thermodynamic_states[0].is_periodic
+
+    @property
+    def metadata(self):
+        return copy.deepcopy(self._metadata)
+
+    @property
+    def is_completed(self):
+        return self._is_completed()
+
+    @classmethod
+    def default_options(cls):
+        import inspect
+        opts = {}
+        for c in reversed(cls.__mro__):
+            if c is object:
+                continue
+            for n, p in inspect.signature(c.__init__).parameters.items():
+                if p.default is not inspect.Parameter.empty and p.kind is not inspect.Parameter.VAR_KEYWORD:
+                    opts[n] = p.default
+        return opts
+
+    @property
+    def options(self):
+        return {n: getattr(self, n, getattr(self, '_' + n, None)) for n in self.default_options()}
+
+    @classmethod
+    def from_storage(cls, storage):
+        raise NotImplementedError('storage / resume is outside the hot path (SURVEY.md section 8f-1)')
+
+    @classmethod
+    def read_status(cls, storage):
+        raise NotImplementedError('storage / resume is outside the hot path (SURVEY.md section 8f-1)')
+
+    # ------------------------------------------------------------------ create (multistatesampler.py:537-609)
+    def create(self, thermodynamic_states, sampler_states, storage=None, initial_thermodynamic_states=None,
+               unsampled_thermodynamic_states=None, metadata=None):
+        if storage is not None:
+            raise NotImplementedError('storage (MultiStateReporter/NetCDF) is outside the hot path; pass storage=None')
+        if self._thermodynamic_states is not None:
+            raise RuntimeError('Cannot initialize the same sampler twice (create() was already called).')
+        if unsampled_thermodynamic_states:
+            raise NotImplementedError('unsampled thermodynamic states are not provided yet')
+        if isinstance(sampler_states, states.SamplerState):
+            sampler_states = [sampler_states]
+        self._pre_write_create(list(thermodynamic_states), list(sampler_states),
+                               initial_thermodynamic_states=initial_thermodynamic_states, metadata=metadata)
+
+    def _pre_write_create(self, thermodynamic_states, sampler_states, initial_thermodynamic_states=None,
+                          unsampled_thermodynamic_states=None, metadata=None):
+        # checks of multistatesampler.py:850-869
+        n_particles = thermodynamic_states[0].n_particles
+        for s in thermodynamic_states:
+            if s.is_periodic != thermodynamic_states[0].is_periodic:
+                raise Exception('Thermodynamic states contain a mixture of systems with and without periodic boundary conditions.')
+            if s.n_particles != n_particles:
+                raise ValueError('All ThermodynamicStates must have the same number of particles')
+        for ss in sampler_states:
+            if ss.n_particles != n_particles:
+                raise ValueError('All SamplerStates must have the same number of particles')
+            if thermodynamic_states[0].is_periodic and ss.box_vectors is None:
+                raise Exception('All sampler states must have box_vectors defined if the system is periodic.')
+        self._metadata = metadata
+        self._thermodynamic_states = [copy.deepcopy(s) for s in thermodynamic_states]
+        self._unsampled_states = []
+        self._sampler_states = [copy.deepcopy(s) for s in sampler_states]
+        K, M = len(self._sampler_states), len(self._thermodynamic_states)
+        # initial assignment (multistatesampler.py:892-895, 1118-1143)
+        if initial_thermodynamic_states is None:
+            if K != M:
+                raise ValueError('initial_thermodynamic_states must be given when n_replicas != n_states')
+            self._replica_thermodynamic_states = np.arange(K, dtype=np.int64)
+        else:
+            init = np.array(initial_thermodynamic_states, dtype=np.int64)
+            if len(init) != K or init.min() < 0 or init.max() >= M:
+                raise ValueError('initial_thermodynamic_states must hold one valid state index per replica')
+            self._replica_thermodynamic_states = init
+        # one (deep-copied) move per state (multistatesampler.py:906-910)
+        if isinstance(self._mcmc_moves, mcmc.MCMCMove):
+            self._mcmc_moves = [copy.deepcopy(self._mcmc_moves) for _ in range(M)]
+        elif len(self._mcmc_moves) != M:
+            raise RuntimeError('The number of MCMCMoves ({}) and ThermodynamicStates ({}) must be the same.'.format(
+                len(self._mcmc_moves), M))
+        for mv in self._mcmc_moves[1:]:
+            if not mcmc.same_integrator(mv, self._mcmc_moves[0]):
+                raise NotImplementedError('per-state moves with different integrator parameters are not provided '
+                                          '(one fused kernel propagates all replicas)')
+        self._n_accepted_matrix = np.zeros([M, M], np.int64)
+        self._n_proposed_matrix = np.zeros([M, M], np.int64)
+        self._energy_thermodynamic_states = np.zeros([K, M], np.float64)
+        self._neighborhoods = np.ones([K, M], np.int8)
+        self._energy_unsampled_states = np.zeros([K, 0], np.float64)
+        self._iteration = 0
+        self._create_engine()
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _create_engine(self):
+        K = len(self._sampler_states)
+        device = _backend.default_device(self.sampler_context_cache)
+        self._engine = _backend.build_engine(self._thermodynamic_states, K, device=device, rank=self._rank,
+                                             world_size=self._world_size)
+        if self._world_size > 1:
+            self._init_communicator()
+        dt, gamma, n_steps, splitting = self._mcmc_moves[0]._integrator_parameters()
+        self._engine.set_integrator(dt, gamma, n_steps, splitting)
+        self._reassign = bool(self._mcmc_moves[0].reassign_velocities)
+        if self._seed is None:
+            self._seed = int(np.random.SeedSequence().entropy & 0x7FFFFFFFFFFFFFFF)
+            if self._world_size > 1:
+                self._seed = self._bcast_int(self._seed)
+        self._engine.set_replica_states(self._replica_thermodynamic_states)
+        self._seed_mixing_streams()
+        self._upload_sampler_states()
+
+    def _seed_mixing_streams(self):
+        # the reference never seeds numba's / numpy's generators (os.urandom); a user seed makes runs reproducible
+        self._engine.mix_seed(self._seed & 0xFFFFFFFF, _lib.RX_STREAM_NUMBA)
+        self._engine.mix_seed((self._seed >> 16) & 0xFFFFFFFF, _lib.RX_STREAM_NUMPY)
+
+    def _init_communicator(self):
+        """Distribute an NCCL unique id (rank 0 creates it) and initialise the engine's communicator."""
+        comm = self._communicator
+        if comm is None:
+            from .._dist import default_communicator
+            comm = self._communicator = default_communicator()
+        uid = self._engine.comm_unique_id() if self._rank == 0 else None
+        uid = comm.bcast_bytes(uid, 128)
+        self._engine.comm_init(uid)
+
+    def _bcast_int(self, v):
+        comm = self._communicator
+        if comm is None:
+            from .._dist import default_communicator
+            comm = self._communicator = default_communicator()
+        return int.from_bytes(comm.bcast_bytes(int(v).to_bytes(8, 'little') if self._rank == 0 else None, 8), 'little')
+
+    def _upload_sampler_states(self):
+        e = self._engine
+        K = len(self._sampler_states)
+        x = np.stack([s._positions for s in self._sampler_states])
+        e.set_positions(x)
+        have_v = [s._velocities is not None for s in self._sampler_states]
+        if all(have_v):
+            e.set_velocities(np.stack([s._velocities for s in self._sampler_states]))
+        else:
+            # replicas without velocities get Maxwell-Boltzmann ones (what BaseIntegratorMove.apply would do through
+            # a fresh Context, mcmc.py:709-711)
+            e.randomize_velocities(self._seed, 0)
+            if any(have_v):
+                for k, hv in enumerate(have_v):
+                    if hv:
+                        e.set_velocities(self._sampler_states[k]._velocities[None], first=k)
+        self._states_stale = False
+
+    def _sync_sampler_states(self):
+        """Pull positions/velocities/energies of the owned replicas back into the host SamplerStates."""
+        if self._engine is None or not self._states_stale:
+            return
+        e = self._engine
+        x, v = e.get_positions(), e.get_velocities()
+        pot, kin = e.get_replica_energies()
+        for r, k in enumerate(range(e.k0, e.k1)):
+            self._sampler_states[k]._update(x[r], v[r], pot[k], kin[k])
+        self._states_stale = False
+
+    # ------------------------------------------------------------------ run (multistatesampler.py:724-804)
+    def run(self, n_iterations=None):
+        if self._engine is None:
+            raise RuntimeError('Cannot run a sampler that has not been created (call create()).')
+        if self._is_completed():
+            return
+        if self._iteration == 0:
+            self._compute_energies()
+            self._check_nan_energy()
+        iteration_limit = self.number_of_iterations if n_iterations is None else \
+            min(self._iteration + n_iterations, self.number_of_iterations)
+        timer_start = time.time()
+        run_initial_iteration = self._iteration
+        while not self._is_completed(iteration_limit):
+            self._iteration += 1
+            t0 = time.time()
+            self._replica_thermodynamic_states = self._mix_replicas()
+            t1 = time.time()
+            self._propagate_replicas()
+            t2 = time.time()
+            self._compute_energies()
+            t3 = time.time()
+            self._report_iteration()
+            self._update_timing(t3 - t0, time.time() - timer_start, run_initial_iteration, iteration_limit,
+                                phases=(t1 - t0, t2 - t1, t3 - t2))
+            self._check_nan_energy()
+
+    def extend(self, n_iterations):
+        if self._iteration + n_iterations > self.number_of_iterations:
+            self.number_of_iterations = self._iteration + n_iterations
+        self.run(n_iterations)
+
+    def equilibrate(self, n_iterations, mcmc_moves=None):
+        """propagate -> energies -> mix without advancing the iteration counter (multistatesampler.py:649-720)."""
+        if self._engine is None:
+            raise RuntimeError('Cannot equilibrate a sampler that has not been created.')
+        if mcmc_moves is not None:
+            mv = mcmc_moves if isinstance(mcmc_moves, mcmc.MCMCMove) else mcmc_moves[0]
+            self._engine.set_integrator(*mv._integrator_parameters())
+            reassign = bool(mv.reassign_velocities)
+        else:
+            reassign = self._reassign
+        self._equil_counter = getattr(self, '_equil_counter', 0)
+        for _ in range(n_iterations):
+            self._equil_counter += 1
+            self._propagate_replicas(iteration=(1 << 40) + self._equil_counter, reassign=reassign)
+            self._compute_energies()
+            self._replica_thermodynamic_states = self._mix_replicas()
+        if mcmc_moves is not None:
+            self._engine.set_integrator(*self._mcmc_moves[0]._integrator_parameters())
+
+    def minimize(self, tolerance=None, max_iterations=0):
+        raise NotImplementedError('minimisation (FIRE/L-BFGS in OpenMM) is outside the hot path; the LJ and HO '
+                                  'configurations do not need it (testsystems.py:1877-1879)')
+
+    # ------------------------------------------------------------------ the three hooks
+    def _mix_replicas(self):
+        """Base class: no swaps (multistatesampler.py:1500-1517)."""
+        self._n_accepted_matrix[:, :] = 0
+        self._n_proposed_matrix[:, :] = 0
+        return self._replica_thermodynamic_states
+
+    def _propagate_replicas(self, iteration=None, reassign=None):
+        """One fused launch propagates every owned replica in its current state (multistatesampler.py:1287-1337)."""
+        e = self._engine
+        if self.host_resident_states:
+            # reference semantics: sampler states live on the host and are pushed to the device every iteration
+            # (SamplerState.apply_to_context, mcmc.py:709)
+            x = np.stack([s._positions for s in self._sampler_states[e.k0:e.k1]])
+            v = np.stack([s._velocities for s in self._sampler_states[e.k0:e.k1]])
+            e.set_positions(x, first=e.k0)
+            e.set_velocities(v, first=e.k0)
+        it = self._iteration if iteration is None else iteration
+        n_restart = self._mcmc_moves[0].n_restart_attempts
+        for attempt in range(n_restart + 1):
+            try:
+                e.propagate(self._seed + attempt * 0x9E3779B9, it, self._reassign if reassign is None else reassign)
+                break
+            except EngineError as err:
+                if err.code != _lib.RX_ERR_NAN:
+                    raise
+                if attempt == n_restart:
+                    bad = np.nonzero(err.nan_flags)[0]
+                    raise SimulationNaNError('Propagating replica {} at state {} resulted in a NaN!'.format(
+                        bad[0], self._replica_thermodynamic_states[bad[0]]))
+                # restart policy of mcmc.py:706-759: retry the failed replicas from their last good state
+                self._restore_replicas(np.nonzero(err.nan_flags)[0])
+        self._states_stale = True
+        if self.host_resident_states:
+            self._sync_sampler_states()
+
+    def _restore_replicas(self, replicas):
+        for k in replicas:
+            s = self._sampler_states[k]
+            self._engine.set_positions(s._positions[None], first=int(k))
+            if s._velocities is not None:
+                self._engine.set_velocities(s._velocities[None], first=int(k))
+
+    def _compute_energies(self):
+        """u[k, l] for all replicas and states in one launch (+ NCCL all-gather) (multistatesampler.py:1436-1494)."""
+        self._neighborhoods[:, :] = 1
+        self._energy_thermodynamic_states[:, :] = self._engine.compute_energies()
+
+    # ------------------------------------------------------------------ bookkeeping
+    def _report_iteration(self):
+        pass   # no reporter on the hot path
+
+    def _is_completed(self, iteration_limit=None):
+        if iteration_limit is None:
+            iteration_limit = self.number_of_iterations
+        return self._iteration is not None and self._iteration >= iteration_limit
+
+    def _check_nan_energy(self):
+        """multistatesampler.py:1049-1081"""
+        diag = self._energy_thermodynamic_states[np.arange(self.n_replicas), self._replica_thermodynamic_states]
+        if np.any(np.isnan(diag)):
+            bad = np.nonzero(np.isnan(diag))[0]
+            raise SimulationNaNError('NaN encountered in energies for replicas {}'.format(bad.tolist()))
+
+    def _update_timing(self, iteration_time, partial_total_time, run_initial_iteration, iteration_limit, phases=None):
+        """Timing dictionary with the reference's keys (multistatesampler.py:1766-1803)."""
+        t = self._timing_data
+        t['iteration_seconds'] = iteration_time
+        t['average_seconds_per_iteration'] = partial_total_time / max(self._iteration - run_initial_iteration, 1)
+        t['estimated_time_remaining'] = t['average_seconds_per_iteration'] * (iteration_limit - self._iteration)
+        t['estimated_total_time'] = t['average_seconds_per_iteration'] * self.number_of_iterations \
+            if np.isfinite(self.number_of_iterations) else np.inf
+        mv = self._mcmc_moves[0]
+        try:
+            dt_ns = unit.to_md(mv.timestep) * mv.n_steps * 1e-3
+            t['ns_per_day'] = dt_ns / (t['average_seconds_per_iteration'] / 86400.0)
+        except Exception:
+            t['ns_per_day'] = None
+        if phases is not None:
+            t['mixing_seconds'], t['propagation_seconds'], t['energy_seconds'] = phases
+        t['device_phase_ms'] = self._engine.phase_times()
+
+    def __del__(self):
+        try:
+            if self._engine is not None:
+                self._engine.close()
+        except Exception:
+            pass

@@ -1,0 +1,140 @@
+"""End-to-end ReplicaExchangeSampler runs on the GPU through the public (reference-shaped) API."""
+import numpy as np
+import pytest
+from openmmtools_b200 import unit, states, alchemy, mcmc, testsystems, multistate, _backend
+from helpers import KB
+
+pytestmark = pytest.mark.gpu
+
+
+def lj_sampler(K=16, N=128, n_alch=4, n_steps=25, scheme='swap-all', seed=1234, **kw):
+    fluid = testsystems.LennardJonesFluid(nparticles=N)
+    asys = alchemy.AbsoluteAlchemicalFactory(disable_alchemical_dispersion_correction=True).create_alchemical_system(
+        fluid.system, alchemy.AlchemicalRegion(alchemical_atoms=range(n_alch)))
+    lambdas = [1.0 - l / (K - 1) for l in range(K)]
+    tstates = states.create_thermodynamic_state_protocol(
+        asys, {'lambda_sterics': lambdas}, constants={'temperature': 300.0 * unit.kelvin},
+        composable_states=alchemy.AlchemicalState.from_system(asys))
+    sstate = states.SamplerState(fluid.positions, box_vectors=asys.getDefaultPeriodicBoxVectors())
+    move = mcmc.LangevinSplittingDynamicsMove(timestep=1.0 * unit.femtosecond, n_steps=n_steps)
+    s = multistate.ReplicaExchangeSampler(mcmc_moves=move, number_of_iterations=1000, replica_mixing_scheme=scheme,
+                                          seed=seed, **kw)
+    s.create(tstates, [sstate])
+    return s, asys, lambdas
+
+
+def oracle_energy(asys, lambdas, x):
+    from oracle import oracle
+    L = asys.box_vectors[0, 0]
+    osys = oracle.LJSystem(asys.sigma, asys.epsilon, asys.masses, asys.alchemical_mask(), (L, L, L), asys.cutoff,
+                           asys.switching_distance, use_switch=True)
+    K = len(lambdas)
+    off = np.full(K, _backend.lj_dispersion_correction(asys))
+    return osys.energy_matrix(x, np.array(lambdas), np.full(K, 1.0 / (KB * 300.0)), off)
+
+
+@pytest.mark.parametrize('scheme', ['swap-all', 'swap-neighbors'])
+def test_iteration_history_matches_oracle_replay(scheme):
+    """Each iteration: the device energy matrix equals the oracle's on the device's positions (1e-5 relative), and the
+    permutation + swap statistics equal the oracle's mixing of that matrix on the same MT19937 stream (bit-exact)."""
+    from oracle import oracle
+    K = 16
+    x0 = np.stack([np.asarray(testsystems.LennardJonesFluid(nparticles=128).positions.value_in_unit(unit.nanometer), np.float64)] * K)
+    s2, asys, lambdas = lj_sampler(K=K, scheme=scheme, seed=78)
+    seed = 78 & 0xFFFFFFFF if scheme == 'swap-all' else (78 >> 16) & 0xFFFFFFFF
+    mt = oracle.MT(seed)
+    perm = np.arange(K, dtype=np.int64)
+    s2._compute_energies()
+    u_prev = s2._energy_thermodynamic_states.copy()
+    ref0 = oracle_energy(asys, lambdas, x0)
+    assert np.abs(u_prev - ref0).max() / np.abs(ref0).max() < 1e-5
+    for it in range(1, 5):
+        s2.run(1)
+        na = np.zeros((K, K), np.int64); npr = np.zeros((K, K), np.int64)
+        if scheme == 'swap-all':
+            oracle.mix_swap_all(mt, K ** 3, perm, u_prev, na, npr)
+        else:
+            oracle.mix_swap_neighbors(mt, perm, u_prev, na, npr)
+        assert np.array_equal(perm, s2._replica_thermodynamic_states), it
+        assert np.array_equal(na, s2._n_accepted_matrix) and np.array_equal(npr, s2._n_proposed_matrix)
+        x = np.stack([st.positions.value_in_unit(unit.nanometer) for st in s2.sampler_states])
+        ref = oracle_energy(asys, lambdas, x)
+        u_prev = s2._energy_thermodynamic_states.copy()
+        assert np.abs(u_prev - ref).max() / np.abs(ref).max() < 1e-5
+        assert s2.iteration == it
+
+
+def test_fused_loop_equals_phase_by_phase():
+    """rx_run_iterations (no host round trips) and the Python-level run() produce identical trajectories."""
+    a, _, _ = lj_sampler(K=16, seed=5)
+    b, _, _ = lj_sampler(K=16, seed=5)
+    a.run(3)
+    b._compute_energies()
+    b._engine.run_iterations(3, 'swap-all', b._seed, 1)
+    assert np.array_equal(a._engine.get_replica_states(), b._engine.get_replica_states())
+    assert np.array_equal(a._engine.get_energies(), b._engine.get_energies())
+    assert np.array_equal(a._engine.get_positions(), b._engine.get_positions())
+
+
+def test_host_resident_states_round_trip_is_equivalent():
+    a, _, _ = lj_sampler(K=8, seed=9)
+    b, _, _ = lj_sampler(K=8, seed=9, host_resident_states=True)
+    a.run(3); b.run(3)
+    assert np.array_equal(a._replica_thermodynamic_states, b._replica_thermodynamic_states)
+    xa = np.stack([s._positions for s in a.sampler_states]); xb = np.stack([s._positions for s in b.sampler_states])
+    assert np.array_equal(xa, xb)
+    assert a.sampler_states[0].potential_energy is not None and a.sampler_states[0].kinetic_energy is not None
+
+
+def test_config1_harmonic_oscillator_three_temperatures():
+    """BASELINE.json configs[0]: HarmonicOscillator, 3 temperature states, 10 iterations."""
+    ho = testsystems.HarmonicOscillator()
+    temps = [300.0, 310.0, 320.0]
+    tstates = [states.ThermodynamicState(ho.system, T * unit.kelvin) for T in temps]
+    sstate = states.SamplerState(ho.positions)
+    move = mcmc.LangevinSplittingDynamicsMove(timestep=1.0 * unit.femtosecond, n_steps=500)
+    hist = []
+    for rep in range(2):
+        s = multistate.ReplicaExchangeSampler(mcmc_moves=move, number_of_iterations=10, seed=1234)
+        s.create(tstates, [sstate])
+        h = []
+        for it in range(10):
+            s.run(1)
+            h.append(s._replica_thermodynamic_states.copy())
+            assert s._n_proposed_matrix.sum() == 2 * 27
+        hist.append(np.array(h))
+        assert s.is_completed and s.iteration == 10
+        # u[k,l] = beta_l * K/2 |x_k|^2
+        x = np.stack([st._positions for st in s.sampler_states])
+        ref = np.array([[0.5 * ho.system.ho_K * (x[k] ** 2).sum() / (KB * T) for T in temps] for k in range(3)])
+        assert np.allclose(s._energy_thermodynamic_states, ref, rtol=1e-5)
+    assert np.array_equal(hist[0], hist[1])          # reproducible for a fixed seed
+
+
+def test_reference_static_mixing_entry_point():
+    """tests/test_mixing.py of the reference calls ReplicaExchangeSampler._mix_all_replicas_numba directly."""
+    from oracle import oracle
+    K = 16
+    u = np.zeros((K, K))
+    st = np.arange(K, dtype=np.int64); na = np.zeros((K, K), np.int64); npr = np.zeros((K, K), np.int64)
+    multistate.ReplicaExchangeSampler._mix_all_replicas_numba(K ** 4, K, st, u, na, npr, seed=1234)
+    st_o = np.arange(K, dtype=np.int64); nao = np.zeros((K, K), np.int64); npo = np.zeros((K, K), np.int64)
+    oracle.mix_swap_all(oracle.MT(1234), K ** 4, st_o, u, nao, npo)
+    assert np.array_equal(st, st_o) and np.array_equal(na, nao) and np.array_equal(npr, npo)
+
+
+def test_thermodynamic_state_reduced_potential_and_single_move():
+    fluid = testsystems.LennardJonesFluid(nparticles=128)
+    ts = states.ThermodynamicState(fluid.system, 300 * unit.kelvin)
+    ss = states.SamplerState(fluid.positions, box_vectors=fluid.system.getDefaultPeriodicBoxVectors())
+    u0 = ts.reduced_potential(ss)
+    from oracle import oracle
+    s = fluid.system; L = s.box_vectors[0, 0]
+    osys = oracle.LJSystem(s.sigma, s.epsilon, s.masses, s.alchemical_mask(), (L, L, L), s.cutoff, s.switching_distance)
+    U, _ = osys.energy(ss._positions, 1.0)
+    ref = (U + _backend.lj_dispersion_correction(s)) / (KB * 300)
+    assert u0 == pytest.approx(ref, rel=1e-5)
+    move = mcmc.LangevinSplittingDynamicsMove(n_steps=50)
+    move.apply(ts, ss)
+    assert ss.velocities is not None and ss.potential_energy is not None and not ss.has_nan()
+    assert ts.reduced_potential(ss) != u0

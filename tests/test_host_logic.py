@@ -1,0 +1,218 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU): units, states, alchemy, splitting grammar,
+test systems, long-range corrections against the oracle, and that the C-ABI library loads and exports every
+symbol include/rx_b200.h declares."""
+import copy
+import os
+import re
+import numpy as np
+import pytest
+from openmmtools_b200 import unit, states, alchemy, mcmc, testsystems, multistate, _lib, _backend, cache
+from openmmtools_b200.constants import kB
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'rx_b200.h')).read()
+    declared = set(re.findall(r'RX_API\s+[\w\s\*]+?\b(rx_\w+)\s*\(', hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.rx_abi_version() == _lib.RX_ABI_VERSION
+
+
+def test_engine_fails_loudly_without_gpu():
+    """No CPU fallback: on a box without a CUDA device engine creation raises."""
+    import ctypes
+    from openmmtools_b200._engine import Engine, EngineError
+    try:
+        ctypes.CDLL('libcuda.so.1')
+        have_driver = True
+    except OSError:
+        have_driver = False
+    if have_driver:
+        pytest.skip('CUDA driver present')
+    with pytest.raises(EngineError):
+        Engine(0, 4, 4)
+
+
+def test_units():
+    assert (1.0 * unit.femtosecond).value_in_unit(unit.picosecond) == pytest.approx(1e-3)
+    assert (0.238 * unit.kilocalories_per_mole).value_in_unit_system(unit.md_unit_system) == pytest.approx(0.995792)
+    K = 100.0 * unit.kilocalories_per_mole / unit.angstroms ** 2
+    assert K.value_in_unit_system(unit.md_unit_system) == pytest.approx(41840.0)
+    kT = kB * (300.0 * unit.kelvin)
+    assert kT.value_in_unit(unit.kilojoule_per_mole) == pytest.approx(8.31446261815324e-3 * 300)
+    assert (10.0 / unit.picosecond).value_in_unit(unit.picosecond ** -1) == 10.0
+    q = unit.Quantity(np.ones((4, 3)), unit.angstrom)
+    assert q.value_in_unit(unit.nanometer).shape == (4, 3) and q[0].value_in_unit(unit.nanometer)[0] == pytest.approx(0.1)
+    assert kT / kT == pytest.approx(1.0)
+    with pytest.raises(TypeError):
+        (1.0 * unit.kelvin).value_in_unit(unit.nanometer)
+    assert unit.to_md(3.0) == 3.0
+
+
+def test_lj_fluid_parameters_match_reference_definition():
+    fl = testsystems.LennardJonesFluid(nparticles=512)
+    s = fl.system
+    # testsystems.py:1932-1939: L = (N sigma^3 / rho*)^(1/3)
+    assert s.box_vectors[0, 0] == pytest.approx((512 * 0.34 ** 3 / 0.05) ** (1 / 3))
+    assert s.cutoff == pytest.approx(1.02) and s.switching_distance == pytest.approx(0.68)
+    assert s.epsilon[0] == pytest.approx(0.238 * 4.184)
+    G = np.load(os.path.join(ROOT, 'tests', 'golden', 'sobol_golden.npz'))
+    ref = np.array(G['sobol3_n512_skip1'], np.float32).T * np.float32(1.0)
+    got = fl.positions.value_in_unit(unit.nanometer)
+    L = s.box_vectors[0, 0]
+    assert np.allclose(got, np.array(G['sobol3_n512_skip1'], np.float32).T * L, rtol=1e-6)
+    assert got.dtype == np.float32 or got.dtype == np.float64
+    with pytest.raises(ValueError):
+        testsystems.LennardJonesFluid(nparticles=8)   # cutoff > L/2
+
+
+def test_sobol_matches_reference_generator():
+    from openmmtools_b200 import sobol
+    G = np.load(os.path.join(ROOT, 'tests', 'golden', 'sobol_golden.npz'))
+    for n in (1, 8, 100, 512, 1000):
+        assert np.array_equal(sobol.sobol_generate(3, n, 1), G[f'sobol3_n{n}_skip1'])
+
+
+def make_alch(n=64, n_alch=4, **kw):
+    fl = testsystems.LennardJonesFluid(nparticles=n)
+    f = alchemy.AbsoluteAlchemicalFactory(**kw)
+    return fl, f.create_alchemical_system(fl.system, alchemy.AlchemicalRegion(alchemical_atoms=range(n_alch)))
+
+
+def test_alchemical_state_and_compound_state():
+    fl, asys = make_alch()
+    a = alchemy.AlchemicalState.from_system(asys)
+    assert a.lambda_sterics == 1.0 and a.lambda_electrostatics == 1.0 and a.lambda_bonds is None
+    ts = states.ThermodynamicState(asys, 300 * unit.kelvin)
+    cs = states.CompoundThermodynamicState(ts, [a])
+    cs.lambda_sterics = 0.25
+    assert cs.lambda_sterics == 0.25 and a.lambda_sterics == 1.0          # composable states are copied
+    with pytest.raises(ValueError):
+        cs.lambda_sterics = 1.5
+    c2 = copy.deepcopy(cs)
+    c2.lambda_sterics = 0.5
+    c2.temperature = 310 * unit.kelvin
+    assert cs.lambda_sterics == 0.25 and cs.temperature.value_in_unit(unit.kelvin) == 300.0
+    assert c2._standard_system is cs._standard_system                      # states.py:1244-1253
+    assert cs.is_state_compatible(c2)
+    cs.set_alchemical_parameters(0.0)
+    assert cs.lambda_sterics == 0.0 and cs.lambda_electrostatics == 0.0
+    assert cs.get_system().global_parameters['lambda_sterics'] == 0.0
+    with pytest.raises(states.GlobalParameterError):
+        alchemy.AlchemicalState.from_system(fl.system)
+    with pytest.raises(states.GlobalParameterError):
+        a.lambda_bonds = 0.5
+
+
+def test_protocol_and_engine_tables():
+    fl, asys = make_alch(disable_alchemical_dispersion_correction=True)
+    lam = [1.0, 0.5, 0.0]
+    ps = states.create_thermodynamic_state_protocol(asys, {'lambda_sterics': lam, 'temperature': [300, 310, 320] * unit.kelvin},
+                                                    composable_states=alchemy.AlchemicalState.from_system(asys))
+    sys0, tab = _backend.engine_tables(ps)
+    assert np.allclose(tab['lambda_sterics'], lam) and np.allclose(tab['temperature'], [300, 310, 320])
+    assert np.allclose(tab['energy_offset'], _backend.lj_dispersion_correction(asys))
+    with pytest.raises(ValueError):
+        states.create_thermodynamic_state_protocol(asys, {'lambda_sterics': [1, 0], 'temperature': [300] * unit.kelvin})
+
+
+def test_dispersion_correction_matches_oracle():
+    from oracle import oracle
+    for n_alch in (0, 4):
+        fl = testsystems.LennardJonesFluid(nparticles=216)
+        s = fl.system
+        if n_alch:
+            s = alchemy.AbsoluteAlchemicalFactory().create_alchemical_system(s, alchemy.AlchemicalRegion(alchemical_atoms=range(n_alch)))
+        L = s.box_vectors[0, 0]
+        osys = oracle.LJSystem(s.sigma, s.epsilon, s.masses, s.alchemical_mask(), (L, L, L), s.cutoff, s.switching_distance)
+        assert _backend.lj_dispersion_correction(s) == pytest.approx(osys.dispersion_correction(), rel=1e-9)
+    # analytic check without the switch: 8 pi N^2/V eps [sig^12/(9 rc^9) - sig^6/(3 rc^3)] * N(N)/(N(N+1))... pair average
+    fl = testsystems.LennardJonesFluid(nparticles=216, switch_width=None)
+    s = fl.system
+    N, V, rc, sg, e = 216, np.linalg.det(s.box_vectors), s.cutoff, 0.34, 0.238 * 4.184
+    ref = 8 * np.pi * N * N / V * e * (sg ** 12 / (9 * rc ** 9) - sg ** 6 / (3 * rc ** 3))
+    assert _backend.lj_dispersion_correction(s) == pytest.approx(ref, rel=1e-12)
+
+
+def test_alchemical_dispersion_correction_limits():
+    fl, asys = make_alch(n=216, n_alch=6)     # correction enabled (reference default)
+    assert asys.alchemical_dispersion_correction
+    full = _backend.alchemical_dispersion_correction(asys, 1.0)
+    none = _backend.alchemical_dispersion_correction(asys, 0.0)
+    assert full < 0 and abs(none) < abs(full)
+    # at lambda = 1 the softcore is plain LJ: NonbondedForce LRC (alchemical eps zeroed) + custom LRC equals the LRC of
+    # the unmodified fluid up to the N(N+1)/2 pair-count convention
+    tot = _backend.lj_dispersion_correction(asys) + full
+    ref = _backend.lj_dispersion_correction(fl.system)
+    assert tot == pytest.approx(ref, rel=2e-2)
+    fl2, asys2 = make_alch(n=216, n_alch=6, disable_alchemical_dispersion_correction=True)
+    assert _backend.alchemical_dispersion_correction(asys2, 0.3) == 0.0
+
+
+def test_splitting_grammar():
+    assert mcmc.parse_splitting('V R O R V') == 'VRORV'
+    assert mcmc.parse_splitting('O V R V O') == 'OVRVO'
+    with pytest.raises(ValueError):
+        mcmc.parse_splitting('V R X')
+    with pytest.raises(AssertionError):
+        mcmc.parse_splitting('V R V')
+    with pytest.raises(NotImplementedError):
+        mcmc.parse_splitting('V0 R O R V0')
+    with pytest.raises(NotImplementedError):
+        mcmc.parse_splitting('{ V R O R V }')
+    with pytest.raises(ValueError):
+        mcmc.parse_splitting('V40 R O')
+    m = mcmc.LangevinSplittingDynamicsMove(timestep=2.0 * unit.femtosecond, collision_rate=5.0 / unit.picosecond, n_steps=7)
+    assert m._integrator_parameters() == (0.002, 5.0, 7, 'VRORV')
+    m2 = mcmc.LangevinSplittingDynamicsMove.__new__(mcmc.LangevinSplittingDynamicsMove)
+    m2.__setstate__(m.__getstate__())
+    assert mcmc.same_integrator(m, m2)
+    assert mcmc.LangevinDynamicsMove()._integrator_parameters()[3] == 'VROR'
+    with pytest.raises(NotImplementedError):
+        mcmc.LangevinSplittingDynamicsMove(measure_heat=True)
+
+
+def test_sampler_state_semantics():
+    fl = testsystems.LennardJonesFluid(nparticles=64)
+    ss = states.SamplerState(fl.positions, box_vectors=fl.system.getDefaultPeriodicBoxVectors())
+    assert ss.n_particles == 64 and ss.velocities is None and ss.potential_energy is None
+    assert ss.volume.value_in_unit(unit.nanometer ** 3) == pytest.approx(np.linalg.det(fl.system.box_vectors))
+    ss._update(ss._positions, np.zeros((64, 3)), -3.0, 2.0)
+    assert ss.total_energy.value_in_unit(unit.kilojoule_per_mole) == pytest.approx(-1.0)
+    ss.positions = ss.positions            # new positions invalidate the cached potential (states.py:2386-2390)
+    assert ss.potential_energy is None
+    d = ss.__getstate__()
+    s2 = states.SamplerState.__new__(states.SamplerState)
+    s2.__setstate__(d)
+    assert np.array_equal(s2._positions, ss._positions) and s2.n_particles == 64
+    sub = ss[2:5]
+    assert sub.n_particles == 3
+    assert not ss.has_nan()
+    with pytest.raises(states.SamplerStateError):
+        ss.velocities = np.zeros((3, 3))
+    with pytest.raises(AttributeError):
+        ss.potential_energy = 1.0
+
+
+def test_sampler_option_validation():
+    with pytest.raises(ValueError):
+        multistate.ReplicaExchangeSampler(replica_mixing_scheme='bogus')
+    s = multistate.ReplicaExchangeSampler(replica_mixing_scheme='swap-neighbors', number_of_iterations=3)
+    assert s.replica_mixing_scheme == 'swap-neighbors' and s.n_replicas is None and s.iteration is None
+    with pytest.raises(RuntimeError):
+        s.run()
+    assert multistate.ReplicaExchangeSampler.default_options()['replica_mixing_scheme'] == 'swap-all'
+    c = cache.ContextCache(platform='CUDA', platform_properties={'DeviceIndex': '3'})
+    assert c.device_index == 3
+
+
+def test_harmonic_oscillator_system():
+    ho = testsystems.HarmonicOscillator()
+    assert ho.system.ho_K == pytest.approx(41840.0) and ho.system.masses[0] == pytest.approx(39.948)
+    ts = states.ThermodynamicState(ho.system, 300 * unit.kelvin)
+    assert not ts.is_periodic and ts.n_particles == 1
+    assert ho.get_potential_expectation(ts).value_in_unit(unit.kilojoule_per_mole) == pytest.approx(1.5 * 8.31446261815324e-3 * 300)
