@@ -55,6 +55,8 @@ extern "C" int rx_create(const rx_config *cfg, rx_engine **out) {
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream_rng, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) CREATE_CUDA(cudaEventCreate(&h->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&h->ev_user[i]));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_prepared, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_consumed, cudaEventDisableTiming));
     CREATE_CUDA(cudaMalloc(&h->d_perm, sizeof(int) * K));
     CREATE_CUDA(cudaMalloc(&h->d_u, sizeof(double) * (size_t)K * M));
     CREATE_CUDA(cudaMemset(h->d_u, 0, sizeof(double) * (size_t)K * M));
@@ -97,6 +99,9 @@ extern "C" void rx_destroy(rx_engine *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream_rng) cudaStreamSynchronize(h->stream_rng);
+    if (h->ev_prepared) cudaEventDestroy(h->ev_prepared);
+    if (h->ev_consumed) cudaEventDestroy(h->ev_consumed);
     if (h->nccl_comm && h->nccl_lib) {
         typedef int (*destroy_t)(void *);
         destroy_t f = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");

@@ -13,6 +13,7 @@
 #include "rx_internal.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator: noise is a pure function of (seed, iteration, replica, atom, step)
@@ -57,6 +58,8 @@ struct DynParams {
     float sc_c;                 // softcore_c
     float dt, a, b;             // timestep, O-step coefficients exp(-gamma h), sqrt(1-exp(-2 gamma h))
     int n_steps, n_prog, nV, nR, nO;
+    int maxnb;                  // Verlet-list capacity per atom (0: all-pairs only)
+    float rl2, half_skin2;      // (cutoff + skin)^2, (skin/2)^2
     char prog[RX_MAX_PROGRAM];
 };
 
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     extern __shared__ float4 s_dyn[];
     float4 *s_pos = s_dyn;                         // [N] xyz, w = sigma
     float2 *s_par = (float2 *)(s_dyn + p.N);       // [N] (sqrt_eps, alch)
+    unsigned short *s_nb = (unsigned short *)(s_par + p.N);  // [maxnb][N] Verlet list, slot-major (conflict free)
     __shared__ double s_red[32];
     const int r = blockIdx.x, k = k0 + r, t = threadIdx.x;
     const bool active = t < p.N;
@@ -136,19 +140,49 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     bool f_valid = false;
     const float hx0 = (float)st.ho_x0[0], hx1 = (float)st.ho_x0[1], hx2 = (float)st.ho_x0[2], hK = (float)st.ho_K;
 
+    // Verlet neighbour list (full list: every thread owns its atom's force, no atomics, deterministic):
+    // rebuilt whenever any atom has moved more than skin/2 since the last build.  If an atom has more than
+    // maxnb neighbours the CTA falls back to the all-pairs loop for the rest of the launch.
+    bool use_list = p.kind != RX_SYSTEM_HARMONIC && p.maxnb > 0;
+    int nb_count = 0;
+    float xr = x, yr = y, zr = z;  // position at the last list build
+    auto build_list = [&]() {
+        int c = 0;
+        bool over = false;
+        if (active) {
+            for (int j = 0; j < p.N; j++) {
+                const float4 pj = s_pos[j];
+                float dx = x - pj.x, dy = y - pj.y, dz = z - pj.z;
+                dx -= p.Lx * rintf(dx * p.iLx); dy -= p.Ly * rintf(dy * p.iLy); dz -= p.Lz * rintf(dz * p.iLz);
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 < p.rl2 && j != t) {
+                    if (c < p.maxnb) s_nb[c * p.N + t] = (unsigned short)j;
+                    else over = true;
+                    c++;
+                }
+            }
+        }
+        nb_count = c;
+        xr = x; yr = y; zr = z;
+        if (__syncthreads_or(over ? 1 : 0)) use_list = false;
+    };
+    if (use_list) build_list();
+
     auto compute_forces = [&](bool want_energy, float &e_out) {
         float ax = 0, ay = 0, az = 0, en = 0;
         if (p.kind == RX_SYSTEM_HARMONIC) {
             ax = -hK * (x - hx0); ay = -hK * (y - hx1); az = -hK * (z - hx2);
             if (want_energy) en = 0.5f * hK * ((x - hx0) * (x - hx0) + (y - hx1) * (y - hx1) + (z - hx2) * (z - hx2));
         } else if (active) {
-            for (int j = 0; j < p.N; j++) {
+            const int n_it = use_list ? nb_count : p.N;
+            for (int c = 0; c < n_it; c++) {
+                const int j = use_list ? (int)s_nb[c * p.N + t] : c;
                 const float4 pj = s_pos[j];
-                const float2 qj = s_par[j];
                 float dx = x - pj.x, dy = y - pj.y, dz = z - pj.z;
                 dx -= p.Lx * rintf(dx * p.iLx); dy -= p.Ly * rintf(dy * p.iLy); dz -= p.Lz * rintf(dz * p.iLz);
                 const float r2 = dx * dx + dy * dy + dz * dz;
                 if (r2 < p.rc2 && j != t) {
+                    const float2 qj = s_par[j];
                     const bool alch_j = qj.y != 0.f;
                     const bool soft = (alch_i != alch_j) || (alch_i && alch_j && p.annihilate);
                     float e;
@@ -176,9 +210,12 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
                 const float h = p.dt / (float)p.nR;
                 x += h * vx; y += h * vy; z += h * vz;
                 if (p.kind != RX_SYSTEM_HARMONIC) {
-                    __syncthreads();  // everyone finished reading the old positions
+                    // barrier 1: everyone finished reading the old positions (and votes on a list rebuild)
+                    const float mx = x - xr, my = y - yr, mz = z - zr;
+                    const int moved = __syncthreads_or((use_list && active && (mx * mx + my * my + mz * mz > p.half_skin2)) ? 1 : 0);
                     if (active) s_pos[t] = make_float4(x, y, z, sig_i);
                     __syncthreads();
+                    if (moved) build_list();
                 }
                 f_valid = false;
             } else {  // 'O'
@@ -414,6 +451,7 @@ static int fill_dyn(rx_engine *h, DynParams &p) {
     int nV = 0, nR = 0, nO = 0, n = 0;
     for (const char *q = h->program; *q; q++, n++) { if (*q == 'V') nV++; else if (*q == 'R') nR++; else nO++; p.prog[n] = *q; }
     p.n_prog = n; p.nV = nV; p.nR = nR; p.nO = nO;
+    p.maxnb = 0; p.rl2 = p.rc2; p.half_skin2 = 0.f;
     const double hO = h->dt / (nO > 0 ? nO : 1);   // integrators.py:1141-1146
     p.a = (float)exp(-h->gamma * hO);
     p.b = (float)sqrt(1.0 - exp(-2.0 * h->gamma * hO));
@@ -427,7 +465,25 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     const int N = h->cfg.n_atoms;
     if (N > 1024) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: more than 1024 atoms per replica is not supported yet");
     const int threads = ((N + 31) / 32) * 32;
-    const size_t smem = (size_t)N * (sizeof(float4) + sizeof(float2));
+    size_t smem = (size_t)N * (sizeof(float4) + sizeof(float2));
+    if (h->cfg.system_kind == RX_SYSTEM_LJ_ALCH && N >= 64 && !getenv("RX_NO_VERLET")) {
+        // Verlet list: skin 0.25 nm (rebuild about every hundred 1-fs steps at 300 K), capacity from the shared-memory
+        // budget (two CTAs per SM), at most 96 neighbours per atom; denser systems fall back to all-pairs in the kernel.
+        const double skin = 0.25;
+        double rl = h->cfg.r_cutoff + skin;
+        for (int d = 0; d < 3; d++) if (rl > 0.5 * h->cfg.box[d]) rl = 0.5 * h->cfg.box[d];
+        if (rl > h->cfg.r_cutoff + 0.02) {
+            int cap = (int)((100 * 1024 - smem) / ((size_t)N * sizeof(unsigned short)));
+            if (cap > 96) cap = 96;
+            if (cap >= 8) {
+                p.maxnb = cap;
+                p.rl2 = (float)(rl * rl);
+                const double hs = 0.5 * (rl - h->cfg.r_cutoff);
+                p.half_skin2 = (float)(hs * hs);
+                smem += (size_t)cap * N * sizeof(unsigned short);
+            }
+        }
+    }
     if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
     k_propagate<<<h->kloc, threads, smem, h->stream>>>(p, h->d_atom, h->d_states, h->d_perm, h->d_pos, h->d_vel, h->k0, key,

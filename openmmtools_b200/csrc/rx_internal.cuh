@@ -44,6 +44,7 @@ struct MixCtl {          // device-resident control block of the resumable mixin
     int status;          // 0 done, 1 need more words
     int rounds;          // statistics: speculation rounds executed
     long long slow_exp;  // statistics: exact exp() fallbacks
+    long long log_count; // entries written to the commit log by this launch
 };
 
 struct rx_engine {
@@ -83,6 +84,11 @@ struct rx_engine {
     SlotRec *d_slots = nullptr;
     size_t slots_cap = 0;
     MixCtl *d_ctl = nullptr;
+    uint32_t *d_log = nullptr;   // commit log of the walker: packed (si, sj, accepted)
+    size_t log_cap = 0;
+    bool prepared = false;        // words + slot records for the next swap-all call were produced on stream_rng
+    size_t slots_for_avail = 0;   // S.avail the slot records were built for
+    cudaEvent_t ev_prepared = nullptr, ev_consumed = nullptr;
     // timing
     double phase_ms[4] = {0, 0, 0, 0};
     long long phase_launches[4] = {0, 0, 0, 0};

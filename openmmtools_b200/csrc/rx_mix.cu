@@ -16,6 +16,7 @@
 #include "rx_internal.cuh"
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------------
 // MT19937 generation: x[n+624] = x[n+397] ^ twist(x[n], x[n+1]); 227 words are independent per step and
@@ -126,28 +127,61 @@ __global__ void __launch_bounds__(256) k_slots_build(const uint32_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------
-// The speculative chain walker (one warp).  K must be a power of two <= 65536.
+// The speculative chain walker (one warp).  K must be a power of two <= 16384.
+//
+// Per round the warp (1) reads 32 slot records (prefetched into L1 a few hundred slots ahead), (2) looks up
+// the current states of both replicas (shared memory), (3) fetches u[i,sj], u[j,si] (shared memory when the
+// matrix fits, else L2) and the maintained diagonal d[k] = u[k, perm[k]], (4) evaluates log_p and the accept
+// test, (5) resolves the visited chain and staleness with ballots and bit tricks, (6) commits the valid
+// prefix: permutation + diagonal in shared memory and ONE coalesced store of packed (si, sj, accepted)
+// entries into a commit log.  The count matrices are built from the log afterwards by k_mix_count (parallel).
 // ------------------------------------------------------------------------------------------------------
+#define LOG_ACC_BIT 28
+#define LOG_STATE_BITS 14
+#define PF_DIST 384
+
+template <bool U_SMEM>
 __global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict__ rec, const uint32_t *__restrict__ words,
                                                       long long nslots, const double *__restrict__ u, int K, int M,
-                                                      int *__restrict__ perm_g, unsigned long long *__restrict__ nacc,
-                                                      unsigned long long *__restrict__ nprop, MixCtl *ctl) {
-    extern __shared__ int s_perm[];
+                                                      int *__restrict__ perm_g, uint32_t *__restrict__ commit_log,
+                                                      MixCtl *ctl) {
+    extern __shared__ double s_mix[];
+    double *s_diag = s_mix;                                  // [K]
+    double *s_u = s_mix + K;                                 // [K*M] when U_SMEM
+    int *s_perm = (int *)(s_mix + K + (U_SMEM ? (size_t)K * M : 0));  // [K]
     const int lane = threadIdx.x;
-    for (int q = lane; q < K; q += 32) s_perm[q] = perm_g[q];
+    for (int q = lane; q < K; q += 32) {
+        const int st = perm_g[q];
+        s_perm[q] = st;
+        s_diag[q] = u[(size_t)q * M + st];
+    }
+    if (U_SMEM)
+        for (int q = lane; q < K * M; q += 32) s_u[q] = u[q];
     __syncwarp();
     long long h = ctl->head;
     long long remaining = ctl->remaining;
+    long long logpos = 0;
+    long long pf = h;
     int rounds = 0;
-    long long slow = 0;
+    unsigned slow = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
     while (remaining > 0 && h + 33 <= nslots) {
         rounds++;
+        // software prefetch of the record stream (it comes from DRAM: written once by k_slots_build, read once)
+        if (pf < h + PF_DIST) {
+            if (pf < h + 32) pf = h + 32;
+            if (pf + lane * 8 < nslots) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + pf + lane * 8));
+            pf += 256;  // 32 lanes x 8 records x 16 B = 32 lines of 128 B
+        }
         const SlotRec r = rec[h + lane];
-        const double logU_next = rec[h + lane + 1].logU;  // the uniform an attempt at this slot would draw
+        // the uniform an attempt at this slot would draw belongs to the NEXT slot's words
+        double logU_next = __shfl_down_sync(0xffffffffu, r.logU, 1);
+        if (lane == 31) logU_next = rec[h + 32].logU;
         const int i = r.ij & 0xffffu, j = r.ij >> 16;
         const int si = s_perm[i], sj = s_perm[j];
-        const double e_ij = u[(size_t)i * M + sj], e_ji = u[(size_t)j * M + si];
-        const double e_ii = u[(size_t)i * M + si], e_jj = u[(size_t)j * M + sj];
+        const double e_ii = s_diag[i], e_jj = s_diag[j];
+        const double e_ij = U_SMEM ? s_u[i * M + sj] : u[(size_t)i * M + sj];
+        const double e_ji = U_SMEM ? s_u[j * M + si] : u[(size_t)j * M + si];
         const double logp = swap_logp(e_ij, e_ji, e_ii, e_jj);
         const bool ge0 = logp >= 0.0;
         bool acc = ge0;
@@ -197,29 +231,46 @@ __global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict_
             advance = 32 + skip32;
         }
         if ((cm >> lane) & 1u) {
-            atomicAdd(&nprop[(size_t)si * M + sj], 1ull);
-            atomicAdd(&nprop[(size_t)sj * M + si], 1ull);
-            if (acc) {
-                atomicAdd(&nacc[(size_t)si * M + sj], 1ull);
-                atomicAdd(&nacc[(size_t)sj * M + si], 1ull);
-                if (i != j) {  // an i == j lane must not write: a later committed lane may swap this replica
-                    s_perm[i] = sj;
-                    s_perm[j] = si;
-                }
+            commit_log[logpos + __popc(cm & lt_mask)] =
+                (uint32_t)si | ((uint32_t)sj << LOG_STATE_BITS) | ((acc ? 1u : 0u) << LOG_ACC_BIT);
+            if (acc && i != j) {  // an i == j lane must not write: a later committed lane may swap this replica
+                s_perm[i] = sj;
+                s_perm[j] = si;
+                s_diag[i] = e_ij;
+                s_diag[j] = e_ji;
             }
         }
+        logpos += n;
         h += advance;
         remaining -= n;
         __syncwarp();
     }
     for (int q = lane; q < K; q += 32) perm_g[q] = s_perm[q];
-    slow = __reduce_add_sync(0xffffffffu, (unsigned)slow);
+    slow = __reduce_add_sync(0xffffffffu, slow);
     if (lane == 0) {
         ctl->head = h;
         ctl->remaining = remaining;
         ctl->status = remaining > 0 ? 1 : 0;
         ctl->rounds += rounds;
         ctl->slow_exp += slow;
+        ctl->log_count = logpos;
+    }
+}
+
+// Build the (symmetric) proposal / acceptance count matrices from the commit log (replicaexchange.py:339-349).
+__global__ void k_mix_count(const uint32_t *__restrict__ commit_log, long long n, int M, unsigned long long *__restrict__ nacc,
+                            unsigned long long *__restrict__ nprop) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        const uint32_t e = commit_log[t];
+        const uint32_t si = e & ((1u << LOG_STATE_BITS) - 1u), sj = (e >> LOG_STATE_BITS) & ((1u << LOG_STATE_BITS) - 1u);
+        atomicAdd(&nprop[(size_t)si * M + sj], 1ull);
+        atomicAdd(&nprop[(size_t)sj * M + si], 1ull);
+        if ((e >> LOG_ACC_BIT) & 1u) {
+            atomicAdd(&nacc[(size_t)si * M + sj], 1ull);
+            atomicAdd(&nacc[(size_t)sj * M + si], 1ull);
+        }
     }
 }
 
@@ -329,7 +380,7 @@ static int stream_reserve(rx_engine *h, MTStream &S, size_t cap) {
     RX_CHECK_CUDA(h, cudaMalloc(&a, cap * sizeof(uint32_t)));
     RX_CHECK_CUDA(h, cudaMalloc(&b, cap * sizeof(uint32_t)));
     if (S.avail) RX_CHECK_CUDA(h, cudaMemcpyAsync(a, S.d_words, S.avail * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
-    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    RX_CHECK_CUDA(h, cudaDeviceSynchronize());
     cudaFree(S.d_words);
     cudaFree(S.d_words_alt);
     S.d_words = a;
@@ -339,12 +390,12 @@ static int stream_reserve(rx_engine *h, MTStream &S, size_t cap) {
 }
 
 // make at least `need` unconsumed words available
-static int stream_fill(rx_engine *h, MTStream &S, size_t need, int *launches) {
+static int stream_fill(rx_engine *h, MTStream &S, size_t need, int *launches, cudaStream_t st) {
     if (S.avail >= need) return RX_OK;
     int rc = stream_reserve(h, S, need);
     if (rc) return rc;
     long long n = (long long)(need - S.avail);
-    k_mt_generate<<<1, 256, 0, h->stream>>>(S.d_window, S.d_words + S.avail, n);
+    k_mt_generate<<<1, 256, 0, st>>>(S.d_window, S.d_words + S.avail, n);
     RX_CHECK_CUDA(h, cudaGetLastError());
     S.avail = need;
     (*launches)++;
@@ -374,6 +425,8 @@ int rxi_mix_seed(rx_engine *h, int stream, uint32_t seed) {
     for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
     if (!S.d_window) RX_CHECK_CUDA(h, cudaMalloc(&S.d_window, 624 * sizeof(uint32_t)));
     RX_CHECK_CUDA(h, cudaMemcpy(S.d_window, mt, sizeof(mt), cudaMemcpyHostToDevice));
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream_rng));
+    if (stream == RX_STREAM_NUMBA) h->prepared = false;
     S.avail = 0;
     S.consumed = 0;
     S.seeded = true;
@@ -381,6 +434,41 @@ int rxi_mix_seed(rx_engine *h, int stream, uint32_t seed) {
 }
 
 static inline bool is_pow2(int k) { return k >= 2 && (k & (k - 1)) == 0; }
+
+static inline size_t pass_need(long long remaining, bool fast) {
+    const size_t chunk_words = (size_t)1 << 26;  // 64 Mi words per pass
+    size_t need = fast ? (size_t)(4 * remaining + 160) : (size_t)(8 * remaining + 512);
+    if (need > chunk_words) need = chunk_words;
+    if (need < 512) need = 512;
+    return need;
+}
+
+// Top the stream up to what a pass over `remaining` attempts may consume and (fast path) build its slot records,
+// on stream `st`.  Both are state independent, so for the NEXT mixing call this runs on the side stream while the
+// replicas are being propagated.
+static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fast, int K, cudaStream_t st, int *launches) {
+    const size_t need = pass_need(remaining, fast);
+    int rc = stream_fill(h, S, need, launches, st);
+    if (rc) return rc;
+    if (fast) {
+        const long long nslots = (long long)(S.avail / 2);
+        if ((size_t)nslots > h->slots_cap) {
+            RX_CHECK_CUDA(h, cudaDeviceSynchronize());
+            cudaFree(h->d_slots);
+            cudaFree(h->d_log);
+            h->d_slots = nullptr; h->d_log = nullptr;
+            h->slots_cap = 0;
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_slots, (size_t)nslots * sizeof(SlotRec)));
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_log, (size_t)nslots * sizeof(uint32_t)));
+            h->slots_cap = (size_t)nslots;
+        }
+        k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, nslots, (uint32_t)(K - 1), h->d_slots);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        (*launches)++;
+    }
+    h->slots_for_avail = S.avail;
+    return RX_OK;
+}
 
 int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     MTStream &S = h->streams[RX_STREAM_NUMBA];
@@ -398,43 +486,57 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
         return RX_OK;
     }
-    const bool fast = is_pow2(K) && K <= 65536;
-    const size_t smem = (size_t)K * sizeof(int);
+    const bool fast = is_pow2(K) && K <= (1 << LOG_STATE_BITS);
+    const size_t smem_small = (size_t)K * sizeof(int);
+    const size_t smem_global_u = (size_t)K * (sizeof(double) + sizeof(int));
+    const size_t smem_smem_u = smem_global_u + (size_t)K * M * sizeof(double);
+    const bool u_smem = fast && smem_smem_u <= 200 * 1024;
+    const size_t smem = !fast ? smem_small : (u_smem ? smem_smem_u : smem_global_u);
     if (smem > 48 * 1024) {
-        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (!fast) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else if (u_smem) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     long long remaining = nswap;
     h->mix_stats[0] = h->mix_stats[1] = h->mix_stats[2] = 0;
     const uint64_t consumed0 = S.consumed;
-    const size_t chunk_words = (size_t)1 << 26;  // 64 Mi words per pass
+    const size_t chunk_words = (size_t)1 << 26;
     while (remaining > 0) {
-        size_t need = fast ? (size_t)(4 * remaining + 160) : (size_t)(8 * remaining + 512);
-        if (need > chunk_words) need = chunk_words;
-        if (need < 512) need = 512;
-        int rc = stream_fill(h, S, need, launches);
-        if (rc) return rc;
-        MixCtl ctl = {0, remaining, 0, 0, 0};
+        const size_t need = pass_need(remaining, fast);
+        int rc;
+        if (h->prepared && S.avail >= need && h->slots_for_avail == S.avail) {
+            // produced on the side stream while the replicas were propagating
+            RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_prepared, 0));
+            float ms = 0;
+            if (cudaEventSynchronize(h->ev[7]) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess)
+                h->phase_ms[3] += ms;
+        } else {
+            if (h->prepared) RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream_rng));
+            rc = prepare_pass(h, S, remaining, fast, K, h->stream, launches);
+            if (rc) return rc;
+        }
+        h->prepared = false;
+        MixCtl ctl = {0, remaining, 0, 0, 0, 0};
         RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->stream));
         size_t consumed_words;
         if (fast) {
-            long long nslots = (long long)(S.avail / 2);
-            if ((size_t)nslots > h->slots_cap) {
-                cudaFree(h->d_slots);
-                h->d_slots = nullptr;
-                h->slots_cap = 0;
-                RX_CHECK_CUDA(h, cudaMalloc(&h->d_slots, (size_t)nslots * sizeof(SlotRec)));
-                h->slots_cap = (size_t)nslots;
-            }
-            k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(S.d_words, nslots, (uint32_t)(K - 1), h->d_slots);
+            const long long nslots = (long long)(S.avail / 2);
+            if (u_smem)
+                k_mix_walk_pow2<true><<<1, 32, smem, h->stream>>>(h->d_slots, S.d_words, nslots, h->d_u, K, M, h->d_perm, h->d_log, h->d_ctl);
+            else
+                k_mix_walk_pow2<false><<<1, 32, smem, h->stream>>>(h->d_slots, S.d_words, nslots, h->d_u, K, M, h->d_perm, h->d_log, h->d_ctl);
             RX_CHECK_CUDA(h, cudaGetLastError());
-            k_mix_walk_pow2<<<1, 32, smem, h->stream>>>(h->d_slots, S.d_words, nslots, h->d_u, K, M, h->d_perm, h->d_nacc,
-                                                      h->d_nprop, h->d_ctl);
-            RX_CHECK_CUDA(h, cudaGetLastError());
-            *launches += 2;
+            *launches += 1;
             RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
             RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
             consumed_words = (size_t)(2 * ctl.head);
+            if (ctl.log_count > 0) {
+                long long nb = (ctl.log_count + 255) / 256;
+                if (nb > 148 * 16) nb = 148 * 16;
+                k_mix_count<<<(unsigned)nb, 256, 0, h->stream>>>(h->d_log, ctl.log_count, M, h->d_nacc, h->d_nprop);
+                RX_CHECK_CUDA(h, cudaGetLastError());
+                *launches += 1;
+            }
         } else {
             k_mix_walk_serial<<<1, 32, smem, h->stream>>>(S.d_words, (long long)S.avail, h->d_u, K, M, h->d_perm, h->d_nacc,
                                                         h->d_nprop, h->d_ctl);
@@ -454,6 +556,19 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         if (rc) return rc;
     }
     h->mix_stats[3] = (long long)(S.consumed - consumed0);
+    if (!getenv("RX_NO_ASYNC_RNG")) {
+        // overlap the next call's stream generation + slot records with whatever runs next on the main stream
+        RX_CHECK_CUDA(h, cudaEventRecord(h->ev_consumed, h->stream));
+        RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream_rng, h->ev_consumed, 0));
+        RX_CHECK_CUDA(h, cudaEventRecord(h->ev[6], h->stream_rng));
+        int l2 = 0;
+        int rc2 = prepare_pass(h, S, nswap, fast, K, h->stream_rng, &l2);
+        if (rc2) return rc2;
+        RX_CHECK_CUDA(h, cudaEventRecord(h->ev[7], h->stream_rng));
+        RX_CHECK_CUDA(h, cudaEventRecord(h->ev_prepared, h->stream_rng));
+        h->phase_launches[3] += l2;
+        h->prepared = true;
+    }
     return RX_OK;
 }
 
@@ -465,12 +580,12 @@ int rxi_mix_swap_neighbors(rx_engine *h, int *launches) {
     const size_t mm = (size_t)M * M * sizeof(unsigned long long);
     RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_nacc, 0, mm, h->stream));
     RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_nprop, 0, mm, h->stream));
-    int rc = stream_fill(h, S, (size_t)K + 64, launches);
+    int rc = stream_fill(h, S, (size_t)K + 64, launches, h->stream);
     if (rc) return rc;
     const size_t smem = 2 * (size_t)K * sizeof(int);
     if (smem > 48 * 1024)
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_neighbors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MixCtl ctl = {0, 0, 0, 0, 0};
+    MixCtl ctl = {0, 0, 0, 0, 0, 0};
     RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->stream));
     k_mix_neighbors<<<1, 32, smem, h->stream>>>(S.d_words, (long long)S.avail, h->d_u, K, M, h->d_perm, h->d_nacc, h->d_nprop,
                                               h->d_ctl);
@@ -488,5 +603,6 @@ void rxi_mix_free(rx_engine *h) {
         cudaFree(h->streams[s].d_words_alt);
     }
     cudaFree(h->d_slots);
+    cudaFree(h->d_log);
     cudaFree(h->d_ctl);
 }

@@ -269,7 +269,10 @@ class MultiStateSampler:
                 for k, hv in enumerate(have_v):
                     if hv:
                         e.set_velocities(self._sampler_states[k]._velocities[None], first=k)
-        self._states_stale = False
+        # velocities drawn on the device are not on the host yet
+        self._states_stale = not all(have_v)
+        if self.host_resident_states:
+            self._sync_sampler_states()
 
     def _sync_sampler_states(self):
         """Pull positions/velocities/energies of the owned replicas back into the host SamplerStates."""
@@ -350,6 +353,7 @@ class MultiStateSampler:
         if self.host_resident_states:
             # reference semantics: sampler states live on the host and are pushed to the device every iteration
             # (SamplerState.apply_to_context, mcmc.py:709)
+            self._sync_sampler_states()
             x = np.stack([s._positions for s in self._sampler_states[e.k0:e.k1]])
             v = np.stack([s._velocities for s in self._sampler_states[e.k0:e.k1]])
             e.set_positions(x, first=e.k0)
