@@ -35,19 +35,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     }
     return make_uint4(c0, c1, c2, c3);
 }
-// three standard normals from one Philox block (Box-Muller on words 0,1 and 2,3)
+// three standard normals from one Philox block (Box-Muller on words 0,1 and 2,3); fast-math intrinsics: the
+// absolute error (~1e-6) is far below the float32 resolution of the velocity update it feeds
 __device__ __forceinline__ float3 philox_normal3(uint4 r) {
     const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u4 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
-    float s1, c1, s2, c2;
-    sincospif(2.0f * u2, &s1, &c1);
-    sincospif(2.0f * u4, &s2, &c2);
-    (void)s2;
+    const float ra = sqrtf(-2.0f * __logf(u1)), rb = sqrtf(-2.0f * __logf(u3));
+    float s1, c1;
+    __sincosf(6.283185307179586f * u2, &s1, &c1);
+    const float c2 = __cosf(6.283185307179586f * u4);
     return make_float3(ra * c1, ra * s1, rb * c2);
 }
+
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ---------------------------------------------------------------------------------------------------
 struct DynParams {
@@ -66,30 +69,29 @@ struct DynParams {
 struct PairLam { float la, ob; };
 
 // Pair interaction in float: returns -dU/dr / r (so f_i += ret * (xi - xj)) and optionally the energy.
+// One formula for every pair kind: plain LJ is the soft core with lambda^a = 1, alpha (1-lambda)^b = 0
+// (x = (sigma/r)^6), so a warp never diverges on the pair kind.  Approximate reciprocals (1 ulp-class MUFU ops).
 template <bool ENERGY>
 __device__ __forceinline__ float lj_pair_f(const DynParams &p, float r2, float sig, float eps, bool softcore,
                                            PairLam lam, float &energy) {
-    float e, fr;  // energy, -dU/dr / r
-    const float inv_r2 = 1.0f / r2;
-    if (!softcore) {
-        const float s2 = sig * sig * inv_r2, s6 = s2 * s2 * s2;
-        e = 4.0f * eps * (s6 * s6 - s6);
-        fr = 4.0f * eps * (12.0f * s6 * s6 - 6.0f * s6) * inv_r2;
-    } else {
-        const float q = r2 / (sig * sig);
-        float rsc, x;
-        if (p.c_is_6) { rsc = q * q * q; x = 1.0f / (lam.ob + rsc); }
-        else { rsc = powf(q, 0.5f * p.sc_c); x = powf(lam.ob + rsc, -6.0f / p.sc_c); }
-        const float D = lam.ob + rsc;
-        e = lam.la * 4.0f * eps * x * (x - 1.0f);
-        fr = lam.la * 4.0f * eps * (2.0f * x - 1.0f) * 6.0f * x * rsc / (D * r2);
-    }
+    const float la = softcore ? lam.la : 1.0f, ob = softcore ? lam.ob : 0.0f;
+    const float inv_r2 = fast_rcp(r2);
+    const float q = r2 * fast_rcp(sig * sig);
+    float rsc, x, D;
+    if (p.c_is_6) { rsc = q * q * q; D = ob + rsc; x = fast_rcp(D); }
+    else { rsc = __powf(q, 0.5f * p.sc_c); D = ob + rsc; x = __powf(D, -6.0f / p.sc_c); }
+    const float t4 = la * 4.0f * eps;
+    float e = t4 * x * (x - 1.0f);
+    // -dU/dr / r = t4 (2x-1) 6 x (r/sigma)^c / (D r^2)
+    float fr = t4 * (2.0f * x - 1.0f) * 6.0f * x * rsc * fast_rcp(D) * inv_r2;
     if (p.use_switch && r2 > p.rs2) {
-        const float r = sqrtf(r2);
+        const float rinv = fast_rsqrt(r2);
+        const float r = r2 * rinv;
         const float t = (r - p.rs) * p.inv_w;
-        const float S = 1.0f + t * t * t * (-10.0f + t * (15.0f - 6.0f * t));
-        const float dS = t * t * (-30.0f + t * (60.0f - 30.0f * t)) * p.inv_w;
-        fr = fr * S - e * dS / r;
+        const float t2 = t * t;
+        const float S = 1.0f + t2 * t * (-10.0f + t * (15.0f - 6.0f * t));
+        const float dS = t2 * (-30.0f + t * (60.0f - 30.0f * t)) * p.inv_w;
+        fr = fr * S - e * dS * rinv;
         e *= S;
     }
     if (ENERGY) energy = e;

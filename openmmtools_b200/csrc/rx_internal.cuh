@@ -86,6 +86,8 @@ struct rx_engine {
     MixCtl *d_ctl = nullptr;
     uint32_t *d_log = nullptr;   // commit log of the walker: packed (si, sj, accepted)
     size_t log_cap = 0;
+    unsigned char *d_filt = nullptr;   // 24-bit row image of u for the K=256 walker
+    double *d_filt_scale = nullptr;    // [K] scales + [K] row abs-max
     bool prepared = false;        // words + slot records for the next swap-all call were produced on stream_rng
     size_t slots_for_avail = 0;   // S.avail the slot records were built for
     cudaEvent_t ev_prepared = nullptr, ev_consumed = nullptr;

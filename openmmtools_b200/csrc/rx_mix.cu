@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <vector>
 
 // ------------------------------------------------------------------------------------------------------
 // MT19937 generation: x[n+624] = x[n+397] ^ twist(x[n], x[n+1]); 227 words are independent per step and
@@ -127,108 +128,203 @@ __global__ void __launch_bounds__(256) k_slots_build(const uint32_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------
-// The speculative chain walker (one warp).  K must be a power of two <= 16384.
+// The speculative chain walker.  K must be a power of two <= 16384.
 //
-// Per round the warp (1) reads 32 slot records (prefetched into L1 a few hundred slots ahead), (2) looks up
-// the current states of both replicas (shared memory), (3) fetches u[i,sj], u[j,si] (shared memory when the
-// matrix fits, else L2) and the maintained diagonal d[k] = u[k, perm[k]], (4) evaluates log_p and the accept
-// test, (5) resolves the visited chain and staleness with ballots and bit tricks, (6) commits the valid
-// prefix: permutation + diagonal in shared memory and ONE coalesced store of packed (si, sj, accepted)
-// entries into a commit log.  The count matrices are built from the log afterwards by k_mix_count (parallel).
+// CTA = 2 warps.  Warp 1 streams the slot records from global memory into a shared-memory ring far ahead of the
+// walker (the records come from DRAM: written once by k_slots_build, read once).  Warp 0 walks: per round it
+// (1) reads 32 records from the ring, (2) looks up the current states of both replicas, (3) fetches u[i,sj], u[j,si]
+// and the maintained diagonal d[k] = u[k, perm[k]], (4) evaluates log_p and the accept test, (5) resolves the
+// visited chain and staleness with ballots and bit tricks, (6) commits the valid prefix: permutation + diagonal
+// in shared memory and ONE coalesced store of packed (si, sj, accepted) entries into a commit log (the count
+// matrices are built from the log afterwards by k_mix_count, in parallel).
+//
+// Where the energies live (UMODE):
+//   U_F64_SMEM   the f64 matrix itself is in shared memory (K <= 128)
+//   U_FILTER24   K = 256: 512 KB of f64 do not fit, so shared memory holds a 24-bit fixed-point image of every row
+//                (q = round((u - c_row)/s_row), 3 bytes) that gives log_p to within a RIGOROUS bound eps = 1.01 (s_i+s_j)
+//                + tiny; the decision is taken from the image whenever it is more than eps away from both thresholds
+//                (log_p = 0 and log_p = log U), otherwise the lane falls back to the exact f64 values in L2.  The
+//                result is therefore still bit-identical to the reference.
+//   U_GLOBAL     exact f64 values from L2 every round (any larger K)
 // ------------------------------------------------------------------------------------------------------
 #define LOG_ACC_BIT 28
 #define LOG_STATE_BITS 14
-#define PF_DIST 384
+#define RING 1024
+enum { U_F64_SMEM = 0, U_FILTER24 = 1, U_GLOBAL = 2 };
 
-template <bool U_SMEM>
-__global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict__ rec, const uint32_t *__restrict__ words,
-                                                      long long nslots, const double *__restrict__ u, int K, int M,
+struct WalkShared {     // control words shared by the two warps
+    volatile unsigned prod;   // records [0, prod) of this pass are in the ring (modulo RING)
+    volatile unsigned head;   // walker position
+    volatile unsigned done;
+};
+
+template <int UMODE>
+__global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict__ rec, const uint32_t *__restrict__ words,
+                                                      unsigned nslots, const double *__restrict__ u, int K, int logK,
                                                       int *__restrict__ perm_g, uint32_t *__restrict__ commit_log,
-                                                      MixCtl *ctl) {
+                                                      const unsigned char *__restrict__ filt, const double *__restrict__ filt_scale,
+                                                      double filt_abs, MixCtl *ctl) {
     extern __shared__ double s_mix[];
-    double *s_diag = s_mix;                                  // [K]
-    double *s_u = s_mix + K;                                 // [K*M] when U_SMEM
-    int *s_perm = (int *)(s_mix + K + (U_SMEM ? (size_t)K * M : 0));  // [K]
-    const int lane = threadIdx.x;
-    for (int q = lane; q < K; q += 32) {
+    __shared__ WalkShared sh;
+    // layout: ring_lu[RING] f64 | diag[K] f64 | (u f64 [K*K]) | (scale[K] f64) | ring_ij[RING] u32 | ring_bm[RING] u32 | perm[K] i32 | (q24 [3*K*K] bytes)
+    double *ring_lu = s_mix;
+    double *s_diag = ring_lu + RING;
+    double *s_u = s_diag + K;
+    double *s_scale = s_u + (UMODE == U_F64_SMEM ? (size_t)K * K : 0);
+    uint32_t *ring_ij = (uint32_t *)(s_scale + (UMODE == U_FILTER24 ? K : 0));
+    uint32_t *ring_bm = ring_ij + RING;
+    int *s_perm = (int *)(ring_bm + RING);
+    unsigned char *s_q = (unsigned char *)(s_perm + K);   // [K*K][3] little-endian 24-bit two's complement
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = tid; q < K; q += 64) {
         const int st = perm_g[q];
         s_perm[q] = st;
-        s_diag[q] = u[(size_t)q * M + st];
+        s_diag[q] = u[((size_t)q << logK) + st];
+        if (UMODE == U_FILTER24) s_scale[q] = filt_scale[q];
     }
-    if (U_SMEM)
-        for (int q = lane; q < K * M; q += 32) s_u[q] = u[q];
-    __syncwarp();
-    long long h = ctl->head;
+    if (UMODE == U_F64_SMEM)
+        for (int q = tid; q < K * K; q += 64) s_u[q] = u[q];
+    if (UMODE == U_FILTER24) {
+        const uint32_t *src = (const uint32_t *)filt;
+        uint32_t *dst = (uint32_t *)s_q;
+        for (int q = tid; q < (3 * K * K) / 4; q += 64) dst[q] = src[q];
+    }
+    const unsigned head0 = (unsigned)ctl->head;
+    if (tid == 0) { sh.prod = head0; sh.head = head0; sh.done = 0; }
+    __syncthreads();
+
+    if (warp == 1) {
+        // ---------------- producer: keep the ring filled up to head + RING - 64
+        unsigned prod = head0;
+        while (!sh.done) {
+            const unsigned head = sh.head;
+            unsigned limit = head + RING - 64;
+            if (limit > nslots) limit = nslots;
+            if (prod < limit) {
+                SlotRec r[4];
+                unsigned cnt = limit - prod;
+                if (cnt > 128) cnt = 128;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const unsigned o = b * 32 + lane;
+                    if (o < cnt) r[b] = rec[prod + o];
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const unsigned o = b * 32 + lane;
+                    if (o < cnt) {
+                        const unsigned w = (prod + o) & (RING - 1);
+                        ring_ij[w] = r[b].ij; ring_bm[w] = r[b].backmask; ring_lu[w] = r[b].logU;
+                    }
+                }
+                prod += cnt;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) sh.prod = prod;
+            } else {
+                __nanosleep(40);
+            }
+        }
+        return;
+    }
+
+    // ---------------- walker (warp 0)
+    unsigned h = head0;
     long long remaining = ctl->remaining;
-    long long logpos = 0;
-    long long pf = h;
+    unsigned logpos = 0;
     int rounds = 0;
     unsigned slow = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned sh_amt = lane ? (32 - lane) : 31, lane_nz = lane ? 0xffffffffu : 0u;
     while (remaining > 0 && h + 33 <= nslots) {
         rounds++;
-        // software prefetch of the record stream (it comes from DRAM: written once by k_slots_build, read once)
-        if (pf < h + PF_DIST) {
-            if (pf < h + 32) pf = h + 32;
-            if (pf + lane * 8 < nslots) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + pf + lane * 8));
-            pf += 256;  // 32 lanes x 8 records x 16 B = 32 lines of 128 B
-        }
-        const SlotRec r = rec[h + lane];
-        // the uniform an attempt at this slot would draw belongs to the NEXT slot's words
-        double logU_next = __shfl_down_sync(0xffffffffu, r.logU, 1);
-        if (lane == 31) logU_next = rec[h + 32].logU;
-        const int i = r.ij & 0xffffu, j = r.ij >> 16;
+        while (sh.prod < h + 33) { /* the producer is behind (start of a pass) */ }
+        __threadfence_block();
+        const unsigned w = (h + lane) & (RING - 1);
+        const uint32_t ij = ring_ij[w], backmask = ring_bm[w];
+        const double logU_next = ring_lu[(w + 1) & (RING - 1)];  // the uniform an attempt here would draw: NEXT slot
+        const unsigned i = ij & 0xffffu, j = ij >> 16;
         const int si = s_perm[i], sj = s_perm[j];
-        const double e_ii = s_diag[i], e_jj = s_diag[j];
-        const double e_ij = U_SMEM ? s_u[i * M + sj] : u[(size_t)i * M + sj];
-        const double e_ji = U_SMEM ? s_u[j * M + si] : u[(size_t)j * M + si];
-        const double logp = swap_logp(e_ij, e_ji, e_ii, e_jj);
-        const bool ge0 = logp >= 0.0;
-        bool acc = ge0;
-        if (!ge0) {
+        const unsigned a_ij = (i << logK) | (unsigned)sj, a_ji = (j << logK) | (unsigned)si;
+        bool ge0, acc;
+        double e_ij = 0.0, e_ji = 0.0;   // exact off-diagonal values, needed by the commit (new diagonal)
+        if (UMODE == U_FILTER24) {
+            // image of u: logp~ = s_i (q_ii - q_ij) + s_j (q_jj - q_ji), |logp~ - logp_ref| <= eps
+            const unsigned a_ii = (i << logK) | (unsigned)si, a_jj = (j << logK) | (unsigned)sj;
+            auto q24 = [&](unsigned a) -> int {
+                const unsigned char *b = s_q + 3u * a;
+                return (int)((unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)(signed char)b[2] << 16));
+            };
+            const double sc_i = s_scale[i], sc_j = s_scale[j];
+            const double lp = sc_i * (double)(q24(a_ii) - q24(a_ij)) + sc_j * (double)(q24(a_jj) - q24(a_ji));
+            const double eps = 1.01 * (sc_i + sc_j) + filt_abs;
+            const double d = lp - logU_next;
+            const bool sure_ge0 = lp > eps, sure_neg = lp < -eps;
+            const bool sure_acc = d > eps + 1e-9, sure_rej = d < -(eps + 1e-9);
+            // i == j: the reference's log_p is exactly 0 for finite energies (-(e+e)+e+e), accepted without a draw
+            const bool same = (i == j) && (sc_i == sc_i);
+            ge0 = sure_ge0 || same;
+            acc = ge0 || (sure_neg && sure_acc);
+            const bool decided = ge0 || (sure_neg && (sure_acc || sure_rej));
+            if (__any_sync(0xffffffffu, !decided)) {
+                if (!decided) {   // exact path for this lane: the f64 values from L2
+                    const double logp = swap_logp(u[a_ij], u[a_ji], u[a_ii], u[a_jj]);
+                    ge0 = logp >= 0.0;
+                    acc = ge0;
+                    if (!ge0) {
+                        const double dd = logp - logU_next;
+                        if (dd > 1e-9) acc = true;
+                        else if (dd < -1e-9) acc = false;
+                        else { const unsigned s1 = h + lane + 1; acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp); }
+                    }
+                    slow++;
+                }
+            }
+        } else {
+            e_ij = (UMODE == U_F64_SMEM) ? s_u[a_ij] : u[a_ij];
+            e_ji = (UMODE == U_F64_SMEM) ? s_u[a_ji] : u[a_ji];
+            const double logp = swap_logp(e_ij, e_ji, s_diag[i], s_diag[j]);
             const double d = logp - logU_next;
-            if (d > 1e-9) acc = true;
-            else if (d < -1e-9) acc = false;
-            else {  // too close to call in the log domain: do exactly what the reference does
-                const long long s1 = h + lane + 1;
-                const double U = mt_double(words[2 * s1], words[2 * s1 + 1]);
-                acc = U < exp(logp);
-                slow++;
+            ge0 = logp >= 0.0;
+            acc = ge0 || d > 1e-9;
+            const bool ambiguous = !ge0 && !(d > 1e-9) && !(d < -1e-9) && (d == d);
+            if (__any_sync(0xffffffffu, ambiguous)) {
+                if (ambiguous) {  // too close to call in the log domain: do exactly what the reference does
+                    const unsigned s1 = h + lane + 1;
+                    acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp);
+                    slow++;
+                }
             }
         }
         const unsigned G = __ballot_sync(0xffffffffu, ge0);
         const unsigned A = __ballot_sync(0xffffffffu, acc);
         const unsigned E = __ballot_sync(0xffffffffu, i == j);
-        // Visited chain: from a visited slot s the next attempt starts at s+1 if log_p >= 0 (no uniform drawn)
-        // else at s+2.  skip[s+1] = NG[s] & ~skip[s]: inside a run of NG ones the skip flag alternates, so
-        // skip[s] = parity of (s - run start); runs are split by start parity with an add-carry.
-        const unsigned long long X = (unsigned long long)(~G);
-        const unsigned long long starts = X & ~(X << 1);
-        const unsigned long long SE = starts & 0x5555555555555555ull, SO = starts & 0xAAAAAAAAAAAAAAAAull;
-        const unsigned long long DE = ((X + SE) ^ X) & ~SE, DO = ((X + SO) ^ X) & ~SO;
-        const unsigned long long skip = (DE & 0xAAAAAAAAAAAAAAAAull) | (DO & 0x5555555555555555ull);
-        const unsigned V = ~(unsigned)skip;
-        const unsigned skip32 = (unsigned)(skip >> 32) & 1u;
+        // Visited chain: from a visited slot s the next attempt starts at s+1 if log_p >= 0 (no uniform drawn) else at
+        // s+2.  skip[s+1] = NG[s] & ~skip[s]: inside a run of NG ones the skip flag alternates, so skip[s] = parity of
+        // (s - run start); runs are split by the parity of their start with an add-carry (32-bit adds + carry out).
+        const unsigned X = ~G;
+        const unsigned starts = X & ~(X << 1);
+        const unsigned SE = starts & 0x55555555u, SO = starts & 0xAAAAAAAAu;
+        const unsigned sumE = X + SE, sumO = X + SO;
+        const unsigned DE = (sumE ^ X) & ~SE, DO = (sumO ^ X) & ~SO;
+        const unsigned skip = (DE & 0xAAAAAAAAu) | (DO & 0x55555555u);
+        const unsigned skip32 = (sumO < X) ? 1u : 0u;   // bit 32 (even position) can only be set by an odd-start run
+        const unsigned V = ~skip;
         const unsigned VA = V & A & ~E;  // visited, accepted, really changing the permutation
         // lane t is stale if an earlier visited state-changing swap in this window shares a replica with it
-        const unsigned earlier = lane ? (__brev(VA) >> (32 - lane)) : 0u;
-        const bool stale = (earlier & r.backmask) != 0u;
-        const unsigned C = __ballot_sync(0xffffffffu, stale) & V;
-        const int first = C ? (__ffs(C) - 1) : 32;
-        unsigned cm = V & (first == 32 ? 0xffffffffu : ((1u << first) - 1u));
+        const unsigned earlier = (__brev(VA) >> sh_amt) & lane_nz;
+        const unsigned C = __ballot_sync(0xffffffffu, (earlier & backmask) != 0u) & V;
+        const unsigned low = C & (0u - C);
+        unsigned cm = V & (low - 1u);           // low == 0 -> all lanes
         int n = __popc(cm);
-        long long advance;
+        unsigned advance = C ? (unsigned)__popc(low - 1u) : 32u + skip32;
         if ((long long)n > remaining) {
-            int pos = 0;  // the first visited lane we must NOT run: the (remaining+1)-th set bit of cm
+            unsigned pos = 0;  // the first visited lane we must NOT run: the (remaining+1)-th set bit of cm
             for (int cnt = 0; pos < 32; pos++)
                 if ((cm >> pos) & 1u) { if (cnt == (int)remaining) break; cnt++; }
             cm &= (1u << pos) - 1u;
             n = (int)remaining;
             advance = pos;
-        } else if (first < 32) {
-            advance = first;
-        } else {
-            advance = 32 + skip32;
         }
         if ((cm >> lane) & 1u) {
             commit_log[logpos + __popc(cm & lt_mask)] =
@@ -236,15 +332,16 @@ __global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict_
             if (acc && i != j) {  // an i == j lane must not write: a later committed lane may swap this replica
                 s_perm[i] = sj;
                 s_perm[j] = si;
-                s_diag[i] = e_ij;
-                s_diag[j] = e_ji;
+                if (UMODE != U_FILTER24) { s_diag[i] = e_ij; s_diag[j] = e_ji; }   // the image needs no f64 diagonal
             }
         }
         logpos += n;
         h += advance;
         remaining -= n;
+        if (lane == 0) sh.head = h;
         __syncwarp();
     }
+    if (lane == 0) sh.done = 1;
     for (int q = lane; q < K; q += 32) perm_g[q] = s_perm[q];
     slow = __reduce_add_sync(0xffffffffu, slow);
     if (lane == 0) {
@@ -255,6 +352,44 @@ __global__ void __launch_bounds__(32) k_mix_walk_pow2(const SlotRec *__restrict_
         ctl->slow_exp += slow;
         ctl->log_count = logpos;
     }
+}
+
+// 24-bit row image of the energy matrix for the U_FILTER24 walker: per row c = u[k,0]-ish centre, scale s_k, q = rint((u-c)/s).
+// scale[k] = NaN when the row contains non-finite values (every decision then takes the exact path).
+__global__ void k_mix_filter_build(const double *__restrict__ u, int K, unsigned char *__restrict__ filt, double *__restrict__ scale,
+                                   double *__restrict__ absmax_out) {
+    __shared__ double s_lo[8], s_hi[8], s_am[8];
+    const int k = blockIdx.x, t = threadIdx.x;
+    double lo = INFINITY, hi = -INFINITY, am = 0.0;
+    bool bad = false;
+    for (int l = t; l < K; l += blockDim.x) {
+        const double v = u[(size_t)k * K + l];
+        if (!isfinite(v)) bad = true;
+        lo = fmin(lo, v); hi = fmax(hi, v); am = fmax(am, fabs(v));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, o));
+        am = fmax(am, __shfl_down_sync(0xffffffffu, am, o));
+    }
+    const int anybad = __syncthreads_or(bad ? 1 : 0);
+    if ((t & 31) == 0) { s_lo[t >> 5] = lo; s_hi[t >> 5] = hi; s_am[t >> 5] = am; }
+    __syncthreads();
+    lo = s_lo[0]; hi = s_hi[0]; am = s_am[0];
+    for (int q = 1; q < (int)(blockDim.x >> 5); q++) { lo = fmin(lo, s_lo[q]); hi = fmax(hi, s_hi[q]); am = fmax(am, s_am[q]); }
+    const double c = 0.5 * (lo + hi);
+    double sc = (0.5 * (hi - lo)) / 8388000.0;   // |q| <= 2^23 - 608
+    if (!(sc > 0.0)) sc = 1e-300;                  // constant row
+    if (anybad || !isfinite(sc)) sc = NAN;
+    for (int l = t; l < K; l += blockDim.x) {
+        const double v = u[(size_t)k * K + l];
+        int q = anybad ? 0 : (int)rint((v - c) / sc);
+        if (q > 8388607) q = 8388607;
+        if (q < -8388608) q = -8388608;
+        unsigned char *b = filt + 3 * ((size_t)k * K + l);
+        b[0] = (unsigned char)(q & 0xff); b[1] = (unsigned char)((q >> 8) & 0xff); b[2] = (unsigned char)((q >> 16) & 0xff);
+    }
+    if (t == 0) { scale[k] = sc; absmax_out[k] = anybad ? INFINITY : am; }
 }
 
 // Build the (symmetric) proposal / acceptance count matrices from the commit log (replicaexchange.py:339-349).
@@ -487,15 +622,40 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         return RX_OK;
     }
     const bool fast = is_pow2(K) && K <= (1 << LOG_STATE_BITS);
+    int logK = 0;
+    while ((1 << logK) < K) logK++;
     const size_t smem_small = (size_t)K * sizeof(int);
-    const size_t smem_global_u = (size_t)K * (sizeof(double) + sizeof(int));
-    const size_t smem_smem_u = smem_global_u + (size_t)K * M * sizeof(double);
-    const bool u_smem = fast && smem_smem_u <= 200 * 1024;
-    const size_t smem = !fast ? smem_small : (u_smem ? smem_smem_u : smem_global_u);
+    // ring (lu 8 + ij 4 + bm 4) + diag + perm
+    const size_t smem_base = (size_t)RING * 16 + (size_t)K * (sizeof(double) + sizeof(int));
+    const size_t smem_f64 = smem_base + (size_t)K * K * sizeof(double);
+    const size_t smem_f24 = smem_base + (size_t)K * sizeof(double) + (size_t)3 * K * K;
+    int umode = U_GLOBAL;
+    if (fast && smem_f64 <= 200 * 1024) umode = U_F64_SMEM;
+    else if (fast && smem_f24 <= 224 * 1024 && !getenv("RX_NO_FILTER")) umode = U_FILTER24;
+    const size_t smem = !fast ? smem_small : (umode == U_F64_SMEM ? smem_f64 : (umode == U_FILTER24 ? smem_f24 : smem_base));
     if (smem > 48 * 1024) {
         if (!fast) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else if (u_smem) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else if (umode == U_F64_SMEM) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_F64_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else if (umode == U_FILTER24) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_FILTER24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    double filt_abs = 0.0;
+    if (umode == U_FILTER24) {
+        if (!h->d_filt) {
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_filt, (size_t)3 * K * K + 16));
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_filt_scale, sizeof(double) * 2 * K));
+        }
+        k_mix_filter_build<<<K, 256, 0, h->stream>>>(h->d_u, K, h->d_filt, h->d_filt_scale, h->d_filt_scale + K);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        (*launches)++;
+        std::vector<double> am(K);
+        RX_CHECK_CUDA(h, cudaMemcpyAsync(am.data(), h->d_filt_scale + K, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+        RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+        double amax = 0;
+        for (int k = 0; k < K; k++) amax = am[k] > amax ? am[k] : amax;
+        // rounding of the reference's own f64 evaluation (3 adds of values <= 2 amax) plus our centring subtractions
+        filt_abs = 64.0 * 2.220446049250313e-16 * (amax + 1.0);
+        if (!(filt_abs < 1e-3)) umode = U_GLOBAL;   // absurd magnitudes: just use the exact path
     }
     long long remaining = nswap;
     h->mix_stats[0] = h->mix_stats[1] = h->mix_stats[2] = 0;
@@ -521,10 +681,12 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         size_t consumed_words;
         if (fast) {
             const long long nslots = (long long)(S.avail / 2);
-            if (u_smem)
-                k_mix_walk_pow2<true><<<1, 32, smem, h->stream>>>(h->d_slots, S.d_words, nslots, h->d_u, K, M, h->d_perm, h->d_log, h->d_ctl);
+            if (umode == U_F64_SMEM)
+                k_mix_walk_pow2<U_F64_SMEM><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, 0.0, h->d_ctl);
+            else if (umode == U_FILTER24)
+                k_mix_walk_pow2<U_FILTER24><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, h->d_filt, h->d_filt_scale, filt_abs, h->d_ctl);
             else
-                k_mix_walk_pow2<false><<<1, 32, smem, h->stream>>>(h->d_slots, S.d_words, nslots, h->d_u, K, M, h->d_perm, h->d_log, h->d_ctl);
+                k_mix_walk_pow2<U_GLOBAL><<<1, 64, smem_base, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, 0.0, h->d_ctl);
             RX_CHECK_CUDA(h, cudaGetLastError());
             *launches += 1;
             RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
@@ -604,5 +766,7 @@ void rxi_mix_free(rx_engine *h) {
     }
     cudaFree(h->d_slots);
     cudaFree(h->d_log);
+    cudaFree(h->d_filt);
+    cudaFree(h->d_filt_scale);
     cudaFree(h->d_ctl);
 }
