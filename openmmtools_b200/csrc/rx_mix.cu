@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     uint32_t *ring_ij = (uint32_t *)(s_scale + (UMODE == U_FILTER24 ? K : 0));
     uint32_t *ring_bm = ring_ij + RING;
     int *s_perm = (int *)(ring_bm + RING);
-    unsigned char *s_q = (unsigned char *)(s_perm + K);   // [K*K][3] little-endian 24-bit two's complement
+    unsigned char *s_q = (unsigned char *)(s_perm + K);   // 24-bit image: int16 high plane [K*K] then uint8 low plane [K*K]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int q = tid; q < K; q += 64) {
         const int st = perm_g[q];
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         unsigned prod = head0;
         while (!sh.done) {
             const unsigned head = sh.head;
-            unsigned limit = head + RING - 64;
+            unsigned limit = head + RING - 64;   // `head` may lag the walker by 8 rounds; it only ever lags (safe)
             if (limit > nslots) limit = nslots;
             if (prod < limit) {
                 SlotRec r[4];
@@ -228,18 +228,23 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         return;
     }
 
-    // ---------------- walker (warp 0)
+    // ---------------- walker (warp 0).  The loop is latency bound (one warp, one dependent chain per round), so it is
+    // written for a short instruction stream: 32-bit indices, cached producer position, head published every 8 rounds.
     unsigned h = head0;
-    long long remaining = ctl->remaining;
-    unsigned logpos = 0;
-    int rounds = 0;
-    unsigned slow = 0;
+    const long long remaining0 = ctl->remaining;
+    unsigned rem = remaining0 > 0x7fffffffLL ? 0x7fffffffu : (unsigned)remaining0;   // attempts this launch may still do
+    const unsigned rem0 = rem;
+    unsigned logpos = 0, rounds = 0, slow = 0, prod_seen = head0;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned sh_amt = lane ? (32 - lane) : 31, lane_nz = lane ? 0xffffffffu : 0u;
-    while (remaining > 0 && h + 33 <= nslots) {
+    const short *s_qhi = (const short *)s_q;                              // [K*K] high 16 bits (signed)
+    const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;                  // [K*K] low 8 bits
+    while (rem > 0 && h + 33 <= nslots) {
         rounds++;
-        while (sh.prod < h + 33) { /* the producer is behind (start of a pass) */ }
-        __threadfence_block();
+        if (prod_seen < h + 33) {
+            do { prod_seen = sh.prod; } while (prod_seen < h + 33);   // the producer is behind (start of a pass)
+            asm volatile("" ::: "memory");
+        }
         const unsigned w = (h + lane) & (RING - 1);
         const uint32_t ij = ring_ij[w], backmask = ring_bm[w];
         const double logU_next = ring_lu[(w + 1) & (RING - 1)];  // the uniform an attempt here would draw: NEXT slot
@@ -251,12 +256,10 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         if (UMODE == U_FILTER24) {
             // image of u: logp~ = s_i (q_ii - q_ij) + s_j (q_jj - q_ji), |logp~ - logp_ref| <= eps
             const unsigned a_ii = (i << logK) | (unsigned)si, a_jj = (j << logK) | (unsigned)sj;
-            auto q24 = [&](unsigned a) -> int {
-                const unsigned char *b = s_q + 3u * a;
-                return (int)((unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)(signed char)b[2] << 16));
-            };
+            const int q_ii = ((int)s_qhi[a_ii] << 8) | (int)s_qlo[a_ii], q_ij = ((int)s_qhi[a_ij] << 8) | (int)s_qlo[a_ij];
+            const int q_jj = ((int)s_qhi[a_jj] << 8) | (int)s_qlo[a_jj], q_ji = ((int)s_qhi[a_ji] << 8) | (int)s_qlo[a_ji];
             const double sc_i = s_scale[i], sc_j = s_scale[j];
-            const double lp = sc_i * (double)(q24(a_ii) - q24(a_ij)) + sc_j * (double)(q24(a_jj) - q24(a_ji));
+            const double lp = sc_i * (double)(q_ii - q_ij) + sc_j * (double)(q_jj - q_ji);
             const double eps = 1.01 * (sc_i + sc_j) + filt_abs;
             const double d = lp - logU_next;
             const bool sure_ge0 = lp > eps, sure_neg = lp < -eps;
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             const double d = logp - logU_next;
             ge0 = logp >= 0.0;
             acc = ge0 || d > 1e-9;
-            const bool ambiguous = !ge0 && !(d > 1e-9) && !(d < -1e-9) && (d == d);
+            const bool ambiguous = !ge0 && fabs(d) <= 1e-9;   // NaN compares false: rejected, like the reference
             if (__any_sync(0xffffffffu, ambiguous)) {
                 if (ambiguous) {  // too close to call in the log domain: do exactly what the reference does
                     const unsigned s1 = h + lane + 1;
@@ -306,9 +309,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const unsigned starts = X & ~(X << 1);
         const unsigned SE = starts & 0x55555555u, SO = starts & 0xAAAAAAAAu;
         const unsigned sumE = X + SE, sumO = X + SO;
-        const unsigned DE = (sumE ^ X) & ~SE, DO = (sumO ^ X) & ~SO;
-        const unsigned skip = (DE & 0xAAAAAAAAu) | (DO & 0x55555555u);
-        const unsigned skip32 = (sumO < X) ? 1u : 0u;   // bit 32 (even position) can only be set by an odd-start run
+        const unsigned skip = (((sumE ^ X) & ~SE) & 0xAAAAAAAAu) | (((sumO ^ X) & ~SO) & 0x55555555u);
         const unsigned V = ~skip;
         const unsigned VA = V & A & ~E;  // visited, accepted, really changing the permutation
         // lane t is stale if an earlier visited state-changing swap in this window shares a replica with it
@@ -316,14 +317,15 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const unsigned C = __ballot_sync(0xffffffffu, (earlier & backmask) != 0u) & V;
         const unsigned low = C & (0u - C);
         unsigned cm = V & (low - 1u);           // low == 0 -> all lanes
-        int n = __popc(cm);
-        unsigned advance = C ? (unsigned)__popc(low - 1u) : 32u + skip32;
-        if ((long long)n > remaining) {
-            unsigned pos = 0;  // the first visited lane we must NOT run: the (remaining+1)-th set bit of cm
-            for (int cnt = 0; pos < 32; pos++)
-                if ((cm >> pos) & 1u) { if (cnt == (int)remaining) break; cnt++; }
+        unsigned n = __popc(cm);
+        // bit 32 (even position) of the skip word can only be set by the carry of an odd-start run
+        unsigned advance = C ? (unsigned)__popc(low - 1u) : 32u + (sumO < X ? 1u : 0u);
+        if (n > rem) {
+            unsigned pos = 0;  // the first visited lane we must NOT run: the (rem+1)-th set bit of cm
+            for (unsigned cnt = 0; pos < 32; pos++)
+                if ((cm >> pos) & 1u) { if (cnt == rem) break; cnt++; }
             cm &= (1u << pos) - 1u;
-            n = (int)remaining;
+            n = rem;
             advance = pos;
         }
         if ((cm >> lane) & 1u) {
@@ -337,18 +339,19 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         }
         logpos += n;
         h += advance;
-        remaining -= n;
-        if (lane == 0) sh.head = h;
+        rem -= n;
+        if ((rounds & 7u) == 0u && lane == 0) sh.head = h;
         __syncwarp();
     }
     if (lane == 0) sh.done = 1;
     for (int q = lane; q < K; q += 32) perm_g[q] = s_perm[q];
     slow = __reduce_add_sync(0xffffffffu, slow);
     if (lane == 0) {
+        const long long remaining = remaining0 - (long long)(rem0 - rem);
         ctl->head = h;
         ctl->remaining = remaining;
         ctl->status = remaining > 0 ? 1 : 0;
-        ctl->rounds += rounds;
+        ctl->rounds += (int)rounds;
         ctl->slow_exp += slow;
         ctl->log_count = logpos;
     }
@@ -386,8 +389,9 @@ __global__ void k_mix_filter_build(const double *__restrict__ u, int K, unsigned
         int q = anybad ? 0 : (int)rint((v - c) / sc);
         if (q > 8388607) q = 8388607;
         if (q < -8388608) q = -8388608;
-        unsigned char *b = filt + 3 * ((size_t)k * K + l);
-        b[0] = (unsigned char)(q & 0xff); b[1] = (unsigned char)((q >> 8) & 0xff); b[2] = (unsigned char)((q >> 16) & 0xff);
+        // q = hi * 256 + lo with hi = q >> 8 (arithmetic), lo = q & 255
+        ((short *)filt)[(size_t)k * K + l] = (short)(q >> 8);
+        filt[2 * (size_t)K * K + (size_t)k * K + l] = (unsigned char)(q & 0xff);
     }
     if (t == 0) { scale[k] = sc; absmax_out[k] = anybad ? INFINITY : am; }
 }
