@@ -146,11 +146,13 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     // rebuilt whenever any atom has moved more than skin/2 since the last build.  If an atom has more than
     // maxnb neighbours the CTA falls back to the all-pairs loop for the rest of the launch.
     bool use_list = p.kind != RX_SYSTEM_HARMONIC && p.maxnb > 0;
-    int nb_count = 0;
+    // The list is kept in two regions: neighbours that were inside the cutoff at build time fill the slots from the
+    // front, skin-only neighbours from the back.  A warp then meets the expensive in-range work in its first iterations
+    // (most lanes active) and almost none in the later ones, instead of a ~46 % active mix in every iteration.
+    int nb_in = 0, nb_out = 0;
     float xr = x, yr = y, zr = z;  // position at the last list build
     auto build_list = [&]() {
-        int c = 0;
-        bool over = false;
+        int cin = 0, cout = 0;
         if (active) {
             for (int j = 0; j < p.N; j++) {
                 const float4 pj = s_pos[j];
@@ -158,13 +160,16 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
                 dx -= p.Lx * rintf(dx * p.iLx); dy -= p.Ly * rintf(dy * p.iLy); dz -= p.Lz * rintf(dz * p.iLz);
                 const float r2 = dx * dx + dy * dy + dz * dz;
                 if (r2 < p.rl2 && j != t) {
-                    if (c < p.maxnb) s_nb[c * p.N + t] = (unsigned short)j;
-                    else over = true;
-                    c++;
+                    if (cin + cout < p.maxnb) {
+                        const int slot = (r2 < p.rc2) ? cin : (p.maxnb - 1 - cout);
+                        s_nb[slot * p.N + t] = (unsigned short)j;
+                    }
+                    if (r2 < p.rc2) cin++; else cout++;
                 }
             }
         }
-        nb_count = c;
+        const bool over = cin + cout > p.maxnb;
+        nb_in = cin; nb_out = cout;
         xr = x; yr = y; zr = z;
         if (__syncthreads_or(over ? 1 : 0)) use_list = false;
     };
@@ -176,9 +181,9 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
             ax = -hK * (x - hx0); ay = -hK * (y - hx1); az = -hK * (z - hx2);
             if (want_energy) en = 0.5f * hK * ((x - hx0) * (x - hx0) + (y - hx1) * (y - hx1) + (z - hx2) * (z - hx2));
         } else if (active) {
-            const int n_it = use_list ? nb_count : p.N;
+            const int n_it = use_list ? nb_in + nb_out : p.N;
             for (int c = 0; c < n_it; c++) {
-                const int j = use_list ? (int)s_nb[c * p.N + t] : c;
+                const int j = use_list ? (int)s_nb[(c < nb_in ? c : p.maxnb - 1 - (c - nb_in)) * p.N + t] : c;
                 const float4 pj = s_pos[j];
                 float dx = x - pj.x, dy = y - pj.y, dz = z - pj.z;
                 dx -= p.Lx * rintf(dx * p.iLx); dy -= p.Ly * rintf(dy * p.iLy); dz -= p.Lz * rintf(dz * p.iLz);

@@ -180,7 +180,6 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const int st = perm_g[q];
         s_perm[q] = st;
         s_diag[q] = u[((size_t)q << logK) + st];
-        if (UMODE == U_FILTER24) s_scale[q] = filt_scale[q];
     }
     if (UMODE == U_F64_SMEM)
         for (int q = tid; q < K * K; q += 64) s_u[q] = u[q];
@@ -237,8 +236,8 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     unsigned logpos = 0, rounds = 0, slow = 0, prod_seen = head0;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned sh_amt = lane ? (32 - lane) : 31, lane_nz = lane ? 0xffffffffu : 0u;
-    const short *s_qhi = (const short *)s_q;                              // [K*K] high 16 bits (signed)
-    const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;                  // [K*K] low 8 bits
+    const unsigned short *s_qhi = (const unsigned short *)s_q;            // [K*K] sign, exponent, 7 mantissa bits
+    const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;                  // [K*K] next 8 mantissa bits
     while (rem > 0 && h + 33 <= nslots) {
         rounds++;
         if (prod_seen < h + 33) {
@@ -254,18 +253,20 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         bool ge0, acc;
         double e_ij = 0.0, e_ji = 0.0;   // exact off-diagonal values, needed by the commit (new diagonal)
         if (UMODE == U_FILTER24) {
-            // image of u: logp~ = s_i (q_ii - q_ij) + s_j (q_jj - q_ji), |logp~ - logp_ref| <= eps
+            // image of u: 24-bit floats of delta = u - rowmin; logp~ = (d_ii - d_ij) + (d_jj - d_ji), |logp~ - logp_ref| <= eps
             const unsigned a_ii = (i << logK) | (unsigned)si, a_jj = (j << logK) | (unsigned)sj;
-            const int q_ii = ((int)s_qhi[a_ii] << 8) | (int)s_qlo[a_ii], q_ij = ((int)s_qhi[a_ij] << 8) | (int)s_qlo[a_ij];
-            const int q_jj = ((int)s_qhi[a_jj] << 8) | (int)s_qlo[a_jj], q_ji = ((int)s_qhi[a_ji] << 8) | (int)s_qlo[a_ji];
-            const double sc_i = s_scale[i], sc_j = s_scale[j];
-            const double lp = sc_i * (double)(q_ii - q_ij) + sc_j * (double)(q_jj - q_ji);
-            const double eps = 1.01 * (sc_i + sc_j) + filt_abs;
+            const float f_ii = __uint_as_float(((unsigned)s_qhi[a_ii] << 16) | ((unsigned)s_qlo[a_ii] << 8));
+            const float f_ij = __uint_as_float(((unsigned)s_qhi[a_ij] << 16) | ((unsigned)s_qlo[a_ij] << 8));
+            const float f_jj = __uint_as_float(((unsigned)s_qhi[a_jj] << 16) | ((unsigned)s_qlo[a_jj] << 8));
+            const float f_ji = __uint_as_float(((unsigned)s_qhi[a_ji] << 16) | ((unsigned)s_qlo[a_ji] << 8));
+            const double lp = ((double)f_ii - (double)f_ij) + ((double)f_jj - (double)f_ji);
+            // every image value is within 2^-15 (relative) of the true delta: truncation to a 15-bit mantissa + f32 rounding
+            const double eps = (double)(fabsf(f_ii) + fabsf(f_ij) + fabsf(f_jj) + fabsf(f_ji)) * 3.2e-5 + filt_abs;
             const double d = lp - logU_next;
             const bool sure_ge0 = lp > eps, sure_neg = lp < -eps;
             const bool sure_acc = d > eps + 1e-9, sure_rej = d < -(eps + 1e-9);
             // i == j: the reference's log_p is exactly 0 for finite energies (-(e+e)+e+e), accepted without a draw
-            const bool same = (i == j) && (sc_i == sc_i);
+            const bool same = (i == j) && (fabsf(f_ii) <= 3.0e38f);
             ge0 = sure_ge0 || same;
             acc = ge0 || (sure_neg && sure_acc);
             const bool decided = ge0 || (sure_neg && (sure_acc || sure_rej));
@@ -357,43 +358,38 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     }
 }
 
-// 24-bit row image of the energy matrix for the U_FILTER24 walker: per row c = u[k,0]-ish centre, scale s_k, q = rint((u-c)/s).
-// scale[k] = NaN when the row contains non-finite values (every decision then takes the exact path).
+// 24-bit row image of the energy matrix for the U_FILTER24 walker: delta = u[k,l] - min_l u[k,l] as a float32 truncated to
+// its top 24 bits (sign, 8 exponent, 15 mantissa bits), stored as a uint16 plane followed by a uint8 plane.  Relative
+// precision 2^-15 per entry, so huge entries (a decoupled atom overlapping another one evaluated at lambda = 1) cost no
+// precision where the decisions are made.  absmax_out[k] = max |u[k,:]| (inf for rows with non-finite values).
 __global__ void k_mix_filter_build(const double *__restrict__ u, int K, unsigned char *__restrict__ filt, double *__restrict__ scale,
                                    double *__restrict__ absmax_out) {
-    __shared__ double s_lo[8], s_hi[8], s_am[8];
+    __shared__ double s_lo[8], s_am[8];
     const int k = blockIdx.x, t = threadIdx.x;
-    double lo = INFINITY, hi = -INFINITY, am = 0.0;
+    double lo = INFINITY, am = 0.0;
     bool bad = false;
     for (int l = t; l < K; l += blockDim.x) {
         const double v = u[(size_t)k * K + l];
         if (!isfinite(v)) bad = true;
-        lo = fmin(lo, v); hi = fmax(hi, v); am = fmax(am, fabs(v));
+        lo = fmin(lo, v); am = fmax(am, fabs(v));
     }
     for (int o = 16; o > 0; o >>= 1) {
         lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, o));
-        hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, o));
         am = fmax(am, __shfl_down_sync(0xffffffffu, am, o));
     }
     const int anybad = __syncthreads_or(bad ? 1 : 0);
-    if ((t & 31) == 0) { s_lo[t >> 5] = lo; s_hi[t >> 5] = hi; s_am[t >> 5] = am; }
+    if ((t & 31) == 0) { s_lo[t >> 5] = lo; s_am[t >> 5] = am; }
     __syncthreads();
-    lo = s_lo[0]; hi = s_hi[0]; am = s_am[0];
-    for (int q = 1; q < (int)(blockDim.x >> 5); q++) { lo = fmin(lo, s_lo[q]); hi = fmax(hi, s_hi[q]); am = fmax(am, s_am[q]); }
-    const double c = 0.5 * (lo + hi);
-    double sc = (0.5 * (hi - lo)) / 8388000.0;   // |q| <= 2^23 - 608
-    if (!(sc > 0.0)) sc = 1e-300;                  // constant row
-    if (anybad || !isfinite(sc)) sc = NAN;
+    lo = s_lo[0]; am = s_am[0];
+    for (int q = 1; q < (int)(blockDim.x >> 5); q++) { lo = fmin(lo, s_lo[q]); am = fmax(am, s_am[q]); }
+    if (!isfinite(lo)) lo = 0.0;
     for (int l = t; l < K; l += blockDim.x) {
-        const double v = u[(size_t)k * K + l];
-        int q = anybad ? 0 : (int)rint((v - c) / sc);
-        if (q > 8388607) q = 8388607;
-        if (q < -8388608) q = -8388608;
-        // q = hi * 256 + lo with hi = q >> 8 (arithmetic), lo = q & 255
-        ((short *)filt)[(size_t)k * K + l] = (short)(q >> 8);
-        filt[2 * (size_t)K * K + (size_t)k * K + l] = (unsigned char)(q & 0xff);
+        const float f = (float)(u[(size_t)k * K + l] - lo);     // round to nearest f32; inf/NaN stay inf/NaN
+        const unsigned bits = __float_as_uint(f) & 0xffffff00u;  // truncate to 24 bits (toward zero)
+        ((unsigned short *)filt)[(size_t)k * K + l] = (unsigned short)(bits >> 16);
+        filt[2 * (size_t)K * K + (size_t)k * K + l] = (unsigned char)((bits >> 8) & 0xffu);
     }
-    if (t == 0) { scale[k] = sc; absmax_out[k] = anybad ? INFINITY : am; }
+    if (t == 0) { scale[k] = lo; absmax_out[k] = anybad ? INFINITY : am; }
 }
 
 // Build the (symmetric) proposal / acceptance count matrices from the commit log (replicaexchange.py:339-349).
@@ -565,7 +561,7 @@ int rxi_mix_seed(rx_engine *h, int stream, uint32_t seed) {
     if (!S.d_window) RX_CHECK_CUDA(h, cudaMalloc(&S.d_window, 624 * sizeof(uint32_t)));
     RX_CHECK_CUDA(h, cudaMemcpy(S.d_window, mt, sizeof(mt), cudaMemcpyHostToDevice));
     RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream_rng));
-    if (stream == RX_STREAM_NUMBA) h->prepared = false;
+    if (stream == RX_STREAM_NUMBA) { h->prepared = false; h->last_consumed = 0; }
     S.avail = 0;
     S.consumed = 0;
     S.seeded = true;
@@ -587,7 +583,9 @@ static inline size_t pass_need(long long remaining, bool fast) {
 // replicas are being propagated.
 static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fast, int K, cudaStream_t st, int *launches) {
     const size_t need = pass_need(remaining, fast);
-    int rc = stream_fill(h, S, need, launches, st);
+    int rc = stream_reserve(h, S, 2 * need + 1024);   // room for the words generated ahead while the walker runs
+    if (rc) return rc;
+    rc = stream_fill(h, S, need, launches, st);
     if (rc) return rc;
     if (fast) {
         const long long nslots = (long long)(S.avail / 2);
@@ -636,12 +634,20 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     int umode = U_GLOBAL;
     if (fast && smem_f64 <= 200 * 1024) umode = U_F64_SMEM;
     else if (fast && smem_f24 <= 224 * 1024 && !getenv("RX_NO_FILTER")) umode = U_FILTER24;
-    const size_t smem = !fast ? smem_small : (umode == U_F64_SMEM ? smem_f64 : (umode == U_FILTER24 ? smem_f24 : smem_base));
-    if (smem > 48 * 1024) {
-        if (!fast) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else if (umode == U_F64_SMEM) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_F64_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else if (umode == U_FILTER24) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_FILTER24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = !fast ? smem_small : (umode == U_F64_SMEM ? smem_f64 : (umode == U_FILTER24 ? smem_f24 : smem_base));
+    // The walker is one latency-bound CTA: claim (almost) a whole SM's shared memory so that no other CTA -- in particular
+    // the stream generator that runs concurrently on the side stream -- is scheduled onto the same SM and steals issue slots.
+    size_t smem_base_launch = smem_base;
+    if (fast) {
+        if (smem < 216 * 1024) smem = 216 * 1024;
+        smem_base_launch = 216 * 1024;
+    }
+    if (!fast) {
+        if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_F64_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_FILTER24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_base_launch));
     }
     double filt_abs = 0.0;
     if (umode == U_FILTER24) {
@@ -685,17 +691,31 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         size_t consumed_words;
         if (fast) {
             const long long nslots = (long long)(S.avail / 2);
+            // While the walker runs (it only reads words [0, avail)), generate on the side stream about as many words
+            // as the previous call consumed: they are appended behind the valid region and adopted afterwards.
+            size_t ahead = 0;
+            if (!getenv("RX_NO_ASYNC_RNG") && h->last_consumed > 0 && S.avail + h->last_consumed <= S.cap) {
+                ahead = h->last_consumed;
+                k_mt_generate<<<1, 256, 0, h->stream_rng>>>(S.d_window, S.d_words + S.avail, (long long)ahead);
+                RX_CHECK_CUDA(h, cudaGetLastError());
+                RX_CHECK_CUDA(h, cudaEventRecord(h->ev_prepared, h->stream_rng));
+                *launches += 1;
+            }
             if (umode == U_F64_SMEM)
                 k_mix_walk_pow2<U_F64_SMEM><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, 0.0, h->d_ctl);
             else if (umode == U_FILTER24)
                 k_mix_walk_pow2<U_FILTER24><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, h->d_filt, h->d_filt_scale, filt_abs, h->d_ctl);
             else
-                k_mix_walk_pow2<U_GLOBAL><<<1, 64, smem_base, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, 0.0, h->d_ctl);
+                k_mix_walk_pow2<U_GLOBAL><<<1, 64, smem_base_launch, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, 0.0, h->d_ctl);
             RX_CHECK_CUDA(h, cudaGetLastError());
             *launches += 1;
             RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
             RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
             consumed_words = (size_t)(2 * ctl.head);
+            if (ahead) {   // adopt the words generated during the walk
+                RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_prepared, 0));
+                S.avail += ahead;
+            }
             if (ctl.log_count > 0) {
                 long long nb = (ctl.log_count + 255) / 256;
                 if (nb > 148 * 16) nb = 148 * 16;
@@ -722,6 +742,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         if (rc) return rc;
     }
     h->mix_stats[3] = (long long)(S.consumed - consumed0);
+    h->last_consumed = (size_t)(S.consumed - consumed0);
     if (!getenv("RX_NO_ASYNC_RNG")) {
         // overlap the next call's stream generation + slot records with whatever runs next on the main stream
         RX_CHECK_CUDA(h, cudaEventRecord(h->ev_consumed, h->stream));
