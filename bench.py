@@ -241,7 +241,7 @@ def main():
     # ---------------- device-resident loop
     eng.run_iterations(args.warmup, mixing, sampler._seed, 1)
     eng.phase_times(reset=True)
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    clocks = ClockSampler(local_rank) if (rank == 0 and not os.environ.get('RX_BENCH_NO_CLOCKS')) else None
     dist.barrier()
     eng.timer_mark(0)
     t0 = time.time()
@@ -269,8 +269,14 @@ def main():
     t_prop = pt['propagate_ms'] / max(args.steps, 1) * 1e-3
     ach = b_prop / t_prop / 1e9 if t_prop > 0 else 0.0
     b_iter = K * N * args.md_steps * 64.0 / world + K * N * 16.0 / world + 2 * K * K * 8.0 + K * 8.0
+    traffic = None
+    try:    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture (K=256 on one GPU)
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'k_propagate_traffic.json')))
+        traffic = (tj['dram_bytes_read'] + tj['dram_bytes_write']) * (kloc / 256.0)
+    except Exception:
+        pass
     roof = {'kernel': 'k_propagate', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-            'frac': ach / peak, 'traffic': None,
+            'frac': ach / peak, 'traffic': traffic,
             'peak_source': 'MEASURED_PEAKS.json (of measured)' if peaks else 'fallback 6650 GB/s',
             'algorithmic_bytes_per_launch': b_prop,
             'whole_iteration': {'bytes': b_iter, 'achieved': b_iter / (ms * 1e-3 / args.steps) / 1e9,

@@ -109,6 +109,72 @@ __device__ __forceinline__ double block_reduce_sum(double v, double *s_red) {
     return t;  // valid on thread 0
 }
 
+// Shared-memory loads by 32-bit shared-space address: the generic-pointer path re-derives the CTA's shared window
+// (S2R SR_CgaCtaId + LEA) inside the pair loop.
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// Everything the pair loop needs that does not change inside a launch, gathered in registers once.
+struct PairCtx {
+    float Lx, Ly, Lz, iLx, iLy, iLz, rc2;
+    float x, y, z, sig_i, se_i;
+    bool alch_i;
+    PairLam lam;
+};
+
+template <bool ENERGY>
+__device__ __forceinline__ void pair_term(const DynParams &p, const PairCtx &c, unsigned pos_base, unsigned par_base, int j,
+                                          float &ax, float &ay, float &az, float &en) {
+    const float4 pj = lds_f4(pos_base + 16u * (unsigned)j);
+    float dx = c.x - pj.x, dy = c.y - pj.y, dz = c.z - pj.z;
+    dx -= c.Lx * rintf(dx * c.iLx); dy -= c.Ly * rintf(dy * c.iLy); dz -= c.Lz * rintf(dz * c.iLz);
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 < c.rc2) {
+        const float2 qj = lds_f2(par_base + 8u * (unsigned)j);
+        const bool alch_j = qj.y != 0.f;
+        const bool soft = (c.alch_i != alch_j) || (c.alch_i && alch_j && p.annihilate);
+        float e;
+        const float fr = lj_pair_f<ENERGY>(p, r2, 0.5f * (c.sig_i + pj.w), c.se_i * qj.x, soft, c.lam, e);
+        ax += fr * dx; ay += fr * dy; az += fr * dz;
+        if (ENERGY) en += 0.5f * e;
+    }
+}
+
+// Force on one atom from its Verlet list (front region: in range at build time, back region: skin) or, in the
+// fallback, from all other atoms.  Plain loops over shared memory with address bumps: nothing is re-derived per pair.
+template <bool ENERGY>
+__device__ __forceinline__ void lj_forces(const DynParams &p, const PairCtx &c, unsigned pos_base, unsigned par_base,
+                                          unsigned nb_t, int N, int t, bool use_list, int nb_in, int nb_out, int maxnb,
+                                          float &fx, float &fy, float &fz, float &en) {
+    float ax = 0.f, ay = 0.f, az = 0.f, e = 0.f;
+    if (use_list) {
+        const unsigned stride = 2u * (unsigned)N;
+        unsigned q = nb_t;
+        for (int n = 0; n < nb_in; n++, q += stride)
+            pair_term<ENERGY>(p, c, pos_base, par_base, (int)lds_u16(q), ax, ay, az, e);
+        q = nb_t + (unsigned)(maxnb - 1) * stride;
+        for (int n = 0; n < nb_out; n++, q -= stride)
+            pair_term<ENERGY>(p, c, pos_base, par_base, (int)lds_u16(q), ax, ay, az, e);
+    } else {
+        for (int j = 0; j < N; j++)
+            if (j != t) pair_term<ENERGY>(p, c, pos_base, par_base, j, ax, ay, az, e);
+    }
+    fx = ax; fy = ay; fz = az; en = e;
+}
+
 // One CTA per owned replica; thread t owns atom t (N <= 1024).
 __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *__restrict__ atom,
                                                     const StateDev *__restrict__ states, const int *__restrict__ perm,
@@ -175,33 +241,23 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     };
     if (use_list) build_list();
 
+    PairCtx pc;
+    pc.Lx = p.Lx; pc.Ly = p.Ly; pc.Lz = p.Lz; pc.iLx = p.iLx; pc.iLy = p.iLy; pc.iLz = p.iLz; pc.rc2 = p.rc2;
+    pc.sig_i = sig_i; pc.se_i = se_i; pc.alch_i = alch_i; pc.lam = lam;
+    const unsigned pos_base = (unsigned)__cvta_generic_to_shared(s_pos), par_base = (unsigned)__cvta_generic_to_shared(s_par);
+    const unsigned nb_t = (unsigned)__cvta_generic_to_shared(s_nb + t);
+    const int N = p.N, maxnb = p.maxnb;
     auto compute_forces = [&](bool want_energy, float &e_out) {
-        float ax = 0, ay = 0, az = 0, en = 0;
         if (p.kind == RX_SYSTEM_HARMONIC) {
-            ax = -hK * (x - hx0); ay = -hK * (y - hx1); az = -hK * (z - hx2);
-            if (want_energy) en = 0.5f * hK * ((x - hx0) * (x - hx0) + (y - hx1) * (y - hx1) + (z - hx2) * (z - hx2));
+            fx = -hK * (x - hx0); fy = -hK * (y - hx1); fz = -hK * (z - hx2);
+            e_out = want_energy ? 0.5f * hK * ((x - hx0) * (x - hx0) + (y - hx1) * (y - hx1) + (z - hx2) * (z - hx2)) : 0.f;
         } else if (active) {
-            const int n_it = use_list ? nb_in + nb_out : p.N;
-            for (int c = 0; c < n_it; c++) {
-                const int j = use_list ? (int)s_nb[(c < nb_in ? c : p.maxnb - 1 - (c - nb_in)) * p.N + t] : c;
-                const float4 pj = s_pos[j];
-                float dx = x - pj.x, dy = y - pj.y, dz = z - pj.z;
-                dx -= p.Lx * rintf(dx * p.iLx); dy -= p.Ly * rintf(dy * p.iLy); dz -= p.Lz * rintf(dz * p.iLz);
-                const float r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 < p.rc2 && j != t) {
-                    const float2 qj = s_par[j];
-                    const bool alch_j = qj.y != 0.f;
-                    const bool soft = (alch_i != alch_j) || (alch_i && alch_j && p.annihilate);
-                    float e;
-                    const float fr = want_energy ? lj_pair_f<true>(p, r2, 0.5f * (sig_i + pj.w), se_i * qj.x, soft, lam, e)
-                                                 : lj_pair_f<false>(p, r2, 0.5f * (sig_i + pj.w), se_i * qj.x, soft, lam, e);
-                    ax += fr * dx; ay += fr * dy; az += fr * dz;
-                    if (want_energy) en += 0.5f * e;
-                }
-            }
+            pc.x = x; pc.y = y; pc.z = z;
+            if (want_energy) lj_forces<true>(p, pc, pos_base, par_base, nb_t, N, t, use_list, nb_in, nb_out, maxnb, fx, fy, fz, e_out);
+            else lj_forces<false>(p, pc, pos_base, par_base, nb_t, N, t, use_list, nb_in, nb_out, maxnb, fx, fy, fz, e_out);
+        } else {
+            fx = fy = fz = 0.f; e_out = 0.f;
         }
-        fx = ax; fy = ay; fz = az;
-        e_out = en;
     };
 
     uint32_t ocount = 0;

@@ -639,8 +639,9 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     // the stream generator that runs concurrently on the side stream -- is scheduled onto the same SM and steals issue slots.
     size_t smem_base_launch = smem_base;
     if (fast) {
-        if (smem < 216 * 1024) smem = 216 * 1024;
-        smem_base_launch = 216 * 1024;
+        // 226 KB + this kernel's static shared memory + the generator's 8 KB exceed the SM's 228 KB
+        if (smem < 226 * 1024) smem = 226 * 1024;
+        smem_base_launch = 226 * 1024;
     }
     if (!fast) {
         if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

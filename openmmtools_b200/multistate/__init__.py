@@ -1,4 +1,5 @@
 """multistate samplers on the B200 engine (mirrors openmmtools.multistate for the replica-exchange path)."""
 from .multistatesampler import MultiStateSampler
 from .replicaexchange import ReplicaExchangeSampler
+from .paralleltempering import ParallelTemperingSampler
 from .utils import SimulationNaNError

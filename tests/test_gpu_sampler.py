@@ -138,3 +138,41 @@ def test_thermodynamic_state_reduced_potential_and_single_move():
     move.apply(ts, ss)
     assert ss.velocities is not None and ss.potential_energy is not None and not ss.has_nan()
     assert ts.reduced_potential(ss) != u0
+
+
+def test_parallel_tempering_on_lj_fluid():
+    """ParallelTemperingSampler (paralleltempering.py:109-173): temperatures follow the reference's np.logspace spacing,
+    u[k,l] = beta_l U(x_k), swaps reproduce the oracle's mixing of that matrix."""
+    from oracle import oracle
+    import math
+    fluid = testsystems.LennardJonesFluid(nparticles=128)
+    ts = states.ThermodynamicState(fluid.system, 300 * unit.kelvin)
+    ss = states.SamplerState(fluid.positions, box_vectors=fluid.system.getDefaultPeriodicBoxVectors())
+    move = mcmc.LangevinSplittingDynamicsMove(timestep=1.0 * unit.femtosecond, n_steps=50)
+    s = multistate.ParallelTemperingSampler(mcmc_moves=move, number_of_iterations=100, seed=11)
+    K = 8
+    s.create(ts, ss, min_temperature=300 * unit.kelvin, max_temperature=600 * unit.kelvin, n_temperatures=K)
+    T = [st.temperature.value_in_unit(unit.kelvin) for st in s._thermodynamic_states]
+    ref_T = list(np.logspace(np.log10(300.0), np.log10(600.0), num=K))
+    assert np.allclose(T, ref_T)
+    s.run(3)
+    u = s._energy_thermodynamic_states
+    # rows are one potential energy scaled by beta_l
+    kT = KB * np.array(T)
+    U = u * kT[None, :]
+    assert np.allclose(U, U[:, :1], rtol=1e-9)
+    mt = oracle.MT(11)
+    perm = np.arange(K, dtype=np.int64)
+    s2 = multistate.ParallelTemperingSampler(mcmc_moves=move, number_of_iterations=100, seed=11)
+    s2.create(ts, ss, temperatures=[t * unit.kelvin for t in ref_T])
+    s2._compute_energies()
+    u_prev = s2._energy_thermodynamic_states.copy()
+    for it in range(3):
+        s2.run(1)
+        na = np.zeros((K, K), np.int64); npr = np.zeros((K, K), np.int64)
+        oracle.mix_swap_all(mt, K ** 3, perm, u_prev, na, npr)
+        assert np.array_equal(perm, s2._replica_thermodynamic_states)
+        u_prev = s2._energy_thermodynamic_states.copy()
+    assert np.array_equal(s2._replica_thermodynamic_states, s._replica_thermodynamic_states)
+    with pytest.raises(ValueError):
+        multistate.ParallelTemperingSampler().create(ts, ss, temperatures=[300 * unit.kelvin], n_temperatures=3)

@@ -8,6 +8,7 @@ from openmmtools_b200._engine import Engine
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 n_steps = int(sys.argv[3]) if len(sys.argv) > 3 else 500
+batch = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 fl = testsystems.LennardJonesFluid(nparticles=512)
 s = fl.system
 L = s.box_vectors[0, 0]
@@ -27,12 +28,12 @@ print('u[0,:4]', u[0, :4], 'spread', u.max() - u.min())
 for it in range(iters):
     e.phase_times(reset=True)
     t0 = time.time()
-    e.run_iterations(1, 'swap-all', 7, it)
+    e.run_iterations(batch, 'swap-all', 7, it * batch)
     dt = time.time() - t0
     pt = e.phase_times()
     nacc, nprop = e.get_mix_counts()
     print('iter %d wall %.1f ms  mix %.2f prop %.2f energy %.2f  acc %.3f  words %d' % (
-        it, dt * 1e3, pt['mix_ms'], pt['propagate_ms'], pt['energies_ms'], nacc.sum() / max(nprop.sum(), 1),
+        it, dt * 1e3 / batch, pt['mix_ms'] / batch, pt['propagate_ms'] / batch, pt['energies_ms'] / batch, nacc.sum() / max(nprop.sum(), 1),
         e.mix_stream_position(0)))
 pot, kin = e.get_replica_energies()
 print('T_kin', (2 * kin / (3 * 512 * 8.31446261815324e-3))[:4], 'pot', pot[:3])
