@@ -91,3 +91,33 @@ def test_unseeded_stream_is_an_error():
     with pytest.raises(EngineError):
         e.mix_swap_all(10)
     e.close()
+
+
+@pytest.mark.parametrize('K', [16, 64, 256])
+def test_swap_all_with_nonfinite_and_huge_energies(K):
+    """NaN, +/-inf and 1e300 entries (a decoupled atom on top of another one gives astronomically large energies):
+    the reference's IEEE semantics (NaN compares false, exp(-inf) = 0) must be reproduced exactly, also through the
+    K=256 row-image filter (which must fall back to the exact path)."""
+    from oracle import oracle
+    u = energies('flat', K, 31337 + K)
+    rng = np.random.default_rng(K)
+    for v in (np.nan, np.inf, -np.inf, 1e300, -1e300, 2.4e6):
+        for _ in range(max(2, K // 16)):
+            u[rng.integers(K), rng.integers(K)] = v
+    for variant in range(2):
+        if variant == 1:
+            u = np.where(np.isfinite(u) & (np.abs(u) < 1e7), u, 1e6)   # finite, huge dynamic range per row: filter path
+        e = gpu_engine(0, K, K)
+        e.set_energies(u)
+        e.set_replica_states(np.arange(K))
+        e.mix_seed(99, 0)
+        mt = oracle.MT(99)
+        st_o = np.arange(K, dtype=np.int64)
+        nswap = min(K ** 3, 2_000_000)
+        for it in range(2):
+            st, nacc, nprop = e.mix_swap_all(nswap)
+            na = np.zeros((K, K), np.int64); npr = np.zeros((K, K), np.int64)
+            oracle.mix_swap_all(mt, nswap, st_o, u, na, npr)
+            assert np.array_equal(st, st_o), (K, variant, it)
+            assert np.array_equal(nacc, na) and np.array_equal(nprop, npr)
+        e.close()
