@@ -136,7 +136,9 @@ RX_API int rx_mix_swap_all(rx_engine *h, int64_t nswap_attempts, int64_t *states
                     int64_t *n_accepted /*[M][M] or NULL*/, int64_t *n_proposed /*[M][M] or NULL*/);
 RX_API int rx_mix_swap_neighbors(rx_engine *h, int64_t *states_out, int64_t *n_accepted, int64_t *n_proposed);
 RX_API int rx_get_mix_counts(rx_engine *h, int64_t *n_accepted, int64_t *n_proposed);
-/* MT words consumed so far on a stream (for checkpoints: state = seed + position). */
+/* MT words consumed so far on a stream (for checkpoints: state = seed + position); rx_mix_skip advances a freshly
+ * seeded stream by n words (resume: rx_mix_seed(seed) + rx_mix_skip(position)).                              */
+RX_API int rx_mix_skip(rx_engine *h, int32_t stream, uint64_t n_words);
 RX_API int rx_mix_stream_position(rx_engine *h, int32_t stream, uint64_t *words_consumed);
 
 /* Fused hot loop: n_iterations x (mix -> propagate -> energies), multistatesampler.py:776-782, with no host

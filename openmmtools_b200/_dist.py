@@ -30,6 +30,12 @@ class TorchCommunicator:
     def barrier(self):
         self.dist.barrier()
 
+    def gather_object(self, obj):
+        """List of every rank's object on rank 0, None elsewhere (checkpoint gather; small control-plane traffic)."""
+        out = [None] * self.world_size if self.rank == 0 else None
+        self.dist.gather_object(obj, out, dst=0)
+        return out
+
 
 class SocketCommunicator:
     """Rank 0 listens; the others connect and receive.  Enough for a broadcast of a few bytes."""
@@ -73,6 +79,44 @@ class SocketCommunicator:
 
     def barrier(self):
         self.bcast_bytes(b'x', 1)
+
+    def gather_object(self, obj):
+        import pickle
+        import struct
+        if self.world_size == 1:
+            return [obj]
+        if self.rank == 0:
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((self.addr, self.port + 1))
+            srv.listen(self.world_size)
+            out = [None] * self.world_size
+            out[0] = obj
+            for _ in range(self.world_size - 1):
+                c, _a = srv.accept()
+                hdr = b''
+                while len(hdr) < 12:
+                    hdr += c.recv(12 - len(hdr))
+                r, n = struct.unpack('<iq', hdr)
+                buf = b''
+                while len(buf) < n:
+                    buf += c.recv(min(1 << 20, n - len(buf)))
+                out[r] = pickle.loads(buf)
+                c.close()
+            srv.close()
+            return out
+        payload = pickle.dumps(obj)
+        for _ in range(600):
+            try:
+                c = socket.create_connection((self.addr, self.port + 1), timeout=5)
+                break
+            except OSError:
+                time.sleep(0.1)
+        else:
+            raise RuntimeError('could not reach rank 0')
+        c.sendall(struct.pack('<iq', self.rank, len(payload)) + payload)
+        c.close()
+        return None
 
 
 def default_communicator():

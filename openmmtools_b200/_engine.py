@@ -161,6 +161,9 @@ class Engine:
     def mix_seed(self, seed, stream=_lib.RX_STREAM_NUMBA):
         self._check(self._lib.rx_mix_seed(self._h, stream, int(seed) & 0xFFFFFFFF))
 
+    def mix_skip(self, n_words, stream=_lib.RX_STREAM_NUMBA):
+        self._check(self._lib.rx_mix_skip(self._h, stream, int(n_words)))
+
     def mix_swap_all(self, nswap_attempts=None, fetch=True):
         n = self.K ** 3 if nswap_attempts is None else int(nswap_attempts)
         if not fetch:

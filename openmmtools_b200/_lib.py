@@ -20,7 +20,7 @@ SYMBOLS = [
     'rx_set_integrator', 'rx_set_positions', 'rx_set_velocities', 'rx_get_positions', 'rx_get_velocities',
     'rx_get_replica_energies', 'rx_randomize_velocities', 'rx_set_replica_states', 'rx_get_replica_states',
     'rx_propagate', 'rx_compute_energies', 'rx_set_energies', 'rx_get_energies', 'rx_mix_seed',
-    'rx_mix_swap_all', 'rx_mix_swap_neighbors', 'rx_get_mix_counts', 'rx_mix_stream_position',
+    'rx_mix_skip', 'rx_mix_swap_all', 'rx_mix_swap_neighbors', 'rx_get_mix_counts', 'rx_mix_stream_position',
     'rx_run_iterations', 'rx_get_phase_times', 'rx_timer_mark', 'rx_timer_elapsed', 'rx_get_mix_stats', 'rx_comm_unique_id', 'rx_comm_init',
 ]
 
@@ -72,6 +72,7 @@ def load():
     lib.rx_set_energies.argtypes = [vp, vp]
     lib.rx_get_energies.argtypes = [vp, vp]
     lib.rx_mix_seed.argtypes = [vp, i32, C.c_uint32]
+    lib.rx_mix_skip.argtypes = [vp, i32, u64]
     lib.rx_mix_swap_all.argtypes = [vp, i64, vp, vp, vp]
     lib.rx_mix_swap_neighbors.argtypes = [vp, vp, vp, vp]
     lib.rx_get_mix_counts.argtypes = [vp, vp, vp]

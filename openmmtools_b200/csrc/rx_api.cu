@@ -367,6 +367,10 @@ extern "C" int rx_mix_seed(rx_engine *h, int32_t stream, uint32_t seed) {
     ENTER(h);
     return rxi_mix_seed(h, stream, seed);
 }
+extern "C" int rx_mix_skip(rx_engine *h, int32_t stream, uint64_t n_words) {
+    ENTER(h);
+    return rxi_mix_skip(h, stream, n_words);
+}
 
 static int fetch_mix_results(rx_engine *h, int64_t *states_out, int64_t *nacc, int64_t *nprop) {
     const size_t mm = (size_t)h->cfg.n_states * h->cfg.n_states;

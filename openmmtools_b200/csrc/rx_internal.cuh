@@ -135,6 +135,7 @@ struct PhaseTimer {
 
 // ---- implemented in rx_mix.cu ----
 int rxi_mix_seed(rx_engine *h, int stream, uint32_t seed);
+int rxi_mix_skip(rx_engine *h, int stream, unsigned long long n);
 int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches);
 int rxi_mix_swap_neighbors(rx_engine *h, int *launches);
 void rxi_mix_free(rx_engine *h);

@@ -52,13 +52,13 @@ __global__ void __launch_bounds__(256) k_mt_generate(uint32_t *__restrict__ wind
             uint32_t c = buf[(base + t + 397) & (MT_RING - 1)];
             uint32_t x = mt_twist(a, b, c);
             buf[(base + t + 624) & (MT_RING - 1)] = x;
-            if (produced + t < n) out[produced + t] = mt_temper(x);
+            if (out && produced + t < n) out[produced + t] = mt_temper(x);
             // second step: x[n+227+t+624] needs x[n+227+t], x[n+228+t] (old) and this thread's x[n+624+t]
             a = buf[(base + 227 + t) & (MT_RING - 1)];
             b = buf[(base + 228 + t) & (MT_RING - 1)];
             uint32_t x2 = mt_twist(a, b, x);
             buf[(base + 227 + t + 624) & (MT_RING - 1)] = x2;
-            if (produced + 227 + t < n) out[produced + 227 + t] = mt_temper(x2);
+            if (out && produced + 227 + t < n) out[produced + 227 + t] = mt_temper(x2);
         }
         __syncthreads();
         produced += 454;
@@ -565,6 +565,40 @@ int rxi_mix_seed(rx_engine *h, int stream, uint32_t seed) {
     S.avail = 0;
     S.consumed = 0;
     S.seeded = true;
+    return RX_OK;
+}
+
+int rxi_mix_skip(rx_engine *h, int stream, unsigned long long n) {
+    if (stream < 0 || stream > 1) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_skip: stream must be 0 (numba) or 1 (numpy)");
+    MTStream &S = h->streams[stream];
+    if (!S.seeded) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_skip: seed the stream first");
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream_rng));
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (stream == RX_STREAM_NUMBA) h->prepared = false;
+    // drop buffered words first, then advance the generator without storing
+    unsigned long long todo = n;
+    if (S.avail) {
+        const size_t c = (size_t)(todo < S.avail ? todo : S.avail);
+        {
+            size_t left = S.avail - c;
+            if (left && c) {
+                k_copy_words<<<1184, 1024, 0, h->stream>>>(S.d_words + c, S.d_words_alt, (long long)left);
+                RX_CHECK_CUDA(h, cudaGetLastError());
+                std::swap(S.d_words, S.d_words_alt);
+            }
+            S.avail = left;
+            S.consumed += c;
+        }
+        todo -= c;
+    }
+    while (todo > 0) {
+        const long long chunk = todo > (1ull << 30) ? (1ll << 30) : (long long)todo;
+        k_mt_generate<<<1, 256, 0, h->stream>>>(S.d_window, nullptr, chunk);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        todo -= (unsigned long long)chunk;
+        S.consumed += (unsigned long long)chunk;
+    }
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
     return RX_OK;
 }
 

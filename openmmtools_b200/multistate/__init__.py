@@ -3,3 +3,4 @@ from .multistatesampler import MultiStateSampler
 from .replicaexchange import ReplicaExchangeSampler
 from .paralleltempering import ParallelTemperingSampler
 from .utils import SimulationNaNError
+from .multistatereporter import MultiStateReporter

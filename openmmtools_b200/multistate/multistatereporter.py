@@ -1,0 +1,264 @@
+"""MultiStateReporter: analysis + checkpoint storage for the multistate samplers, without netCDF4.
+
+Mirrors the part of /root/reference/openmmtools/multistate/multistatereporter.py the samplers use
+(``write_energies`` :865, ``write_replica_thermodynamic_states`` :763, ``write_mixing_statistics`` :957,
+``write_sampler_states`` :664, ``write_last_iteration`` :1184, ``read_*`` counterparts, ``read_checkpoint_iterations``,
+``write_dict``/``read_dict``, ``write_thermodynamic_states``, ``write_mcmc_moves``, ``checkpoint_interval`` :131) with
+the reference's variable names and dtypes (``energies`` f8[iteration, replica, state], ``neighborhoods`` i1,
+``states`` i4[iteration, replica], ``accepted``/``proposed`` i4[iteration, state, state], ``last_iteration``).
+
+netCDF4 is not a dependency (it is not installable in the build environment), so the container is a directory:
+
+    <storage>/meta.json                   shapes, options, metadata
+    <storage>/analysis/<name>.bin         fixed-size records appended per iteration (numpy ``fromfile`` readable)
+    <storage>/analysis/last_iteration     commit marker, written last (reference: between two syncs, :1199-1201)
+    <storage>/checkpoint/ckpt_<it>.npz    positions, velocities, box vectors (+ RNG positions: the reference stores no
+                                          RNG state, so its resumed runs are not reproducible; ours are)
+    <storage>/objects.pkl                 pickled thermodynamic states and MCMC moves
+
+Only rank 0 writes (as in the reference, multistatesampler.py:1169-1187).
+"""
+import json
+import os
+import pickle
+import numpy as np
+from .. import states as _states
+from .. import unit
+
+
+class MultiStateReporter:
+    _VARS = {  # name -> (dtype, shape builder from (K, M))
+        'energies': ('f8', lambda K, M: (K, M)),
+        'neighborhoods': ('i1', lambda K, M: (K, M)),
+        'states': ('i4', lambda K, M: (K,)),
+        'accepted': ('i4', lambda K, M: (M, M)),
+        'proposed': ('i4', lambda K, M: (M, M)),
+    }
+
+    def __init__(self, storage, open_mode=None, checkpoint_interval=50, checkpoint_storage=None,
+                 analysis_particle_indices=()):
+        self._storage = str(storage)
+        self._checkpoint_interval = int(checkpoint_interval)
+        self._analysis_particle_indices = tuple(analysis_particle_indices)
+        self._open_mode = None
+        self._meta = None
+        if open_mode is not None:
+            self.open(open_mode)
+
+    # -- properties of the reference
+    @property
+    def filepath(self):
+        return self._storage
+
+    @property
+    def checkpoint_interval(self):
+        return self._checkpoint_interval
+
+    @property
+    def analysis_particle_indices(self):
+        return self._analysis_particle_indices
+
+    def storage_exists(self, skip_size=False):
+        return os.path.exists(os.path.join(self._storage, 'meta.json'))
+
+    def is_open(self):
+        return self._open_mode is not None
+
+    def open(self, mode='r', convention='ReplicaExchange', netcdf_format=None):
+        if mode not in ('r', 'w', 'a'):
+            raise ValueError("open_mode must be 'r', 'w' or 'a'")
+        if mode == 'w':
+            os.makedirs(os.path.join(self._storage, 'analysis'), exist_ok=True)
+            os.makedirs(os.path.join(self._storage, 'checkpoint'), exist_ok=True)
+            for f in os.listdir(os.path.join(self._storage, 'analysis')):
+                os.remove(os.path.join(self._storage, 'analysis', f))
+            for f in os.listdir(os.path.join(self._storage, 'checkpoint')):
+                os.remove(os.path.join(self._storage, 'checkpoint', f))
+            self._meta = {'convention': convention, 'dicts': {}}
+            self._write_meta()
+        else:
+            if not self.storage_exists():
+                raise IOError('storage {} does not exist'.format(self._storage))
+            self._meta = json.load(open(os.path.join(self._storage, 'meta.json')))
+            if 'checkpoint_interval' in self._meta:
+                self._checkpoint_interval = int(self._meta['checkpoint_interval'])
+        self._open_mode = mode
+
+    def close(self):
+        self._open_mode = None
+
+    def sync(self):
+        pass   # every write is flushed and fsync'ed
+
+    def __del__(self):
+        self.close()
+
+    # -- helpers
+    def _write_meta(self):
+        self._meta['checkpoint_interval'] = self._checkpoint_interval
+        tmp = os.path.join(self._storage, 'meta.json.tmp')
+        with open(tmp, 'w') as f:
+            json.dump(self._meta, f)
+            f.flush(); os.fsync(f.fileno())
+        os.replace(tmp, os.path.join(self._storage, 'meta.json'))
+
+    def _path(self, name):
+        return os.path.join(self._storage, 'analysis', name + '.bin')
+
+    def _shape(self, name):
+        K, M = self._meta['n_replicas'], self._meta['n_states']
+        return self._VARS[name][1](K, M)
+
+    def _write_record(self, name, iteration, array):
+        dtype = np.dtype(self._VARS[name][0])
+        a = np.ascontiguousarray(array, dtype=dtype)
+        if 'n_replicas' not in self._meta:
+            raise RuntimeError('write_thermodynamic_states / set_dimensions must be called first')
+        if a.shape != tuple(self._shape(name)):
+            raise ValueError('{}: expected shape {}, got {}'.format(name, self._shape(name), a.shape))
+        mode = 'r+b' if os.path.exists(self._path(name)) else 'w+b'
+        with open(self._path(name), mode) as f:
+            f.seek(int(iteration) * a.nbytes)
+            f.write(a.tobytes())
+            f.flush(); os.fsync(f.fileno())
+
+    def _read_record(self, name, iteration):
+        dtype = np.dtype(self._VARS[name][0])
+        shape = tuple(self._shape(name))
+        rec = int(np.prod(shape)) * dtype.itemsize
+        n = os.path.getsize(self._path(name)) // rec
+        data = np.fromfile(self._path(name), dtype=dtype, count=n * int(np.prod(shape))).reshape((n,) + shape)
+        last = self.read_last_iteration(last_checkpoint=False)
+        data = data[:last + 1]     # never expose records past the commit marker
+        if iteration is None:
+            iteration = slice(None)
+        if isinstance(iteration, (int, np.integer)) and iteration < 0:
+            iteration = last + 1 + iteration
+        return data[iteration]
+
+    def set_dimensions(self, n_replicas, n_states, n_particles):
+        self._meta.update(n_replicas=int(n_replicas), n_states=int(n_states), n_particles=int(n_particles))
+        self._write_meta()
+
+    # -- objects
+    def write_thermodynamic_states(self, thermodynamic_states, unsampled_states):
+        with open(os.path.join(self._storage, 'objects_states.pkl'), 'wb') as f:
+            pickle.dump((thermodynamic_states, unsampled_states), f)
+
+    def read_thermodynamic_states(self):
+        with open(os.path.join(self._storage, 'objects_states.pkl'), 'rb') as f:
+            return pickle.load(f)
+
+    def write_mcmc_moves(self, mcmc_moves):
+        with open(os.path.join(self._storage, 'objects_moves.pkl'), 'wb') as f:
+            pickle.dump(mcmc_moves, f)
+
+    def read_mcmc_moves(self):
+        with open(os.path.join(self._storage, 'objects_moves.pkl'), 'rb') as f:
+            return pickle.load(f)
+
+    def write_dict(self, name, data, fixed_dimension=False):
+        self._meta['dicts'][name] = _jsonable(data)
+        self._write_meta()
+
+    def read_dict(self, name):
+        return self._meta['dicts'].get(name)
+
+    # -- per-iteration analysis data (reference variable names)
+    def write_energies(self, energy_thermodynamic_states, energy_neighborhoods, energy_unsampled_states, iteration):
+        self._write_record('energies', iteration, energy_thermodynamic_states)
+        self._write_record('neighborhoods', iteration, energy_neighborhoods)
+
+    def read_energies(self, iteration=slice(None)):
+        e = self._read_record('energies', iteration)
+        n = self._read_record('neighborhoods', iteration)
+        unsampled = np.zeros(e.shape[:-1] + (0,))
+        return e, n, unsampled
+
+    def write_replica_thermodynamic_states(self, state_indices, iteration):
+        self._write_record('states', iteration, state_indices)
+
+    def read_replica_thermodynamic_states(self, iteration=slice(None)):
+        return self._read_record('states', iteration).astype(np.int64)
+
+    def write_mixing_statistics(self, n_accepted_matrix, n_proposed_matrix, iteration):
+        self._write_record('accepted', iteration, n_accepted_matrix)
+        self._write_record('proposed', iteration, n_proposed_matrix)
+
+    def read_mixing_statistics(self, iteration=slice(None)):
+        return self._read_record('accepted', iteration), self._read_record('proposed', iteration)
+
+    def write_last_iteration(self, last_iteration):
+        """The commit marker: everything up to this iteration is complete (multistatereporter.py:1184-1201)."""
+        tmp = os.path.join(self._storage, 'analysis', 'last_iteration.tmp')
+        with open(tmp, 'w') as f:
+            f.write(str(int(last_iteration)))
+            f.flush(); os.fsync(f.fileno())
+        os.replace(tmp, os.path.join(self._storage, 'analysis', 'last_iteration'))
+
+    def read_last_iteration(self, last_checkpoint=True):
+        p = os.path.join(self._storage, 'analysis', 'last_iteration')
+        last = int(open(p).read()) if os.path.exists(p) else -1
+        if last_checkpoint:
+            cps = [c for c in self.read_checkpoint_iterations() if c <= last]
+            return cps[-1] if cps else -1
+        return last
+
+    # -- checkpoints
+    def _ckpt(self, iteration):
+        return os.path.join(self._storage, 'checkpoint', 'ckpt_%09d.npz' % int(iteration))
+
+    def write_sampler_states(self, sampler_states, iteration, extra=None):
+        """Positions/velocities/box of every replica, only on checkpoint iterations (multistatereporter.py:664-700)."""
+        if int(iteration) % self._checkpoint_interval != 0:
+            return False
+        x = np.stack([s._positions for s in sampler_states])
+        have_v = all(s._velocities is not None for s in sampler_states)
+        v = np.stack([s._velocities for s in sampler_states]) if have_v else np.zeros((0,))
+        boxes = [s._box_vectors for s in sampler_states]
+        have_box = all(b is not None for b in boxes)
+        b = np.stack(boxes) if have_box else np.zeros((0,))
+        tmp = self._ckpt(iteration) + '.tmp.npz'
+        np.savez(tmp, positions=x, velocities=v, box_vectors=b, extra=json.dumps(extra or {}))
+        os.replace(tmp, self._ckpt(iteration))
+        return True
+
+    def read_sampler_states(self, iteration, analysis_particles_only=False):
+        if isinstance(iteration, (int, np.integer)) and iteration < 0:
+            iteration = self.read_checkpoint_iterations()[iteration]
+        if not os.path.exists(self._ckpt(iteration)):
+            return None
+        d = np.load(self._ckpt(iteration))
+        out = []
+        for k in range(d['positions'].shape[0]):
+            v = d['velocities'][k] if d['velocities'].ndim == 3 else None
+            b = d['box_vectors'][k] if d['box_vectors'].ndim == 3 else None
+            out.append(_states.SamplerState(unit.Quantity(d['positions'][k], unit.nanometer),
+                                            velocities=None if v is None else unit.Quantity(v, unit.nanometer / unit.picosecond),
+                                            box_vectors=None if b is None else unit.Quantity(b, unit.nanometer)))
+        return out
+
+    def read_checkpoint_extra(self, iteration):
+        d = np.load(self._ckpt(iteration))
+        return json.loads(str(d['extra']))
+
+    def read_checkpoint_iterations(self):
+        d = os.path.join(self._storage, 'checkpoint')
+        its = sorted(int(f[5:14]) for f in os.listdir(d) if f.startswith('ckpt_') and f.endswith('.npz') and '.tmp' not in f)
+        return its
+
+
+def _jsonable(x):
+    if isinstance(x, dict):
+        return {str(k): _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, (np.integer,)):
+        return int(x)
+    if isinstance(x, (np.floating,)):
+        return float(x)
+    if isinstance(x, unit.Quantity):
+        return {'__quantity__': _jsonable(np.asarray(x._md()).tolist()), 'unit_md': str(x.unit)}
+    if isinstance(x, (str, int, float, bool)) or x is None:
+        return x
+    return repr(x)

@@ -7,8 +7,10 @@ Mirrors /root/reference/openmmtools/multistate/multistatesampler.py for the hot 
 What is different by design: the replicas are resident on the GPU (float4 positions/velocities for all K
 replicas, the K x M energy matrix, the replica->state map, the swap statistics), the three phases are three
 kernel launches, and ``sampler_states`` are materialised on the host only when asked for (or every iteration with
-``host_resident_states=True``, which reproduces the reference's per-iteration host round trip).  Storage
-(NetCDF reporter), online MBAR analysis and minimisation are outside the hot path.
+``host_resident_states=True``, which reproduces the reference's per-iteration host round trip).  Storage goes
+through :class:`MultiStateReporter` (a netCDF4-free container with the reference's variable names; checkpoints also
+carry the RNG positions, so a resumed run is bit-identical to an uninterrupted one).  Online MBAR analysis and
+minimisation are outside the hot path.
 
 Multi-GPU: one process per GPU (torchrun style: RANK / WORLD_SIZE / LOCAL_RANK); replicas are sharded in contiguous
 blocks, energy rows are all-gathered with NCCL, mixing is replicated from identical generator state.
@@ -23,6 +25,7 @@ from .. import unit, mcmc, states, _backend, _lib
 from .._engine import EngineError
 from ..cache import ContextCache
 from .utils import SimulationNaNError
+from .multistatereporter import MultiStateReporter
 
 logger = logging.getLogger(__name__)
 
@@ -68,6 +71,7 @@ class MultiStateSampler:
         self.host_resident_states = host_resident_states
         self.energy_context_cache = ContextCache()
         self.sampler_context_cache = ContextCache()
+        self._reporter = None
         self._engine = None
         self._states_stale = False     # host copies of sampler states are behind the device
         self._seed = seed
@@ -143,19 +147,86 @@ class MultiStateSampler:
     def options(self):
         return {n: getattr(self, n, getattr(self, '_' + n, None)) for n in self.default_options()}
 
+    # options that are stored with the data and restored by from_storage (the reference stores every __init__ kwarg
+    # through _StoredProperty, multistatesampler.py:438-518)
+    _STORED_OPTIONS = ('number_of_iterations', 'online_analysis_interval', 'online_analysis_target_error',
+                       'online_analysis_minimum_iterations', 'locality', 'host_resident_states', 'replica_mixing_scheme')
+
     @classmethod
-    def from_storage(cls, storage):
-        raise NotImplementedError('storage / resume is outside the hot path (SURVEY.md section 8f-1)')
+    def from_storage(cls, storage, communicator=None):
+        """Restore a sampler from disk and prepare it to resume (multistatesampler.py:264-300, 956-1047): the most
+        recent checkpoint is loaded (positions, velocities, states, energies of that iteration) and -- unlike the
+        reference, whose generators are not stored -- the RNG streams are put back where they were, so the continuation
+        is bit-identical to an uninterrupted run."""
+        reporter = storage if isinstance(storage, MultiStateReporter) else MultiStateReporter(storage)
+        if not reporter.is_open():
+            reporter.open('a')
+        options = reporter.read_dict('options') or {}
+        kwargs = {k: v for k, v in options.items() if k in cls._STORED_OPTIONS and k in cls.default_options()}
+        if kwargs.get('number_of_iterations') == 'inf':
+            kwargs['number_of_iterations'] = np.inf
+        sampler = cls(mcmc_moves=reporter.read_mcmc_moves(), seed=options.get('seed'), communicator=communicator, **kwargs)
+        sampler._restore_sampler_from_reporter(reporter)
+        return sampler
 
     @classmethod
     def read_status(cls, storage):
-        raise NotImplementedError('storage / resume is outside the hot path (SURVEY.md section 8f-1)')
+        """Iteration, target error and completion state of a stored run (multistatesampler.py:308-360)."""
+        reporter = storage if isinstance(storage, MultiStateReporter) else MultiStateReporter(storage)
+        was_open = reporter.is_open()
+        if not was_open:
+            reporter.open('r')
+        options = reporter.read_dict('options') or {}
+        iteration = reporter.read_last_iteration(last_checkpoint=False)
+        n_it = options.get('number_of_iterations')
+        n_it = np.inf if n_it == 'inf' else n_it
+        if not was_open:
+            reporter.close()
+        return cls.Status(iteration=iteration, target_error=None, is_completed=(n_it is not None and iteration >= n_it))
+
+    def _restore_sampler_from_reporter(self, reporter):
+        metadata = reporter.read_dict('metadata')
+        thermodynamic_states, unsampled_states = reporter.read_thermodynamic_states()
+        last = reporter.read_last_iteration(last_checkpoint=False)
+        checkpoints = [c for c in reporter.read_checkpoint_iterations() if c <= last]
+        if not checkpoints:
+            raise RuntimeError('Attempting to restore from any checkpoint failed.')
+        checkpoint = checkpoints[-1]
+        self._iteration = int(checkpoint)
+        self._thermodynamic_states = thermodynamic_states
+        self._unsampled_states = unsampled_states or []
+        self._sampler_states = reporter.read_sampler_states(iteration=checkpoint)
+        self._replica_thermodynamic_states = np.array(reporter.read_replica_thermodynamic_states(iteration=checkpoint), dtype=np.int64)
+        e, nb, _ = reporter.read_energies(iteration=checkpoint)
+        self._energy_thermodynamic_states = np.array(e, dtype=np.float64)
+        self._neighborhoods = np.array(nb, dtype=np.int8)
+        self._energy_unsampled_states = np.zeros((len(self._sampler_states), 0))
+        na, npr = reporter.read_mixing_statistics(iteration=checkpoint)
+        self._n_accepted_matrix = np.array(na, dtype=np.int64)
+        self._n_proposed_matrix = np.array(npr, dtype=np.int64)
+        self._metadata = metadata
+        self._timing_data = dict()
+        if isinstance(self._mcmc_moves, mcmc.MCMCMove):
+            self._mcmc_moves = [copy.deepcopy(self._mcmc_moves) for _ in thermodynamic_states]
+        self._reporter = reporter
+        extra = reporter.read_checkpoint_extra(checkpoint)
+        if self._seed is None:
+            self._seed = extra.get('seed')
+        self._create_engine()
+        # energies of the checkpoint iteration are what the next mixing uses
+        self._engine.set_energies(self._energy_thermodynamic_states)
+        # put the two MT19937 streams back where they were
+        for stream, key in ((_lib.RX_STREAM_NUMBA, 'mt_numba_words'), (_lib.RX_STREAM_NUMPY, 'mt_numpy_words')):
+            n = int(extra.get(key, 0))
+            if n:
+                self._engine.mix_skip(n, stream)
+        self._equil_counter = int(extra.get('equil_counter', 0))
 
     # ------------------------------------------------------------------ create (multistatesampler.py:537-609)
     def create(self, thermodynamic_states, sampler_states, storage=None, initial_thermodynamic_states=None,
                unsampled_thermodynamic_states=None, metadata=None):
         if storage is not None:
-            raise NotImplementedError('storage (MultiStateReporter/NetCDF) is outside the hot path; pass storage=None')
+            self._reporter = storage if isinstance(storage, MultiStateReporter) else MultiStateReporter(storage)
         if self._thermodynamic_states is not None:
             raise RuntimeError('Cannot initialize the same sampler twice (create() was already called).')
         if unsampled_thermodynamic_states:
@@ -164,6 +235,7 @@ class MultiStateSampler:
             sampler_states = [sampler_states]
         self._pre_write_create(list(thermodynamic_states), list(sampler_states),
                                initial_thermodynamic_states=initial_thermodynamic_states, metadata=metadata)
+        self._initialize_reporter()
 
     def _pre_write_create(self, thermodynamic_states, sampler_states, initial_thermodynamic_states=None,
                           unsampled_thermodynamic_states=None, metadata=None):
@@ -293,6 +365,9 @@ class MultiStateSampler:
             return
         if self._iteration == 0:
             self._compute_energies()
+            if self._reporter is not None and self._rank == 0:      # multistatesampler.py:741-746
+                self._reporter.write_energies(self._energy_thermodynamic_states, self._neighborhoods,
+                                              self._energy_unsampled_states, 0)
             self._check_nan_energy()
         iteration_limit = self.number_of_iterations if n_iterations is None else \
             min(self._iteration + n_iterations, self.number_of_iterations)
@@ -390,8 +465,67 @@ class MultiStateSampler:
         self._energy_thermodynamic_states[:, :] = self._engine.compute_energies()
 
     # ------------------------------------------------------------------ bookkeeping
+    def _initialize_reporter(self):
+        """Write everything that identifies the run plus iteration 0 (multistatesampler.py:1169-1187); rank 0 only."""
+        if self._reporter is None or self._rank != 0:
+            return
+        r = self._reporter
+        if r.is_open():
+            r.close()
+        r.open('w')
+        r.set_dimensions(self.n_replicas, self.n_states, self._thermodynamic_states[0].n_particles)
+        r.write_thermodynamic_states(self._thermodynamic_states, self._unsampled_states)
+        r.write_mcmc_moves(self._mcmc_moves)
+        opts = {k: getattr(self, k, None) for k in self._STORED_OPTIONS if hasattr(self, k)}
+        if opts.get('number_of_iterations') == np.inf:
+            opts['number_of_iterations'] = 'inf'
+        opts['seed'] = self._seed
+        r.write_dict('options', opts)
+        r.write_dict('metadata', self._metadata)
+        self._report_iteration()
+
+    def _checkpoint_extra(self):
+        e = self._engine
+        return dict(seed=int(self._seed), iteration=int(self._iteration),
+                    mt_numba_words=int(e.mix_stream_position(_lib.RX_STREAM_NUMBA)),
+                    mt_numpy_words=int(e.mix_stream_position(_lib.RX_STREAM_NUMPY)),
+                    equil_counter=int(getattr(self, '_equil_counter', 0)))
+
     def _report_iteration(self):
-        pass   # no reporter on the hot path
+        """multistatesampler.py:1191-1207: states, checkpointed positions, mixing statistics, energies, commit marker."""
+        if self._reporter is None:
+            return
+        it = self._iteration
+        checkpoint = (it % self._reporter.checkpoint_interval == 0)
+        if checkpoint:
+            self._sync_sampler_states()
+            if self._world_size > 1:
+                self._gather_sampler_states()
+        if self._rank != 0:
+            return
+        r = self._reporter
+        r.write_replica_thermodynamic_states(self._replica_thermodynamic_states, it)
+        if checkpoint:
+            r.write_sampler_states(self._sampler_states, it, extra=self._checkpoint_extra())
+        r.write_mixing_statistics(self._n_accepted_matrix, self._n_proposed_matrix, it)
+        r.write_energies(self._energy_thermodynamic_states, self._neighborhoods, self._energy_unsampled_states, it)
+        r.write_last_iteration(it)
+
+    def _gather_sampler_states(self):
+        """Multi-GPU checkpoint: every rank sends its shard of positions/velocities/energies to rank 0 (the role of
+        mpiplus.distribute(..., send_results_to=0), multistatesampler.py:1296-1302)."""
+        e = self._engine
+        comm = self._communicator
+        if comm is None:
+            from .._dist import default_communicator
+            comm = self._communicator = default_communicator()
+        shard = [(k, s._positions, s._velocities, s._potential_energy, s._kinetic_energy)
+                 for k, s in zip(range(e.k0, e.k1), self._sampler_states[e.k0:e.k1])]
+        gathered = comm.gather_object(shard)
+        if self._rank == 0:
+            for part in gathered:
+                for k, x, v, pe, ke in part:
+                    self._sampler_states[k]._update(x, v, pe, ke)
 
     def _is_completed(self, iteration_limit=None):
         if iteration_limit is None:

@@ -25,6 +25,11 @@ k0 = (c.rank * K) // c.world_size; k1 = ((c.rank + 1) * K) // c.world_size
 import torch
 t = torch.tensor([float(k1 - k0)]); dist.all_reduce(t)
 assert t.item() == K
+g = c.gather_object({'rank': c.rank, 'rows': list(range(k0, k1))})
+if c.rank == 0:
+    assert [d['rank'] for d in g] == [0, 1] and sum(len(d['rows']) for d in g) == K
+else:
+    assert g is None
 c.barrier()
 print('ok', c.rank, k0, k1)
 '''
