@@ -140,11 +140,11 @@ __global__ void __launch_bounds__(256) k_slots_build(const uint32_t *__restrict_
 //
 // Where the energies live (UMODE):
 //   U_F64_SMEM   the f64 matrix itself is in shared memory (K <= 128)
-//   U_FILTER24   K = 256: 512 KB of f64 do not fit, so shared memory holds a 24-bit fixed-point image of every row
-//                (q = round((u - c_row)/s_row), 3 bytes) that gives log_p to within a RIGOROUS bound eps = 1.01 (s_i+s_j)
-//                + tiny; the decision is taken from the image whenever it is more than eps away from both thresholds
-//                (log_p = 0 and log_p = log U), otherwise the lane falls back to the exact f64 values in L2.  The
-//                result is therefore still bit-identical to the reference.
+//   U_FILTER24   K = 256: 512 KB of f64 do not fit, so shared memory holds a 24-bit floating image of every row
+//                (delta = u - rowmin as a float32 truncated to sign + 8 exponent + 15 mantissa bits) that gives log_p
+//                to within a RIGOROUS bound eps = 3.2e-5 * sum|delta| + tiny; the decision is taken from the image
+//                whenever it is more than eps away from both thresholds (log_p = 0 and log_p = log U), otherwise the
+//                lane falls back to the exact f64 values in L2.  The result is therefore still bit-identical.
 //   U_GLOBAL     exact f64 values from L2 every round (any larger K)
 // ------------------------------------------------------------------------------------------------------
 #define LOG_ACC_BIT 28
@@ -162,16 +162,15 @@ template <int UMODE>
 __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict__ rec, const uint32_t *__restrict__ words,
                                                       unsigned nslots, const double *__restrict__ u, int K, int logK,
                                                       int *__restrict__ perm_g, uint32_t *__restrict__ commit_log,
-                                                      const unsigned char *__restrict__ filt, const double *__restrict__ filt_scale,
+                                                      const unsigned char *__restrict__ filt,
                                                       double filt_abs, MixCtl *ctl) {
     extern __shared__ double s_mix[];
     __shared__ WalkShared sh;
-    // layout: ring_lu[RING] f64 | diag[K] f64 | (u f64 [K*K]) | (scale[K] f64) | ring_ij[RING] u32 | ring_bm[RING] u32 | perm[K] i32 | (q24 [3*K*K] bytes)
+    // layout: ring_lu[RING] f64 | diag[K] f64 | (u f64 [K*K]) | ring_ij[RING] u32 | ring_bm[RING] u32 | perm[K] i32 | (image: u16[K*K] + u8[K*K])
     double *ring_lu = s_mix;
     double *s_diag = ring_lu + RING;
     double *s_u = s_diag + K;
-    double *s_scale = s_u + (UMODE == U_F64_SMEM ? (size_t)K * K : 0);
-    uint32_t *ring_ij = (uint32_t *)(s_scale + (UMODE == U_FILTER24 ? K : 0));
+    uint32_t *ring_ij = (uint32_t *)(s_u + (UMODE == U_F64_SMEM ? (size_t)K * K : 0));
     uint32_t *ring_bm = ring_ij + RING;
     int *s_perm = (int *)(ring_bm + RING);
     unsigned char *s_q = (unsigned char *)(s_perm + K);   // 24-bit image: int16 high plane [K*K] then uint8 low plane [K*K]
@@ -664,7 +663,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     // ring (lu 8 + ij 4 + bm 4) + diag + perm
     const size_t smem_base = (size_t)RING * 16 + (size_t)K * (sizeof(double) + sizeof(int));
     const size_t smem_f64 = smem_base + (size_t)K * K * sizeof(double);
-    const size_t smem_f24 = smem_base + (size_t)K * sizeof(double) + (size_t)3 * K * K;
+    const size_t smem_f24 = smem_base + (size_t)3 * K * K;
     int umode = U_GLOBAL;
     if (fast && smem_f64 <= 200 * 1024) umode = U_F64_SMEM;
     else if (fast && smem_f24 <= 224 * 1024 && !getenv("RX_NO_FILTER")) umode = U_FILTER24;
@@ -737,11 +736,11 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
                 *launches += 1;
             }
             if (umode == U_F64_SMEM)
-                k_mix_walk_pow2<U_F64_SMEM><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, 0.0, h->d_ctl);
+                k_mix_walk_pow2<U_F64_SMEM><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, 0.0, h->d_ctl);
             else if (umode == U_FILTER24)
-                k_mix_walk_pow2<U_FILTER24><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, h->d_filt, h->d_filt_scale, filt_abs, h->d_ctl);
+                k_mix_walk_pow2<U_FILTER24><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, h->d_filt, filt_abs, h->d_ctl);
             else
-                k_mix_walk_pow2<U_GLOBAL><<<1, 64, smem_base_launch, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, 0.0, h->d_ctl);
+                k_mix_walk_pow2<U_GLOBAL><<<1, 64, smem_base_launch, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, 0.0, h->d_ctl);
             RX_CHECK_CUDA(h, cudaGetLastError());
             *launches += 1;
             RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
