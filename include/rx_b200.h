@@ -122,6 +122,10 @@ RX_API int rx_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int32_t
  * ThermodynamicState.reduced_potential_at_states (states.py:911-992).  Fills the device-resident
  * u[K][M]; with world_size > 1 the rows are all-gathered over NCCL.  u_out (may be NULL): [K][M].        */
 RX_API int rx_compute_energies(rx_engine *h, double *u_out);
+/* Reduced potentials of every replica at `n` OTHER states (MultiStateSampler's unsampled_thermodynamic_states,
+ * multistatesampler.py:1452-1456,1489-1494; ThermodynamicState.reduced_potential_at_states, states.py:911-992): same
+ * kernel, temporary state table, does not touch the resident matrix.  u_out: [K][n].                                */
+RX_API int rx_compute_energies_at(rx_engine *h, const rx_state_params *states, int32_t n, double *u_out);
 RX_API int rx_set_energies(rx_engine *h, const double *u /*[K][M]*/);
 RX_API int rx_get_energies(rx_engine *h, double *u /*[K][M]*/);
 

@@ -73,8 +73,9 @@ class Engine:
         mask = None if alchemical_mask is None else np.ascontiguousarray(alchemical_mask, dtype=np.uint8)
         self._check(self._lib.rx_set_particles(self._h, _ptr(sigma), _ptr(epsilon), _ptr(mass), _ptr(mask)))
 
-    def set_states(self, temperature, lambda_sterics=None, energy_offset=None, ho_K=None, ho_x0=None):
-        M = self.M
+    @staticmethod
+    def _state_table(temperature, lambda_sterics=None, energy_offset=None, ho_K=None, ho_x0=None):
+        M = len(temperature)
         arr = (_lib.RxStateParams * M)()
         for l in range(M):
             arr[l].temperature = float(temperature[l])
@@ -84,7 +85,21 @@ class Engine:
             x0 = (0.0, 0.0, 0.0) if ho_x0 is None else ho_x0[l]
             for q in range(3):
                 arr[l].ho_x0[q] = float(x0[q])
+        return arr
+
+    def set_states(self, temperature, lambda_sterics=None, energy_offset=None, ho_K=None, ho_x0=None):
+        if len(temperature) != self.M:
+            raise ValueError('expected %d states' % self.M)
+        arr = self._state_table(temperature, lambda_sterics, energy_offset, ho_K, ho_x0)
         self._check(self._lib.rx_set_states(self._h, C.cast(arr, C.c_void_p)))
+
+    def compute_energies_at(self, temperature, lambda_sterics=None, energy_offset=None, ho_K=None, ho_x0=None):
+        """u[K][n] of every replica at n other states (unsampled states); the resident matrix is untouched."""
+        arr = self._state_table(temperature, lambda_sterics, energy_offset, ho_K, ho_x0)
+        n = len(temperature)
+        out = np.zeros((self.K, n))
+        self._check(self._lib.rx_compute_energies_at(self._h, C.cast(arr, C.c_void_p), n, _ptr(out)))
+        return out
 
     def set_integrator(self, timestep, collision_rate, n_steps, splitting='V R O R V'):
         self._check(self._lib.rx_set_integrator(self._h, float(timestep), float(collision_rate), int(n_steps),

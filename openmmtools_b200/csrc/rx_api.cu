@@ -161,16 +161,13 @@ extern "C" int rx_set_particles(rx_engine *h, const double *sigma, const double 
     return RX_OK;
 }
 
-extern "C" int rx_set_states(rx_engine *h, const rx_state_params *s) {
-    ENTER(h);
-    if (!s) RX_FAIL(h, RX_ERR_INVALID, "rx_set_states: null");
-    const int M = h->cfg.n_states;
-    h->h_states.resize(M);
-    for (int l = 0; l < M; l++) {
-        if (!(s[l].temperature > 0)) RX_FAIL(h, RX_ERR_INVALID, "rx_set_states: temperature must be > 0");
+static int convert_states(rx_engine *h, const rx_state_params *s, int n, std::vector<StateDev> &out, const char *who) {
+    out.resize(n);
+    for (int l = 0; l < n; l++) {
+        if (!(s[l].temperature > 0)) RX_FAIL(h, RX_ERR_INVALID, std::string(who) + ": temperature must be > 0");
         if (h->cfg.system_kind == RX_SYSTEM_LJ_ALCH && !(s[l].lambda_sterics >= 0.0 && s[l].lambda_sterics <= 1.0))
-            RX_FAIL(h, RX_ERR_INVALID, "rx_set_states: lambda_sterics must be in [0, 1]");
-        StateDev &d = h->h_states[l];
+            RX_FAIL(h, RX_ERR_INVALID, std::string(who) + ": lambda_sterics must be in [0, 1]");
+        StateDev &d = out[l];
         d.kT = RX_KB * s[l].temperature;
         d.beta = 1.0 / d.kT;
         d.lambda = s[l].lambda_sterics;
@@ -180,6 +177,15 @@ extern "C" int rx_set_states(rx_engine *h, const rx_state_params *s) {
         d.ho_K = s[l].ho_K;
         for (int q = 0; q < 3; q++) d.ho_x0[q] = s[l].ho_x0[q];
     }
+    return RX_OK;
+}
+
+extern "C" int rx_set_states(rx_engine *h, const rx_state_params *s) {
+    ENTER(h);
+    if (!s) RX_FAIL(h, RX_ERR_INVALID, "rx_set_states: null");
+    const int M = h->cfg.n_states;
+    int rc = convert_states(h, s, M, h->h_states, "rx_set_states");
+    if (rc) return rc;
     RX_CHECK_CUDA(h, cudaMemcpy(h->d_states, h->h_states.data(), sizeof(StateDev) * M, cudaMemcpyHostToDevice));
     h->have_states = true;
     return RX_OK;
@@ -363,6 +369,38 @@ extern "C" int rx_get_energies(rx_engine *h, double *u) {
     return RX_OK;
 }
 
+extern "C" int rx_compute_energies_at(rx_engine *h, const rx_state_params *st, int32_t n, double *u_out) {
+    ENTER(h);
+    int rc = check_ready(h, "rx_compute_energies_at");
+    if (rc) return rc;
+    if (!st || !u_out || n < 1) RX_FAIL(h, RX_ERR_INVALID, "rx_compute_energies_at: bad arguments");
+    std::vector<StateDev> hs;
+    rc = convert_states(h, st, n, hs, "rx_compute_energies_at");
+    if (rc) return rc;
+    const int K = h->cfg.n_replicas;
+    StateDev *d_st = nullptr;
+    double *d_out = nullptr;
+    RX_CHECK_CUDA(h, cudaMalloc(&d_st, sizeof(StateDev) * n));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)K * n);
+    if (e != cudaSuccess) { cudaFree(d_st); RX_FAIL(h, RX_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    int launches = 0;
+    cudaMemcpyAsync(d_st, hs.data(), sizeof(StateDev) * n, cudaMemcpyHostToDevice, h->stream);
+    cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)K * n, h->stream);
+    rc = rxi_compute_energy_rows_at(h, d_st, n, d_out, &launches);
+    if (!rc) rc = rxi_allgather_rows(h, d_out, n);
+    if (!rc) {
+        e = cudaMemcpyAsync(u_out, d_out, sizeof(double) * (size_t)K * n, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { h->err = std::string("rx_compute_energies_at: ") + cudaGetErrorString(e); rc = RX_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_st);
+    cudaFree(d_out);
+    if (rc) return rc;
+    h->phase_launches[2] += launches;
+    return check_device_error(h);
+}
+
 extern "C" int rx_mix_seed(rx_engine *h, int32_t stream, uint32_t seed) {
     ENTER(h);
     return rxi_mix_seed(h, stream, seed);
@@ -527,14 +565,16 @@ extern "C" int rx_comm_init(rx_engine *h, const char *path, const void *unique_i
     return RX_OK;
 }
 
-int rxi_allgather_energies(rx_engine *h) {
+int rxi_allgather_rows(rx_engine *h, double *d_matrix, int n_cols) {
     if (h->cfg.world_size == 1) return RX_OK;
     if (!h->nccl_comm) RX_FAIL(h, RX_ERR_COMM, "world_size > 1 but rx_comm_init has not been called");
     nccl_allgather_t f = (nccl_allgather_t)dlsym(h->nccl_lib, "ncclAllGather");
     if (!f) RX_FAIL(h, RX_ERR_COMM, "ncclAllGather not found");
-    const size_t cnt = (size_t)h->kloc * h->cfg.n_states;
-    // in place: each rank's rows already sit at their final offset in d_u
-    int r = f(h->d_u + (size_t)h->k0 * h->cfg.n_states, h->d_u, cnt, RX_NCCL_FLOAT64, h->nccl_comm, h->stream);
+    const size_t cnt = (size_t)h->kloc * n_cols;
+    // in place: each rank's rows already sit at their final offset
+    int r = f(d_matrix + (size_t)h->k0 * n_cols, d_matrix, cnt, RX_NCCL_FLOAT64, h->nccl_comm, h->stream);
     if (r != 0) RX_FAIL(h, RX_ERR_COMM, "ncclAllGather failed");
     return RX_OK;
 }
+
+int rxi_allgather_energies(rx_engine *h) { return rxi_allgather_rows(h, h->d_u, h->cfg.n_states); }

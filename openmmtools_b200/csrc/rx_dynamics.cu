@@ -566,12 +566,14 @@ int rxi_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream_id) {
     return RX_OK;
 }
 
-int rxi_compute_energy_rows(rx_engine *h, int *launches) {
+// Energy rows of the owned replicas at `n_states` states described by the device table `d_states`, written to
+// d_out[K][n_states] (rows [k0, k0+kloc)).  The resident table/matrix are the default.
+int rxi_compute_energy_rows_at(rx_engine *h, const StateDev *d_states, int n_states, double *d_out, int *launches) {
     if (h->kloc == 0) return RX_OK;
     const rx_config &c = h->cfg;
     EnParams p;
     memset(&p, 0, sizeof(p));
-    p.N = c.n_atoms; p.M = c.n_states; p.kind = c.system_kind; p.n_alch = h->n_alch;
+    p.N = c.n_atoms; p.M = n_states; p.kind = c.system_kind; p.n_alch = h->n_alch;
     p.Lx = c.box[0]; p.Ly = c.box[1]; p.Lz = c.box[2];
     p.rc2 = c.r_cutoff * c.r_cutoff; p.rs = c.r_switch; p.rc = c.r_cutoff;
     p.inv_w = 1.0 / (c.r_cutoff - c.r_switch);
@@ -580,9 +582,13 @@ int rxi_compute_energy_rows(rx_engine *h, int *launches) {
     p.pair_cap = h->pair_cap;
     const size_t smem = (size_t)3 * c.n_atoms * sizeof(double);
     if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_energy_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_energy_rows<<<h->kloc, 512, smem, h->stream>>>(p, h->d_atom_d, h->d_alch_list, h->d_states, h->d_pos, h->k0,
-                                                    (double2 *)h->d_pairs, h->d_u, h->d_err);
+    k_energy_rows<<<h->kloc, 512, smem, h->stream>>>(p, h->d_atom_d, h->d_alch_list, d_states, h->d_pos, h->k0,
+                                                    (double2 *)h->d_pairs, d_out, h->d_err);
     RX_CHECK_CUDA(h, cudaGetLastError());
     (*launches)++;
     return RX_OK;
+}
+
+int rxi_compute_energy_rows(rx_engine *h, int *launches) {
+    return rxi_compute_energy_rows_at(h, h->d_states, h->cfg.n_states, h->d_u, launches);
 }

@@ -168,11 +168,32 @@ class MultiStateReporter:
     def write_energies(self, energy_thermodynamic_states, energy_neighborhoods, energy_unsampled_states, iteration):
         self._write_record('energies', iteration, energy_thermodynamic_states)
         self._write_record('neighborhoods', iteration, energy_neighborhoods)
+        eu = np.ascontiguousarray(energy_unsampled_states, dtype=np.float64)
+        if eu.size:     # reference variable 'unsampled_energies' f8[iteration, replica, unsampled]
+            self._meta.setdefault('n_unsampled', int(eu.shape[1]))
+            if self._meta.get('_wrote_n_unsampled') is None:
+                self._meta['_wrote_n_unsampled'] = True
+                self._write_meta()
+            with open(self._path('unsampled_energies'), 'r+b' if os.path.exists(self._path('unsampled_energies')) else 'w+b') as f:
+                f.seek(int(iteration) * eu.nbytes)
+                f.write(eu.tobytes())
+                f.flush(); os.fsync(f.fileno())
+
+    def read_unsampled_energies(self, iteration):
+        n = self._meta.get('n_unsampled', 0)
+        if not n or not os.path.exists(self._path('unsampled_energies')):
+            return None
+        K = self._meta['n_replicas']
+        data = np.fromfile(self._path('unsampled_energies'), dtype=np.float64)
+        data = data[:(data.size // (K * n)) * K * n].reshape(-1, K, n)
+        return data[iteration]
 
     def read_energies(self, iteration=slice(None)):
         e = self._read_record('energies', iteration)
         n = self._read_record('neighborhoods', iteration)
-        unsampled = np.zeros(e.shape[:-1] + (0,))
+        unsampled = self.read_unsampled_energies(iteration)
+        if unsampled is None:
+            unsampled = np.zeros(e.shape[:-1] + (0,))
         return e, n, unsampled
 
     def write_replica_thermodynamic_states(self, state_indices, iteration):

@@ -41,8 +41,8 @@ class MultiStateSampler:
     def __init__(self, mcmc_moves=None, number_of_iterations=1, online_analysis_interval=200,
                  online_analysis_target_error=0.0, online_analysis_minimum_iterations=200, locality=None,
                  host_resident_states=False, seed=None, communicator=None):
-        if locality is not None:
-            raise NotImplementedError('locality (neighbourhood-restricted energies) is not provided yet')
+        if locality is not None and (not isinstance(locality, (int, np.integer)) or locality < 1):
+            raise ValueError('locality must be a positive integer or None')     # multistatesampler.py:505-508
         # default move as the reference (multistatesampler.py:222-227)
         if mcmc_moves is None:
             self._mcmc_moves = mcmc.LangevinDynamicsMove(timestep=2.0 * unit.femtosecond,
@@ -72,6 +72,7 @@ class MultiStateSampler:
         self.energy_context_cache = ContextCache()
         self.sampler_context_cache = ContextCache()
         self._reporter = None
+        self._unsampled_table = None
         self._engine = None
         self._states_stale = False     # host copies of sampler states are behind the device
         self._seed = seed
@@ -200,7 +201,8 @@ class MultiStateSampler:
         e, nb, _ = reporter.read_energies(iteration=checkpoint)
         self._energy_thermodynamic_states = np.array(e, dtype=np.float64)
         self._neighborhoods = np.array(nb, dtype=np.int8)
-        self._energy_unsampled_states = np.zeros((len(self._sampler_states), 0))
+        _un = reporter.read_unsampled_energies(checkpoint)
+        self._energy_unsampled_states = np.zeros((len(self._sampler_states), len(self._unsampled_states))) if _un is None else np.array(_un)
         na, npr = reporter.read_mixing_statistics(iteration=checkpoint)
         self._n_accepted_matrix = np.array(na, dtype=np.int64)
         self._n_proposed_matrix = np.array(npr, dtype=np.int64)
@@ -229,12 +231,11 @@ class MultiStateSampler:
             self._reporter = storage if isinstance(storage, MultiStateReporter) else MultiStateReporter(storage)
         if self._thermodynamic_states is not None:
             raise RuntimeError('Cannot initialize the same sampler twice (create() was already called).')
-        if unsampled_thermodynamic_states:
-            raise NotImplementedError('unsampled thermodynamic states are not provided yet')
         if isinstance(sampler_states, states.SamplerState):
             sampler_states = [sampler_states]
         self._pre_write_create(list(thermodynamic_states), list(sampler_states),
-                               initial_thermodynamic_states=initial_thermodynamic_states, metadata=metadata)
+                               initial_thermodynamic_states=initial_thermodynamic_states,
+                               unsampled_thermodynamic_states=unsampled_thermodynamic_states, metadata=metadata)
         self._initialize_reporter()
 
     def _pre_write_create(self, thermodynamic_states, sampler_states, initial_thermodynamic_states=None,
@@ -253,7 +254,10 @@ class MultiStateSampler:
                 raise Exception('All sampler states must have box_vectors defined if the system is periodic.')
         self._metadata = metadata
         self._thermodynamic_states = [copy.deepcopy(s) for s in thermodynamic_states]
-        self._unsampled_states = []
+        self._unsampled_states = [copy.deepcopy(s) for s in (unsampled_thermodynamic_states or [])]
+        for s in self._unsampled_states:
+            if s.n_particles != n_particles:
+                raise ValueError('All ThermodynamicStates must have the same number of particles')
         self._sampler_states = [copy.deepcopy(s) for s in sampler_states]
         K, M = len(self._sampler_states), len(self._thermodynamic_states)
         # initial assignment (multistatesampler.py:892-895, 1118-1143)
@@ -280,7 +284,7 @@ class MultiStateSampler:
         self._n_proposed_matrix = np.zeros([M, M], np.int64)
         self._energy_thermodynamic_states = np.zeros([K, M], np.float64)
         self._neighborhoods = np.ones([K, M], np.int8)
-        self._energy_unsampled_states = np.zeros([K, 0], np.float64)
+        self._energy_unsampled_states = np.zeros([K, len(self._unsampled_states)], np.float64)
         self._iteration = 0
         self._create_engine()
 
@@ -461,8 +465,26 @@ class MultiStateSampler:
 
     def _compute_energies(self):
         """u[k, l] for all replicas and states in one launch (+ NCCL all-gather) (multistatesampler.py:1436-1494)."""
-        self._neighborhoods[:, :] = 1
-        self._energy_thermodynamic_states[:, :] = self._engine.compute_energies()
+        u = self._engine.compute_energies()
+        if self.locality is None:
+            self._neighborhoods[:, :] = 1
+            self._energy_thermodynamic_states[:, :] = u
+        else:
+            # only the states within `locality` of each replica's current state are (re)written, the rest keeps its old
+            # value exactly as in the reference (multistatesampler.py:1263-1281,1441-1456); the device matrix is complete,
+            # and swap-neighbors (forced by locality, replicaexchange.py:228-230) only reads entries inside the band
+            M = self.n_states
+            self._neighborhoods[:, :] = 0
+            for k, st in enumerate(self._replica_thermodynamic_states):
+                lo, hi = max(0, st - self.locality), min(M, st + self.locality + 1)
+                self._neighborhoods[k, lo:hi] = 1
+                self._energy_thermodynamic_states[k, lo:hi] = u[k, lo:hi]
+        if self._unsampled_states:
+            # energies at states that are evaluated but never sampled (multistatesampler.py:1452-1456,1489-1494)
+            if self._unsampled_table is None:
+                _, self._unsampled_table = _backend.engine_tables(list(self._thermodynamic_states[:1]) + list(self._unsampled_states))
+                self._unsampled_table = {k: v[1:] for k, v in self._unsampled_table.items()}
+            self._energy_unsampled_states[:, :] = self._engine.compute_energies_at(**self._unsampled_table)
 
     # ------------------------------------------------------------------ bookkeeping
     def _initialize_reporter(self):

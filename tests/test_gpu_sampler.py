@@ -176,3 +176,47 @@ def test_parallel_tempering_on_lj_fluid():
     assert np.array_equal(s2._replica_thermodynamic_states, s._replica_thermodynamic_states)
     with pytest.raises(ValueError):
         multistate.ParallelTemperingSampler().create(ts, ss, temperatures=[300 * unit.kelvin], n_temperatures=3)
+
+
+def test_unsampled_states_energy_matrix():
+    """Reference tests/test_sampling.py:1668-1717: the energy matrices (sampled and unsampled states) equal an independent
+    double loop through reduced_potential."""
+    K = 6
+    fluid = testsystems.LennardJonesFluid(nparticles=128)
+    asys = alchemy.AbsoluteAlchemicalFactory().create_alchemical_system(fluid.system, alchemy.AlchemicalRegion(alchemical_atoms=range(4)))
+    lam = [1.0 - l / (K - 1) for l in range(K)]
+    a = alchemy.AlchemicalState.from_system(asys)
+    tstates = states.create_thermodynamic_state_protocol(asys, {'lambda_sterics': lam}, constants={'temperature': 300 * unit.kelvin},
+                                                         composable_states=a)
+    un = states.create_thermodynamic_state_protocol(asys, {'lambda_sterics': [0.37, 1.0], 'temperature': [280, 350] * unit.kelvin},
+                                                    composable_states=a)
+    sstate = states.SamplerState(fluid.positions, box_vectors=asys.getDefaultPeriodicBoxVectors())
+    s = multistate.ReplicaExchangeSampler(mcmc_moves=mcmc.LangevinSplittingDynamicsMove(n_steps=30), number_of_iterations=2, seed=4)
+    s.create(tstates, [sstate], unsampled_thermodynamic_states=un)
+    s.run()
+    assert s._energy_unsampled_states.shape == (K, 2)
+    ss = s.sampler_states
+    for k in (0, K - 1):
+        for l in (0, 2, K - 1):
+            assert s._energy_thermodynamic_states[k, l] == pytest.approx(tstates[l].reduced_potential(ss[k]), rel=1e-9)
+        for l in range(2):
+            assert s._energy_unsampled_states[k, l] == pytest.approx(un[l].reduced_potential(ss[k]), rel=1e-9)
+
+
+def test_locality_neighborhoods():
+    """locality (multistatesampler.py:1263-1281): only the band around each replica's state is (re)written; the
+    reference requires swap-neighbors with it (replicaexchange.py:228-230)."""
+    with pytest.raises(ValueError):
+        multistate.ReplicaExchangeSampler(locality=1)                 # default swap-all is rejected, as in the reference
+    s, asys, lambdas = lj_sampler(K=16, scheme='swap-neighbors', seed=6, locality=2)
+    s.run(4)
+    nb = s._neighborhoods
+    for k, st in enumerate(s._replica_thermodynamic_states):
+        band = np.zeros(16, np.int8); band[max(0, st - 2):min(16, st + 3)] = 1
+        assert np.array_equal(nb[k], band)
+    full = s._engine.get_energies()
+    assert np.array_equal(s._energy_thermodynamic_states[nb == 1], full[nb == 1])
+    # same seed without locality: identical permutation history (swap-neighbors only reads entries inside the band)
+    t, _, _ = lj_sampler(K=16, scheme='swap-neighbors', seed=6)
+    t.run(4)
+    assert np.array_equal(s._replica_thermodynamic_states, t._replica_thermodynamic_states)
