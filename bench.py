@@ -64,30 +64,80 @@ def build_workload(K, N):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML in a background
+    thread (two light queries per second, plus one at the end of the region).  A polling `nvidia-smi -lms 100` process measurably perturbs this workload
+    (it holds driver locks while the host issues the dependent launches of each iteration), so it is only the fallback."""
 
-    def __init__(self, device):
-        self.p = None
+    def __init__(self, device, period=1.0):
+        import threading
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._smi = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, args=(period,), daemon=True)
+            self._thread.start()
+        except Exception:
+            self._start_smi(device)
+
+    def _sample(self):
+        nv = self.nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (('hw_slowdown', 0x8), ('sw_power_cap', 0x4), ('sw_thermal_slowdown', 0x20),
+                          ('hw_thermal_slowdown', 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self, period):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(period)
+
+    def _start_smi(self, device):
+        q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
         self.path = '/tmp/rx_clocks_%d.csv' % os.getpid()
         try:
             self.f = open(self.path, 'w')
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(device), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+            self._smi = subprocess.Popen(['nvidia-smi', '-i', str(device), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                          '-lms', '500'], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
-            self.p = None
+            self._smi = None
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        if self.p is None:
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'source': None}
+        if self._thread is not None:
+            try:
+                self._sample()      # at least one sample inside the region even for very short runs
+            except Exception:
+                pass
+            self._stop.set()
+            self._thread.join(timeout=2)
+            if self.samples:
+                out = {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                       'samples': len(self.samples), 'source': 'nvml thread, 1 s period'}
             return out
-        self.p.terminate()
+        if self._smi is None:
+            return out
+        self._smi.terminate()
         try:
-            self.p.wait(timeout=5)
+            self._smi.wait(timeout=5)
         except Exception:
-            self.p.kill()
+            self._smi.kill()
         self.f.close()
         sm, mx, reasons = [], [], set()
         for line in open(self.path):
@@ -107,7 +157,7 @@ class ClockSampler:
             pass
         if sm:
             out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
-                   'samples': len(sm)}
+                   'samples': len(sm), 'source': 'nvidia-smi -lms 500'}
         return out
 
 

@@ -159,9 +159,9 @@ RX_API int rx_get_phase_times(rx_engine *h, double ms[4], int64_t counts[4], int
  * rx_timer_elapsed synchronises and returns the device time between mark 0 and mark 1 in ms.                 */
 RX_API int rx_timer_mark(rx_engine *h, int32_t which);
 RX_API int rx_timer_elapsed(rx_engine *h, double *ms);
-/* Mixing-kernel statistics of the last swap-all call: [0] speculation rounds, [1] exact-exp fallbacks,
- * [2] passes, [3] MT words consumed.                                                                          */
-RX_API int rx_get_mix_stats(rx_engine *h, int64_t out[4]);
+/* Mixing-kernel statistics of the last swap-all call: [0] speculation rounds, [1] exact-path fallbacks,
+ * [2] passes, [3] MT words consumed, [4] walker kernel time (us), [5] host wait for the side-stream pre-pass (us). */
+RX_API int rx_get_mix_stats(rx_engine *h, int64_t out[6]);
 
 /* ---- multi-GPU ------------------------------------------------------------------------------------ */
 /* NCCL is loaded with dlopen(nccl_library_path).  Rank 0 creates an id (rx_comm_unique_id), the host code

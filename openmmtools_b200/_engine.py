@@ -226,9 +226,10 @@ class Engine:
         return v.value
 
     def mix_stats(self):
-        out = np.zeros(4, np.int64)
+        out = np.zeros(6, np.int64)
         self._check(self._lib.rx_get_mix_stats(self._h, _ptr(out)))
-        return dict(rounds=int(out[0]), exact_exp=int(out[1]), passes=int(out[2]), words=int(out[3]))
+        return dict(rounds=int(out[0]), exact_exp=int(out[1]), passes=int(out[2]), words=int(out[3]),
+                    walker_ms=out[4] / 1e3, prepare_wait_ms=out[5] / 1e3)
 
     # -- multi-GPU
     @staticmethod

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 thread_local std::string g_rx_create_error;
 
@@ -55,6 +56,7 @@ extern "C" int rx_create(const rx_config *cfg, rx_engine **out) {
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream_rng, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) CREATE_CUDA(cudaEventCreate(&h->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&h->ev_user[i]));
+    for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&h->ev_walk[i]));
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_prepared, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_consumed, cudaEventDisableTiming));
     CREATE_CUDA(cudaMalloc(&h->d_perm, sizeof(int) * K));
@@ -114,6 +116,7 @@ extern "C" void rx_destroy(rx_engine *h) {
     cudaFree(h->d_err); cudaFree(h->d_pairs);
     for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; i++) if (h->ev_user[i]) cudaEventDestroy(h->ev_user[i]);
+    for (int i = 0; i < 2; i++) if (h->ev_walk[i]) cudaEventDestroy(h->ev_walk[i]);
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_rng) cudaStreamDestroy(h->stream_rng);
@@ -483,7 +486,11 @@ extern "C" int rx_run_iterations(rx_engine *h, int32_t n_iterations, int32_t mix
         if (rc) return rc;
         Te.stop(le);
         RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+        const double m0 = h->phase_ms[0];
         Tm.accumulate(); Tp.accumulate(); Te.accumulate();
+        if (getenv("RX_TRACE_ITER"))
+            fprintf(stderr, "[iter %d] mix %.2f ms (walker %.2f ms, exact-path lanes %lld, rounds %lld)\n", it, h->phase_ms[0] - m0,
+                    h->mix_stats[4] / 1e3, h->mix_stats[1], h->mix_stats[0]);
     }
     rc = check_device_error(h);
     if (rc) return rc;
@@ -519,9 +526,9 @@ extern "C" int rx_timer_elapsed(rx_engine *h, double *ms) {
     *ms = f;
     return RX_OK;
 }
-extern "C" int rx_get_mix_stats(rx_engine *h, int64_t out[4]) {
+extern "C" int rx_get_mix_stats(rx_engine *h, int64_t out[6]) {
     ENTER(h);
-    for (int i = 0; i < 4; i++) out[i] = h->mix_stats[i];
+    for (int i = 0; i < 6; i++) out[i] = h->mix_stats[i];
     return RX_OK;
 }
 

@@ -53,7 +53,8 @@ struct rx_engine {
     cudaStream_t stream = nullptr, stream_rng = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_user[2] = {};
-    long long mix_stats[4] = {0, 0, 0, 0};
+    long long mix_stats[6] = {0, 0, 0, 0, 0, 0};   // rounds, exact-exp, passes, words, walker us, prepare-wait us
+    cudaEvent_t ev_walk[2] = {};
     // particles
     float4 *d_atom = nullptr;     // (sigma, sqrt_eps, inv_mass, alch ? 1 : 0)
     double4 *d_atom_d = nullptr;  // (sigma, eps, mass, alch)

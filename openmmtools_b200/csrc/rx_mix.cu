@@ -18,6 +18,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
+#include <chrono>
+static inline double rx_wall_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // ------------------------------------------------------------------------------------------------------
 // MT19937 generation: x[n+624] = x[n+397] ^ twist(x[n], x[n+1]); 227 words are independent per step and
@@ -163,13 +165,14 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
                                                       unsigned nslots, const double *__restrict__ u, int K, int logK,
                                                       int *__restrict__ perm_g, uint32_t *__restrict__ commit_log,
                                                       const unsigned char *__restrict__ filt,
-                                                      double filt_abs, MixCtl *ctl) {
+                                                      const double *__restrict__ filt_rowabs, MixCtl *ctl) {
     extern __shared__ double s_mix[];
     __shared__ WalkShared sh;
     // layout: ring_lu[RING] f64 | diag[K] f64 | (u f64 [K*K]) | ring_ij[RING] u32 | ring_bm[RING] u32 | perm[K] i32 | (image: u16[K*K] + u8[K*K])
     double *ring_lu = s_mix;
     double *s_diag = ring_lu + RING;
-    double *s_u = s_diag + K;
+    double *s_rowabs = s_diag + K;                                   // [K] |row minimum| (U_FILTER24 only)
+    double *s_u = s_rowabs + (UMODE == U_FILTER24 ? K : 0);
     uint32_t *ring_ij = (uint32_t *)(s_u + (UMODE == U_F64_SMEM ? (size_t)K * K : 0));
     uint32_t *ring_bm = ring_ij + RING;
     int *s_perm = (int *)(ring_bm + RING);
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const int st = perm_g[q];
         s_perm[q] = st;
         s_diag[q] = u[((size_t)q << logK) + st];
+        if (UMODE == U_FILTER24) s_rowabs[q] = filt_rowabs[q];
     }
     if (UMODE == U_F64_SMEM)
         for (int q = tid; q < K * K; q += 64) s_u[q] = u[q];
@@ -260,7 +264,9 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             const float f_ji = __uint_as_float(((unsigned)s_qhi[a_ji] << 16) | ((unsigned)s_qlo[a_ji] << 8));
             const double lp = ((double)f_ii - (double)f_ij) + ((double)f_jj - (double)f_ji);
             // every image value is within 2^-15 (relative) of the true delta: truncation to a 15-bit mantissa + f32 rounding
-            const double eps = (double)(fabsf(f_ii) + fabsf(f_ij) + fabsf(f_jj) + fabsf(f_ji)) * 3.2e-5 + filt_abs;
+            // ... plus the f64 rounding of the reference's own three additions and of our centring (<= 64 ulp of the magnitudes)
+            const double mag = (double)(fabsf(f_ii) + fabsf(f_ij) + fabsf(f_jj) + fabsf(f_ji));
+            const double eps = mag * 3.2e-5 + 1.5e-14 * (mag + s_rowabs[i] + s_rowabs[j] + 1.0);
             const double d = lp - logU_next;
             const bool sure_ge0 = lp > eps, sure_neg = lp < -eps;
             const bool sure_acc = d > eps + 1e-9, sure_rej = d < -(eps + 1e-9);
@@ -388,7 +394,7 @@ __global__ void k_mix_filter_build(const double *__restrict__ u, int K, unsigned
         ((unsigned short *)filt)[(size_t)k * K + l] = (unsigned short)(bits >> 16);
         filt[2 * (size_t)K * K + (size_t)k * K + l] = (unsigned char)((bits >> 8) & 0xffu);
     }
-    if (t == 0) { scale[k] = lo; absmax_out[k] = anybad ? INFINITY : am; }
+    if (t == 0) { scale[k] = fabs(lo); absmax_out[k] = anybad ? INFINITY : am; }
 }
 
 // Build the (symmetric) proposal / acceptance count matrices from the commit log (replicaexchange.py:339-349).
@@ -601,6 +607,18 @@ int rxi_mix_skip(rx_engine *h, int stream, unsigned long long n) {
     return RX_OK;
 }
 
+struct MixTrace {   // RX_TRACE_MIX=1: device-time breakdown of one swap-all call (development aid)
+    cudaEvent_t ev[10]; const char *name[10]; int n = 0; bool on = false; cudaStream_t st;
+    void init(cudaStream_t s_) { st = s_; on = getenv("RX_TRACE_MIX") != nullptr; }
+    void mark(const char *what) { if (!on || n >= 10) return; cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], st); name[n++] = what; }
+    void dump() {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        for (int i = 1; i < n; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, "[mix trace] %-22s %9.3f ms\n", name[i], ms); }
+        for (int i = 0; i < n; i++) cudaEventDestroy(ev[i]);
+    }
+};
+
 static inline bool is_pow2(int k) { return k >= 2 && (k & (k - 1)) == 0; }
 
 static inline size_t pass_need(long long remaining, bool fast) {
@@ -623,14 +641,18 @@ static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fas
     if (fast) {
         const long long nslots = (long long)(S.avail / 2);
         if ((size_t)nslots > h->slots_cap) {
+            // size for the largest stream the buffer can ever hold (2 * need + 1024 words), so that the slightly different
+            // `avail` of every iteration never triggers another cudaFree/cudaMalloc (tens of ms each, device-synchronising)
+            size_t want = (S.cap + 1) / 2;
+            if (want < (size_t)nslots) want = (size_t)nslots;
             RX_CHECK_CUDA(h, cudaDeviceSynchronize());
             cudaFree(h->d_slots);
             cudaFree(h->d_log);
             h->d_slots = nullptr; h->d_log = nullptr;
             h->slots_cap = 0;
-            RX_CHECK_CUDA(h, cudaMalloc(&h->d_slots, (size_t)nslots * sizeof(SlotRec)));
-            RX_CHECK_CUDA(h, cudaMalloc(&h->d_log, (size_t)nslots * sizeof(uint32_t)));
-            h->slots_cap = (size_t)nslots;
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_slots, want * sizeof(SlotRec)));
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_log, want * sizeof(uint32_t)));
+            h->slots_cap = want;
         }
         k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, nslots, (uint32_t)(K - 1), h->d_slots);
         RX_CHECK_CUDA(h, cudaGetLastError());
@@ -646,8 +668,10 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     const int K = h->cfg.n_replicas, M = h->cfg.n_states;
     if (K != M) RX_FAIL(h, RX_ERR_INVALID, "rx_mix_swap_all: requires n_replicas == n_states");
     const size_t mm = (size_t)M * M * sizeof(unsigned long long);
+    MixTrace tr; tr.init(h->stream); tr.mark("enter");
     RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_nacc, 0, mm, h->stream));
     RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_nprop, 0, mm, h->stream));
+    tr.mark("memsets");
     if (nswap <= 0) return RX_OK;
     if (K == 1) {  // randint(1) draws nothing, log_p == 0: every attempt is an accepted no-op
         unsigned long long two_n = 2ull * (unsigned long long)nswap;
@@ -663,7 +687,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     // ring (lu 8 + ij 4 + bm 4) + diag + perm
     const size_t smem_base = (size_t)RING * 16 + (size_t)K * (sizeof(double) + sizeof(int));
     const size_t smem_f64 = smem_base + (size_t)K * K * sizeof(double);
-    const size_t smem_f24 = smem_base + (size_t)3 * K * K;
+    const size_t smem_f24 = smem_base + (size_t)K * sizeof(double) + (size_t)3 * K * K;
     int umode = U_GLOBAL;
     if (fast && smem_f64 <= 200 * 1024) umode = U_F64_SMEM;
     else if (fast && smem_f24 <= 224 * 1024 && !getenv("RX_NO_FILTER")) umode = U_FILTER24;
@@ -683,26 +707,21 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_FILTER24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_base_launch));
     }
-    double filt_abs = 0.0;
+    tr.mark("func attributes");
     if (umode == U_FILTER24) {
         if (!h->d_filt) {
             RX_CHECK_CUDA(h, cudaMalloc(&h->d_filt, (size_t)3 * K * K + 16));
             RX_CHECK_CUDA(h, cudaMalloc(&h->d_filt_scale, sizeof(double) * 2 * K));
         }
+        // row image + |row minimum| for the per-lane error bound; non-finite or astronomically large entries only send the
+        // lanes that touch them to the exact path (no host round trip, no global fallback)
         k_mix_filter_build<<<K, 256, 0, h->stream>>>(h->d_u, K, h->d_filt, h->d_filt_scale, h->d_filt_scale + K);
         RX_CHECK_CUDA(h, cudaGetLastError());
         (*launches)++;
-        std::vector<double> am(K);
-        RX_CHECK_CUDA(h, cudaMemcpyAsync(am.data(), h->d_filt_scale + K, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
-        RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
-        double amax = 0;
-        for (int k = 0; k < K; k++) amax = am[k] > amax ? am[k] : amax;
-        // rounding of the reference's own f64 evaluation (3 adds of values <= 2 amax) plus our centring subtractions
-        filt_abs = 64.0 * 2.220446049250313e-16 * (amax + 1.0);
-        if (!(filt_abs < 1e-3)) umode = U_GLOBAL;   // absurd magnitudes: just use the exact path
     }
+    tr.mark("filter build");
     long long remaining = nswap;
-    h->mix_stats[0] = h->mix_stats[1] = h->mix_stats[2] = 0;
+    h->mix_stats[0] = h->mix_stats[1] = h->mix_stats[2] = h->mix_stats[4] = h->mix_stats[5] = 0;
     const uint64_t consumed0 = S.consumed;
     const size_t chunk_words = (size_t)1 << 26;
     while (remaining > 0) {
@@ -712,14 +731,17 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             // produced on the side stream while the replicas were propagating
             RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_prepared, 0));
             float ms = 0;
+            const double tw0 = rx_wall_us();
             if (cudaEventSynchronize(h->ev[7]) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess)
                 h->phase_ms[3] += ms;
+            h->mix_stats[5] += (long long)(rx_wall_us() - tw0);
         } else {
             if (h->prepared) RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream_rng));
             rc = prepare_pass(h, S, remaining, fast, K, h->stream, launches);
             if (rc) return rc;
         }
         h->prepared = false;
+        tr.mark("prepared/built");
         MixCtl ctl = {0, remaining, 0, 0, 0, 0};
         RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->stream));
         size_t consumed_words;
@@ -735,16 +757,20 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
                 RX_CHECK_CUDA(h, cudaEventRecord(h->ev_prepared, h->stream_rng));
                 *launches += 1;
             }
+            RX_CHECK_CUDA(h, cudaEventRecord(h->ev_walk[0], h->stream));
             if (umode == U_F64_SMEM)
-                k_mix_walk_pow2<U_F64_SMEM><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, 0.0, h->d_ctl);
+                k_mix_walk_pow2<U_F64_SMEM><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, h->d_ctl);
             else if (umode == U_FILTER24)
-                k_mix_walk_pow2<U_FILTER24><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, h->d_filt, filt_abs, h->d_ctl);
+                k_mix_walk_pow2<U_FILTER24><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, h->d_filt, h->d_filt_scale, h->d_ctl);
             else
-                k_mix_walk_pow2<U_GLOBAL><<<1, 64, smem_base_launch, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, 0.0, h->d_ctl);
+                k_mix_walk_pow2<U_GLOBAL><<<1, 64, smem_base_launch, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, h->d_ctl);
             RX_CHECK_CUDA(h, cudaGetLastError());
+            RX_CHECK_CUDA(h, cudaEventRecord(h->ev_walk[1], h->stream));
+            tr.mark("walker");
             *launches += 1;
             RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
             RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+            { float wms = 0; if (cudaEventElapsedTime(&wms, h->ev_walk[0], h->ev_walk[1]) == cudaSuccess) h->mix_stats[4] += (long long)(wms * 1e3f); }
             consumed_words = (size_t)(2 * ctl.head);
             if (ahead) {   // adopt the words generated during the walk
                 RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_prepared, 0));
@@ -757,6 +783,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
                 RX_CHECK_CUDA(h, cudaGetLastError());
                 *launches += 1;
             }
+            tr.mark("adopt-ahead + count");
         } else {
             k_mix_walk_serial<<<1, 32, smem, h->stream>>>(S.d_words, (long long)S.avail, h->d_u, K, M, h->d_perm, h->d_nacc,
                                                         h->d_nprop, h->d_ctl);
@@ -774,7 +801,9 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         h->mix_stats[2] += 1;
         rc = stream_consume(h, S, consumed_words, launches);
         if (rc) return rc;
+        tr.mark("consume copy");
     }
+    tr.dump();
     h->mix_stats[3] = (long long)(S.consumed - consumed0);
     h->last_consumed = (size_t)(S.consumed - consumed0);
     if (!getenv("RX_NO_ASYNC_RNG")) {

@@ -34,6 +34,6 @@ for it in range(iters):
     nacc, nprop = e.get_mix_counts()
     print('iter %d wall %.1f ms  mix %.2f prop %.2f energy %.2f  acc %.3f  words %d' % (
         it, dt * 1e3 / batch, pt['mix_ms'] / batch, pt['propagate_ms'] / batch, pt['energies_ms'] / batch, nacc.sum() / max(nprop.sum(), 1),
-        e.mix_stream_position(0)))
+        e.mix_stream_position(0)), e.mix_stats())
 pot, kin = e.get_replica_energies()
 print('T_kin', (2 * kin / (3 * 512 * 8.31446261815324e-3))[:4], 'pot', pot[:3])
