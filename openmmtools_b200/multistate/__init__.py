@@ -2,5 +2,6 @@
 from .multistatesampler import MultiStateSampler
 from .replicaexchange import ReplicaExchangeSampler
 from .paralleltempering import ParallelTemperingSampler
+from .sams import SAMSSampler
 from .utils import SimulationNaNError
 from .multistatereporter import MultiStateReporter

@@ -42,6 +42,7 @@ class MultiStateReporter:
         self._analysis_particle_indices = tuple(analysis_particle_indices)
         self._open_mode = None
         self._meta = None
+        self._dirty = set()
         if open_mode is not None:
             self.open(open_mode)
 
@@ -88,7 +89,7 @@ class MultiStateReporter:
         self._open_mode = None
 
     def sync(self):
-        pass   # every write is flushed and fsync'ed
+        pass   # data files are fsync'ed by write_last_iteration, right before the commit marker
 
     def __del__(self):
         self.close()
@@ -120,7 +121,7 @@ class MultiStateReporter:
         with open(self._path(name), mode) as f:
             f.seek(int(iteration) * a.nbytes)
             f.write(a.tobytes())
-            f.flush(); os.fsync(f.fileno())
+        self._dirty.add(self._path(name))
 
     def _read_record(self, name, iteration):
         dtype = np.dtype(self._VARS[name][0])
@@ -177,7 +178,7 @@ class MultiStateReporter:
             with open(self._path('unsampled_energies'), 'r+b' if os.path.exists(self._path('unsampled_energies')) else 'w+b') as f:
                 f.seek(int(iteration) * eu.nbytes)
                 f.write(eu.tobytes())
-                f.flush(); os.fsync(f.fileno())
+            self._dirty.add(self._path('unsampled_energies'))
 
     def read_unsampled_energies(self, iteration):
         n = self._meta.get('n_unsampled', 0)
@@ -210,7 +211,15 @@ class MultiStateReporter:
         return self._read_record('accepted', iteration), self._read_record('proposed', iteration)
 
     def write_last_iteration(self, last_iteration):
-        """The commit marker: everything up to this iteration is complete (multistatereporter.py:1184-1201)."""
+        """The commit marker: everything up to this iteration is complete (multistatereporter.py:1184-1201): the data files
+        written since the last marker are synced first, then the marker is replaced atomically."""
+        for path in sorted(self._dirty):
+            fd = os.open(path, os.O_RDONLY)
+            try:
+                os.fsync(fd)
+            finally:
+                os.close(fd)
+        self._dirty.clear()
         tmp = os.path.join(self._storage, 'analysis', 'last_iteration.tmp')
         with open(tmp, 'w') as f:
             f.write(str(int(last_iteration)))
@@ -224,6 +233,36 @@ class MultiStateReporter:
             cps = [c for c in self.read_checkpoint_iterations() if c <= last]
             return cps[-1] if cps else -1
         return last
+
+    # -- online analysis data (reference: write_online_analysis_data / read_online_analysis_data, used by SAMS)
+    def write_online_analysis_data(self, iteration, **kwargs):
+        d = os.path.join(self._storage, 'analysis', 'online')
+        os.makedirs(d, exist_ok=True)
+        for name, value in kwargs.items():
+            a = np.ascontiguousarray(value, dtype=np.float64 if np.asarray(value).dtype.kind == 'f' else np.int64)
+            spec = self._meta.setdefault('online', {})
+            if name not in spec:
+                spec[name] = {'dtype': a.dtype.str, 'shape': list(a.shape)}
+                self._write_meta()
+            path = os.path.join(d, name + '.bin')
+            with open(path, 'r+b' if os.path.exists(path) else 'w+b') as f:
+                f.seek(int(iteration) * a.nbytes)
+                f.write(a.tobytes())
+            self._dirty.add(path)
+
+    def read_online_analysis_data(self, iteration, *keys):
+        out = {}
+        for name in keys:
+            spec = self._meta.get('online', {}).get(name)
+            if spec is None:
+                raise KeyError(name)
+            dt = np.dtype(spec['dtype']); shape = tuple(spec['shape'])
+            n = int(np.prod(shape)) if shape else 1
+            path = os.path.join(self._storage, 'analysis', 'online', name + '.bin')
+            data = np.fromfile(path, dtype=dt)
+            data = data[:(data.size // n) * n].reshape((-1,) + shape)
+            out[name] = data[iteration]
+        return out
 
     # -- checkpoints
     def _ckpt(self, iteration):

@@ -262,9 +262,8 @@ class MultiStateSampler:
         K, M = len(self._sampler_states), len(self._thermodynamic_states)
         # initial assignment (multistatesampler.py:892-895, 1118-1143)
         if initial_thermodynamic_states is None:
-            if K != M:
-                raise ValueError('initial_thermodynamic_states must be given when n_replicas != n_states')
-            self._replica_thermodynamic_states = np.arange(K, dtype=np.int64)
+            self._replica_thermodynamic_states = self._default_initial_thermodynamic_states(
+                self._thermodynamic_states, self._sampler_states)
         else:
             init = np.array(initial_thermodynamic_states, dtype=np.int64)
             if len(init) != K or init.min() < 0 or init.max() >= M:
@@ -287,6 +286,19 @@ class MultiStateSampler:
         self._energy_unsampled_states = np.zeros([K, len(self._unsampled_states)], np.float64)
         self._iteration = 0
         self._create_engine()
+
+    @staticmethod
+    def _default_initial_thermodynamic_states(thermodynamic_states, sampler_states):
+        """multistatesampler.py:1118-1143: one-to-one when the counts match, otherwise whole loops over the states and the
+        remainder spread evenly from the first to the last state."""
+        n_thermo, n_sampler = len(thermodynamic_states), len(sampler_states)
+        thermo_indices = np.arange(n_thermo, dtype=int)
+        initial = np.zeros(n_sampler, dtype=int)
+        loops = n_sampler // n_thermo
+        n_looped = n_thermo * loops
+        initial[:n_looped] = np.tile(thermo_indices, loops)
+        initial[n_looped:] = np.linspace(0, n_thermo - 1, n_sampler - n_looped, dtype=int)
+        return initial.astype(np.int64)
 
     # ------------------------------------------------------------------ engine plumbing
     def _create_engine(self):
