@@ -62,6 +62,7 @@ struct DynParams {
     float dt, a, b;             // timestep, O-step coefficients exp(-gamma h), sqrt(1-exp(-2 gamma h))
     int n_steps, n_prog, nV, nR, nO;
     int maxnb;                  // Verlet-list capacity per atom (0: all-pairs only)
+    int sort_atoms;             // re-deal atoms to threads by neighbour count at every list build
     float rl2, half_skin2;      // (cutoff + skin)^2, (skin/2)^2
     char prog[RX_MAX_PROGRAM];
 };
@@ -71,20 +72,22 @@ struct PairLam { float la, ob; };
 // Pair interaction in float: returns -dU/dr / r (so f_i += ret * (xi - xj)) and optionally the energy.
 // One formula for every pair kind: plain LJ is the soft core with lambda^a = 1, alpha (1-lambda)^b = 0
 // (x = (sigma/r)^6), so a warp never diverges on the pair kind.  Approximate reciprocals (1 ulp-class MUFU ops).
-template <bool ENERGY>
+// C6: softcore_c == 6 (the reference default, alchemy.py:424); SW: the switching function is on.
+template <bool C6, bool SW, bool ENERGY>
 __device__ __forceinline__ float lj_pair_f(const DynParams &p, float r2, float sig, float eps, bool softcore,
                                            PairLam lam, float &energy) {
     const float la = softcore ? lam.la : 1.0f, ob = softcore ? lam.ob : 0.0f;
     const float inv_r2 = fast_rcp(r2);
     const float q = r2 * fast_rcp(sig * sig);
-    float rsc, x, D;
-    if (p.c_is_6) { rsc = q * q * q; D = ob + rsc; x = fast_rcp(D); }
-    else { rsc = __powf(q, 0.5f * p.sc_c); D = ob + rsc; x = __powf(D, -6.0f / p.sc_c); }
+    float rsc, x, iD;
+    if (C6) { rsc = q * q * q; iD = fast_rcp(ob + rsc); x = iD; }
+    else { rsc = __powf(q, 0.5f * p.sc_c); const float D = ob + rsc; iD = fast_rcp(D); x = __powf(D, -6.0f / p.sc_c); }
     const float t4 = la * 4.0f * eps;
-    float e = t4 * x * (x - 1.0f);
+    const float tx = t4 * x;
+    float e = tx * (x - 1.0f);
     // -dU/dr / r = t4 (2x-1) 6 x (r/sigma)^c / (D r^2)
-    float fr = t4 * (2.0f * x - 1.0f) * 6.0f * x * rsc * fast_rcp(D) * inv_r2;
-    if (p.use_switch && r2 > p.rs2) {
+    float fr = tx * (12.0f * x - 6.0f) * (rsc * iD) * inv_r2;
+    if (SW && r2 > p.rs2) {
         const float rinv = fast_rsqrt(r2);
         const float r = r2 * rinv;
         const float t = (r - p.rs) * p.inv_w;
@@ -109,22 +112,37 @@ __device__ __forceinline__ double block_reduce_sum(double v, double *s_red) {
     return t;  // valid on thread 0
 }
 
-// Shared-memory loads by 32-bit shared-space address: the generic-pointer path re-derives the CTA's shared window
+// Shared-memory accesses by 32-bit shared-space address: the generic-pointer path re-derives the CTA's shared window
 // (S2R SR_CgaCtaId + LEA) inside the pair loop.
 __device__ __forceinline__ float4 lds_f4(unsigned a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ float2 lds_f2(unsigned a) {
+// The parameter record of an atom sits RX_PAR_OFFSET bytes after its position record (same 16-byte stride), so the
+// pair loop reaches it through the position's address register plus an immediate.
+#define RX_MAX_ATOMS 1024
+#define RX_PAR_OFFSET (16 * RX_MAX_ATOMS)
+__device__ __forceinline__ float2 lds_par(unsigned a) {
     float2 v;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+16384];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
     return v;
 }
+static_assert(RX_PAR_OFFSET == 16384, "lds_par hard-codes the offset");
 __device__ __forceinline__ unsigned lds_u16(unsigned a) {
     unsigned short v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
     return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) {
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory");
+}
+
+// Minimum image without the XU pipe: round-to-nearest-even of d/L through the 1.5*2^23 magic constant
+// (|d/L| < 2^22), two FMA-pipe operations instead of FMUL + FRND.
+__device__ __forceinline__ float min_image_f(float d, float L, float iL) {
+    const float n = __fadd_rn(__fmaf_rn(d, iL, 12582912.0f), -12582912.0f);
+    return __fmaf_rn(-L, n, d);
 }
 
 // Everything the pair loop needs that does not change inside a launch, gathered in registers once.
@@ -135,47 +153,70 @@ struct PairCtx {
     PairLam lam;
 };
 
-template <bool ENERGY>
-__device__ __forceinline__ void pair_term(const DynParams &p, const PairCtx &c, unsigned pos_base, unsigned par_base, int j,
+// One candidate pair with atom j: returns true when it is inside the cutoff.
+template <bool C6, bool SW, bool ENERGY>
+__device__ __forceinline__ bool pair_term(const DynParams &p, const PairCtx &c, unsigned pos_base, unsigned j,
                                           float &ax, float &ay, float &az, float &en) {
-    const float4 pj = lds_f4(pos_base + 16u * (unsigned)j);
-    float dx = c.x - pj.x, dy = c.y - pj.y, dz = c.z - pj.z;
-    dx -= c.Lx * rintf(dx * c.iLx); dy -= c.Ly * rintf(dy * c.iLy); dz -= c.Lz * rintf(dz * c.iLz);
+    const unsigned aj = pos_base + 16u * j;
+    const float4 pj = lds_f4(aj);
+    const float dx = min_image_f(c.x - pj.x, c.Lx, c.iLx), dy = min_image_f(c.y - pj.y, c.Ly, c.iLy),
+                dz = min_image_f(c.z - pj.z, c.Lz, c.iLz);
     const float r2 = dx * dx + dy * dy + dz * dz;
     if (r2 < c.rc2) {
-        const float2 qj = lds_f2(par_base + 8u * (unsigned)j);
+        const float2 qj = lds_par(aj);
         const bool alch_j = qj.y != 0.f;
         const bool soft = (c.alch_i != alch_j) || (c.alch_i && alch_j && p.annihilate);
         float e;
-        const float fr = lj_pair_f<ENERGY>(p, r2, 0.5f * (c.sig_i + pj.w), c.se_i * qj.x, soft, c.lam, e);
+        const float fr = lj_pair_f<C6, SW, ENERGY>(p, r2, 0.5f * (c.sig_i + pj.w), c.se_i * qj.x, soft, c.lam, e);
         ax += fr * dx; ay += fr * dy; az += fr * dz;
         if (ENERGY) en += 0.5f * e;
+        return true;
     }
+    return false;
 }
 
-// Force on one atom from its Verlet list (front region: in range at build time, back region: skin) or, in the
-// fallback, from all other atoms.  Plain loops over shared memory with address bumps: nothing is re-derived per pair.
-template <bool ENERGY>
-__device__ __forceinline__ void lj_forces(const DynParams &p, const PairCtx &c, unsigned pos_base, unsigned par_base,
-                                          unsigned nb_t, int N, int t, bool use_list, int nb_in, int nb_out, int maxnb,
+// Force on one atom from its Verlet list or, in the fallback, from all other atoms.  The list has two regions: the
+// front (slots 0..nb_in-1) holds neighbours that have been inside the cutoff since the last build, the back
+// (slots maxnb-1 downwards, nb_out of them) the skin-only ones.  A skin neighbour found inside the cutoff is moved to
+// the front on the spot, so the back loop is a bare distance test and the expensive branch runs with most lanes on.
+template <bool C6, bool SW, bool ENERGY>
+__device__ __forceinline__ void lj_forces(const DynParams &p, const PairCtx &c, unsigned at_base, unsigned nb_t,
+                                          int N, int a, bool use_list, int &nb_in, int &nb_out, int maxnb,
                                           float &fx, float &fy, float &fz, float &en) {
     float ax = 0.f, ay = 0.f, az = 0.f, e = 0.f;
     if (use_list) {
         const unsigned stride = 2u * (unsigned)N;
         unsigned q = nb_t;
         for (int n = 0; n < nb_in; n++, q += stride)
-            pair_term<ENERGY>(p, c, pos_base, par_base, (int)lds_u16(q), ax, ay, az, e);
+            pair_term<C6, SW, ENERGY>(p, c, at_base, lds_u16(q), ax, ay, az, e);
         q = nb_t + (unsigned)(maxnb - 1) * stride;
-        for (int n = 0; n < nb_out; n++, q -= stride)
-            pair_term<ENERGY>(p, c, pos_base, par_base, (int)lds_u16(q), ax, ay, az, e);
+        int n = 0;
+        while (n < nb_out) {
+            const unsigned ej = lds_u16(q);
+            if (pair_term<C6, SW, ENERGY>(p, c, at_base, ej, ax, ay, az, e)) {
+                const unsigned lowest = nb_t + (unsigned)(maxnb - nb_out) * stride;
+                const unsigned el = lds_u16(lowest);
+                sts_u16(nb_t + (unsigned)nb_in * stride, ej);  // == lowest when the list is full: el is already read
+                sts_u16(q, el);
+                nb_in++; nb_out--;  // slot q now holds another skin neighbour (or is past the end): look again
+            } else {
+                n++; q -= stride;
+            }
+        }
     } else {
         for (int j = 0; j < N; j++)
-            if (j != t) pair_term<ENERGY>(p, c, pos_base, par_base, j, ax, ay, az, e);
+            if (j != a) pair_term<C6, SW, ENERGY>(p, c, at_base, (unsigned)j, ax, ay, az, e);
     }
     fx = ax; fy = ay; fz = az; en = e;
 }
 
-// One CTA per owned replica; thread t owns atom t (N <= 1024).
+#define RX_SORT_BINS 128
+
+// One CTA per owned replica, one atom per thread (N <= 1024).  Which atom a thread owns is re-decided at every list
+// build: atoms are dealt to threads in order of their in-range neighbour count, so the lanes of a warp run pair loops
+// of nearly equal length.  Per-atom results do not depend on the assignment (each atom sums its own list in list
+// order, noise is keyed by atom id, the energy reductions run in atom order).
+template <bool C6, bool SW>
 __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *__restrict__ atom,
                                                     const StateDev *__restrict__ states, const int *__restrict__ perm,
                                                     float4 *__restrict__ pos, float4 *__restrict__ vel, int k0,
@@ -183,26 +224,31 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
                                                     double *__restrict__ pot, double *__restrict__ kin,
                                                     int *__restrict__ nan_flag) {
     extern __shared__ float4 s_dyn[];
-    float4 *s_pos = s_dyn;                         // [N] xyz, w = sigma
-    float2 *s_par = (float2 *)(s_dyn + p.N);       // [N] (sqrt_eps, alch)
-    unsigned short *s_nb = (unsigned short *)(s_par + p.N);  // [maxnb][N] Verlet list, slot-major (conflict free)
+    float4 *s_at = s_dyn;                                    // [RX_MAX_ATOMS] (x, y, z, sigma)
+    float4 *s_par = s_dyn + RX_MAX_ATOMS;                    // [RX_MAX_ATOMS] (sqrt_eps, alch, -, -)
+    unsigned short *s_nb = (unsigned short *)(s_dyn + 2 * RX_MAX_ATOMS);  // [maxnb][N] Verlet list, slot-major (conflict free)
     __shared__ double s_red[32];
-    const int r = blockIdx.x, k = k0 + r, t = threadIdx.x;
-    const bool active = t < p.N;
+    const int r = blockIdx.x, k = k0 + r, t = threadIdx.x, nthr = blockDim.x;
+    const bool active = t < p.N;   // threads beyond N own no atom (they keep a >= N through every re-assignment)
+    int a = t;                     // the atom this thread owns
     const StateDev st = states[perm[k]];
     const PairLam lam = {(float)st.la, (float)st.ob};
-    float4 a4 = active ? atom[t] : make_float4(1.f, 0.f, 1.f, 0.f);
-    const float sig_i = a4.x, se_i = a4.y, inv_m = a4.z;
-    const bool alch_i = a4.w != 0.f;
+    float sig_i, se_i, inv_m, sigma_v;
+    bool alch_i;
+    auto load_atom = [&]() {
+        const float4 a4 = active ? atom[a] : make_float4(1.f, 0.f, 1.f, 0.f);
+        sig_i = a4.x; se_i = a4.y; inv_m = a4.z; alch_i = a4.w != 0.f;
+        sigma_v = sqrtf((float)st.kT * inv_m);  // sqrt(kT/m), integrators.py:1314
+    };
+    load_atom();
     float4 x4 = active ? pos[(size_t)r * p.N + t] : make_float4(0, 0, 0, 0);
     float4 v4 = active ? vel[(size_t)r * p.N + t] : make_float4(0, 0, 0, 0);
     float x = x4.x, y = x4.y, z = x4.z, vx = v4.x, vy = v4.y, vz = v4.z;
-    const float sigma_v = sqrtf((float)st.kT * inv_m);  // sqrt(kT/m), integrators.py:1314
     if (reassign && active) {  // context.setVelocitiesToTemperature, mcmc.py:711
         const float3 g = philox_normal3(philox4x32_10(make_uint4(t, 0x80000000u, k, iteration), key));
         vx = sigma_v * g.x; vy = sigma_v * g.y; vz = sigma_v * g.z;
     }
-    if (active) { s_pos[t] = make_float4(x, y, z, sig_i); s_par[t] = make_float2(se_i, alch_i ? 1.f : 0.f); }
+    if (active) { s_at[t] = make_float4(x, y, z, sig_i); s_par[t] = make_float4(se_i, alch_i ? 1.f : 0.f, 0.f, 0.f); }
     __syncthreads();
     float fx = 0, fy = 0, fz = 0;
     bool f_valid = false;
@@ -212,20 +258,54 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     // rebuilt whenever any atom has moved more than skin/2 since the last build.  If an atom has more than
     // maxnb neighbours the CTA falls back to the all-pairs loop for the rest of the launch.
     bool use_list = p.kind != RX_SYSTEM_HARMONIC && p.maxnb > 0;
-    // The list is kept in two regions: neighbours that were inside the cutoff at build time fill the slots from the
-    // front, skin-only neighbours from the back.  A warp then meets the expensive in-range work in its first iterations
-    // (most lanes active) and almost none in the later ones, instead of a ~46 % active mix in every iteration.
     int nb_in = 0, nb_out = 0;
     float xr = x, yr = y, zr = z;  // position at the last list build
+    // Deal the atoms to the threads again, sorted by (in-range neighbour count, atom's previous thread): a stable
+    // counting sort through scratch space in the (dead) list area.
+    auto reassign_atoms = [&]() {
+        const int nw = nthr >> 5, lane = t & 31, w = t >> 5;
+        float4 *x_v = (float4 *)s_nb;                                // [nthr] velocities by atom id
+        unsigned short *x_order = (unsigned short *)(x_v + nthr);    // [nthr] atom of each new thread
+        unsigned short *x_cnt = x_order + nthr;                      // [nw][BINS] per-warp bin counts -> offsets
+        unsigned short *x_base = x_cnt + nw * RX_SORT_BINS;          // [BINS] bin totals -> bases
+        const int bin = active ? min(nb_in, RX_SORT_BINS - 2) : RX_SORT_BINS - 1;
+        for (int q = t; q < nw * RX_SORT_BINS; q += nthr) x_cnt[q] = 0;
+        x_v[a] = make_float4(vx, vy, vz, 0.f);
+        __syncthreads();
+        const unsigned m = __match_any_sync(0xffffffffu, bin);
+        if (lane == __ffs(m) - 1) x_cnt[w * RX_SORT_BINS + bin] = (unsigned short)__popc(m);
+        __syncthreads();
+        for (int b = t; b < RX_SORT_BINS; b += nthr) {
+            int run = 0;
+            for (int q = 0; q < nw; q++) { const int c = x_cnt[q * RX_SORT_BINS + b]; x_cnt[q * RX_SORT_BINS + b] = (unsigned short)run; run += c; }
+            x_base[b] = (unsigned short)run;
+        }
+        __syncthreads();
+        if (t == 0) {
+            int run = 0;
+            for (int b = 0; b < RX_SORT_BINS; b++) { const int c = x_base[b]; x_base[b] = (unsigned short)run; run += c; }
+        }
+        __syncthreads();
+        const int rank = x_base[bin] + x_cnt[w * RX_SORT_BINS + bin] + __popc(m & ((1u << lane) - 1u));
+        x_order[rank] = (unsigned short)a;
+        __syncthreads();
+        a = x_order[t];
+        const float4 vv = x_v[a];
+        vx = vv.x; vy = vv.y; vz = vv.z;
+        load_atom();
+        if (active) { const float4 pa = s_at[a]; x = pa.x; y = pa.y; z = pa.z; }
+        __syncthreads();  // the scratch is dead: the list may be written
+    };
     auto build_list = [&]() {
+        if (p.sort_atoms && use_list) reassign_atoms();
         int cin = 0, cout = 0;
         if (active) {
             for (int j = 0; j < p.N; j++) {
-                const float4 pj = s_pos[j];
-                float dx = x - pj.x, dy = y - pj.y, dz = z - pj.z;
-                dx -= p.Lx * rintf(dx * p.iLx); dy -= p.Ly * rintf(dy * p.iLy); dz -= p.Lz * rintf(dz * p.iLz);
+                const float4 pj = s_at[j];
+                const float dx = min_image_f(x - pj.x, p.Lx, p.iLx), dy = min_image_f(y - pj.y, p.Ly, p.iLy),
+                            dz = min_image_f(z - pj.z, p.Lz, p.iLz);
                 const float r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 < p.rl2 && j != t) {
+                if (r2 < p.rl2 && j != a) {
                     if (cin + cout < p.maxnb) {
                         const int slot = (r2 < p.rc2) ? cin : (p.maxnb - 1 - cout);
                         s_nb[slot * p.N + t] = (unsigned short)j;
@@ -239,12 +319,15 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         xr = x; yr = y; zr = z;
         if (__syncthreads_or(over ? 1 : 0)) use_list = false;
     };
-    if (use_list) build_list();
+    if (use_list) {
+        build_list();
+        if (p.sort_atoms && use_list) build_list();  // the first build only counted neighbours for the sort
+    }
 
     PairCtx pc;
     pc.Lx = p.Lx; pc.Ly = p.Ly; pc.Lz = p.Lz; pc.iLx = p.iLx; pc.iLy = p.iLy; pc.iLz = p.iLz; pc.rc2 = p.rc2;
-    pc.sig_i = sig_i; pc.se_i = se_i; pc.alch_i = alch_i; pc.lam = lam;
-    const unsigned pos_base = (unsigned)__cvta_generic_to_shared(s_pos), par_base = (unsigned)__cvta_generic_to_shared(s_par);
+    pc.lam = lam;
+    const unsigned at_base = (unsigned)__cvta_generic_to_shared(s_at);
     const unsigned nb_t = (unsigned)__cvta_generic_to_shared(s_nb + t);
     const int N = p.N, maxnb = p.maxnb;
     auto compute_forces = [&](bool want_energy, float &e_out) {
@@ -252,9 +335,9 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
             fx = -hK * (x - hx0); fy = -hK * (y - hx1); fz = -hK * (z - hx2);
             e_out = want_energy ? 0.5f * hK * ((x - hx0) * (x - hx0) + (y - hx1) * (y - hx1) + (z - hx2) * (z - hx2)) : 0.f;
         } else if (active) {
-            pc.x = x; pc.y = y; pc.z = z;
-            if (want_energy) lj_forces<true>(p, pc, pos_base, par_base, nb_t, N, t, use_list, nb_in, nb_out, maxnb, fx, fy, fz, e_out);
-            else lj_forces<false>(p, pc, pos_base, par_base, nb_t, N, t, use_list, nb_in, nb_out, maxnb, fx, fy, fz, e_out);
+            pc.x = x; pc.y = y; pc.z = z; pc.sig_i = sig_i; pc.se_i = se_i; pc.alch_i = alch_i;
+            if (want_energy) lj_forces<C6, SW, true>(p, pc, at_base, nb_t, N, a, use_list, nb_in, nb_out, maxnb, fx, fy, fz, e_out);
+            else lj_forces<C6, SW, false>(p, pc, at_base, nb_t, N, a, use_list, nb_in, nb_out, maxnb, fx, fy, fz, e_out);
         } else {
             fx = fy = fz = 0.f; e_out = 0.f;
         }
@@ -276,13 +359,13 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
                     // barrier 1: everyone finished reading the old positions (and votes on a list rebuild)
                     const float mx = x - xr, my = y - yr, mz = z - zr;
                     const int moved = __syncthreads_or((use_list && active && (mx * mx + my * my + mz * mz > p.half_skin2)) ? 1 : 0);
-                    if (active) s_pos[t] = make_float4(x, y, z, sig_i);
+                    if (active) s_at[a] = make_float4(x, y, z, sig_i);
                     __syncthreads();
                     if (moved) build_list();
                 }
                 f_valid = false;
             } else {  // 'O'
-                const float3 g = philox_normal3(philox4x32_10(make_uint4(t, ocount, k, iteration), key));
+                const float3 g = philox_normal3(philox4x32_10(make_uint4(a, ocount, k, iteration), key));
                 ocount++;
                 vx = p.a * vx + p.b * sigma_v * g.x;
                 vy = p.a * vy + p.b * sigma_v * g.y;
@@ -290,12 +373,17 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
             }
         }
     }
-    // potential (in the replica's current state) and kinetic energy, SamplerState.potential_energy/kinetic_energy
+    // potential (in the replica's current state) and kinetic energy, SamplerState.potential_energy/kinetic_energy;
+    // summed in atom order whatever the thread assignment is
     float e_i = 0;
     compute_forces(true, e_i);
-    double ke_i = active ? 0.5 * (double)(vx * vx + vy * vy + vz * vz) / (double)inv_m : 0.0;
-    const double U = block_reduce_sum(active ? (double)e_i : 0.0, s_red);
-    const double KE = block_reduce_sum(ke_i, s_red);
+    __syncthreads();  // the list is dead from here: its area carries the per-atom terms
+    double2 *x_e = (double2 *)s_nb;
+    x_e[a] = make_double2((double)e_i, active ? 0.5 * (double)(vx * vx + vy * vy + vz * vz) / (double)inv_m : 0.0);
+    __syncthreads();
+    const double2 et = x_e[t];
+    const double U = block_reduce_sum(active ? et.x : 0.0, s_red);
+    const double KE = block_reduce_sum(active ? et.y : 0.0, s_red);
     const bool bad = active && !(isfinite(x) && isfinite(y) && isfinite(z) && isfinite(vx) && isfinite(vy) && isfinite(vz));
     const int any_bad = __syncthreads_or(bad ? 1 : 0);
     if (t == 0) {
@@ -307,8 +395,8 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         if (p.kind != RX_SYSTEM_HARMONIC) {  // getState(enforcePeriodicBox=True), mcmc.py:731
             x -= p.Lx * floorf(x * p.iLx); y -= p.Ly * floorf(y * p.iLy); z -= p.Lz * floorf(z * p.iLz);
         }
-        pos[(size_t)r * p.N + t] = make_float4(x, y, z, 0.f);
-        vel[(size_t)r * p.N + t] = make_float4(vx, vy, vz, 0.f);
+        pos[(size_t)r * p.N + a] = make_float4(x, y, z, 0.f);
+        vel[(size_t)r * p.N + a] = make_float4(vx, vy, vz, 0.f);
     }
 }
 
@@ -528,29 +616,44 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     const int N = h->cfg.n_atoms;
     if (N > 1024) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: more than 1024 atoms per replica is not supported yet");
     const int threads = ((N + 31) / 32) * 32;
-    size_t smem = (size_t)N * (sizeof(float4) + sizeof(float2));
+    const size_t atoms_bytes = (size_t)2 * RX_MAX_ATOMS * sizeof(float4);
+    size_t area = (size_t)threads * sizeof(double2);  // the list area doubles as scratch for the final reductions
     if (h->cfg.system_kind == RX_SYSTEM_LJ_ALCH && N >= 64 && !getenv("RX_NO_VERLET")) {
         // Verlet list: skin 0.25 nm (rebuild about every hundred 1-fs steps at 300 K), capacity from the shared-memory
         // budget (two CTAs per SM), at most 96 neighbours per atom; denser systems fall back to all-pairs in the kernel.
-        const double skin = 0.25;
+        const char *skin_env = getenv("RX_SKIN");
+        const double skin = skin_env ? atof(skin_env) : 0.25;
         double rl = h->cfg.r_cutoff + skin;
         for (int d = 0; d < 3; d++) if (rl > 0.5 * h->cfg.box[d]) rl = 0.5 * h->cfg.box[d];
         if (rl > h->cfg.r_cutoff + 0.02) {
-            int cap = (int)((100 * 1024 - smem) / ((size_t)N * sizeof(unsigned short)));
+            int cap = (int)((100 * 1024 - atoms_bytes) / ((size_t)N * sizeof(unsigned short)));
             if (cap > 96) cap = 96;
             if (cap >= 8) {
                 p.maxnb = cap;
                 p.rl2 = (float)(rl * rl);
                 const double hs = 0.5 * (rl - h->cfg.r_cutoff);
                 p.half_skin2 = (float)(hs * hs);
-                smem += (size_t)cap * N * sizeof(unsigned short);
+                const size_t list_bytes = (size_t)cap * N * sizeof(unsigned short);
+                // scratch of the atom re-assignment: velocities, order, per-warp bin counts, bin bases
+                const size_t sort_bytes = (size_t)threads * (sizeof(float4) + 2) + (size_t)(threads / 32 + 1) * RX_SORT_BINS * 2;
+                p.sort_atoms = (list_bytes >= sort_bytes && !getenv("RX_NO_SORT")) ? 1 : 0;
+                if (list_bytes > area) area = list_bytes;
             }
         }
     }
-    if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = atoms_bytes + area;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
-    k_propagate<<<h->kloc, threads, smem, h->stream>>>(p, h->d_atom, h->d_states, h->d_perm, h->d_pos, h->d_vel, h->k0, key,
-                                                      (uint32_t)iteration, reassign, h->d_pot, h->d_kin, h->d_nan);
+#define RX_LAUNCH_PROPAGATE(C6, SW)                                                                                        \
+    do {                                                                                                                   \
+        if (smem > 48 * 1024)                                                                                              \
+            RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate<C6, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_propagate<C6, SW><<<h->kloc, threads, smem, h->stream>>>(p, h->d_atom, h->d_states, h->d_perm, h->d_pos, h->d_vel, \
+                                                                   h->k0, key, (uint32_t)iteration, reassign, h->d_pot,    \
+                                                                   h->d_kin, h->d_nan);                                    \
+    } while (0)
+    if (p.c_is_6) { if (p.use_switch) RX_LAUNCH_PROPAGATE(true, true); else RX_LAUNCH_PROPAGATE(true, false); }
+    else { if (p.use_switch) RX_LAUNCH_PROPAGATE(false, true); else RX_LAUNCH_PROPAGATE(false, false); }
+#undef RX_LAUNCH_PROPAGATE
     RX_CHECK_CUDA(h, cudaGetLastError());
     (*launches)++;
     return RX_OK;
