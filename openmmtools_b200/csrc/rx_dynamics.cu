@@ -63,7 +63,8 @@ struct DynParams {
     int n_steps, n_prog, nV, nR, nO;
     int maxnb;                  // Verlet-list capacity per atom (0: all-pairs only)
     int sort_atoms;             // re-deal atoms to threads by neighbour count at every list build
-    float rl2, half_skin2;      // (cutoff + skin)^2, (skin/2)^2
+    float rl2, rin2;            // (cutoff + skin_out)^2, (cutoff + skin_in)^2
+    float half_in2, half_out2;  // (skin_in/2)^2, ((skin_out - skin_in)/2)^2
     char prog[RX_MAX_PROGRAM];
 };
 
@@ -119,16 +120,12 @@ __device__ __forceinline__ float4 lds_f4(unsigned a) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
 }
-// The parameter record of an atom sits RX_PAR_OFFSET bytes after its position record (same 16-byte stride), so the
-// pair loop reaches it through the position's address register plus an immediate.
 #define RX_MAX_ATOMS 1024
-#define RX_PAR_OFFSET (16 * RX_MAX_ATOMS)
-__device__ __forceinline__ float2 lds_par(unsigned a) {
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
     float2 v;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+16384];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
     return v;
 }
-static_assert(RX_PAR_OFFSET == 16384, "lds_par hard-codes the offset");
 __device__ __forceinline__ unsigned lds_u16(unsigned a) {
     unsigned short v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
@@ -153,9 +150,9 @@ struct PairCtx {
     PairLam lam;
 };
 
-// One candidate pair with atom j: returns true when it is inside the cutoff.
+// One candidate pair with atom j (position records at pos_base, parameter records par_off bytes further).
 template <bool C6, bool SW, bool ENERGY>
-__device__ __forceinline__ bool pair_term(const DynParams &p, const PairCtx &c, unsigned pos_base, unsigned j,
+__device__ __forceinline__ void pair_term(const DynParams &p, const PairCtx &c, unsigned pos_base, int par_off, unsigned j,
                                           float &ax, float &ay, float &az, float &en) {
     const unsigned aj = pos_base + 16u * j;
     const float4 pj = lds_f4(aj);
@@ -163,59 +160,53 @@ __device__ __forceinline__ bool pair_term(const DynParams &p, const PairCtx &c, 
                 dz = min_image_f(c.z - pj.z, c.Lz, c.iLz);
     const float r2 = dx * dx + dy * dy + dz * dz;
     if (r2 < c.rc2) {
-        const float2 qj = lds_par(aj);
+        const float2 qj = lds_f2(aj + (unsigned)par_off);
         const bool alch_j = qj.y != 0.f;
         const bool soft = (c.alch_i != alch_j) || (c.alch_i && alch_j && p.annihilate);
         float e;
         const float fr = lj_pair_f<C6, SW, ENERGY>(p, r2, 0.5f * (c.sig_i + pj.w), c.se_i * qj.x, soft, c.lam, e);
         ax += fr * dx; ay += fr * dy; az += fr * dz;
         if (ENERGY) en += 0.5f * e;
-        return true;
     }
-    return false;
 }
 
-// Force on one atom from its Verlet list or, in the fallback, from all other atoms.  The list has two regions: the
-// front (slots 0..nb_in-1) holds neighbours that have been inside the cutoff since the last build, the back
-// (slots maxnb-1 downwards, nb_out of them) the skin-only ones.  A skin neighbour found inside the cutoff is moved to
-// the front on the spot, so the back loop is a bare distance test and the expensive branch runs with most lanes on.
+// Force on one atom from the inner part of its neighbour list or, in the fallback, from all other atoms.
 template <bool C6, bool SW, bool ENERGY>
-__device__ __forceinline__ void lj_forces(const DynParams &p, const PairCtx &c, unsigned at_base, unsigned nb_t,
-                                          int N, int a, bool use_list, int &nb_in, int &nb_out, int maxnb,
+__device__ __forceinline__ void lj_forces(const DynParams &p, const PairCtx &c, unsigned pos_base, int par_off,
+                                          unsigned nb_t, int N, int a, bool use_list, int n_inner,
                                           float &fx, float &fy, float &fz, float &en) {
     float ax = 0.f, ay = 0.f, az = 0.f, e = 0.f;
     if (use_list) {
         const unsigned stride = 2u * (unsigned)N;
         unsigned q = nb_t;
-        for (int n = 0; n < nb_in; n++, q += stride)
-            pair_term<C6, SW, ENERGY>(p, c, at_base, lds_u16(q), ax, ay, az, e);
-        q = nb_t + (unsigned)(maxnb - 1) * stride;
-        int n = 0;
-        while (n < nb_out) {
-            const unsigned ej = lds_u16(q);
-            if (pair_term<C6, SW, ENERGY>(p, c, at_base, ej, ax, ay, az, e)) {
-                const unsigned lowest = nb_t + (unsigned)(maxnb - nb_out) * stride;
-                const unsigned el = lds_u16(lowest);
-                sts_u16(nb_t + (unsigned)nb_in * stride, ej);  // == lowest when the list is full: el is already read
-                sts_u16(q, el);
-                nb_in++; nb_out--;  // slot q now holds another skin neighbour (or is past the end): look again
-            } else {
-                n++; q -= stride;
-            }
-        }
+        for (int n = 0; n < n_inner; n++, q += stride)
+            pair_term<C6, SW, ENERGY>(p, c, pos_base, par_off, lds_u16(q), ax, ay, az, e);
     } else {
         for (int j = 0; j < N; j++)
-            if (j != a) pair_term<C6, SW, ENERGY>(p, c, at_base, (unsigned)j, ax, ay, az, e);
+            if (j != a) pair_term<C6, SW, ENERGY>(p, c, pos_base, par_off, (unsigned)j, ax, ay, az, e);
     }
     fx = ax; fy = ay; fz = az; en = e;
 }
 
 #define RX_SORT_BINS 128
 
-// One CTA per owned replica, one atom per thread (N <= 1024).  Which atom a thread owns is re-decided at every list
-// build: atoms are dealt to threads in order of their in-range neighbour count, so the lanes of a warp run pair loops
-// of nearly equal length.  Per-atom results do not depend on the assignment (each atom sums its own list in list
-// order, noise is keyed by atom id, the energy reductions run in atom order).
+// One CTA per owned replica, one atom per thread (N <= 1024).
+//
+// Neighbour search is a dual list held in shared memory, one column per thread:
+//   outer list  every j with r < cutoff + skin_out when it was built (an all-pairs pass);
+//   inner list  the leading n_inner entries of the column: the outer entries with r < cutoff + skin_in when the
+//               column was last partitioned.  The force loop visits only these.
+// The column is re-partitioned when some atom has moved more than skin_in/2 since the last partition, and the outer
+// list is rebuilt when (checked at that moment) some atom has moved more than (skin_out - skin_in)/2 since the build,
+// so that a pair missing from the outer list is still farther than cutoff + skin_in.
+//
+// Which atom a thread owns is re-decided at every outer build: atoms are dealt to threads in order of their inner
+// neighbour count, so the lanes of a warp run pair loops of nearly equal length.  Per-atom results do not depend on
+// the assignment (each atom sums its own list in list order, noise is keyed by atom id, the energy reductions run in
+// atom order).
+//
+// Positions are double buffered: a force evaluation writes the moved positions into the buffer the previous
+// evaluation did not read, and the displacement vote (__syncthreads_or) is the only barrier of the step.
 template <bool C6, bool SW>
 __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *__restrict__ atom,
                                                     const StateDev *__restrict__ states, const int *__restrict__ perm,
@@ -224,9 +215,9 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
                                                     double *__restrict__ pot, double *__restrict__ kin,
                                                     int *__restrict__ nan_flag) {
     extern __shared__ float4 s_dyn[];
-    float4 *s_at = s_dyn;                                    // [RX_MAX_ATOMS] (x, y, z, sigma)
-    float4 *s_par = s_dyn + RX_MAX_ATOMS;                    // [RX_MAX_ATOMS] (sqrt_eps, alch, -, -)
-    unsigned short *s_nb = (unsigned short *)(s_dyn + 2 * RX_MAX_ATOMS);  // [maxnb][N] Verlet list, slot-major (conflict free)
+    float4 *s_par = s_dyn + RX_MAX_ATOMS;  // [RX_MAX_ATOMS] (sqrt_eps, alch, -, -); s_dyn[0..] / s_dyn[2*MAX..]: positions
+    float4 *s_ref = s_dyn + 3 * RX_MAX_ATOMS;                  // [nthr] the thread's position at the last outer build
+    unsigned short *s_nb = (unsigned short *)(s_ref + blockDim.x);  // [maxnb][N] lists, slot-major (conflict free)
     __shared__ double s_red[32];
     const int r = blockIdx.x, k = k0 + r, t = threadIdx.x, nthr = blockDim.x;
     const bool active = t < p.N;   // threads beyond N own no atom (they keep a >= N through every re-assignment)
@@ -248,27 +239,31 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         const float3 g = philox_normal3(philox4x32_10(make_uint4(t, 0x80000000u, k, iteration), key));
         vx = sigma_v * g.x; vy = sigma_v * g.y; vz = sigma_v * g.z;
     }
-    if (active) { s_at[t] = make_float4(x, y, z, sig_i); s_par[t] = make_float4(se_i, alch_i ? 1.f : 0.f, 0.f, 0.f); }
-    __syncthreads();
+    if (active) s_par[t] = make_float4(se_i, alch_i ? 1.f : 0.f, 0.f, 0.f);
     float fx = 0, fy = 0, fz = 0;
     bool f_valid = false;
     const float hx0 = (float)st.ho_x0[0], hx1 = (float)st.ho_x0[1], hx2 = (float)st.ho_x0[2], hK = (float)st.ho_K;
+    const bool lj = p.kind != RX_SYSTEM_HARMONIC;
 
-    // Verlet neighbour list (full list: every thread owns its atom's force, no atomics, deterministic):
-    // rebuilt whenever any atom has moved more than skin/2 since the last build.  If an atom has more than
-    // maxnb neighbours the CTA falls back to the all-pairs loop for the rest of the launch.
-    bool use_list = p.kind != RX_SYSTEM_HARMONIC && p.maxnb > 0;
-    int nb_in = 0, nb_out = 0;
-    float xr = x, yr = y, zr = z;  // position at the last list build
-    // Deal the atoms to the threads again, sorted by (in-range neighbour count, atom's previous thread): a stable
+    bool use_list = lj && p.maxnb > 0;
+    bool have_list = false;        // an outer list exists
+    int n_all = 0, n_inner = 0;
+    float xi = x, yi = y, zi = z;  // position at the last partition
+    int cur = 1;                   // position buffer of the latest force evaluation (0: s_dyn, 1: s_dyn + 2*MAX)
+    const unsigned dyn_base = (unsigned)__cvta_generic_to_shared(s_dyn);
+    const unsigned nb_t = (unsigned)__cvta_generic_to_shared(s_nb + t);
+    const unsigned stride = 2u * (unsigned)p.N;
+
+    // Deal the atoms to the threads again, sorted by (inner neighbour count, atom's previous thread): a stable
     // counting sort through scratch space in the (dead) list area.
-    auto reassign_atoms = [&]() {
+    auto reassign_atoms = [&](const float4 *s_pos) {
         const int nw = nthr >> 5, lane = t & 31, w = t >> 5;
         float4 *x_v = (float4 *)s_nb;                                // [nthr] velocities by atom id
         unsigned short *x_order = (unsigned short *)(x_v + nthr);    // [nthr] atom of each new thread
         unsigned short *x_cnt = x_order + nthr;                      // [nw][BINS] per-warp bin counts -> offsets
         unsigned short *x_base = x_cnt + nw * RX_SORT_BINS;          // [BINS] bin totals -> bases
-        const int bin = active ? min(nb_in, RX_SORT_BINS - 2) : RX_SORT_BINS - 1;
+        const int bin = active ? min(n_inner, RX_SORT_BINS - 2) : RX_SORT_BINS - 1;
+        __syncthreads();  // every thread is done with its column (a partition may just have run)
         for (int q = t; q < nw * RX_SORT_BINS; q += nthr) x_cnt[q] = 0;
         x_v[a] = make_float4(vx, vy, vz, 0.f);
         __syncthreads();
@@ -293,51 +288,95 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         const float4 vv = x_v[a];
         vx = vv.x; vy = vv.y; vz = vv.z;
         load_atom();
-        if (active) { const float4 pa = s_at[a]; x = pa.x; y = pa.y; z = pa.z; }
+        if (active) { const float4 pa = s_pos[a]; x = pa.x; y = pa.y; z = pa.z; }
         __syncthreads();  // the scratch is dead: the list may be written
     };
-    auto build_list = [&]() {
-        if (p.sort_atoms && use_list) reassign_atoms();
-        int cin = 0, cout = 0;
+    // Move the outer entries with r < cutoff + skin_in to the front of the column (every entry is tested once).
+    auto partition = [&](const float4 *s_pos) {
+        int lo = 0, hi = n_all - 1;
+        if (active) {
+            while (lo <= hi) {
+                const unsigned ql = nb_t + (unsigned)lo * stride;
+                const unsigned e = lds_u16(ql);
+                const float4 pj = s_pos[e];
+                const float dx = min_image_f(x - pj.x, p.Lx, p.iLx), dy = min_image_f(y - pj.y, p.Ly, p.iLy),
+                            dz = min_image_f(z - pj.z, p.Lz, p.iLz);
+                if (dx * dx + dy * dy + dz * dz < p.rin2) lo++;
+                else {
+                    const unsigned qh = nb_t + (unsigned)hi * stride;
+                    sts_u16(ql, lds_u16(qh));
+                    sts_u16(qh, e);
+                    hi--;
+                }
+            }
+        }
+        n_inner = lo;
+        xi = x; yi = y; zi = z;
+    };
+    auto build_outer = [&](const float4 *s_pos) {
+        if (p.sort_atoms) reassign_atoms(s_pos);
+        int cnt = 0;
         if (active) {
             for (int j = 0; j < p.N; j++) {
-                const float4 pj = s_at[j];
+                const float4 pj = s_pos[j];
                 const float dx = min_image_f(x - pj.x, p.Lx, p.iLx), dy = min_image_f(y - pj.y, p.Ly, p.iLy),
                             dz = min_image_f(z - pj.z, p.Lz, p.iLz);
                 const float r2 = dx * dx + dy * dy + dz * dz;
                 if (r2 < p.rl2 && j != a) {
-                    if (cin + cout < p.maxnb) {
-                        const int slot = (r2 < p.rc2) ? cin : (p.maxnb - 1 - cout);
-                        s_nb[slot * p.N + t] = (unsigned short)j;
-                    }
-                    if (r2 < p.rc2) cin++; else cout++;
+                    if (cnt < p.maxnb) s_nb[cnt * p.N + t] = (unsigned short)j;
+                    cnt++;
                 }
             }
         }
-        const bool over = cin + cout > p.maxnb;
-        nb_in = cin; nb_out = cout;
-        xr = x; yr = y; zr = z;
-        if (__syncthreads_or(over ? 1 : 0)) use_list = false;
+        s_ref[t] = make_float4(x, y, z, 0.f);
+        n_all = cnt;
+        have_list = true;
+        if (__syncthreads_or(cnt > p.maxnb ? 1 : 0)) use_list = false;  // denser than the capacity: all-pairs from now on
     };
-    if (use_list) {
-        build_list();
-        if (p.sort_atoms && use_list) build_list();  // the first build only counted neighbours for the sort
-    }
+    // Make the list valid for the positions in buffer s_pos (all threads call this together).
+    auto refresh_list = [&](const float4 *s_pos) {
+        const float4 rf = s_ref[t];
+        const float mx = x - rf.x, my = y - rf.y, mz = z - rf.z;
+        const bool far = !have_list || (active && mx * mx + my * my + mz * mz > p.half_out2);
+        if (__syncthreads_or(far ? 1 : 0)) {
+            const bool first = !have_list;
+            build_outer(s_pos);
+            if (use_list) partition(s_pos);
+            if (first && p.sort_atoms && use_list) {  // the first build only counted neighbours for the sort
+                build_outer(s_pos);
+                if (use_list) partition(s_pos);
+            }
+        } else {
+            partition(s_pos);
+        }
+    };
 
     PairCtx pc;
     pc.Lx = p.Lx; pc.Ly = p.Ly; pc.Lz = p.Lz; pc.iLx = p.iLx; pc.iLy = p.iLy; pc.iLz = p.iLz; pc.rc2 = p.rc2;
     pc.lam = lam;
-    const unsigned at_base = (unsigned)__cvta_generic_to_shared(s_at);
-    const unsigned nb_t = (unsigned)__cvta_generic_to_shared(s_nb + t);
-    const int N = p.N, maxnb = p.maxnb;
+    const int N = p.N;
+    // Publish the current positions and make the neighbour list valid for them: one barrier unless a list is rebuilt.
+    auto publish = [&]() {
+        cur ^= 1;
+        float4 *s_pos = s_dyn + (cur ? 2 * RX_MAX_ATOMS : 0);
+        if (active) s_pos[a] = make_float4(x, y, z, sig_i);
+        const float mx = x - xi, my = y - yi, mz = z - zi;
+        const bool moved = use_list && (!have_list || (active && mx * mx + my * my + mz * mz > p.half_in2));
+        if (__syncthreads_or(moved ? 1 : 0)) refresh_list(s_pos);
+    };
     auto compute_forces = [&](bool want_energy, float &e_out) {
-        if (p.kind == RX_SYSTEM_HARMONIC) {
+        if (!lj) {
             fx = -hK * (x - hx0); fy = -hK * (y - hx1); fz = -hK * (z - hx2);
             e_out = want_energy ? 0.5f * hK * ((x - hx0) * (x - hx0) + (y - hx1) * (y - hx1) + (z - hx2) * (z - hx2)) : 0.f;
-        } else if (active) {
+            return;
+        }
+        if (!f_valid) publish();
+        if (active) {
             pc.x = x; pc.y = y; pc.z = z; pc.sig_i = sig_i; pc.se_i = se_i; pc.alch_i = alch_i;
-            if (want_energy) lj_forces<C6, SW, true>(p, pc, at_base, nb_t, N, a, use_list, nb_in, nb_out, maxnb, fx, fy, fz, e_out);
-            else lj_forces<C6, SW, false>(p, pc, at_base, nb_t, N, a, use_list, nb_in, nb_out, maxnb, fx, fy, fz, e_out);
+            const unsigned pos_base = dyn_base + (cur ? 2u * 16u * RX_MAX_ATOMS : 0u);
+            const int par_off = cur ? -16 * RX_MAX_ATOMS : 16 * RX_MAX_ATOMS;
+            if (want_energy) lj_forces<C6, SW, true>(p, pc, pos_base, par_off, nb_t, N, a, use_list, n_inner, fx, fy, fz, e_out);
+            else lj_forces<C6, SW, false>(p, pc, pos_base, par_off, nb_t, N, a, use_list, n_inner, fx, fy, fz, e_out);
         } else {
             fx = fy = fz = 0.f; e_out = 0.f;
         }
@@ -355,14 +394,6 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
             } else if (op == 'R') {
                 const float h = p.dt / (float)p.nR;
                 x += h * vx; y += h * vy; z += h * vz;
-                if (p.kind != RX_SYSTEM_HARMONIC) {
-                    // barrier 1: everyone finished reading the old positions (and votes on a list rebuild)
-                    const float mx = x - xr, my = y - yr, mz = z - zr;
-                    const int moved = __syncthreads_or((use_list && active && (mx * mx + my * my + mz * mz > p.half_skin2)) ? 1 : 0);
-                    if (active) s_at[a] = make_float4(x, y, z, sig_i);
-                    __syncthreads();
-                    if (moved) build_list();
-                }
                 f_valid = false;
             } else {  // 'O'
                 const float3 g = philox_normal3(philox4x32_10(make_uint4(a, ocount, k, iteration), key));
@@ -392,7 +423,7 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         nan_flag[k] = (any_bad || !isfinite(U)) ? 1 : 0;
     }
     if (active) {
-        if (p.kind != RX_SYSTEM_HARMONIC) {  // getState(enforcePeriodicBox=True), mcmc.py:731
+        if (lj) {  // getState(enforcePeriodicBox=True), mcmc.py:731
             x -= p.Lx * floorf(x * p.iLx); y -= p.Ly * floorf(y * p.iLy); z -= p.Lz * floorf(z * p.iLz);
         }
         pos[(size_t)r * p.N + a] = make_float4(x, y, z, 0.f);
@@ -602,7 +633,7 @@ static int fill_dyn(rx_engine *h, DynParams &p) {
     int nV = 0, nR = 0, nO = 0, n = 0;
     for (const char *q = h->program; *q; q++, n++) { if (*q == 'V') nV++; else if (*q == 'R') nR++; else nO++; p.prog[n] = *q; }
     p.n_prog = n; p.nV = nV; p.nR = nR; p.nO = nO;
-    p.maxnb = 0; p.rl2 = p.rc2; p.half_skin2 = 0.f;
+    p.maxnb = 0; p.sort_atoms = 0; p.rl2 = p.rin2 = p.rc2; p.half_in2 = p.half_out2 = 0.f;
     const double hO = h->dt / (nO > 0 ? nO : 1);   // integrators.py:1141-1146
     p.a = (float)exp(-h->gamma * hO);
     p.b = (float)sqrt(1.0 - exp(-2.0 * h->gamma * hO));
@@ -616,24 +647,31 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     const int N = h->cfg.n_atoms;
     if (N > 1024) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: more than 1024 atoms per replica is not supported yet");
     const int threads = ((N + 31) / 32) * 32;
-    const size_t atoms_bytes = (size_t)2 * RX_MAX_ATOMS * sizeof(float4);
+    // shared memory: two position buffers + the parameter records + per-thread reference positions + the list area
+    const size_t atoms_bytes = (size_t)3 * RX_MAX_ATOMS * sizeof(float4) + (size_t)threads * sizeof(float4);
     size_t area = (size_t)threads * sizeof(double2);  // the list area doubles as scratch for the final reductions
     if (h->cfg.system_kind == RX_SYSTEM_LJ_ALCH && N >= 64 && !getenv("RX_NO_VERLET")) {
-        // Verlet list: skin 0.25 nm (rebuild about every hundred 1-fs steps at 300 K), capacity from the shared-memory
-        // budget (two CTAs per SM), at most 96 neighbours per atom; denser systems fall back to all-pairs in the kernel.
-        const char *skin_env = getenv("RX_SKIN");
-        const double skin = skin_env ? atof(skin_env) : 0.25;
-        double rl = h->cfg.r_cutoff + skin;
+        // Dual neighbour list: outer skin 0.30 nm (an all-pairs rebuild about every seventy 1-fs steps at 300 K),
+        // inner skin 0.08 nm (a re-partition of the column about every twenty steps).  Capacity from the
+        // shared-memory budget (two CTAs per SM up to 512 atoms); denser systems fall back to all-pairs in the kernel.
+        const char *so = getenv("RX_SKIN"), *si = getenv("RX_SKIN_IN");
+        const double skin_out = so ? atof(so) : 0.30;
+        double skin_in = si ? atof(si) : 0.08;
+        double rl = h->cfg.r_cutoff + skin_out;
         for (int d = 0; d < 3; d++) if (rl > 0.5 * h->cfg.box[d]) rl = 0.5 * h->cfg.box[d];
-        if (rl > h->cfg.r_cutoff + 0.02) {
-            int cap = (int)((100 * 1024 - atoms_bytes) / ((size_t)N * sizeof(unsigned short)));
-            if (cap > 96) cap = 96;
+        const double eff_out = rl - h->cfg.r_cutoff;
+        if (skin_in > eff_out / 3.0) skin_in = eff_out / 3.0;
+        if (eff_out > 0.03) {
+            const size_t budget = (threads > 512 ? 200 : 112) * 1024;
+            int cap = (int)((budget - atoms_bytes) / ((size_t)N * sizeof(unsigned short)));
+            if (cap > 128) cap = 128;
             if (cap >= 8) {
                 p.maxnb = cap;
                 p.rl2 = (float)(rl * rl);
-                const double hs = 0.5 * (rl - h->cfg.r_cutoff);
-                p.half_skin2 = (float)(hs * hs);
-                const size_t list_bytes = (size_t)cap * N * sizeof(unsigned short);
+                p.rin2 = (float)((h->cfg.r_cutoff + skin_in) * (h->cfg.r_cutoff + skin_in));
+                p.half_in2 = (float)(0.25 * skin_in * skin_in);
+                p.half_out2 = (float)(0.25 * (eff_out - skin_in) * (eff_out - skin_in));
+                const size_t list_bytes = (((size_t)cap * N * sizeof(unsigned short)) + 15) / 16 * 16;
                 // scratch of the atom re-assignment: velocities, order, per-warp bin counts, bin bases
                 const size_t sort_bytes = (size_t)threads * (sizeof(float4) + 2) + (size_t)(threads / 32 + 1) * RX_SORT_BINS * 2;
                 p.sort_atoms = (list_bytes >= sort_bytes && !getenv("RX_NO_SORT")) ? 1 : 0;
