@@ -651,12 +651,13 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     const size_t atoms_bytes = (size_t)3 * RX_MAX_ATOMS * sizeof(float4) + (size_t)threads * sizeof(float4);
     size_t area = (size_t)threads * sizeof(double2);  // the list area doubles as scratch for the final reductions
     if (h->cfg.system_kind == RX_SYSTEM_LJ_ALCH && N >= 64 && !getenv("RX_NO_VERLET")) {
-        // Dual neighbour list: outer skin 0.30 nm (an all-pairs rebuild about every seventy 1-fs steps at 300 K),
-        // inner skin 0.08 nm (a re-partition of the column about every twenty steps).  Capacity from the
+        // Dual neighbour list: outer skin 0.40 nm (at 300 K and 10/ps friction the all-pairs build usually lasts a
+        // whole 500-step launch), inner skin 0.05 nm (a re-partition of the column about every 25 steps; both tuned
+        // on the 512-atom fluid, see profiles/prop_r1_v6.summary.txt).  Capacity from the
         // shared-memory budget (two CTAs per SM up to 512 atoms); denser systems fall back to all-pairs in the kernel.
         const char *so = getenv("RX_SKIN"), *si = getenv("RX_SKIN_IN");
-        const double skin_out = so ? atof(so) : 0.30;
-        double skin_in = si ? atof(si) : 0.08;
+        const double skin_out = so ? atof(so) : 0.40;
+        double skin_in = si ? atof(si) : 0.05;
         double rl = h->cfg.r_cutoff + skin_out;
         for (int d = 0; d < 3; d++) if (rl > 0.5 * h->cfg.box[d]) rl = 0.5 * h->cfg.box[d];
         const double eff_out = rl - h->cfg.r_cutoff;

@@ -24,6 +24,8 @@ ss = states.SamplerState(fluid.positions, box_vectors=asys.getDefaultPeriodicBox
 s = multistate.ReplicaExchangeSampler(mcmc_moves=mcmc.LangevinSplittingDynamicsMove(n_steps=12), number_of_iterations=3, seed=1)
 s.create(ts, [ss]); s.run(); s.sampler_states
 s._engine.run_iterations(2, 'swap-all', 1, 10)
+s._engine.set_integrator(0.002, 1.0, 150, 'V R O R V')  # long enough for list re-partitions and an outer rebuild
+s._engine.run_iterations(1, 'swap-all', 1, 12)
 ho = testsystems.HarmonicOscillator()
 hs = multistate.ReplicaExchangeSampler(mcmc_moves=mcmc.LangevinSplittingDynamicsMove(n_steps=20), number_of_iterations=2, seed=2,
                                        replica_mixing_scheme='swap-neighbors')
