@@ -105,6 +105,11 @@ RX_API int rx_get_velocities(rx_engine *h, int32_t first, int32_t count, double 
 RX_API int rx_get_replica_energies(rx_engine *h, double *potential /*[K] or NULL*/, double *kinetic /*[K] or NULL*/);
 /* context.setVelocitiesToTemperature (mcmc.py:711): v = sqrt(kB T/m) N(0,1) for every owned replica.     */
 RX_API int rx_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream);
+/* Replaces MultiStateSampler.minimize (multistatesampler.py:612-647) -> _minimize_replica (:1339-1402): FIRE descent
+ * of every owned replica in its current state until the RMS force component is below `tolerance` (kJ/mol/nm) or
+ * `max_iterations` steps were taken (0: the built-in cap of 20000).  Velocities are not touched.  rms_force[K] and
+ * iterations[K] (either may be NULL) are filled for the replicas this rank owns, zero elsewhere.                  */
+RX_API int rx_minimize(rx_engine *h, double tolerance, int32_t max_iterations, double *rms_force, int32_t *iterations);
 
 /* replica -> state map (MultiStateSampler._replica_thermodynamic_states, multistatesampler.py:895)       */
 RX_API int rx_set_replica_states(rx_engine *h, const int64_t *states /*[K]*/);

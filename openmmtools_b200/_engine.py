@@ -136,6 +136,12 @@ class Engine:
     def randomize_velocities(self, seed, stream=0):
         self._check(self._lib.rx_randomize_velocities(self._h, int(seed), int(stream)))
 
+    def minimize(self, tolerance, max_iterations=0):
+        """FIRE descent of the owned replicas; returns (rms force [K] in kJ/mol/nm, iterations taken [K])."""
+        rms, its = np.zeros(self.K), np.zeros(self.K, np.int32)
+        self._check(self._lib.rx_minimize(self._h, float(tolerance), int(max_iterations), _ptr(rms), _ptr(its)))
+        return rms, its
+
     def set_replica_states(self, states):
         s = np.ascontiguousarray(states, dtype=np.int64)
         if s.shape != (self.K,):

@@ -274,6 +274,26 @@ extern "C" int rx_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t str
     return rxi_randomize_velocities(h, seed, stream);
 }
 
+extern "C" int rx_minimize(rx_engine *h, double tolerance, int32_t max_iterations, double *rms_force, int32_t *iterations) {
+    ENTER(h);
+    if (!h->have_particles || !h->have_states) RX_FAIL(h, RX_ERR_INVALID, "rx_minimize: set particles and states first");
+    if (!(tolerance > 0.0)) RX_FAIL(h, RX_ERR_INVALID, "rx_minimize: tolerance must be positive");
+    if (max_iterations < 0) RX_FAIL(h, RX_ERR_INVALID, "rx_minimize: max_iterations must be >= 0");
+    const int K = h->cfg.n_replicas;
+    double *d_rms = nullptr;
+    int *d_it = nullptr;
+    RX_CHECK_CUDA(h, cudaMalloc(&d_rms, sizeof(double) * K));
+    if (cudaMalloc(&d_it, sizeof(int) * K) != cudaSuccess) { cudaFree(d_rms); RX_FAIL(h, RX_ERR_CUDA, "rx_minimize: out of device memory"); }
+    cudaMemsetAsync(d_rms, 0, sizeof(double) * K, h->stream);
+    cudaMemsetAsync(d_it, 0, sizeof(int) * K, h->stream);
+    int rc = rxi_minimize(h, tolerance, max_iterations == 0 ? 20000 : max_iterations, d_rms, d_it);
+    if (rc == RX_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "rx_minimize: kernel failed"; rc = RX_ERR_CUDA; }
+    if (rc == RX_OK && rms_force) cudaMemcpy(rms_force, d_rms, sizeof(double) * K, cudaMemcpyDeviceToHost);
+    if (rc == RX_OK && iterations) cudaMemcpy(iterations, d_it, sizeof(int) * K, cudaMemcpyDeviceToHost);
+    cudaFree(d_rms); cudaFree(d_it);
+    return rc;
+}
+
 extern "C" int rx_set_replica_states(rx_engine *h, const int64_t *states) {
     ENTER(h);
     const int K = h->cfg.n_replicas, M = h->cfg.n_states;

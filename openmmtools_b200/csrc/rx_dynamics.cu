@@ -698,6 +698,107 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     return RX_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Energy minimisation of every owned replica in its current state: MultiStateSampler.minimize
+// (multistatesampler.py:612-647) -> _minimize_replica (:1339-1402), which runs a FIRE descent first
+// (integrators.py FIREMinimizationIntegrator).  FIRE as published (Bitzek et al., PRL 97, 170201 (2006)):
+// semi-implicit Euler dynamics with the velocity steered towards the force, the time step grown while the power
+// F.v stays positive and the motion stopped when it turns negative; plus a cap on the displacement per step so the
+// overlapping starts of the reference's test systems cannot blow up.  One CTA per replica, one atom per thread,
+// all-pairs forces (this is a set-up step, not the hot path).  Velocities are left untouched.
+// ---------------------------------------------------------------------------------------------------
+template <bool C6, bool SW>
+__global__ void __launch_bounds__(1024) k_minimize(DynParams p, const float4 *__restrict__ atom,
+                                                   const StateDev *__restrict__ states, const int *__restrict__ perm,
+                                                   float4 *__restrict__ pos, int k0, float tol_rms, int max_iter,
+                                                   double *__restrict__ rms_out, int *__restrict__ iters_out) {
+    extern __shared__ float4 s_dyn[];
+    float4 *s_pos = s_dyn, *s_par = s_dyn + RX_MAX_ATOMS;
+    __shared__ float s_part[32][3];
+    __shared__ float s_sum[3];
+    const int r = blockIdx.x, k = k0 + r, t = threadIdx.x, nw = blockDim.x >> 5;
+    const bool active = t < p.N;
+    const StateDev st = states[perm[k]];
+    const float4 a4 = active ? atom[t] : make_float4(1.f, 0.f, 1.f, 0.f);
+    const float sig_i = a4.x, se_i = a4.y, inv_m = a4.z;
+    const bool alch_i = a4.w != 0.f;
+    const float4 x4 = active ? pos[(size_t)r * p.N + t] : make_float4(0, 0, 0, 0);
+    float x = x4.x, y = x4.y, z = x4.z, vx = 0.f, vy = 0.f, vz = 0.f;
+    if (active) { s_pos[t] = make_float4(x, y, z, sig_i); s_par[t] = make_float4(se_i, alch_i ? 1.f : 0.f, 0.f, 0.f); }
+    __syncthreads();
+    PairCtx pc;
+    pc.Lx = p.Lx; pc.Ly = p.Ly; pc.Lz = p.Lz; pc.iLx = p.iLx; pc.iLy = p.iLy; pc.iLz = p.iLz; pc.rc2 = p.rc2;
+    pc.sig_i = sig_i; pc.se_i = se_i; pc.alch_i = alch_i; pc.lam = {(float)st.la, (float)st.ob};
+    const unsigned pos_base = (unsigned)__cvta_generic_to_shared(s_dyn);
+    const float hx0 = (float)st.ho_x0[0], hx1 = (float)st.ho_x0[1], hx2 = (float)st.ho_x0[2], hK = (float)st.ho_K;
+    const float dt0 = 0.001f, dt_max = 0.010f, alpha0 = 0.1f, max_move = 0.01f;  // ps, ps, -, nm per step
+    float dt = dt0, alpha = alpha0;
+    int n_pos = 0, it = 0;
+    float rms = 0.f;
+    for (;;) {
+        float fx = 0.f, fy = 0.f, fz = 0.f, e = 0.f;
+        if (p.kind == RX_SYSTEM_HARMONIC) { fx = -hK * (x - hx0); fy = -hK * (y - hx1); fz = -hK * (z - hx2); }
+        else if (active) {
+            pc.x = x; pc.y = y; pc.z = z;
+            lj_forces<C6, SW, false>(p, pc, pos_base, 16 * RX_MAX_ATOMS, 0u, p.N, t, false, 0, fx, fy, fz, e);
+        }
+        if (!active) { fx = fy = fz = 0.f; }
+        // block sums of F.F, F.v, v.v (fixed order: deterministic)
+        float q0 = fx * fx + fy * fy + fz * fz, q1 = fx * vx + fy * vy + fz * vz, q2 = vx * vx + vy * vy + vz * vz;
+        for (int o = 16; o > 0; o >>= 1) {
+            q0 += __shfl_down_sync(0xffffffffu, q0, o); q1 += __shfl_down_sync(0xffffffffu, q1, o); q2 += __shfl_down_sync(0xffffffffu, q2, o);
+        }
+        if ((t & 31) == 0) { s_part[t >> 5][0] = q0; s_part[t >> 5][1] = q1; s_part[t >> 5][2] = q2; }
+        __syncthreads();  // also: every thread has finished reading the positions
+        if (t < 3) { float s = 0.f; for (int w = 0; w < nw; w++) s += s_part[w][t]; s_sum[t] = s; }
+        __syncthreads();
+        const float FF = s_sum[0], P = s_sum[1], VV = s_sum[2];
+        rms = sqrtf(FF / (3.0f * (float)p.N));
+        if (!(rms > tol_rms) || it >= max_iter) break;  // converged, out of iterations, or NaN
+        it++;
+        if (P > 0.f) {
+            const float mix = alpha * sqrtf(VV / fmaxf(FF, 1e-30f));
+            vx = (1.f - alpha) * vx + mix * fx; vy = (1.f - alpha) * vy + mix * fy; vz = (1.f - alpha) * vz + mix * fz;
+            if (++n_pos > 5) { dt = fminf(dt * 1.1f, dt_max); alpha *= 0.99f; }
+        } else {
+            vx = vy = vz = 0.f; dt *= 0.5f; alpha = alpha0; n_pos = 0;
+        }
+        vx += dt * fx * inv_m; vy += dt * fy * inv_m; vz += dt * fz * inv_m;
+        float mx = dt * vx, my = dt * vy, mz = dt * vz;
+        const float m2 = mx * mx + my * my + mz * mz;
+        if (m2 > max_move * max_move) {  // displacement cap: rescale this atom's velocity
+            const float sc = max_move * rsqrtf(m2);
+            vx *= sc; vy *= sc; vz *= sc; mx *= sc; my *= sc; mz *= sc;
+        }
+        x += mx; y += my; z += mz;
+        if (active) s_pos[t] = make_float4(x, y, z, sig_i);
+        __syncthreads();
+    }
+    if (t == 0) { rms_out[k] = (double)rms; iters_out[k] = it; }
+    if (active) {
+        if (p.kind != RX_SYSTEM_HARMONIC) { x -= p.Lx * floorf(x * p.iLx); y -= p.Ly * floorf(y * p.iLy); z -= p.Lz * floorf(z * p.iLz); }
+        pos[(size_t)r * p.N + t] = make_float4(x, y, z, 0.f);
+    }
+}
+
+int rxi_minimize(rx_engine *h, double tolerance, int max_iterations, double *d_rms, int *d_iters) {
+    if (h->kloc == 0) return RX_OK;
+    DynParams p;
+    fill_dyn(h, p);
+    const int N = h->cfg.n_atoms;
+    if (N > 1024) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_minimize: more than 1024 atoms per replica is not supported yet");
+    const int threads = ((N + 31) / 32) * 32;
+    const size_t smem = (size_t)2 * RX_MAX_ATOMS * sizeof(float4);
+#define RX_LAUNCH_MINIMIZE(C6, SW)                                                                                         \
+    k_minimize<C6, SW><<<h->kloc, threads, smem, h->stream>>>(p, h->d_atom, h->d_states, h->d_perm, h->d_pos, h->k0,       \
+                                                              (float)tolerance, max_iterations, d_rms, d_iters)
+    if (p.c_is_6) { if (p.use_switch) RX_LAUNCH_MINIMIZE(true, true); else RX_LAUNCH_MINIMIZE(true, false); }
+    else { if (p.use_switch) RX_LAUNCH_MINIMIZE(false, true); else RX_LAUNCH_MINIMIZE(false, false); }
+#undef RX_LAUNCH_MINIMIZE
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    return RX_OK;
+}
+
 int rxi_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream_id) {
     if (h->kloc == 0) return RX_OK;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));

@@ -427,9 +427,28 @@ class MultiStateSampler:
         if mcmc_moves is not None:
             self._engine.set_integrator(*self._mcmc_moves[0]._integrator_parameters())
 
-    def minimize(self, tolerance=None, max_iterations=0):
-        raise NotImplementedError('minimisation (FIRE/L-BFGS in OpenMM) is outside the hot path; the LJ and HO '
-                                  'configurations do not need it (testsystems.py:1877-1879)')
+    def minimize(self, tolerance=1.0 * unit.kilojoules_per_mole / unit.nanometers, max_iterations=0):
+        """Minimize all replicas, each in its current thermodynamic state (multistatesampler.py:611-647).
+
+        One fused FIRE launch (``rx_minimize``) in place of the per-replica FIRE -> L-BFGS of
+        ``_minimize_replica`` (multistatesampler.py:1339-1402); ``tolerance`` bounds the RMS force component.
+        Minimized positions are stored at the end, velocities are left as they are.
+        """
+        if self._engine is None or self.n_replicas == 0:
+            raise RuntimeError('Cannot minimize replicas. The simulation must be created first.')
+        tol = float(unit.to_md(tolerance, unit.kilojoules_per_mole / unit.nanometers, 'tolerance'))
+        e = self._engine
+        self._sync_sampler_states()
+        rms, n_it = e.minimize(tol, max_iterations)
+        x = e.get_positions()
+        for r, k in enumerate(range(e.k0, e.k1)):
+            self._sampler_states[k].positions = unit.Quantity(x[r], unit.nanometer)
+        self._last_minimization = {'rms_force': rms[e.k0:e.k1].copy(), 'iterations': n_it[e.k0:e.k1].copy()}
+        if self._reporter is not None:
+            if self._world_size > 1:
+                self._gather_sampler_states()
+            if self._rank == 0:
+                self._reporter.write_sampler_states(self._sampler_states, self._iteration, extra=self._checkpoint_extra())
 
     # ------------------------------------------------------------------ the three hooks
     def _mix_replicas(self):

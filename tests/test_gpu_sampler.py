@@ -220,3 +220,50 @@ def test_locality_neighborhoods():
     t, _, _ = lj_sampler(K=16, scheme='swap-neighbors', seed=6)
     t.run(4)
     assert np.array_equal(s._replica_thermodynamic_states, t._replica_thermodynamic_states)
+
+
+def test_minimize_lowers_energy_and_meets_force_tolerance():
+    """MultiStateSampler.minimize (multistatesampler.py:611-647): every replica is relaxed in its own state until the
+    RMS force component is below the tolerance; checked with the oracle's f64 forces on the returned positions."""
+    from oracle import oracle
+    K = 4
+    s, asys, lambdas = lj_sampler(K=K, N=128, n_steps=5)
+    with pytest.raises(TypeError):
+        s.minimize(tolerance=1.0 * unit.nanometer)
+    L = asys.box_vectors[0, 0]
+    osys = oracle.LJSystem(asys.sigma, asys.epsilon, asys.masses, asys.alchemical_mask(), (L, L, L), asys.cutoff,
+                           asys.switching_distance, use_switch=True)
+    x0 = np.stack([st.positions.value_in_unit(unit.nanometer) for st in s.sampler_states])
+    v0 = [st.velocities for st in s.sampler_states]
+    tol = 5.0
+    s.minimize(tolerance=tol * unit.kilojoules_per_mole / unit.nanometers)
+    x1 = np.stack([st.positions.value_in_unit(unit.nanometer) for st in s.sampler_states])
+    assert np.all(np.isfinite(x1)) and np.all(x1 >= 0) and np.all(x1 <= L)
+    for k in range(K):
+        e0 = osys.energy(x0[k], lambdas[k])[0]
+        e1, _, f1 = osys.energy(x1[k], lambdas[k], forces=True)
+        assert e1 < e0, (k, e0, e1)
+        rms = np.sqrt(np.mean(np.asarray(f1) ** 2))
+        assert rms < tol * 1.02, (k, rms)
+        assert s.sampler_states[k].potential_energy is None  # new positions invalidate the cached energy
+    info = s._last_minimization
+    assert np.all(info['rms_force'] <= tol) and np.all(info['iterations'] > 0)
+    for a, b in zip(v0, [st.velocities for st in s.sampler_states]):
+        assert (a is None and b is None) or np.array_equal(a.value_in_unit(a.unit), b.value_in_unit(b.unit))
+    # a capped descent stops at max_iterations
+    s.minimize(tolerance=1e-6 * unit.kilojoules_per_mole / unit.nanometers, max_iterations=7)
+    assert np.all(s._last_minimization['iterations'] == 7)
+    s.run(1)  # the sampler continues from the minimized configuration
+    assert s.iteration == 1
+
+
+def test_minimize_harmonic_oscillator_reaches_the_well():
+    ho = testsystems.HarmonicOscillator()
+    x = np.array([[0.3, -0.2, 0.1]])
+    hs = multistate.ReplicaExchangeSampler(mcmc_moves=mcmc.LangevinSplittingDynamicsMove(n_steps=5), number_of_iterations=2, seed=3)
+    hs.create([states.ThermodynamicState(ho.system, T * unit.kelvin) for T in (300, 320)],
+              [states.SamplerState(unit.Quantity(x, unit.nanometer))])
+    hs.minimize(tolerance=0.5 * unit.kilojoules_per_mole / unit.nanometers)
+    for st in hs.sampler_states:
+        r = np.linalg.norm(st.positions.value_in_unit(unit.nanometer))
+        assert r < 0.3 * 0.01, r
