@@ -105,3 +105,54 @@ def test_harmonic_oscillator_steps():
             ref = (0.5 * Ks[l] * ((xg[k][0] - x0s[l]) ** 2).sum() + [0.0, 1.0, 2.0][l]) / (KB * temps[l])
             assert abs(u[k, l] - ref) < 1e-5 * max(1, abs(ref))
     e.close()
+
+
+def test_neighbour_list_run_equals_all_pairs_run(monkeypatch):
+    """300 hot 2-fs steps (the inner list is re-partitioned many times, the outer list rebuilt, atoms re-dealt to
+    threads) against the same launch with the all-pairs force loop: a pair missing from a list would show up as a
+    different trajectory; only the float32 summation order differs between the two."""
+    N, K, M = 256, 3, 3
+    s = lj_setup(N=N, n_alch=6, seed=21)
+    lambdas = np.array([1.0, 0.5, 0.0]); temps = np.array([600.0, 600.0, 600.0])
+    rng = np.random.default_rng(5)
+    v0 = rng.normal(scale=0.35, size=(K, N, 3)).astype(np.float32).astype(np.float64)
+    out = []
+    for no_list in (False, True):
+        if no_list:
+            monkeypatch.setenv('RX_NO_VERLET', '1')
+        e = make_engine(s, K, M, lambdas, temps, 0.002, 1.0, 300, 'V R O R V')
+        e.set_positions(np.stack([s['x']] * K)); e.set_velocities(v0)
+        e.set_replica_states(np.arange(K))
+        e.propagate(99, 3)
+        out.append((e.get_positions(), e.get_velocities(), e.get_replica_energies()[0]))
+        e.close()
+    (xa, va, pa), (xb, vb, pb) = out
+    d = xa - xb
+    d -= s['L'] * np.round(d / s['L'])
+    assert np.abs(d).max() < 2e-3, np.abs(d).max()           # chaotic growth of float32 round-off, not a missed pair
+    assert np.median(np.abs(d)) < 2e-5
+    assert np.abs(pa - pb).max() < 0.05 * max(1.0, np.abs(pb).max())
+
+
+def test_dense_fluid_falls_back_to_all_pairs_and_matches_oracle():
+    """Liquid density: more neighbours than a list column holds -> the CTA switches to the all-pairs loop."""
+    N, K, M = 256, 2, 2
+    s = lj_setup(N=N, n_alch=4, reduced_density=0.6, seed=31)
+    lambdas = np.array([1.0, 0.4]); temps = np.array([300.0, 300.0])
+    dt, gamma, n_steps = 0.001, 10.0, 4
+    e = make_engine(s, K, M, lambdas, temps, dt, gamma, n_steps, 'V R O R V')
+    x0 = np.stack([s['x']] * K)
+    v0 = np.random.default_rng(8).normal(scale=0.2, size=(K, N, 3)).astype(np.float32).astype(np.float64)
+    e.set_positions(x0); e.set_velocities(v0); e.set_replica_states(np.arange(K))
+    e.propagate(5, 1)
+    xg, vg = e.get_positions(), e.get_velocities()
+    osys = oracle_system(s)
+    for k in range(K):
+        x = x0[k].copy(); v = v0[k].copy()
+        osys.langevin(x, v, device_noise(5, 1, k, N, n_steps), lambdas[k], KB * temps[k], dt, gamma, n_steps, 'VRORV')
+        d = xg[k] - (x - s['L'] * np.floor(x / s['L']))
+        d -= s['L'] * np.round(d / s['L'])
+        assert np.abs(d).max() < 5e-5, (k, np.abs(d).max())
+        # forces of a dense, roughly packed start are large: velocities to float32 accuracy of those forces
+        assert np.abs(vg[k] - v).max() < 1e-3 * max(1.0, np.abs(v).max()), (k, np.abs(vg[k] - v).max())
+    e.close()
