@@ -236,6 +236,8 @@ class MultiStateReporter:
 
     # -- online analysis data (reference: write_online_analysis_data / read_online_analysis_data, used by SAMS)
     def write_online_analysis_data(self, iteration, **kwargs):
+        """Per-iteration record of each keyword, or -- ``iteration=None`` -- one static record that is overwritten
+        (multistatereporter.py:1204-1339)."""
         d = os.path.join(self._storage, 'analysis', 'online')
         os.makedirs(d, exist_ok=True)
         for name, value in kwargs.items():
@@ -244,11 +246,16 @@ class MultiStateReporter:
             if name not in spec:
                 spec[name] = {'dtype': a.dtype.str, 'shape': list(a.shape)}
                 self._write_meta()
-            path = os.path.join(d, name + '.bin')
+            path = os.path.join(d, name + ('.static.bin' if iteration is None else '.bin'))
             with open(path, 'r+b' if os.path.exists(path) else 'w+b') as f:
-                f.seek(int(iteration) * a.nbytes)
+                f.seek(0 if iteration is None else int(iteration) * a.nbytes)
                 f.write(a.tobytes())
             self._dirty.add(path)
+
+    def write_online_data_dynamic_and_static(self, iteration, **kwargs):
+        """multistatereporter.py:1341-1351"""
+        self.write_online_analysis_data(None, **kwargs)
+        self.write_online_analysis_data(iteration, **kwargs)
 
     def read_online_analysis_data(self, iteration, *keys):
         out = {}
@@ -258,10 +265,10 @@ class MultiStateReporter:
                 raise KeyError(name)
             dt = np.dtype(spec['dtype']); shape = tuple(spec['shape'])
             n = int(np.prod(shape)) if shape else 1
-            path = os.path.join(self._storage, 'analysis', 'online', name + '.bin')
+            path = os.path.join(self._storage, 'analysis', 'online', name + ('.static.bin' if iteration is None else '.bin'))
             data = np.fromfile(path, dtype=dt)
             data = data[:(data.size // n) * n].reshape((-1,) + shape)
-            out[name] = data[iteration]
+            out[name] = data[0 if iteration is None else iteration]
         return out
 
     # -- checkpoints

@@ -68,6 +68,8 @@ class MultiStateSampler:
         self.online_analysis_target_error = online_analysis_target_error
         self.online_analysis_minimum_iterations = online_analysis_minimum_iterations
         self.locality = locality
+        self._last_mbar_f_k = None
+        self._last_err_free_energy = None
         self.host_resident_states = host_resident_states
         self.energy_context_cache = ContextCache()
         self.sampler_context_cache = ContextCache()
@@ -208,6 +210,10 @@ class MultiStateSampler:
         self._n_proposed_matrix = np.array(npr, dtype=np.int64)
         self._metadata = metadata
         self._timing_data = dict()
+        try:  # the online free-energy estimate of the checkpoint iteration (multistatesampler.py:1697-1718)
+            self._last_mbar_f_k = np.array(reporter.read_online_analysis_data(int(checkpoint), 'f_k')['f_k'])
+        except (KeyError, IndexError, FileNotFoundError):
+            self._last_mbar_f_k = None
         if isinstance(self._mcmc_moves, mcmc.MCMCMove):
             self._mcmc_moves = [copy.deepcopy(self._mcmc_moves) for _ in thermodynamic_states]
         self._reporter = reporter
@@ -399,6 +405,7 @@ class MultiStateSampler:
             self._compute_energies()
             t3 = time.time()
             self._report_iteration()
+            self._update_analysis()
             self._update_timing(t3 - t0, time.time() - timer_start, run_initial_iteration, iteration_limit,
                                 phases=(t1 - t0, t2 - t1, t3 - t2))
             self._check_nan_energy()
@@ -579,6 +586,49 @@ class MultiStateSampler:
             for part in gathered:
                 for k, x, v, pe, ke in part:
                     self._sampler_states[k]._update(x, v, pe, ke)
+
+    # ------------------------------------------------------------------ online analysis (multistatesampler.py:1625-1695)
+    @staticmethod
+    def _online_f_k_update(f_k, u, replica_states, locality, iteration, gamma0=1.0):
+        """One stochastic-approximation step of the online free-energy estimate (multistatesampler.py:1625-1664):
+        every replica adds gamma * P(l | x_k) over its neighbourhood to logZ_l, gamma = gamma0 / (iteration + 1), then
+        logZ is shifted so that logZ_0 = 0.  Returns the new f_k = -logZ."""
+        u = np.asarray(u, dtype=np.float64)
+        K, M = u.shape
+        st = np.asarray(replica_states)
+        logZ = -np.asarray(f_k, dtype=np.float64)
+        if locality is None:
+            mask = np.ones((K, M), dtype=bool)
+        else:
+            l = np.arange(M)[None, :]
+            mask = (l >= st[:, None] - locality) & (l <= st[:, None] + locality)
+        log_p = np.where(mask, -u, -np.inf)
+        top = log_p.max(axis=1, keepdims=True)
+        p = np.exp(log_p - top)
+        p /= p.sum(axis=1, keepdims=True)
+        logZ = logZ + (gamma0 / float(iteration + 1)) * p.sum(axis=0)
+        return -(logZ - logZ[0])
+
+    def _online_analysis(self, gamma0=1.0):
+        if self._last_mbar_f_k is None:
+            self._last_mbar_f_k = np.zeros(self.n_states)
+        self._last_mbar_f_k = self._online_f_k_update(self._last_mbar_f_k, self._energy_thermodynamic_states,
+                                                      self._replica_thermodynamic_states, self.locality,
+                                                      self._iteration, gamma0)
+        self._last_err_free_energy = np.inf
+        if self._reporter is not None and self._rank == 0:
+            free_energy = self._last_mbar_f_k[-1] - self._last_mbar_f_k[0]
+            self._reporter.write_online_data_dynamic_and_static(
+                self._iteration, f_k=self._last_mbar_f_k, free_energy=np.array([free_energy, self._last_err_free_energy]))
+        return self._last_err_free_energy
+
+    def _update_analysis(self):
+        """multistatesampler.py:1676-1695.  The cheap online estimate runs every iteration; the periodic offline MBAR
+        pass of the reference (MultiStateSamplerAnalyzer, every ``online_analysis_interval`` iterations) is outside
+        the hot path and not run, so the error estimate stays +inf and never ends a run early."""
+        if self.online_analysis_interval is None:
+            return
+        self._last_err_free_energy = self._online_analysis()
 
     def _is_completed(self, iteration_limit=None):
         if iteration_limit is None:

@@ -40,3 +40,18 @@ def energies(model, K, key):
         a = 2.0 * pseudo_normal(K, key)
         return -600.0 + a[:, None] * lam[None, :]
     raise ValueError(model)
+
+
+def ladder_energies(it, K, M, key):
+    """u[k, l] of iteration `it` for the SAMS / online-analysis goldens: harmonic-ish ladder plus iteration
+    dependent noise (exact arithmetic only)."""
+    import numpy as np
+    x = pseudo_normal(K, key * 1000 + it)
+    mu = 0.7 * np.arange(M, dtype=np.float64)
+    return 0.5 * (3.0 * x[:, None] - mu[None, :]) ** 2 * 0.1 + 0.05 * mu[None, :]
+
+
+def ladder_states(it, K, M, key):
+    """A deterministic replica -> state map of iteration `it` (not a permutation: the online update does not need one)."""
+    import numpy as np
+    return (np.floor(np.abs(pseudo_normal(K, key * 77 + it)) * 1e6).astype(np.int64) + it) % M

@@ -216,3 +216,24 @@ def test_harmonic_oscillator_system():
     ts = states.ThermodynamicState(ho.system, 300 * unit.kelvin)
     assert not ts.is_periodic and ts.n_particles == 1
     assert ho.get_potential_expectation(ts).value_in_unit(unit.kilojoule_per_mole) == pytest.approx(1.5 * 8.31446261815324e-3 * 300)
+
+
+def test_online_free_energy_update_matches_reference_golden():
+    """MultiStateSampler._online_analysis (multistatesampler.py:1625-1664) lifted from the reference and run on
+    synthetic energies (tests/golden/make_online_golden.py): 40 iterations, global and local neighbourhoods."""
+    import os, sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    sys.path.insert(0, here)
+    from energy_models import ladder_energies as energies_for, ladder_states as states_for
+    from openmmtools_b200.multistate import MultiStateSampler
+    g = np.load(os.path.join(here, 'online_golden.npz'))
+    for tag in g['cases']:
+        tag = str(tag)
+        hist, key = g[tag + '_f_k'], int(g[tag + '_key'])
+        K, M = int(tag.split('_K')[1].split('_')[0]), hist.shape[1]
+        loc = tag.split('_loc')[1]
+        loc = None if loc == 'None' else int(loc)
+        f_k = np.zeros(M)
+        for it in range(1, hist.shape[0] + 1):
+            f_k = MultiStateSampler._online_f_k_update(f_k, energies_for(it, K, M, key), states_for(it, K, M, key), loc, it)
+            assert np.abs(f_k - hist[it - 1]).max() < 1e-12, (tag, it)

@@ -100,6 +100,13 @@ def test_resume_is_bit_identical_to_uninterrupted_run(tmp_path):
     assert np.array_equal(c._replica_thermodynamic_states, pa)
     assert np.array_equal(c._energy_thermodynamic_states, ua)
     assert np.array_equal(np.stack([s._positions for s in c.sampler_states]), xa)
+    # the online free-energy estimate (multistatesampler.py:1625-1664) is stored per iteration and carried over the resume
+    assert a._last_mbar_f_k.shape == (K,) and a._last_mbar_f_k[0] == 0.0 and np.all(np.isfinite(a._last_mbar_f_k))
+    assert np.array_equal(c._last_mbar_f_k, a._last_mbar_f_k)
+    assert np.array_equal(ra.read_online_analysis_data(6, 'f_k')['f_k'], a._last_mbar_f_k)
+    assert np.array_equal(ra.read_online_analysis_data(None, 'f_k')['f_k'], a._last_mbar_f_k)
+    fe = ra.read_online_analysis_data(6, 'free_energy')['free_energy']
+    assert fe[0] == a._last_mbar_f_k[-1] and np.isinf(fe[1])
     rb = MultiStateReporter(str(tmp_path / 'b.store'), open_mode='r')
     for it in range(7):
         assert np.array_equal(rb.read_energies(it)[0], ra.read_energies(it)[0]), it
