@@ -156,3 +156,35 @@ def test_dense_fluid_falls_back_to_all_pairs_and_matches_oracle():
         # forces of a dense, roughly packed start are large: velocities to float32 accuracy of those forces
         assert np.abs(vg[k] - v).max() < 1e-3 * max(1.0, np.abs(v).max()), (k, np.abs(vg[k] - v).max())
     e.close()
+
+
+@pytest.mark.parametrize('use_switch,annihilate,alpha,a,b,c', [(False, False, 0.5, 1.0, 1.0, 6.0), (True, True, 0.5, 1.0, 1.0, 6.0),
+                                                                (True, False, 0.3, 2.0, 1.5, 12.0), (False, True, 0.7, 1.0, 2.0, 4.0)])
+def test_pair_kernel_variants_match_oracle(use_switch, annihilate, alpha, a, b, c):
+    """Every specialisation of the pair function (switch on/off, softcore_c == 6 or not) and the annihilating A-A
+    pairs, 6 steps against the oracle with the same noise (alchemy.py:1383-1388 energy expression)."""
+    N, K, M = 256, 3, 3
+    s = lj_setup(N=N, n_alch=8, seed=41)
+    lambdas = np.array([0.8, 0.45, 0.1]); temps = np.array([300.0, 300.0, 300.0])
+    dt, gamma, n_steps = 0.002, 5.0, 6
+    e = gpu_engine(1, K, M, N, box=(s['L'],) * 3, r_cutoff=s['rc'], r_switch=s['rs'], use_switch=use_switch,
+                   annihilate_sterics=annihilate, softcore_alpha=alpha, softcore_a=a, softcore_b=b, softcore_c=c)
+    e.set_particles(s['sigma'], s['eps'], s['mass'], s['alch'])
+    e.set_states(temps, lambdas)
+    e.set_integrator(dt, gamma, n_steps, 'V R O R V')
+    x0 = np.stack([s['x']] * K)
+    v0 = np.random.default_rng(3).normal(scale=0.25, size=(K, N, 3)).astype(np.float32).astype(np.float64)
+    e.set_positions(x0); e.set_velocities(v0); e.set_replica_states(np.arange(K))
+    e.propagate(11, 2)
+    xg, vg = e.get_positions(), e.get_velocities()
+    pot = e.get_replica_energies()[0]
+    osys = oracle_system(s, annihilate=annihilate, alpha=alpha, a=a, b=b, c=c, use_switch=use_switch)
+    for k in range(K):
+        x = x0[k].copy(); v = v0[k].copy()
+        U = osys.langevin(x, v, device_noise(11, 2, k, N, n_steps), lambdas[k], KB * temps[k], dt, gamma, n_steps, 'VRORV')
+        d = xg[k] - (x - s['L'] * np.floor(x / s['L']))
+        d -= s['L'] * np.round(d / s['L'])
+        assert np.abs(d).max() < 2e-5, (k, np.abs(d).max())
+        assert np.abs(vg[k] - v).max() < 3e-4, (k, np.abs(vg[k] - v).max())
+        assert abs(pot[k] - U) < 2e-3 * max(1.0, abs(U)), (pot[k], U)
+    e.close()
