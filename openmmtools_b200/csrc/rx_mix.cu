@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const int st = perm_g[q];
         s_perm[q] = st;
         s_diag[q] = u[((size_t)q << logK) + st];
-        if (UMODE == U_FILTER24) s_rowabs[q] = filt_rowabs[q];
+        if (UMODE == U_FILTER24) ((float *)s_rowabs)[q] = __double2float_ru(filt_rowabs[q]);  // f32, rounded up
     }
     if (UMODE == U_F64_SMEM)
         for (int q = tid; q < K * K; q += 64) s_u[q] = u[q];
@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
                     const unsigned o = b * 32 + lane;
                     if (o < cnt) {
                         const unsigned w = (prod + o) & (RING - 1);
-                        ring_ij[w] = r[b].ij; ring_bm[w] = r[b].backmask; ring_lu[w] = r[b].logU;
+                        ring_ij[w] = r[b].ij; ring_bm[w] = r[b].backmask;
+                        if (UMODE == U_FILTER24) ((float *)ring_lu)[w] = (float)r[b].logU;   // the filter works in f32
+                        else ring_lu[w] = r[b].logU;
                     }
                 }
                 prod += cnt;
@@ -249,7 +251,8 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         }
         const unsigned w = (h + lane) & (RING - 1);
         const uint32_t ij = ring_ij[w], backmask = ring_bm[w];
-        const double logU_next = ring_lu[(w + 1) & (RING - 1)];  // the uniform an attempt here would draw: NEXT slot
+        // the uniform an attempt here would draw belongs to the NEXT slot
+        const double logU_next = (UMODE == U_FILTER24) ? 0.0 : ring_lu[(w + 1) & (RING - 1)];
         const unsigned i = ij & 0xffffu, j = ij >> 16;
         const int si = s_perm[i], sj = s_perm[j];
         const unsigned a_ij = (i << logK) | (unsigned)sj, a_ji = (j << logK) | (unsigned)si;
@@ -262,14 +265,18 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             const float f_ij = __uint_as_float(((unsigned)s_qhi[a_ij] << 16) | ((unsigned)s_qlo[a_ij] << 8));
             const float f_jj = __uint_as_float(((unsigned)s_qhi[a_jj] << 16) | ((unsigned)s_qlo[a_jj] << 8));
             const float f_ji = __uint_as_float(((unsigned)s_qhi[a_ji] << 16) | ((unsigned)s_qlo[a_ji] << 8));
-            const double lp = ((double)f_ii - (double)f_ij) + ((double)f_jj - (double)f_ji);
-            // every image value is within 2^-15 (relative) of the true delta: truncation to a 15-bit mantissa + f32 rounding
-            // ... plus the f64 rounding of the reference's own three additions and of our centring (<= 64 ulp of the magnitudes)
-            const double mag = (double)(fabsf(f_ii) + fabsf(f_ij) + fabsf(f_jj) + fabsf(f_ji));
-            const double eps = mag * 3.2e-5 + 1.5e-14 * (mag + s_rowabs[i] + s_rowabs[j] + 1.0);
-            const double d = lp - logU_next;
+            // All in f32.  Every image value is within 2^-15 (relative) of the true delta (truncation to a 15-bit
+            // mantissa + f32 rounding); the f32 additions below add at most 2^-23 of the magnitudes; the f64 rounding
+            // of the reference's own three additions and of our centring is <= 64 ulp(f64) of the magnitudes.
+            const float lp = (f_ii - f_ij) + (f_jj - f_ji);
+            const float mag = fabsf(f_ii) + fabsf(f_ij) + fabsf(f_jj) + fabsf(f_ji);
+            const float eps = mag * 3.2e-5f + 1.6e-14f * (mag + ((const float *)s_rowabs)[i] + ((const float *)s_rowabs)[j] + 1.0f);
+            // log of the uniform, rounded to f32 by the producer: |lu - logU| <= 2^-24 |lu|; d carries one more rounding
+            const float lu = ((const float *)ring_lu)[(w + 1) & (RING - 1)];
+            const float d = lp - lu;
+            const float mar = eps + 1e-9f + 1.3e-7f * (fabsf(lp) + fabsf(lu));
             const bool sure_ge0 = lp > eps, sure_neg = lp < -eps;
-            const bool sure_acc = d > eps + 1e-9, sure_rej = d < -(eps + 1e-9);
+            const bool sure_acc = d > mar, sure_rej = d < -mar;
             // i == j: the reference's log_p is exactly 0 for finite energies (-(e+e)+e+e), accepted without a draw
             const bool same = (i == j) && (fabsf(f_ii) <= 3.0e38f);
             ge0 = sure_ge0 || same;
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
                     ge0 = logp >= 0.0;
                     acc = ge0;
                     if (!ge0) {
-                        const double dd = logp - logU_next;
+                        const double dd = logp - rec[h + lane + 1].logU;
                         if (dd > 1e-9) acc = true;
                         else if (dd < -1e-9) acc = false;
                         else { const unsigned s1 = h + lane + 1; acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp); }
