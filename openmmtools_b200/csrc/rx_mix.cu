@@ -14,6 +14,7 @@
 // permutation, the visited-slot chain is resolved with a carry-propagation bit trick, and the longest prefix
 // in which no visited slot touches a replica swapped earlier in the same window is committed.
 #include "rx_internal.cuh"
+#include <type_traits>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -243,12 +244,10 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     const unsigned sh_amt = lane ? (32 - lane) : 31, lane_nz = lane ? 0xffffffffu : 0u;
     const unsigned short *s_qhi = (const unsigned short *)s_q;            // [K*K] sign, exponent, 7 mantissa bits
     const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;                  // [K*K] next 8 mantissa bits
-    while (rem > 0 && h + 33 <= nslots) {
+    // One round.  TAIL = the launch's attempt budget may end inside the window (checked only in the last rounds).
+    auto round = [&](auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
         rounds++;
-        if (prod_seen < h + 33) {
-            do { prod_seen = sh.prod; } while (prod_seen < h + 33);   // the producer is behind (start of a pass)
-            asm volatile("" ::: "memory");
-        }
         const unsigned w = (h + lane) & (RING - 1);
         const uint32_t ij = ring_ij[w], backmask = ring_bm[w];
         // the uniform an attempt here would draw belongs to the NEXT slot
@@ -333,7 +332,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         unsigned n = __popc(cm);
         // bit 32 (even position) of the skip word can only be set by the carry of an odd-start run
         unsigned advance = C ? (unsigned)__popc(low - 1u) : 32u + (sumO < X ? 1u : 0u);
-        if (n > rem) {
+        if (TAIL && n > rem) {
             unsigned pos = 0;  // the first visited lane we must NOT run: the (rem+1)-th set bit of cm
             for (unsigned cnt = 0; pos < 32; pos++)
                 if ((cm >> pos) & 1u) { if (cnt == rem) break; cnt++; }
@@ -341,20 +340,32 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             n = rem;
             advance = pos;
         }
-        if ((cm >> lane) & 1u) {
-            commit_log[logpos + __popc(cm & lt_mask)] =
-                (uint32_t)si | ((uint32_t)sj << LOG_STATE_BITS) | ((acc ? 1u : 0u) << LOG_ACC_BIT);
-            if (acc && i != j) {  // an i == j lane must not write: a later committed lane may swap this replica
-                s_perm[i] = sj;
-                s_perm[j] = si;
-                if (UMODE != U_FILTER24) { s_diag[i] = e_ij; s_diag[j] = e_ji; }   // the image needs no f64 diagonal
-            }
-        }
+        // commit: everything is computed by every lane, only the stores are predicated (no divergent block)
+        const bool mine = (cm >> lane) & 1u;
+        const unsigned log_at = logpos + __popc(cm & lt_mask);
+        const uint32_t entry = (uint32_t)si | ((uint32_t)sj << LOG_STATE_BITS) | ((acc ? 1u : 0u) << LOG_ACC_BIT);
+        const bool swaps = mine && acc && i != j;  // an i == j lane must not write: a later committed lane may swap this replica
+        if (mine) commit_log[log_at] = entry;
+        if (swaps) { s_perm[i] = sj; s_perm[j] = si; }
+        if (UMODE != U_FILTER24) { if (swaps) { s_diag[i] = e_ij; s_diag[j] = e_ji; } }   // the image needs no f64 diagonal
         logpos += n;
         h += advance;
         rem -= n;
         if ((rounds & 7u) == 0u && lane == 0) sh.head = h;
         __syncwarp();
+    };
+    while (rem > 0 && h + 33 <= nslots) {
+        if (prod_seen < h + 33) {
+            do { prod_seen = sh.prod; } while (prod_seen < h + 33);   // the producer is behind (start of a pass)
+            asm volatile("" ::: "memory");
+        }
+        if (rem >= 33) {
+            // main loop: a round commits at most 32 attempts, so the budget cannot end inside it, and the slots
+            // [h, prod_seen) are in the ring: one loop condition covers the producer, the budget and the end of the pass
+            do { round(std::false_type()); } while (rem >= 33 && h + 33 <= prod_seen);
+        } else {
+            round(std::true_type());
+        }
     }
     if (lane == 0) sh.done = 1;
     for (int q = lane; q < K; q += 32) perm_g[q] = s_perm[q];
