@@ -34,7 +34,7 @@ struct MTStream {
 
 struct SlotRec {        // one 2-word "slot" of the stream, state independent (pow2 K fast path)
     uint32_t ij;        // i | j << 16 (masked replica indices)
-    uint32_t backmask;  // bit b: slot s-1-b shares a replica index with slot s
+    uint32_t backmask;  // bit 31-b: slot s-1-b shares a replica index with slot s (b = 0..30)
     double logU;        // log of the uniform the two words of THIS slot would produce
 };
 

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_slots_build(const uint32_t *__restrict_
         uint32_t o = s_ij[t + 32 - 1 - b];
         uint32_t oi = o & 0xffffu, oj = o >> 16;
         bool hit = (o != 0xffffffffu) && (oi == i || oi == j || oj == i || oj == j);
-        bm |= (hit ? 1u : 0u) << b;
+        bm |= (hit ? 1u : 0u) << (31 - b);
     }
     double U = mt_double(w0, w1);
     SlotRec r;
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const int st = perm_g[q];
         s_perm[q] = st;
         s_diag[q] = u[((size_t)q << logK) + st];
-        if (UMODE == U_FILTER24) ((float *)s_rowabs)[q] = __double2float_ru(filt_rowabs[q]);  // f32, rounded up
+        // per-row share of the f64-rounding bound, f32 rounded up: 1.6e-14 (|row minimum| + 1/2)
+        if (UMODE == U_FILTER24) ((float *)s_rowabs)[q] = __fmul_ru(1.6e-14f, __fadd_ru(__double2float_ru(filt_rowabs[q]), 0.5f));
     }
     if (UMODE == U_F64_SMEM)
         for (int q = tid; q < K * K; q += 64) s_u[q] = u[q];
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     const unsigned rem0 = rem;
     unsigned logpos = 0, rounds = 0, slow = 0, prod_seen = head0;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned sh_amt = lane ? (32 - lane) : 31, lane_nz = lane ? 0xffffffffu : 0u;
+    const unsigned sh_amt = 32u - (unsigned)lane;
     const unsigned short *s_qhi = (const unsigned short *)s_q;            // [K*K] sign, exponent, 7 mantissa bits
     const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;                  // [K*K] next 8 mantissa bits
     // One round.  TAIL = the launch's attempt budget may end inside the window (checked only in the last rounds).
@@ -260,16 +261,17 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         if (UMODE == U_FILTER24) {
             // image of u: 24-bit floats of delta = u - rowmin; logp~ = (d_ii - d_ij) + (d_jj - d_ji), |logp~ - logp_ref| <= eps
             const unsigned a_ii = (i << logK) | (unsigned)si, a_jj = (j << logK) | (unsigned)sj;
-            const float f_ii = __uint_as_float(((unsigned)s_qhi[a_ii] << 16) | ((unsigned)s_qlo[a_ii] << 8));
-            const float f_ij = __uint_as_float(((unsigned)s_qhi[a_ij] << 16) | ((unsigned)s_qlo[a_ij] << 8));
-            const float f_jj = __uint_as_float(((unsigned)s_qhi[a_jj] << 16) | ((unsigned)s_qlo[a_jj] << 8));
-            const float f_ji = __uint_as_float(((unsigned)s_qhi[a_ji] << 16) | ((unsigned)s_qlo[a_ji] << 8));
+            // (hi << 16) | (lo << 8) in one byte permute
+            const float f_ii = __uint_as_float(__byte_perm((unsigned)s_qhi[a_ii], (unsigned)s_qlo[a_ii], 0x1045));
+            const float f_ij = __uint_as_float(__byte_perm((unsigned)s_qhi[a_ij], (unsigned)s_qlo[a_ij], 0x1045));
+            const float f_jj = __uint_as_float(__byte_perm((unsigned)s_qhi[a_jj], (unsigned)s_qlo[a_jj], 0x1045));
+            const float f_ji = __uint_as_float(__byte_perm((unsigned)s_qhi[a_ji], (unsigned)s_qlo[a_ji], 0x1045));
             // All in f32.  Every image value is within 2^-15 (relative) of the true delta (truncation to a 15-bit
             // mantissa + f32 rounding); the f32 additions below add at most 2^-23 of the magnitudes; the f64 rounding
             // of the reference's own three additions and of our centring is <= 64 ulp(f64) of the magnitudes.
             const float lp = (f_ii - f_ij) + (f_jj - f_ji);
             const float mag = fabsf(f_ii) + fabsf(f_ij) + fabsf(f_jj) + fabsf(f_ji);
-            const float eps = mag * 3.2e-5f + 1.6e-14f * (mag + ((const float *)s_rowabs)[i] + ((const float *)s_rowabs)[j] + 1.0f);
+            const float eps = mag * 3.2e-5f + (((const float *)s_rowabs)[i] + ((const float *)s_rowabs)[j]);   // 1.6e-14 mag is inside the slack of 3.2e-5
             // log of the uniform, rounded to f32 by the producer: |lu - logU| <= 2^-24 |lu|; d carries one more rounding
             const float lu = ((const float *)ring_lu)[(w + 1) & (RING - 1)];
             const float d = lp - lu;
@@ -325,7 +327,8 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const unsigned V = ~skip;
         const unsigned VA = V & A & ~E;  // visited, accepted, really changing the permutation
         // lane t is stale if an earlier visited state-changing swap in this window shares a replica with it
-        const unsigned earlier = (__brev(VA) >> sh_amt) & lane_nz;
+        unsigned earlier;   // bit 31-b: lane t-1-b is a visited state-changing swap (shl by 32 gives 0 for lane 0)
+        asm("shl.b32 %0, %1, %2;" : "=r"(earlier) : "r"(VA), "r"(sh_amt));
         const unsigned C = __ballot_sync(0xffffffffu, (earlier & backmask) != 0u) & V;
         const unsigned low = C & (0u - C);
         unsigned cm = V & (low - 1u);           // low == 0 -> all lanes
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         if (rem >= 33) {
             // main loop: a round commits at most 32 attempts, so the budget cannot end inside it, and the slots
             // [h, prod_seen) are in the ring: one loop condition covers the producer, the budget and the end of the pass
-            do { round(std::false_type()); } while (rem >= 33 && h + 33 <= prod_seen);
+            do { round(std::false_type()); } while ((unsigned)(rem >= 33u) & (unsigned)(h + 33u <= prod_seen));
         } else {
             round(std::true_type());
         }
