@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     const unsigned sh_amt = 32u - (unsigned)lane;
     const unsigned short *s_qhi = (const unsigned short *)s_q;            // [K*K] sign, exponent, 7 mantissa bits
     const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;                  // [K*K] next 8 mantissa bits
+    // (through a shuffle so that it stays in a register instead of being re-derived from SR_CgaCtaId every round)
+    const unsigned a_head = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)&sh.head), 0);
     // One round.  TAIL = the launch's attempt budget may end inside the window (checked only in the last rounds).
     auto round = [&](auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
@@ -276,13 +278,13 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             const float lu = ((const float *)ring_lu)[(w + 1) & (RING - 1)];
             const float d = lp - lu;
             const float mar = eps + 1e-9f + 1.3e-7f * (fabsf(lp) + fabsf(lu));
-            const bool sure_ge0 = lp > eps, sure_neg = lp < -eps;
-            const bool sure_acc = d > mar, sure_rej = d < -mar;
+            // |lp| > eps decides the sign of log_p, |d| > mar decides the comparison with the uniform (NaN: undecided)
+            const bool dec_lp = fabsf(lp) > eps, dec_d = fabsf(d) > mar;
             // i == j: the reference's log_p is exactly 0 for finite energies (-(e+e)+e+e), accepted without a draw
             const bool same = (i == j) && (fabsf(f_ii) <= 3.0e38f);
-            ge0 = sure_ge0 || same;
-            acc = ge0 || (sure_neg && sure_acc);
-            const bool decided = ge0 || (sure_neg && (sure_acc || sure_rej));
+            ge0 = (dec_lp && lp > 0.f) || same;
+            acc = ge0 || (dec_lp && dec_d && d > 0.f);
+            const bool decided = ge0 || (dec_lp && dec_d);
             if (__any_sync(0xffffffffu, !decided)) {
                 if (!decided) {   // exact path for this lane: the f64 values from L2
                     const double logp = swap_logp(u[a_ij], u[a_ji], u[a_ii], u[a_jj]);
@@ -314,8 +316,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             }
         }
         const unsigned G = __ballot_sync(0xffffffffu, ge0);
-        const unsigned A = __ballot_sync(0xffffffffu, acc);
-        const unsigned E = __ballot_sync(0xffffffffu, i == j);
+        const unsigned A = __ballot_sync(0xffffffffu, acc && i != j);   // accepted and really changing the permutation
         // Visited chain: from a visited slot s the next attempt starts at s+1 if log_p >= 0 (no uniform drawn) else at
         // s+2.  skip[s+1] = NG[s] & ~skip[s]: inside a run of NG ones the skip flag alternates, so skip[s] = parity of
         // (s - run start); runs are split by the parity of their start with an add-carry (32-bit adds + carry out).
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const unsigned sumE = X + SE, sumO = X + SO;
         const unsigned skip = (((sumE ^ X) & ~SE) & 0xAAAAAAAAu) | (((sumO ^ X) & ~SO) & 0x55555555u);
         const unsigned V = ~skip;
-        const unsigned VA = V & A & ~E;  // visited, accepted, really changing the permutation
+        const unsigned VA = V & A;  // visited, accepted, really changing the permutation
         // lane t is stale if an earlier visited state-changing swap in this window shares a replica with it
         unsigned earlier;   // bit 31-b: lane t-1-b is a visited state-changing swap (shl by 32 gives 0 for lane 0)
         asm("shl.b32 %0, %1, %2;" : "=r"(earlier) : "r"(VA), "r"(sh_amt));
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         logpos += n;
         h += advance;
         rem -= n;
-        if ((rounds & 7u) == 0u && lane == 0) sh.head = h;
+        if ((rounds & 7u) == 0u && lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a_head), "r"(h) : "memory");
         __syncwarp();
     };
     while (rem > 0 && h + 33 <= nslots) {
