@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         const unsigned i = ij & 0xffffu, j = ij >> 16;
         const int si = s_perm[i], sj = s_perm[j];
         const unsigned a_ij = (i << logK) | (unsigned)sj, a_ji = (j << logK) | (unsigned)si;
-        bool ge0, acc;
+        bool ge0, acc, undecided = false;
         double e_ij = 0.0, e_ji = 0.0;   // exact off-diagonal values, needed by the commit (new diagonal)
         if (UMODE == U_FILTER24) {
             // image of u: 24-bit floats of delta = u - rowmin; logp~ = (d_ii - d_ij) + (d_jj - d_ji), |logp~ - logp_ref| <= eps
@@ -285,20 +285,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             ge0 = (dec_lp && lp > 0.f) || same;
             acc = ge0 || (dec_lp && dec_d && d > 0.f);
             const bool decided = ge0 || (dec_lp && dec_d);
-            if (__any_sync(0xffffffffu, !decided)) {
-                if (!decided) {   // exact path for this lane: the f64 values from L2
-                    const double logp = swap_logp(u[a_ij], u[a_ji], u[a_ii], u[a_jj]);
-                    ge0 = logp >= 0.0;
-                    acc = ge0;
-                    if (!ge0) {
-                        const double dd = logp - rec[h + lane + 1].logU;
-                        if (dd > 1e-9) acc = true;
-                        else if (dd < -1e-9) acc = false;
-                        else { const unsigned s1 = h + lane + 1; acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp); }
-                    }
-                    slow++;
-                }
-            }
+            undecided = !decided;   // resolved below, and only if the lane turns out to matter
         } else {
             e_ij = (UMODE == U_F64_SMEM) ? s_u[a_ij] : u[a_ij];
             e_ji = (UMODE == U_F64_SMEM) ? s_u[a_ji] : u[a_ji];
@@ -315,27 +302,57 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
                 }
             }
         }
-        const unsigned G = __ballot_sync(0xffffffffu, ge0);
-        const unsigned A = __ballot_sync(0xffffffffu, acc && i != j);   // accepted and really changing the permutation
-        // Visited chain: from a visited slot s the next attempt starts at s+1 if log_p >= 0 (no uniform drawn) else at
-        // s+2.  skip[s+1] = NG[s] & ~skip[s]: inside a run of NG ones the skip flag alternates, so skip[s] = parity of
-        // (s - run start); runs are split by the parity of their start with an add-carry (32-bit adds + carry out).
-        const unsigned X = ~G;
-        const unsigned starts = X & ~(X << 1);
-        const unsigned SE = starts & 0x55555555u, SO = starts & 0xAAAAAAAAu;
-        const unsigned sumE = X + SE, sumO = X + SO;
-        const unsigned skip = (((sumE ^ X) & ~SE) & 0xAAAAAAAAu) | (((sumO ^ X) & ~SO) & 0x55555555u);
-        const unsigned V = ~skip;
-        const unsigned VA = V & A;  // visited, accepted, really changing the permutation
-        // lane t is stale if an earlier visited state-changing swap in this window shares a replica with it
-        unsigned earlier;   // bit 31-b: lane t-1-b is a visited state-changing swap (shl by 32 gives 0 for lane 0)
-        asm("shl.b32 %0, %1, %2;" : "=r"(earlier) : "r"(VA), "r"(sh_amt));
-        const unsigned C = __ballot_sync(0xffffffffu, (earlier & backmask) != 0u) & V;
-        const unsigned low = C & (0u - C);
-        unsigned cm = V & (low - 1u);           // low == 0 -> all lanes
-        unsigned n = __popc(cm);
-        // bit 32 (even position) of the skip word can only be set by the carry of an odd-start run
-        unsigned advance = C ? (unsigned)__popc(low - 1u) : 32u + (sumO < X ? 1u : 0u);
+        unsigned V, C, low, cm, n, advance;
+        auto resolve = [&]() {
+            const unsigned G = __ballot_sync(0xffffffffu, ge0);
+            const unsigned A = __ballot_sync(0xffffffffu, acc && i != j);   // accepted and really changing the permutation
+            // Visited chain: from a visited slot s the next attempt starts at s+1 if log_p >= 0 (no uniform drawn) else
+            // at s+2.  skip[s+1] = NG[s] & ~skip[s]: inside a run of NG ones the skip flag alternates, so skip[s] =
+            // parity of (s - run start); runs are split by the parity of their start with an add-carry (32-bit adds +
+            // carry out).
+            const unsigned X = ~G;
+            const unsigned starts = X & ~(X << 1);
+            const unsigned SE = starts & 0x55555555u, SO = starts & 0xAAAAAAAAu;
+            const unsigned sumE = X + SE, sumO = X + SO;
+            const unsigned skip = (((sumE ^ X) & ~SE) & 0xAAAAAAAAu) | (((sumO ^ X) & ~SO) & 0x55555555u);
+            V = ~skip;
+            const unsigned VA = V & A;  // visited, accepted, really changing the permutation
+            // lane t is stale if an earlier visited state-changing swap in this window shares a replica with it
+            unsigned earlier;   // bit 31-b: lane t-1-b is a visited state-changing swap (shl by 32 gives 0 for lane 0)
+            asm("shl.b32 %0, %1, %2;" : "=r"(earlier) : "r"(VA), "r"(sh_amt));
+            C = __ballot_sync(0xffffffffu, (earlier & backmask) != 0u) & V;
+            low = C & (0u - C);
+            cm = V & (low - 1u);           // low == 0 -> all lanes
+            n = __popc(cm);
+            // bit 32 (even position) of the skip word can only be set by the carry of an odd-start run
+            advance = C ? (unsigned)__popc(low - 1u) : 32u + (sumO < X ? 1u : 0u);
+        };
+        if (UMODE == U_FILTER24) {
+            // The filter's undecided lanes carry arbitrary ge0/acc.  Bits of V, C and cm below the lowest undecided
+            // visited lane do not depend on them (the chain and the staleness test only look downwards), so the round
+            // is resolved speculatively and redone with exact values only when such a lane lies inside the committed
+            // prefix -- the ballot of the undecided lanes is off the critical path and rarely matters.
+            const unsigned U = __ballot_sync(0xffffffffu, undecided);
+            resolve();
+            if (U & cm) {
+                if (undecided) {   // exact path for this lane: the f64 values from L2
+                    const unsigned a_ii = (i << logK) | (unsigned)si, a_jj = (j << logK) | (unsigned)sj;
+                    const double logp = swap_logp(u[a_ij], u[a_ji], u[a_ii], u[a_jj]);
+                    ge0 = logp >= 0.0;
+                    acc = ge0;
+                    if (!ge0) {
+                        const double dd = logp - rec[h + lane + 1].logU;
+                        if (dd > 1e-9) acc = true;
+                        else if (dd < -1e-9) acc = false;
+                        else { const unsigned s1 = h + lane + 1; acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp); }
+                    }
+                    slow++;
+                }
+                resolve();
+            }
+        } else {
+            resolve();
+        }
         if (TAIL && n > rem) {
             unsigned pos = 0;  // the first visited lane we must NOT run: the (rem+1)-th set bit of cm
             for (unsigned cnt = 0; pos < 32; pos++)
