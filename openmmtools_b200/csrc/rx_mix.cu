@@ -272,12 +272,14 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             // mantissa + f32 rounding); the f32 additions below add at most 2^-23 of the magnitudes; the f64 rounding
             // of the reference's own three additions and of our centring is <= 64 ulp(f64) of the magnitudes.
             const float lp = (f_ii - f_ij) + (f_jj - f_ji);
-            const float mag = fabsf(f_ii) + fabsf(f_ij) + fabsf(f_jj) + fabsf(f_ji);
-            const float eps = mag * 3.2e-5f + (((const float *)s_rowabs)[i] + ((const float *)s_rowabs)[j]);   // 1.6e-14 mag is inside the slack of 3.2e-5
+            const float mag = (fabsf(f_ii) + fabsf(f_ij)) + (fabsf(f_jj) + fabsf(f_ji));
+            // the guard band's 1e-9 rides in eps (a slightly wider eps for the sign test is only more conservative);
+            // 1.6e-14 mag is inside the slack of 3.2e-5
+            const float eps = fmaf(mag, 3.2e-5f, (((const float *)s_rowabs)[i] + ((const float *)s_rowabs)[j]) + 1e-9f);
             // log of the uniform, rounded to f32 by the producer: |lu - logU| <= 2^-24 |lu|; d carries one more rounding
             const float lu = ((const float *)ring_lu)[(w + 1) & (RING - 1)];
             const float d = lp - lu;
-            const float mar = eps + 1e-9f + 1.3e-7f * (fabsf(lp) + fabsf(lu));
+            const float mar = fmaf(fabsf(lp) + fabsf(lu), 1.3e-7f, eps);
             // |lp| > eps decides the sign of log_p, |d| > mar decides the comparison with the uniform (NaN: undecided)
             const bool dec_lp = fabsf(lp) > eps, dec_d = fabsf(d) > mar;
             // i == j: the reference's log_p is exactly 0 for finite energies (-(e+e)+e+e), accepted without a draw
@@ -383,7 +385,8 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         if (rem >= 33) {
             // main loop: a round commits at most 32 attempts, so the budget cannot end inside it, and the slots
             // [h, prod_seen) are in the ring: one loop condition covers the producer, the budget and the end of the pass
-            do { round(std::false_type()); } while ((unsigned)(rem >= 33u) & (unsigned)(h + 33u <= prod_seen));
+            // rem >= 33 and h + 33 <= prod_seen in one signed test (all values are far below 2^31)
+            do { round(std::false_type()); } while ((int)((rem - 33u) | (prod_seen - 33u - h)) >= 0);
         } else {
             round(std::true_type());
         }
