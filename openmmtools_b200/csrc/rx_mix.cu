@@ -247,11 +247,12 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;                  // [K*K] next 8 mantissa bits
     // (through a shuffle so that it stays in a register instead of being re-derived from SR_CgaCtaId every round)
     const unsigned a_head = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)&sh.head), 0);
+    unsigned wpos = (h + (unsigned)lane) & (RING - 1);   // this lane's ring slot
     // One round.  TAIL = the launch's attempt budget may end inside the window (checked only in the last rounds).
     auto round = [&](auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
         rounds++;
-        const unsigned w = (h + lane) & (RING - 1);
+        const unsigned w = wpos;   // (h + lane) & (RING - 1), carried from round to round
         const uint32_t ij = ring_ij[w], backmask = ring_bm[w];
         // the uniform an attempt here would draw belongs to the NEXT slot
         const double logU_next = (UMODE == U_FILTER24) ? 0.0 : ring_lu[(w + 1) & (RING - 1)];
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         if (UMODE != U_FILTER24) { if (swaps) { s_diag[i] = e_ij; s_diag[j] = e_ji; } }   // the image needs no f64 diagonal
         logpos += n;
         h += advance;
+        wpos = (wpos + advance) & (RING - 1);
         rem -= n;
         if ((rounds & 7u) == 0u && lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a_head), "r"(h) : "memory");
         __syncwarp();
