@@ -256,8 +256,23 @@ def workload_config(args):
                   '4 MB replica state is the resident working set by design'}
 
 
+_REAL_STDOUT = sys.stdout
+
+
 # ------------------------------------------------------------------------------------------------------------
+def _emit(line):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout."""
+    _REAL_STDOUT.write(json.dumps(line) + '\n')
+    _REAL_STDOUT.flush()
+
+
 def main():
+    # Native libraries may write to file descriptor 1 (NCCL prints its version banner there when NCCL_DEBUG is set):
+    # keep the original stdout for the JSON line only and point fd 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     args = parse()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -265,7 +280,7 @@ def main():
         if rank != 0:
             return 0
         line = cpu_arm(args, args.steps, max(args.warmup, 0), True)
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     if world != args.gpus and world > 1:
@@ -370,7 +385,7 @@ def main():
             line['cpu_baseline'] = cpu_arm(args, 2, 1, False)
         except Exception as e:   # the oracle is test infrastructure; never fail the GPU number because of it
             line['cpu_baseline'] = {'error': repr(e)}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
