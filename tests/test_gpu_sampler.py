@@ -267,3 +267,11 @@ def test_minimize_harmonic_oscillator_reaches_the_well():
     for st in hs.sampler_states:
         r = np.linalg.norm(st.positions.value_in_unit(unit.nanometer))
         assert r < 0.3 * 0.01, r
+
+
+def test_graft_entry_smoke_runs():
+    """The driver's smoke(): one small iteration through the public API, checked against the oracle inside."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as g
+    g.smoke()
