@@ -733,8 +733,9 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     const size_t smem_f64 = smem_base + (size_t)K * K * sizeof(double);
     const size_t smem_f24 = smem_base + (size_t)K * sizeof(double) + (size_t)3 * K * K;
     int umode = U_GLOBAL;
-    if (fast && smem_f64 <= 200 * 1024) umode = U_F64_SMEM;
-    else if (fast && smem_f24 <= 224 * 1024 && !getenv("RX_NO_FILTER")) umode = U_FILTER24;
+    // the f32 row-image filter wherever it fits (K <= 256): it beats the f64 comparisons of U_F64_SMEM at every size
+    if (fast && smem_f24 <= 224 * 1024 && !getenv("RX_NO_FILTER") && !getenv("RX_F64_SMEM")) umode = U_FILTER24;
+    else if (fast && smem_f64 <= 200 * 1024) umode = U_F64_SMEM;
     size_t smem = !fast ? smem_small : (umode == U_F64_SMEM ? smem_f64 : (umode == U_FILTER24 ? smem_f24 : smem_base));
     // The walker is one latency-bound CTA: claim (almost) a whole SM's shared memory so that no other CTA -- in particular
     // the stream generator that runs concurrently on the side stream -- is scheduled onto the same SM and steals issue slots.
