@@ -121,3 +121,27 @@ def test_swap_all_with_nonfinite_and_huge_energies(K):
             assert np.array_equal(st, st_o), (K, variant, it)
             assert np.array_equal(nacc, na) and np.array_equal(nprop, npr)
         e.close()
+
+
+@pytest.mark.parametrize('env,K,model', [('RX_F64_SMEM', 16, 'flat'), ('RX_F64_SMEM', 64, 'normal'), ('RX_F64_SMEM', 128, 'flat'),
+                                         ('RX_NO_FILTER', 64, 'flat'), ('RX_NO_FILTER', 256, 'flat')])
+def test_swap_all_other_energy_placements_vs_oracle(monkeypatch, env, K, model):
+    """The walker variants the default selection no longer reaches: the f64 matrix in shared memory (RX_F64_SMEM /
+    RX_NO_FILTER at K <= 128) and the exact values from L2 every round (RX_NO_FILTER at K = 256)."""
+    from oracle import oracle
+    monkeypatch.setenv(env, '1')
+    u = energies(model, K, 977 + K)
+    e = gpu_engine(0, K, K)
+    e.set_energies(u)
+    e.set_replica_states(np.arange(K))
+    e.mix_seed(21, 0)
+    mt = oracle.MT(21)
+    st_o = np.arange(K, dtype=np.int64)
+    nswap = min(K ** 3, 1_500_000)
+    for it in range(2):
+        st, nacc, nprop = e.mix_swap_all(nswap)
+        na = np.zeros((K, K), np.int64); npr = np.zeros((K, K), np.int64)
+        oracle.mix_swap_all(mt, nswap, st_o, u, na, npr)
+        assert np.array_equal(st, st_o), (env, K, it)
+        assert np.array_equal(nacc, na) and np.array_equal(nprop, npr)
+    e.close()
