@@ -142,13 +142,20 @@ __global__ void __launch_bounds__(256) k_slots_build(const uint32_t *__restrict_
 // matrices are built from the log afterwards by k_mix_count, in parallel).
 //
 // Where the energies live (UMODE):
-//   U_F64_SMEM   the f64 matrix itself is in shared memory (K <= 128)
-//   U_FILTER24   K = 256: 512 KB of f64 do not fit, so shared memory holds a 24-bit floating image of every row
+//   U_FILTER24   the default for K <= 256 (at K = 256 the 512 KB of f64 do not fit; at smaller K the f32 filter is
+//                still faster than f64 comparisons): shared memory holds a 24-bit floating image of every row
 //                (delta = u - rowmin as a float32 truncated to sign + 8 exponent + 15 mantissa bits) that gives log_p
-//                to within a RIGOROUS bound eps = 3.2e-5 * sum|delta| + tiny; the decision is taken from the image
-//                whenever it is more than eps away from both thresholds (log_p = 0 and log_p = log U), otherwise the
-//                lane falls back to the exact f64 values in L2.  The result is therefore still bit-identical.
-//   U_GLOBAL     exact f64 values from L2 every round (any larger K)
+//                to within a RIGOROUS bound eps = 3.2e-5 * sum|delta| + tiny; the decision is taken from the image, in
+//                f32, whenever it is more than eps away from both thresholds (log_p = 0 and log_p = log U); a round
+//                whose committed prefix contains an undecided lane is redone with the exact f64 values from L2.
+//                The result is therefore still bit-identical.
+//   U_F64_SMEM   the f64 matrix itself is in shared memory (K <= 128; RX_F64_SMEM=1 or RX_NO_FILTER=1)
+//   U_GLOBAL     exact f64 values from L2 every round (any larger K, or K = 256 with RX_NO_FILTER=1)
+//
+// The walker's round is one dependent chain (~105 instructions, ~0.2 us); what was measured to matter, on one box:
+// no f64 on the chain (-65 ns), no data-dependent branch besides the loop's (-60 ns: one loop condition, predicated
+// commit), no sub-word shared stores (a byte-wide permutation table costs +40 ns), the absolute-to-relative lane
+// conversion as one shift (back-mask bit order), and nothing re-derived from special registers inside the loop.
 // ------------------------------------------------------------------------------------------------------
 #define LOG_ACC_BIT 28
 #define LOG_STATE_BITS 14
