@@ -17,6 +17,12 @@ class ParallelTemperingSampler(ReplicaExchangeSampler):
     _TITLE_TEMPLATE = ('Parallel tempering simulation created using ParallelTemperingSampler '
                        'class of openmmtools_b200.multistate on {}')
 
+    @staticmethod
+    def _temperature_ladder(tmin, tmax, n):
+        """paralleltempering.py:162: np.logspace(log10(Tmin), log10(Tmax), num=n), in kelvin."""
+        import numpy as np
+        return [float(t) for t in np.logspace(np.log10(tmin), np.log10(tmax), num=n)]
+
     def create(self, thermodynamic_state, sampler_states, storage=None, min_temperature=None, max_temperature=None,
                n_temperatures=None, temperatures=None, **kwargs):
         if not isinstance(sampler_states, (list, tuple)):
@@ -29,10 +35,7 @@ class ParallelTemperingSampler(ReplicaExchangeSampler):
         elif all(v is not None for v in (min_temperature, max_temperature, n_temperatures)):
             tmin = float(unit.to_md(min_temperature, unit.kelvin, 'min_temperature'))
             tmax = float(unit.to_md(max_temperature, unit.kelvin, 'max_temperature'))
-            n = int(n_temperatures)
-            # paralleltempering.py:162: np.logspace(log10(Tmin), log10(Tmax), num=n)
-            import numpy as np
-            temperatures = [float(t) for t in np.logspace(np.log10(tmin), np.log10(tmax), num=n)]
+            temperatures = self._temperature_ladder(tmin, tmax, int(n_temperatures))
         else:
             raise ValueError("Either 'temperatures' or all of 'min_temperature', 'max_temperature', and "
                              "'n_temperatures' must be provided.")

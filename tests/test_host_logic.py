@@ -237,3 +237,19 @@ def test_online_free_energy_update_matches_reference_golden():
         for it in range(1, hist.shape[0] + 1):
             f_k = MultiStateSampler._online_f_k_update(f_k, energies_for(it, K, M, key), states_for(it, K, M, key), loc, it)
             assert np.abs(f_k - hist[it - 1]).max() < 1e-12, (tag, it)
+
+
+def test_initial_state_assignment_and_pt_ladder_match_reference_golden():
+    """MultiStateSampler._default_initial_thermodynamic_states (multistatesampler.py:1116-1143) and the temperature
+    ladder of ParallelTemperingSampler.create (paralleltempering.py:156-162), both lifted from the reference
+    (tests/golden/make_hostlogic_golden.py)."""
+    import os
+    from openmmtools_b200.multistate import MultiStateSampler, ParallelTemperingSampler
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hostlogic_golden.npz'))
+    for n_thermo, n_sampler in g['init_cases']:
+        mine = MultiStateSampler._default_initial_thermodynamic_states([None] * int(n_thermo), [None] * int(n_sampler))
+        assert np.array_equal(np.asarray(mine), g['init_%d_%d' % (n_thermo, n_sampler)]), (n_thermo, n_sampler)
+    for tmin, tmax, n in g['pt_cases']:
+        ref = g['pt_%g_%g_%d' % (tmin, tmax, int(n))]
+        mine = ParallelTemperingSampler._temperature_ladder(float(tmin), float(tmax), int(n))
+        assert np.allclose(mine, ref, rtol=1e-14, atol=0), (tmin, tmax, n)
