@@ -36,10 +36,12 @@ class MultiStateReporter:
     }
 
     def __init__(self, storage, open_mode=None, checkpoint_interval=50, checkpoint_storage=None,
-                 analysis_particle_indices=()):
+                 analysis_particle_indices=(), position_interval=1, velocity_interval=1):
         self._storage = str(storage)
         self._checkpoint_interval = int(checkpoint_interval)
-        self._analysis_particle_indices = tuple(analysis_particle_indices)
+        self._analysis_particle_indices = tuple(int(i) for i in analysis_particle_indices)
+        self._position_interval = int(position_interval)    # multistatereporter.py:109-116: 0 disables the stream
+        self._velocity_interval = int(velocity_interval)
         self._open_mode = None
         self._meta = None
         self._dirty = set()
@@ -58,6 +60,23 @@ class MultiStateReporter:
     @property
     def analysis_particle_indices(self):
         return self._analysis_particle_indices
+
+    @property
+    def position_interval(self):
+        return self._position_interval
+
+    @property
+    def velocity_interval(self):
+        return self._velocity_interval
+
+    def wants_analysis_states(self, iteration):
+        """True when positions or velocities of the analysis particles are due at this iteration
+        (multistatereporter.py:1686-1692)."""
+        if not self._analysis_particle_indices:
+            return False
+        it = int(iteration)
+        return (self._position_interval != 0 and it % self._position_interval == 0) or \
+               (self._velocity_interval != 0 and it % self._velocity_interval == 0)
 
     def storage_exists(self, skip_size=False):
         return os.path.exists(os.path.join(self._storage, 'meta.json'))
@@ -83,6 +102,11 @@ class MultiStateReporter:
             self._meta = json.load(open(os.path.join(self._storage, 'meta.json')))
             if 'checkpoint_interval' in self._meta:
                 self._checkpoint_interval = int(self._meta['checkpoint_interval'])
+            # an existing file keeps its analysis-particle settings (the reference reads them back from the .nc file)
+            if 'analysis_particle_indices' in self._meta:
+                self._analysis_particle_indices = tuple(self._meta['analysis_particle_indices'])
+                self._position_interval = int(self._meta.get('position_interval', 1))
+                self._velocity_interval = int(self._meta.get('velocity_interval', 1))
         self._open_mode = mode
 
     def close(self):
@@ -97,6 +121,9 @@ class MultiStateReporter:
     # -- helpers
     def _write_meta(self):
         self._meta['checkpoint_interval'] = self._checkpoint_interval
+        self._meta['analysis_particle_indices'] = list(self._analysis_particle_indices)
+        self._meta['position_interval'] = self._position_interval
+        self._meta['velocity_interval'] = self._velocity_interval
         tmp = os.path.join(self._storage, 'meta.json.tmp')
         with open(tmp, 'w') as f:
             json.dump(self._meta, f)
@@ -276,7 +303,10 @@ class MultiStateReporter:
         return os.path.join(self._storage, 'checkpoint', 'ckpt_%09d.npz' % int(iteration))
 
     def write_sampler_states(self, sampler_states, iteration, extra=None):
-        """Positions/velocities/box of every replica, only on checkpoint iterations (multistatereporter.py:664-700)."""
+        """Positions/velocities/box of every replica on checkpoint iterations, and of the analysis particles at their
+        own intervals (multistatereporter.py:664-700, 1670-1730)."""
+        if self.wants_analysis_states(iteration):
+            self._write_analysis_particles(sampler_states, int(iteration))
         if int(iteration) % self._checkpoint_interval != 0:
             return False
         x = np.stack([s._positions for s in sampler_states])
@@ -290,7 +320,56 @@ class MultiStateReporter:
         os.replace(tmp, self._ckpt(iteration))
         return True
 
+    def _analysis_file(self, what):
+        return os.path.join(self._storage, 'analysis', 'particles_' + what + '.bin')
+
+    def _write_analysis_particles(self, sampler_states, it):
+        idx = np.array(self._analysis_particle_indices, dtype=np.int64)
+        streams = []
+        if self._position_interval != 0 and it % self._position_interval == 0:
+            streams.append(('positions', np.stack([s._positions[idx] for s in sampler_states]), self._position_interval))
+            if all(s._box_vectors is not None for s in sampler_states):
+                streams.append(('box_vectors', np.stack([s._box_vectors for s in sampler_states]), self._position_interval))
+        if self._velocity_interval != 0 and it % self._velocity_interval == 0 and all(s._velocities is not None for s in sampler_states):
+            streams.append(('velocities', np.stack([s._velocities[idx] for s in sampler_states]), self._velocity_interval))
+        for what, a, interval in streams:
+            a = np.ascontiguousarray(a, dtype=np.float32)          # the reference stores these as float32
+            spec = self._meta.setdefault('analysis_particles', {})
+            if what not in spec:
+                spec[what] = {'shape': list(a.shape), 'interval': interval, 'indices': list(self._analysis_particle_indices)}
+                self._write_meta()
+            path = self._analysis_file(what)
+            with open(path, 'r+b' if os.path.exists(path) else 'w+b') as f:
+                f.seek((it // interval) * a.nbytes)
+                f.write(a.tobytes())
+            self._dirty.add(path)
+
+    def _read_analysis_particles(self, what, it):
+        spec = self._meta.get('analysis_particles', {}).get(what)
+        if spec is None or it % spec['interval'] != 0:
+            return None
+        shape = tuple(spec['shape'])
+        n = int(np.prod(shape))
+        path = self._analysis_file(what)
+        rec = it // spec['interval']
+        if not os.path.exists(path) or os.path.getsize(path) < (rec + 1) * n * 4:
+            return None
+        return np.fromfile(path, dtype=np.float32, count=n, offset=rec * n * 4).reshape(shape).astype(np.float64)
+
     def read_sampler_states(self, iteration, analysis_particles_only=False):
+        if analysis_particles_only:
+            # the per-iteration streams of the analysis particles (None when there are none, like the reference)
+            if isinstance(iteration, (int, np.integer)) and iteration < 0:
+                iteration = self.read_last_iteration(last_checkpoint=False) + 1 + int(iteration)
+            x = self._read_analysis_particles('positions', int(iteration))
+            if x is None:
+                return None
+            v = self._read_analysis_particles('velocities', int(iteration))
+            b = self._read_analysis_particles('box_vectors', int(iteration))
+            return [_states.SamplerState(unit.Quantity(x[k], unit.nanometer),
+                                         velocities=None if v is None else unit.Quantity(v[k], unit.nanometer / unit.picosecond),
+                                         box_vectors=None if b is None else unit.Quantity(b[k], unit.nanometer))
+                    for k in range(x.shape[0])]
         if isinstance(iteration, (int, np.integer)) and iteration < 0:
             iteration = self.read_checkpoint_iterations()[iteration]
         if not os.path.exists(self._ckpt(iteration)):

@@ -557,7 +557,8 @@ class MultiStateSampler:
             return
         it = self._iteration
         checkpoint = (it % self._reporter.checkpoint_interval == 0)
-        if checkpoint:
+        analysis = self._reporter.wants_analysis_states(it)   # per-iteration streams of the analysis particles
+        if checkpoint or analysis:
             self._sync_sampler_states()
             if self._world_size > 1:
                 self._gather_sampler_states()
@@ -565,7 +566,7 @@ class MultiStateSampler:
             return
         r = self._reporter
         r.write_replica_thermodynamic_states(self._replica_thermodynamic_states, it)
-        if checkpoint:
+        if checkpoint or analysis:
             r.write_sampler_states(self._sampler_states, it, extra=self._checkpoint_extra())
         r.write_mixing_statistics(self._n_accepted_matrix, self._n_proposed_matrix, it)
         r.write_energies(self._energy_thermodynamic_states, self._neighborhoods, self._energy_unsampled_states, it)

@@ -50,6 +50,38 @@ def test_reporter_records_and_commit_marker(tmp_path):
         MultiStateReporter(path).open('x')
 
 
+def test_analysis_particle_streams_follow_the_reference_intervals(tmp_path):
+    """analysis_particle_indices / position_interval / velocity_interval (multistatereporter.py:106-116, 1686-1692):
+    the listed particles are stored at their own intervals, as float32, next to the sparse checkpoints."""
+    path = str(tmp_path / 'an.store')
+    r = MultiStateReporter(path, open_mode='w', checkpoint_interval=10, analysis_particle_indices=(4, 1), position_interval=2,
+                           velocity_interval=0)
+    assert r.analysis_particle_indices == (4, 1) and r.position_interval == 2 and r.velocity_interval == 0
+    K, M, N = 2, 2, 6
+    r.set_dimensions(K, M, N)
+    rng = np.random.default_rng(1)
+    kept = {}
+    for it in range(6):
+        ss = [states.SamplerState(rng.normal(size=(N, 3)), velocities=rng.normal(size=(N, 3)), box_vectors=np.eye(3) * 3.0)
+              for _ in range(K)]
+        assert r.wants_analysis_states(it) == (it % 2 == 0)
+        r.write_sampler_states(ss, it)
+        r.write_last_iteration(it)
+        kept[it] = ss
+    r.close()
+    r2 = MultiStateReporter(path, open_mode='r')
+    assert r2.analysis_particle_indices == (4, 1) and r2.position_interval == 2 and r2.velocity_interval == 0
+    assert r2.read_sampler_states(3, analysis_particles_only=True) is None
+    got = r2.read_sampler_states(4, analysis_particles_only=True)
+    assert len(got) == K and got[0].n_particles == 2 and got[0].velocities is None
+    want = kept[4][1]._positions[[4, 1]].astype(np.float32).astype(np.float64)
+    assert np.array_equal(got[1]._positions, want)
+    assert np.array_equal(got[1]._box_vectors, np.eye(3) * 3.0)
+    assert r2.read_checkpoint_iterations() == [0]                   # full states only at the checkpoint interval
+    no = MultiStateReporter(str(tmp_path / 'none.store'), open_mode='w')
+    assert no.wants_analysis_states(0) is False and no.position_interval == 1 and no.velocity_interval == 1
+
+
 @pytest.mark.gpu
 def test_resume_is_bit_identical_to_uninterrupted_run(tmp_path):
     import sys
