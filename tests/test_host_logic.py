@@ -253,3 +253,22 @@ def test_initial_state_assignment_and_pt_ladder_match_reference_golden():
         ref = g['pt_%g_%g_%d' % (tmin, tmax, int(n))]
         mine = ParallelTemperingSampler._temperature_ladder(float(tmin), float(tmax), int(n))
         assert np.allclose(mine, ref, rtol=1e-14, atol=0), (tmin, tmax, n)
+
+
+def test_protocol_builder_follows_the_reference_rules():
+    """states.create_thermodynamic_state_protocol (states.py:39-141): one state per protocol entry, protocol values
+    assigned by attribute, composable states wrapped once, ValueError on ragged protocols or a missing temperature."""
+    from openmmtools_b200 import states, alchemy, testsystems, unit
+    fluid = testsystems.LennardJonesFluid(nparticles=32)
+    asys = alchemy.AbsoluteAlchemicalFactory().create_alchemical_system(fluid.system, alchemy.AlchemicalRegion(alchemical_atoms=range(3)))
+    proto = {'lambda_sterics': [1.0, 0.5, 0.0], 'temperature': [300 * unit.kelvin, 310 * unit.kelvin, 320 * unit.kelvin]}
+    out = states.create_thermodynamic_state_protocol(asys, proto, composable_states=alchemy.AlchemicalState.from_system(asys))
+    assert [s.lambda_sterics for s in out] == [1.0, 0.5, 0.0]
+    assert [round(s.temperature.value_in_unit(unit.kelvin), 9) for s in out] == [300.0, 310.0, 320.0]
+    assert len({id(s) for s in out}) == 3
+    with pytest.raises(ValueError):
+        states.create_thermodynamic_state_protocol(asys, {'lambda_sterics': [1.0, 0.0], 'temperature': [300 * unit.kelvin]},
+                                                   composable_states=alchemy.AlchemicalState.from_system(asys))
+    with pytest.raises(ValueError):
+        states.create_thermodynamic_state_protocol(asys, {'lambda_sterics': [1.0, 0.0]},
+                                                   composable_states=alchemy.AlchemicalState.from_system(asys))
