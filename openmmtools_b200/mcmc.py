@@ -31,10 +31,11 @@ class IntegratorMoveError(Exception):
 
 
 def parse_splitting(splitting):
-    """Validate a splitting string, returning it without spaces (integrators.py:1319-1363)."""
+    """Validate a splitting string, returning it without spaces (integrators.py:1319-1402; behaviour per string pinned
+    by tests/golden/splitting_golden.json).  ``V0`` is the plain ``V`` of a system whose forces all sit in group 0."""
     tokens = splitting.split()
-    if not tokens:
-        raise ValueError('empty splitting string')
+    steps = []
+    groups = set()
     for step in tokens:
         if step in ('{', '}'):
             raise NotImplementedError('Metropolized splittings ({ }) are not provided on the B200 path')
@@ -45,10 +46,15 @@ def parse_splitting(splitting):
                 raise ValueError('You must use an integer force group')
             if group > 31:
                 raise ValueError('OpenMM only allows up to 32 force groups')
-            raise NotImplementedError('multiple-time-step splittings (V<group>) are not provided on the B200 path')
+            groups.add(group)
+            steps.append('V')
+            continue
         if step not in ('R', 'V', 'O'):
             raise ValueError("Invalid step name '{}' used; valid step names are R, V, O".format(step))
-    joined = ''.join(tokens)
+        steps.append(step)
+    if groups - {0}:
+        raise NotImplementedError('multiple-time-step splittings (V<group>) are not provided on the B200 path')
+    joined = ''.join(steps)
     for need in 'RVO':
         assert need in joined, 'splitting must contain R, V and O steps'
     return joined
