@@ -10,7 +10,6 @@ the same expression with lambda fixed to 1 unless ``annihilate_sterics`` (:1776-
 electrostatic, GB and multi-region branches need a molecular force field and are out of scope.
 """
 import collections
-import copy
 from . import unit
 from .states import GlobalParameterState, GlobalParameterError   # noqa: F401
 from .system import System, LJ

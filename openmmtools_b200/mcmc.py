@@ -7,7 +7,6 @@ Mirrors /root/reference/openmmtools/mcmc.py: ``LangevinSplittingDynamicsMove`` (
 Metropolization (``{ }``), shadow-work and heat bookkeeping need per-substep energy sums and are not provided.
 GHMC/HMC/MC displacement/barostat moves (:1323-1917) are other kernels and out of scope.
 """
-import copy
 import numpy as np
 from . import unit
 from . import _backend

@@ -8,9 +8,8 @@ is what the engine's energy kernel does for every system anyway (one potential e
 multiply per state), so nothing is overridden here.
 """
 import copy
-import math
 from .replicaexchange import ReplicaExchangeSampler
-from .. import states, unit
+from .. import unit
 
 
 class ParallelTemperingSampler(ReplicaExchangeSampler):

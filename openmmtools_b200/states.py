@@ -11,7 +11,7 @@ barostats, surface tension; states.py:1510-1843) is out of scope (the configurat
 import copy
 import numpy as np
 from . import unit
-from .constants import kB, KB_MD
+from .constants import kB
 from .system import System
 
 
