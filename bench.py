@@ -199,13 +199,16 @@ def cpu_arm(args, steps, warmup, full_line):
     """The reference's CPU path restated (oracle/rx_oracle.c): numba-identical mixing (single thread, it is a
     serial chain), Verlet-list Langevin propagation and the energy matrix with OpenMP over replicas on all host
     cores.  One step = one full iteration of the same workload."""
+    os.environ.setdefault('OMP_PROC_BIND', 'true')     # pinned threads: a repeatable CPU arm (read when libgomp starts)
+    os.environ.setdefault('OMP_PLACES', 'threads')
     from oracle import oracle
     K, N = args.replicas, args.atoms
     fluid, asys, tstates, sstate, lambdas = build_workload(K, N)
     L = asys.box_vectors[0, 0]
     osys = oracle.LJSystem(asys.sigma, asys.epsilon, asys.masses, asys.alchemical_mask(), (L, L, L), asys.cutoff,
                            asys.switching_distance, use_switch=True)
-    threads = oracle.max_threads()
+    # every host core this process may run on, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     rng = np.random.default_rng(2024)
     x = np.stack([np.asarray(sstate._positions)] * K)
     v = rng.normal(scale=np.sqrt(KB * 300.0 / asys.masses[0]), size=x.shape)
@@ -248,12 +251,36 @@ def cpu_arm(args, steps, warmup, full_line):
 
 
 def workload_config(args):
-    return {'workload': 'configs[2]: alchemical LennardJonesFluid(%d), %d lambda-replicas, %d BAOAB steps/iter, %s'
-                        % (args.atoms, args.replicas, args.md_steps, args.mixing),
+    std = args.atoms == 512 and args.md_steps == 500 and args.mixing == 'swap-all'
+    label = {64: 'configs[1]', 256: 'configs[2]'}.get(args.replicas) if std else None
+    return {'workload': '%s: alchemical LennardJonesFluid(%d), %d lambda-replicas, %d BAOAB steps/iter, %s'
+                        % (label or 'non-BASELINE variant', args.atoms, args.replicas, args.md_steps, args.mixing),
             'replicas': args.replicas, 'atoms': args.atoms, 'md_steps': args.md_steps, 'mixing': args.mixing,
             'parallelism': 'replica-sharded x%d, NCCL allgather of energy rows, replicated mixing' % args.gpus,
             'l2': 'no explicit flush: each iteration streams ~0.8 GB of RNG words + slot records (> 126 MB L2); the '
                   '4 MB replica state is the resident working set by design'}
+
+
+def state_digest(sampler, dist):
+    """A digest of the trajectory that must not depend on the number of GPUs: CRC32 of every replica's positions (each rank
+    contributes the replicas it owns), of the replica -> state map and of the energy matrix, after all timed work."""
+    import zlib
+    e = sampler._engine
+    K = sampler.n_replicas
+    x = e.get_positions()
+    crc = np.zeros(K, np.float64)
+    for r, k in enumerate(range(e.k0, e.k1)):
+        crc[k] = float(zlib.crc32(np.ascontiguousarray(x[r]).tobytes()))
+    if dist.dist:
+        import torch
+        t = torch.from_numpy(crc)
+        dist.dist.all_reduce(t, op=dist.dist.ReduceOp.SUM)
+        crc = t.numpy()
+    perm = np.asarray(sampler._engine.get_replica_states(), np.int64)
+    u = e.get_energies()
+    return {'positions': '%08x' % zlib.crc32(crc.astype(np.uint64).tobytes()), 'replica_states': '%08x' % zlib.crc32(perm.tobytes()),
+            'energies': '%08x' % zlib.crc32(np.ascontiguousarray(u).tobytes()),
+            'note': 'after warm-up + timed + end-to-end iterations; equal digests at every --gpus = the same trajectory'}
 
 
 _REAL_STDOUT = sys.stdout
@@ -335,19 +362,45 @@ def main():
     ach = b_prop / t_prop / 1e9 if t_prop > 0 else 0.0
     b_iter = K * N * args.md_steps * 64.0 / world + K * N * 16.0 / world + 2 * K * K * 8.0 + K * 8.0
     traffic = None
+    tj = {}
     try:    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture (K=256 on one GPU)
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'k_propagate_traffic.json')))
         traffic = (tj['dram_bytes_read'] + tj['dram_bytes_write']) * (kloc / 256.0)
     except Exception:
         pass
+    ms_iter = ms / args.steps
+    t_mix = pt['mix_ms'] / max(args.steps, 1)
+    issue = None
+    try:    # instruction-issue roofline of k_propagate: warp instructions of one launch from the same committed capture
+        winst = tj['warp_instructions'] * (kloc / 256.0) * (args.md_steps / 500.0)
+        sm_hz = (ck or {}).get('sm_mhz') or 1965.0
+        peak_ipc = 148 * 4 * sm_hz * 1e6
+        issue = {'warp_instructions_per_launch': winst, 'peak_warp_instructions_per_s': peak_ipc,
+                 'frac': winst / t_prop / peak_ipc if t_prop > 0 else None,
+                 'source': 'smsp__inst_executed.sum of profiles/k_propagate_traffic.json (ncu capture, K=256, 500 steps), '
+                           'scaled by replicas and steps; 148 SMs x 4 issue slots x the SM clock sampled in this run'}
+    except Exception:
+        pass
     roof = {'kernel': 'k_propagate', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
             'frac': ach / peak, 'traffic': traffic,
+            'traffic_source': 'dram__bytes_read+write of one launch in the committed ncu capture profiles/k_propagate_traffic.json '
+                              '(K=256), scaled by replicas per GPU; NOT measured in this run',
             'peak_source': 'MEASURED_PEAKS.json (of measured)' if peaks else 'fallback 6650 GB/s',
             'algorithmic_bytes_per_launch': b_prop,
-            'whole_iteration': {'bytes': b_iter, 'achieved': b_iter / (ms * 1e-3 / args.steps) / 1e9,
-                                'frac': b_iter / (ms * 1e-3 / args.steps) / 1e9 / peak},
-            'note': 'wall-clock is dominated by the exact swap-all mixing chain (serial dependency, latency bound), '
-                    'not by HBM traffic; see phases_ms'}
+            'share_of_step': pt['propagate_ms'] / max(args.steps, 1) / ms_iter,
+            'issue_roofline': issue,
+            'note': 'the streaming model of SURVEY.md 8(d) (x, v read + written per atom-step); the state stays on chip for '
+                    'all steps, so real DRAM traffic is `traffic` and the kernel is instruction-issue bound: see issue_roofline',
+            'whole_iteration': {'bytes': b_iter, 'achieved': b_iter / (ms_iter * 1e-3) / 1e9,
+                                'frac': b_iter / (ms_iter * 1e-3) / 1e9 / peak},
+            'dominant_kernel': {
+                'name': 'k_mix_walk2 (+ k_mix_walk_pow2 tail)' if mixing == 'swap-all' else 'k_propagate',
+                'share_of_step': (mstats['walker_ms'] / ms_iter) if mixing == 'swap-all' else pt['propagate_ms'] / max(args.steps, 1) / ms_iter,
+                'bound': 'latency: one warp, one dependent chain per speculation round (exact swap-all chain); neither '
+                         'HBM nor FP throughput' if mixing == 'swap-all' else 'instruction issue',
+                'rounds': mstats['rounds'], 'ns_per_round': 1e6 * mstats['walker_ms'] / max(mstats['rounds'], 1),
+                'attempts_per_round': (K ** 3) / max(mstats['rounds'], 1) if mixing == 'swap-all' else None,
+                'mix_phase_ms': t_mix}}
 
     # ---------------- end to end through the public API with host-resident sampler states
     e2e = None
@@ -369,6 +422,7 @@ def main():
         e2e = {'value': n_e2e / dt, 'unit': 'iterations/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                'iterations': n_e2e, 'api': 'ReplicaExchangeSampler.run(host_resident_states=True)'}
 
+    digest = state_digest(sampler, dist)
     if rank != 0:
         return 0
     line = {'metric': 'replica-exchange iterations/sec, 256-replica alchemical LJ fluid',
@@ -378,7 +432,7 @@ def main():
             'config': workload_config(args), 'roofline': roof,
             'phases_ms': {'mix': pt['mix_ms'] / args.steps, 'propagate': pt['propagate_ms'] / args.steps,
                           'energies_incl_allgather': pt['energies_ms'] / args.steps},
-            'mixing_stats': mstats, 'clocks': ck, 'e2e': e2e, 'gpu_launches': int(launches),
+            'mixing_stats': mstats, 'clocks': ck, 'e2e': e2e, 'gpu_launches': int(launches), 'state_digest': digest,
             'host_wall_ms_per_step': 1e3 * wall / args.steps}
     if not args.no_cpu_baseline:
         try:

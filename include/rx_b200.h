@@ -122,6 +122,12 @@ RX_API int rx_get_replica_states(rx_engine *h, int64_t *states /*[K]*/);
  * depend on the number of GPUs.  nan_flags[K] (may be NULL) gets 1 for replicas whose state went NaN.    */
 RX_API int rx_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int32_t reassign_velocities,
                  int32_t *nan_flags);
+/* Replaces the restart loop of BaseIntegratorMove.apply (mcmc.py:706-759, n_restart_attempts): after rx_propagate
+ * returned RX_ERR_NAN, the replicas whose flag is set go back to the state they had when that call began (a
+ * device-side snapshot) and are propagated again -- pass another seed for other noise; replicas that came through
+ * are not touched.                                                                                         */
+RX_API int rx_propagate_retry(rx_engine *h, uint64_t seed, uint64_t iteration, int32_t reassign_velocities,
+                 int32_t *nan_flags);
 
 /* Replaces MultiStateSampler._compute_energies (multistatesampler.py:1436-1494) ->
  * ThermodynamicState.reduced_potential_at_states (states.py:911-992).  Fills the device-resident

@@ -165,6 +165,17 @@ class Engine:
         self._check(rc)
         return flags
 
+    def propagate_retry(self, seed, iteration, reassign_velocities=False):
+        """Replicas whose NaN flag is set restart from the state they had when ``propagate`` began; the others stay."""
+        flags = np.zeros(self.K, np.int32)
+        rc = self._lib.rx_propagate_retry(self._h, int(seed), int(iteration), int(bool(reassign_velocities)), _ptr(flags))
+        if rc == _lib.RX_ERR_NAN:
+            e = EngineError(rc, self._lib.rx_last_error(self._h).decode())
+            e.nan_flags = flags
+            raise e
+        self._check(rc)
+        return flags
+
     def compute_energies(self, fetch=True):
         u = np.zeros((self.K, self.M)) if fetch else None
         self._check(self._lib.rx_compute_energies(self._h, _ptr(u)))

@@ -111,6 +111,7 @@ extern "C" void rx_destroy(rx_engine *h) {
     }
     rxi_mix_free(h);
     cudaFree(h->d_atom); cudaFree(h->d_atom_d); cudaFree(h->d_alch_list); cudaFree(h->d_states);
+    cudaFree(h->d_pos_snap); cudaFree(h->d_vel_snap); cudaFree(h->d_retry);
     cudaFree(h->d_pos); cudaFree(h->d_vel); cudaFree(h->d_io); cudaFree(h->d_perm); cudaFree(h->d_u);
     cudaFree(h->d_nacc); cudaFree(h->d_nprop); cudaFree(h->d_pot); cudaFree(h->d_kin); cudaFree(h->d_nan);
     cudaFree(h->d_err); cudaFree(h->d_pairs);
@@ -332,6 +333,8 @@ static int check_device_error(rx_engine *h) {
     return RX_OK;
 }
 
+static int finish_propagate(rx_engine *h, PhaseTimer &T, int32_t *nan_flags, const char *who);
+
 extern "C" int rx_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int32_t reassign, int32_t *nan_flags) {
     ENTER(h);
     int rc = check_ready(h, "rx_propagate");
@@ -339,9 +342,33 @@ extern "C" int rx_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int
     if (!h->have_integrator) RX_FAIL(h, RX_ERR_INVALID, "rx_propagate: rx_set_integrator must be called first");
     PhaseTimer T(h, 1);
     int launches = 0;
+    rc = rxi_snapshot_state(h);
+    if (rc) return rc;
     rc = rxi_propagate(h, seed, iteration, reassign, &launches);
     if (rc) return rc;
     T.stop(launches);
+    return finish_propagate(h, T, nan_flags, "rx_propagate");
+}
+
+/* Replaces the restart loop of BaseIntegratorMove.apply (openmmtools/mcmc.py:706-759): the replicas whose NaN flag is set
+ * go back to the state they had when rx_propagate began and are propagated again (other noise: pass another seed); the
+ * replicas that came through are left alone. */
+extern "C" int rx_propagate_retry(rx_engine *h, uint64_t seed, uint64_t iteration, int32_t reassign, int32_t *nan_flags) {
+    ENTER(h);
+    int rc = check_ready(h, "rx_propagate_retry");
+    if (rc) return rc;
+    if (!h->have_integrator) RX_FAIL(h, RX_ERR_INVALID, "rx_propagate_retry: rx_set_integrator must be called first");
+    PhaseTimer T(h, 1);
+    int launches = 0;
+    rc = rxi_restore_failed(h);
+    if (rc) return rc;
+    rc = rxi_propagate(h, seed, iteration, reassign, &launches, h->d_retry);
+    if (rc) return rc;
+    T.stop(launches + 1);
+    return finish_propagate(h, T, nan_flags, "rx_propagate_retry");
+}
+
+static int finish_propagate(rx_engine *h, PhaseTimer &T, int32_t *nan_flags, const char *who) {
     RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
     T.accumulate();
     const int K = h->cfg.n_replicas;
@@ -354,7 +381,7 @@ extern "C" int rx_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int
         if (nan_flags) nan_flags[k] = v;
         any |= v;
     }
-    if (any) RX_FAIL(h, RX_ERR_NAN, "rx_propagate: NaN encountered in positions, velocities or potential energy");
+    if (any) RX_FAIL(h, RX_ERR_NAN, std::string(who) + ": NaN encountered in positions, velocities or potential energy");
     return RX_OK;
 }
 

@@ -213,8 +213,9 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
                                                     float4 *__restrict__ pos, float4 *__restrict__ vel, int k0,
                                                     uint2 key, uint32_t iteration, int reassign,
                                                     double *__restrict__ pot, double *__restrict__ kin,
-                                                    int *__restrict__ nan_flag) {
+                                                    int *__restrict__ nan_flag, const int *__restrict__ only) {
     extern __shared__ float4 s_dyn[];
+    if (only && !only[k0 + blockIdx.x]) return;   // a retry launch propagates the replicas that failed, nothing else
     float4 *s_par = s_dyn + RX_MAX_ATOMS;  // [RX_MAX_ATOMS] (sqrt_eps, alch, -, -); s_dyn[0..] / s_dyn[2*MAX..]: positions
     float4 *s_ref = s_dyn + 3 * RX_MAX_ATOMS;                  // [nthr] the thread's position at the last outer build
     unsigned short *s_nb = (unsigned short *)(s_ref + blockDim.x);  // [maxnb][N] lists, slot-major (conflict free)
@@ -640,7 +641,7 @@ static int fill_dyn(rx_engine *h, DynParams &p) {
     return RX_OK;
 }
 
-int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches) {
+int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches, const int *d_only) {
     if (h->kloc == 0) return RX_OK;
     DynParams p;
     fill_dyn(h, p);
@@ -688,13 +689,51 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
             RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate<C6, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_propagate<C6, SW><<<h->kloc, threads, smem, h->stream>>>(p, h->d_atom, h->d_states, h->d_perm, h->d_pos, h->d_vel, \
                                                                    h->k0, key, (uint32_t)iteration, reassign, h->d_pot,    \
-                                                                   h->d_kin, h->d_nan);                                    \
+                                                                   h->d_kin, h->d_nan, d_only);                            \
     } while (0)
     if (p.c_is_6) { if (p.use_switch) RX_LAUNCH_PROPAGATE(true, true); else RX_LAUNCH_PROPAGATE(true, false); }
     else { if (p.use_switch) RX_LAUNCH_PROPAGATE(false, true); else RX_LAUNCH_PROPAGATE(false, false); }
 #undef RX_LAUNCH_PROPAGATE
     RX_CHECK_CUDA(h, cudaGetLastError());
     (*launches)++;
+    return RX_OK;
+}
+
+// Start-of-iteration snapshot of positions and velocities (the restart policy of mcmc.py:706-759 retries a failed replica
+// from the state it had when the move began) and the restore of the replicas whose NaN flag is set.
+int rxi_snapshot_state(rx_engine *h) {
+    if (h->kloc == 0) return RX_OK;
+    const size_t bytes = sizeof(float4) * (size_t)h->kloc * h->cfg.n_atoms;
+    if (!h->d_pos_snap) {
+        RX_CHECK_CUDA(h, cudaMalloc(&h->d_pos_snap, bytes));
+        RX_CHECK_CUDA(h, cudaMalloc(&h->d_vel_snap, bytes));
+        RX_CHECK_CUDA(h, cudaMalloc(&h->d_retry, sizeof(int) * h->cfg.n_replicas));
+    }
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_pos_snap, h->d_pos, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_vel_snap, h->d_vel, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    h->have_snapshot = true;
+    return RX_OK;
+}
+
+__global__ void k_restore_failed(const int *__restrict__ nan_flag, int *__restrict__ retry, int k0, int N,
+                                 const float4 *__restrict__ pos_snap, const float4 *__restrict__ vel_snap,
+                                 float4 *__restrict__ pos, float4 *__restrict__ vel) {
+    const int r = blockIdx.x, k = k0 + r;
+    const int failed = nan_flag[k];
+    if (threadIdx.x == 0) retry[k] = failed;
+    if (!failed) return;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        pos[(size_t)r * N + t] = pos_snap[(size_t)r * N + t];
+        vel[(size_t)r * N + t] = vel_snap[(size_t)r * N + t];
+    }
+}
+
+int rxi_restore_failed(rx_engine *h) {
+    if (h->kloc == 0) return RX_OK;
+    if (!h->have_snapshot) RX_FAIL(h, RX_ERR_INVALID, "rx_propagate_retry: no start-of-iteration snapshot (call rx_propagate first)");
+    k_restore_failed<<<h->kloc, 256, 0, h->stream>>>(h->d_nan, h->d_retry, h->k0, h->cfg.n_atoms, h->d_pos_snap, h->d_vel_snap,
+                                                    h->d_pos, h->d_vel);
+    RX_CHECK_CUDA(h, cudaGetLastError());
     return RX_OK;
 }
 

@@ -65,6 +65,9 @@ struct rx_engine {
     std::vector<StateDev> h_states;
     // replica state
     float4 *d_pos = nullptr, *d_vel = nullptr;  // [kloc][N]
+    float4 *d_pos_snap = nullptr, *d_vel_snap = nullptr;   // start-of-iteration copy for the NaN restart policy
+    int *d_retry = nullptr;                     // [K] replicas to propagate again
+    bool have_snapshot = false;
     double *d_io = nullptr;                     // staging for set/get: [kloc][N][3]
     double *h_io = nullptr;                     // pinned host staging of the same size
     int *d_perm = nullptr;                      // [K] replica -> state
@@ -87,8 +90,10 @@ struct rx_engine {
     MixCtl *d_ctl = nullptr;
     uint32_t *d_log = nullptr;   // commit log of the walker: packed (si, sj, accepted)
     size_t log_cap = 0;
+    uint32_t *d_slotlog = nullptr;   // sparse commit log of k_mix_walk2: one word per slot
     unsigned char *d_filt = nullptr;   // 24-bit row image of u for the K=256 walker
     double *d_filt_scale = nullptr;    // [K] scales + [K] row abs-max
+    bool prepared_rec2 = false;   // ... as SlotRec2 records (filter mode)
     bool prepared = false;        // words + slot records for the next swap-all call were produced on stream_rng
     size_t last_consumed = 0;     // words the previous swap-all call consumed (sizes the generate-ahead)
     size_t slots_for_avail = 0;   // S.avail the slot records were built for
@@ -142,7 +147,9 @@ int rxi_mix_swap_neighbors(rx_engine *h, int *launches);
 void rxi_mix_free(rx_engine *h);
 
 // ---- implemented in rx_dynamics.cu ----
-int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches);
+int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches, const int *d_only = nullptr);
+int rxi_snapshot_state(rx_engine *h);   // positions + velocities at the start of a propagation
+int rxi_restore_failed(rx_engine *h);   // replicas with a NaN flag go back to the snapshot; d_retry = the flags
 int rxi_compute_energy_rows(rx_engine *h, int *launches);  // fills d_u rows [k0, k0+kloc)
 int rxi_compute_energy_rows_at(rx_engine *h, const StateDev *d_states, int n_states, double *d_out, int *launches);
 int rxi_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream_id);

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256) k_slots_build(const uint32_t *__restrict_
 #define LOG_STATE_BITS 14
 #define RING 1024
 enum { U_F64_SMEM = 0, U_FILTER24 = 1, U_GLOBAL = 2 };
+#include "rx_walk2.cuh"
 
 struct WalkShared {     // control words shared by the two warps
     volatile unsigned prod;   // records [0, prod) of this pass are in the ring (modulo RING)
@@ -168,7 +169,8 @@ struct WalkShared {     // control words shared by the two warps
     volatile unsigned done;
 };
 
-template <int UMODE>
+// REC2: the records are SlotRec2 (rx_walk2.cuh); only with U_FILTER24, where this kernel finishes the passes of k_mix_walk2.
+template <int UMODE, bool REC2 = false>
 __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict__ rec, const uint32_t *__restrict__ words,
                                                       unsigned nslots, const double *__restrict__ u, int K, int logK,
                                                       int *__restrict__ perm_g, uint32_t *__restrict__ commit_log,
@@ -226,7 +228,12 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
                     if (o < cnt) {
                         const unsigned w = (prod + o) & (RING - 1);
                         ring_ij[w] = r[b].ij; ring_bm[w] = r[b].backmask;
-                        if (UMODE == U_FILTER24) ((float *)ring_lu)[w] = (float)r[b].logU;   // the filter works in f32
+                        if (REC2) {
+                            // SlotRec2: the third word is the f32 log-uniform of the NEXT slot, whose ring entry it is
+                            const uint4 q = *(const uint4 *)&r[b];
+                            ((float *)ring_lu)[(w + 1) & (RING - 1)] = __uint_as_float(q.z);
+                        }
+                        else if (UMODE == U_FILTER24) ((float *)ring_lu)[w] = (float)r[b].logU;   // the filter works in f32
                         else ring_lu[w] = r[b].logU;
                     }
                 }
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     const long long remaining0 = ctl->remaining;
     unsigned rem = remaining0 > 0x7fffffffLL ? 0x7fffffffu : (unsigned)remaining0;   // attempts this launch may still do
     const unsigned rem0 = rem;
-    unsigned logpos = 0, rounds = 0, slow = 0, prod_seen = head0;
+    unsigned logpos = (unsigned)ctl->log_count, rounds = 0, slow = 0, prod_seen = head0;   // the log continues where k_mix_walk2 stopped
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned sh_amt = 32u - (unsigned)lane;
     const unsigned short *s_qhi = (const unsigned short *)s_q;            // [K*K] sign, exponent, 7 mantissa bits
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
                     ge0 = logp >= 0.0;
                     acc = ge0;
                     if (!ge0) {
-                        const double dd = logp - rec[h + lane + 1].logU;
+                        const double dd = logp - (REC2 ? slot_logU(words, h + lane + 1) : rec[h + lane + 1].logU);
                         if (dd > 1e-9) acc = true;
                         else if (dd < -1e-9) acc = false;
                         else { const unsigned s1 = h + lane + 1; acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp); }
@@ -683,7 +690,7 @@ static inline size_t pass_need(long long remaining, bool fast) {
 // Top the stream up to what a pass over `remaining` attempts may consume and (fast path) build its slot records,
 // on stream `st`.  Both are state independent, so for the NEXT mixing call this runs on the side stream while the
 // replicas are being propagated.
-static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fast, int K, cudaStream_t st, int *launches) {
+static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fast, bool rec2, int K, cudaStream_t st, int *launches) {
     const size_t need = pass_need(remaining, fast);
     int rc = stream_reserve(h, S, 2 * need + 1024);   // room for the words generated ahead while the walker runs
     if (rc) return rc;
@@ -703,9 +710,15 @@ static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fas
             h->slots_cap = 0;
             RX_CHECK_CUDA(h, cudaMalloc(&h->d_slots, want * sizeof(SlotRec)));
             RX_CHECK_CUDA(h, cudaMalloc(&h->d_log, want * sizeof(uint32_t)));
+            cudaFree(h->d_slotlog);
+            h->d_slotlog = nullptr;
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_slotlog, want * sizeof(uint32_t)));
             h->slots_cap = want;
         }
-        k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, nslots, (uint32_t)(K - 1), h->d_slots);
+        if (rec2)
+            k_slots_build2<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, nslots, (uint32_t)(K - 1), (SlotRec2 *)h->d_slots);
+        else
+            k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, nslots, (uint32_t)(K - 1), h->d_slots);
         RX_CHECK_CUDA(h, cudaGetLastError());
         (*launches)++;
     }
@@ -743,6 +756,10 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     // the f32 row-image filter wherever it fits (K <= 256): it beats the f64 comparisons of U_F64_SMEM at every size
     if (fast && smem_f24 <= 224 * 1024 && !getenv("RX_NO_FILTER") && !getenv("RX_F64_SMEM")) umode = U_FILTER24;
     else if (fast && smem_f64 <= 200 * 1024) umode = U_F64_SMEM;
+    // filter mode: 16-byte SlotRec2 records, k_mix_walk2 for the bulk of a pass and k_mix_walk_pow2<U_FILTER24, true> for its tail
+    const bool rec2 = (umode == U_FILTER24);
+    const bool walk2 = rec2 && !getenv("RX_WALK_V1");
+    const size_t smem_w2 = (size_t)K * 16 + (size_t)3 * K * K + 16;
     size_t smem = !fast ? smem_small : (umode == U_F64_SMEM ? smem_f64 : (umode == U_FILTER24 ? smem_f24 : smem_base));
     // The walker is one latency-bound CTA: claim (almost) a whole SM's shared memory so that no other CTA -- in particular
     // the stream generator that runs concurrently on the side stream -- is scheduled onto the same SM and steals issue slots.
@@ -756,7 +773,8 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_F64_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_FILTER24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_FILTER24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_base_launch));
     }
     tr.mark("func attributes");
@@ -779,7 +797,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     while (remaining > 0) {
         const size_t need = pass_need(remaining, fast);
         int rc;
-        if (h->prepared && S.avail >= need && h->slots_for_avail == S.avail) {
+        if (h->prepared && h->prepared_rec2 == rec2 && S.avail >= need && h->slots_for_avail == S.avail) {
             // produced on the side stream while the replicas were propagating
             RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_prepared, 0));
             float ms = 0;
@@ -789,7 +807,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             h->mix_stats[5] += (long long)(rx_wall_us() - tw0);
         } else {
             if (h->prepared) RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream_rng));
-            rc = prepare_pass(h, S, remaining, fast, K, h->stream, launches);
+            rc = prepare_pass(h, S, remaining, fast, rec2, K, h->stream, launches);
             if (rc) return rc;
         }
         h->prepared = false;
@@ -812,8 +830,18 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             RX_CHECK_CUDA(h, cudaEventRecord(h->ev_walk[0], h->stream));
             if (umode == U_F64_SMEM)
                 k_mix_walk_pow2<U_F64_SMEM><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, h->d_ctl);
-            else if (umode == U_FILTER24)
-                k_mix_walk_pow2<U_FILTER24><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, h->d_filt, h->d_filt_scale, h->d_ctl);
+            else if (umode == U_FILTER24) {
+                if (walk2) {
+                    static_assert(sizeof(SlotRec2) == sizeof(SlotRec), "both record formats share the d_slots buffer");
+                    if (smem_w2 > smem) RX_FAIL(h, RX_ERR_INVALID, "internal: k_mix_walk2 shared memory");
+                    // sparse commit log: one word per slot, zero = no attempt started there
+                    RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_slotlog, 0, (size_t)nslots * sizeof(uint32_t), h->stream));
+                    k_mix_walk2<<<1, 32, smem, h->stream>>>((const SlotRec2 *)h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_slotlog, h->d_filt, h->d_filt_scale, h->d_ctl);
+                    RX_CHECK_CUDA(h, cudaGetLastError());
+                    *launches += 1;
+                }
+                k_mix_walk_pow2<U_FILTER24, true><<<1, 64, smem, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, h->d_filt, h->d_filt_scale, h->d_ctl);
+            }
             else
                 k_mix_walk_pow2<U_GLOBAL><<<1, 64, smem_base_launch, h->stream>>>(h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_log, nullptr, nullptr, h->d_ctl);
             RX_CHECK_CUDA(h, cudaGetLastError());
@@ -827,6 +855,13 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             if (ahead) {   // adopt the words generated during the walk
                 RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_prepared, 0));
                 S.avail += ahead;
+            }
+            if (walk2 && ctl.head > 0) {
+                long long nb = (ctl.head + 255) / 256;
+                if (nb > 148 * 16) nb = 148 * 16;
+                k_mix_count_slots<<<(unsigned)nb, 256, 0, h->stream>>>(h->d_slotlog, 0, ctl.head, M, h->d_nacc, h->d_nprop);
+                RX_CHECK_CUDA(h, cudaGetLastError());
+                *launches += 1;
             }
             if (ctl.log_count > 0) {
                 long long nb = (ctl.log_count + 255) / 256;
@@ -864,7 +899,8 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream_rng, h->ev_consumed, 0));
         RX_CHECK_CUDA(h, cudaEventRecord(h->ev[6], h->stream_rng));
         int l2 = 0;
-        int rc2 = prepare_pass(h, S, nswap, fast, K, h->stream_rng, &l2);
+        int rc2 = prepare_pass(h, S, nswap, fast, rec2, K, h->stream_rng, &l2);
+        h->prepared_rec2 = rec2;
         if (rc2) return rc2;
         RX_CHECK_CUDA(h, cudaEventRecord(h->ev[7], h->stream_rng));
         RX_CHECK_CUDA(h, cudaEventRecord(h->ev_prepared, h->stream_rng));
@@ -906,6 +942,7 @@ void rxi_mix_free(rx_engine *h) {
     }
     cudaFree(h->d_slots);
     cudaFree(h->d_log);
+    cudaFree(h->d_slotlog);
     cudaFree(h->d_filt);
     cudaFree(h->d_filt_scale);
     cudaFree(h->d_ctl);

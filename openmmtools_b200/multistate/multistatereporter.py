@@ -20,6 +20,7 @@ Only rank 0 writes (as in the reference, multistatesampler.py:1169-1187).
 """
 import json
 import os
+import shutil
 import pickle
 import numpy as np
 from .. import states as _states
@@ -90,10 +91,11 @@ class MultiStateReporter:
         if mode == 'w':
             os.makedirs(os.path.join(self._storage, 'analysis'), exist_ok=True)
             os.makedirs(os.path.join(self._storage, 'checkpoint'), exist_ok=True)
-            for f in os.listdir(os.path.join(self._storage, 'analysis')):
-                os.remove(os.path.join(self._storage, 'analysis', f))
-            for f in os.listdir(os.path.join(self._storage, 'checkpoint')):
-                os.remove(os.path.join(self._storage, 'checkpoint', f))
+            # a fresh container (MultiStateSampler.create refuses to get here when the storage exists): sub-directories
+            # such as analysis/online/ are removed as a whole
+            for sub in ('analysis', 'checkpoint'):
+                shutil.rmtree(os.path.join(self._storage, sub))
+                os.makedirs(os.path.join(self._storage, sub))
             self._meta = {'convention': convention, 'dicts': {}}
             self._write_meta()
         else:
@@ -399,6 +401,8 @@ def _jsonable(x):
         return {str(k): _jsonable(v) for k, v in x.items()}
     if isinstance(x, (list, tuple)):
         return [_jsonable(v) for v in x]
+    if isinstance(x, np.ndarray):
+        return _jsonable(x.tolist())
     if isinstance(x, (np.integer,)):
         return int(x)
     if isinstance(x, (np.floating,)):

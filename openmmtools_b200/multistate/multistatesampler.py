@@ -237,6 +237,10 @@ class MultiStateSampler:
             self._reporter = storage if isinstance(storage, MultiStateReporter) else MultiStateReporter(storage)
         if self._thermodynamic_states is not None:
             raise RuntimeError('Cannot initialize the same sampler twice (create() was already called).')
+        # multistatesampler.py:586-589: an existing storage is never overwritten
+        if self._reporter is not None and self._reporter.storage_exists():
+            raise RuntimeError('Storage file {} already exists; cowardly refusing to overwrite.'.format(
+                self._reporter.filepath))
         if isinstance(sampler_states, states.SamplerState):
             sampler_states = [sampler_states]
         self._pre_write_create(list(thermodynamic_states), list(sampler_states),
@@ -477,9 +481,16 @@ class MultiStateSampler:
             e.set_velocities(v, first=e.k0)
         it = self._iteration if iteration is None else iteration
         n_restart = self._mcmc_moves[0].n_restart_attempts
+        re = self._reassign if reassign is None else reassign
         for attempt in range(n_restart + 1):
             try:
-                e.propagate(self._seed + attempt * 0x9E3779B9, it, self._reassign if reassign is None else reassign)
+                if attempt == 0:
+                    e.propagate(self._seed, it, re)
+                else:
+                    # restart policy of mcmc.py:706-759: ONLY the replicas that failed go back to the state they had at
+                    # the start of this iteration (a device-side snapshot taken by rx_propagate) and run again with
+                    # other noise; the replicas that came through keep their result
+                    e.propagate_retry(self._seed + attempt * 0x9E3779B9, it, re)
                 break
             except EngineError as err:
                 if err.code != _lib.RX_ERR_NAN:
@@ -488,18 +499,9 @@ class MultiStateSampler:
                     bad = np.nonzero(err.nan_flags)[0]
                     raise SimulationNaNError('Propagating replica {} at state {} resulted in a NaN!'.format(
                         bad[0], self._replica_thermodynamic_states[bad[0]]))
-                # restart policy of mcmc.py:706-759: retry the failed replicas from their last good state
-                self._restore_replicas(np.nonzero(err.nan_flags)[0])
         self._states_stale = True
         if self.host_resident_states:
             self._sync_sampler_states()
-
-    def _restore_replicas(self, replicas):
-        for k in replicas:
-            s = self._sampler_states[k]
-            self._engine.set_positions(s._positions[None], first=int(k))
-            if s._velocities is not None:
-                self._engine.set_velocities(s._velocities[None], first=int(k))
 
     def _compute_energies(self):
         """u[k, l] for all replicas and states in one launch (+ NCCL all-gather) (multistatesampler.py:1436-1494)."""
@@ -554,6 +556,7 @@ class MultiStateSampler:
     def _report_iteration(self):
         """multistatesampler.py:1191-1207: states, checkpointed positions, mixing statistics, energies, commit marker."""
         if self._reporter is None:
+            self._report_iteration_items()
             return
         it = self._iteration
         checkpoint = (it % self._reporter.checkpoint_interval == 0)
@@ -563,6 +566,7 @@ class MultiStateSampler:
             if self._world_size > 1:
                 self._gather_sampler_states()
         if self._rank != 0:
+            self._report_iteration_items()
             return
         r = self._reporter
         r.write_replica_thermodynamic_states(self._replica_thermodynamic_states, it)
@@ -570,7 +574,11 @@ class MultiStateSampler:
             r.write_sampler_states(self._sampler_states, it, extra=self._checkpoint_extra())
         r.write_mixing_statistics(self._n_accepted_matrix, self._n_proposed_matrix, it)
         r.write_energies(self._energy_thermodynamic_states, self._neighborhoods, self._energy_unsampled_states, it)
+        self._report_iteration_items()      # subclass records (SAMS) go in before the commit marker
         r.write_last_iteration(it)
+
+    def _report_iteration_items(self):
+        """Hook: per-iteration records of a subclass, written before the commit marker."""
 
     def _gather_sampler_states(self):
         """Multi-GPU checkpoint: every rank sends its shard of positions/velocities/energies to rank 0 (the role of

@@ -21,7 +21,7 @@ class SAMSSampler(MultiStateSampler):
                        'class of openmmtools_b200.multistate on {}')
     _STORED_OPTIONS = MultiStateSampler._STORED_OPTIONS + (
         'state_update_scheme', 'update_stages', 'flatness_criteria', 'flatness_threshold', 'weight_update_method',
-        'adapt_target_probabilities', 'gamma0')
+        'adapt_target_probabilities', 'gamma0', 'log_target_probabilities')   # (a _StoredProperty in the reference, sams.py:281)
 
     def __init__(self, number_of_iterations=1, log_target_probabilities=None, state_update_scheme='global-jump',
                  locality=5, update_stages='two-stage', flatness_criteria='logZ-flatness', flatness_threshold=0.2,
@@ -169,8 +169,9 @@ class SAMSSampler(MultiStateSampler):
         self.log_weights = self.log_target_probabilities[:] - self._logZ[:]
 
     # ------------------------------------------------------------------ reporting / resume
-    def _report_iteration(self):
-        super()._report_iteration()
+    def _report_iteration_items(self):
+        """Runs inside ``_report_iteration`` BEFORE the commit marker, so that an iteration the marker points at always has
+        its logZ / stage / t0 / histogram record (a crash in between leaves the previous iteration as the last one)."""
         # state histogram exactly as the reference accumulates it (sams.py:385-393)
         st, cnt = np.unique(self._replica_thermodynamic_states, return_counts=True)
         self._cached_state_histogram[st] += cnt
