@@ -759,7 +759,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     // filter mode: 16-byte SlotRec2 records, k_mix_walk2 for the bulk of a pass and k_mix_walk_pow2<U_FILTER24, true> for its tail
     const bool rec2 = (umode == U_FILTER24);
     const bool walk2 = rec2 && !getenv("RX_WALK_V1");
-    const size_t smem_w2 = (size_t)K * 16 + (size_t)3 * K * K + 16;
+    const size_t smem_w2 = (size_t)W2_RING * 16 + (size_t)K * 12 + (size_t)3 * K * K + 32;
     size_t smem = !fast ? smem_small : (umode == U_F64_SMEM ? smem_f64 : (umode == U_FILTER24 ? smem_f24 : smem_base));
     // The walker is one latency-bound CTA: claim (almost) a whole SM's shared memory so that no other CTA -- in particular
     // the stream generator that runs concurrently on the side stream -- is scheduled onto the same SM and steals issue slots.

@@ -10,15 +10,12 @@
 //     exact path needs is recomputed from the two words of the stream (same log() as the pre-pass, same value);
 //   * the commit's bookkeeping (log entry, counters, promotion of the lanes that left the window) is issued after the
 //     next round's permutation loads, in their latency shadow;
-//   * there is no producer warp and no shared-memory ring (v1's was synchronised by volatile flags only): a lane reads the
-//     records of its own slot class straight from global memory, two windows ahead (L2 latency is covered by more than
-//     one round), and prefetches the line it will need 1024 slots later into L2 (DRAM latency).
-// The kernel runs the bulk of a pass; the last < 161 slots / < 33 attempts of a pass are left to
+//   * there is no producer warp (v1's ring was synchronised by volatile flags only): every lane keeps the records of its
+//     own slot class in a small shared-memory ring that it fills itself with cp.async, 15 windows ahead of use;
+//     completion is tracked by the hardware (cp.async.wait_group), no flags, no fences.
+// The kernel runs the bulk of a pass; the last < 600 slots / < 130 attempts of a pass are left to
 // k_mix_walk_pow2<U_FILTER24, true>, which reads the same records.
 #pragma once
-#ifndef W2_ZDEP
-#define W2_ZDEP 0
-#endif
 
 struct SlotRec2 {        // 16 bytes, one 2-word slot of the stream, state independent
     uint32_t ij;         // i | j << 16
@@ -95,16 +92,51 @@ __device__ __forceinline__ void w2_filter(float f_ii, float f_ij, float f_jj, fl
 
 // One entry per replica k: the walker's view of the permutation.  `diag` is the image value of u[k, state] - rowmin_k, so
 // a round reads the two diagonal terms of log_p together with the states (one dependent shared-memory level less) and
-// only the two off-diagonal image values afterwards; `rowabs` is the row's share of the filter's rounding bound.
-struct __align__(16) W2Replica {
+// only the two off-diagonal image values afterwards.  8 bytes: two wavefronts per warp-wide access at best.
+struct __align__(8) W2Replica {
     int state;
     float diag;
-    float rowabs;
-    int pad;
 };
 
 __device__ __forceinline__ float w2_image(const unsigned short *__restrict__ s_qhi, const unsigned char *__restrict__ s_qlo, unsigned a) {
     return __uint_as_float(__byte_perm((unsigned)s_qhi[a], (unsigned)s_qlo[a], 0x1045));   // (hi << 16) | (lo << 8)
+}
+
+// Shared-memory accesses of the round loop by explicit 32-bit shared addresses.  (With generic pointers the compiler
+// re-derives the shared window base from SR_CgaCtaId inside the loop -- an S2UR of a few hundred cycles on the chain.)
+__device__ __forceinline__ uint2 w2_lds64(unsigned a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float w2_lds_f32(unsigned a) {   // (read-only table)
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 w2_lds128(unsigned a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void w2_sts64(unsigned a, unsigned x, unsigned y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+// The walker's record ring: 16 entries per lane (= per slot class mod 32), filled by the lane itself with asynchronous
+// global->shared copies 15 windows ahead of use (no register, no scoreboard wait; DRAM latency is far below that).
+#define W2_RING 512
+__device__ __forceinline__ void w2_cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void w2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void w2_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float w2_image_at(unsigned a_hi, unsigned a_lo) {   // the image is read-only while the walker runs
+    unsigned hi, lo;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(a_hi));
+    asm("ld.shared.u8 %0, [%1];" : "=r"(lo) : "r"(a_lo));
+    return __uint_as_float(__byte_perm(hi, lo, 0x1045));
 }
 
 __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ rec, const uint32_t *__restrict__ words,
@@ -113,8 +145,10 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                                                   const unsigned char *__restrict__ filt,
                                                   const double *__restrict__ filt_rowabs, MixCtl *ctl) {
     extern __shared__ uint4 s_w2[];
-    W2Replica *s_rep = (W2Replica *)s_w2;                  // [K]
-    unsigned char *s_q = (unsigned char *)(s_rep + K);     // image: u16 plane [K*K], then u8 plane [K*K]
+    uint4 *s_ring = s_w2;                                  // [W2_RING] slot records
+    W2Replica *s_rep = (W2Replica *)(s_ring + W2_RING);    // [K]
+    float *s_rowabs = (float *)(s_rep + K);                // [K] the row's share of the filter's rounding bound
+    unsigned char *s_q = (unsigned char *)(s_rowabs + K);  // image: u16 plane [K*K], then u8 plane [K*K] (16-byte aligned for K >= 4)
     const unsigned short *s_qhi = (const unsigned short *)s_q;
     const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;
     const int lane = threadIdx.x;
@@ -130,9 +164,8 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
         W2Replica e;
         e.state = perm_g[q];
         e.diag = w2_image(s_qhi, s_qlo, ((unsigned)q << logK) | (unsigned)e.state);
-        e.rowabs = __fmul_ru(1.6e-14f, __fadd_ru(__double2float_ru(filt_rowabs[q]), 0.5f));
-        e.pad = 0;
         s_rep[q] = e;
+        s_rowabs[q] = __fmul_ru(1.6e-14f, __fadd_ru(__double2float_ru(filt_rowabs[q]), 0.5f));
     }
     const unsigned head0 = (unsigned)ctl->head;
     __syncwarp();
@@ -143,53 +176,73 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
     unsigned rem = remaining0 > 0x7fffffffLL ? 0x7fffffffu : (unsigned)remaining0;
     const unsigned rem0 = rem;
     unsigned rounds = 0, slow = 0;
-    // a round may start while h <= h_end: it reads the records of [h, h + 97) (a window, the next window, an advance)
-    const unsigned h_end = nslots >= 300u ? nslots - 161u : 0u;
-    if (rem >= 130 && nslots >= 300u && h + 99u <= h_end) {
+    // a round may start while h <= h_end: its lanes copy the records of slots up to h + 33 + 31 + 480 into the ring
+    const unsigned h_end = nslots >= 1200u ? nslots - 560u : 0u;
+    if (rem >= 130 && nslots >= 1200u && h + 99u <= h_end) {
         unsigned r = h & 31u;                           // lane of window position 0
         unsigned w = ((unsigned)lane - h) & 31u;        // this lane's window position
         unsigned sA = h + w;                            // this lane's slot
         // slot contexts: A = current, B = the slot one window later (raw record qB, loaded a round ahead)
         unsigned iA, jA, bmA, iB, jB, bmB;
-        float luA, luB;
+        float luA, luB, epsA, epsB;
         auto unpack = [&](const uint4 q, unsigned &i, unsigned &j, unsigned &bm, float &lu) {
             i = q.x & 0xffffu; j = q.x >> 16; bm = q.y; lu = __uint_as_float(q.z);
         };
-        unpack(recs[sA], iA, jA, bmA, luA);
-        uint4 qB = recs[sA + 32];
+        const unsigned ring_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_ring), 0);
+        // ring entry of slot s: s mod W2_RING; this lane owns the entries of its class (s mod 32)
+        for (unsigned k = 0; k < 16u; k++) w2_cp_async16(ring_base + (((sA + 32u * k) & (W2_RING - 1)) << 4), recs + (sA + 32u * k));
+        w2_cp_async_commit();
+        w2_cp_async_wait<0>();
+        __syncwarp();
+        unpack(w2_lds128(ring_base + ((sA & (W2_RING - 1)) << 4)), iA, jA, bmA, luA);
+        uint4 qB = w2_lds128(ring_base + (((sA + 32u) & (W2_RING - 1)) << 4));   // raw record one window later
         unpack(qB, iB, jB, bmB, luB);
-        uint4 ei = *(const uint4 *)&s_rep[iA], ej = *(const uint4 *)&s_rep[jA];   // {state, diag, rowabs} of both replicas
+        // 32-bit shared addresses (through a shuffle, so that they live in registers instead of being re-derived)
+        const unsigned rep_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_rep), 0);
+        const unsigned qhi_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_qhi), 0);
+        const unsigned qlo_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_qlo), 0);
+        const unsigned rowabs_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_rowabs), 0);
+        auto eps_of = [&](unsigned i, unsigned j) { return (w2_lds_f32(rowabs_base + (i << 2)) + w2_lds_f32(rowabs_base + (j << 2))) + 1e-9f; };
+        epsA = eps_of(iA, jA); epsB = eps_of(iB, jB);
+        uint2 ei = w2_lds64(rep_base + (iA << 3)), ej = w2_lds64(rep_base + (jA << 3));   // {state, diag} of both replicas
         // what the round resolved last leaves to the next block (predicates are computed where their inputs appear, so
         // that their latency overlaps the loop branch): this lane commits / swaps / leaves the window
         bool p_mine = false, p_swaps = false, p_promoted = false;
         unsigned p_entry = 0, p_advance = 0, p_n = 0;
         float f_ij = 0.f, f_ji = 0.f;
-        unsigned z = 0;
+        uint32_t *log_ptr = slot_log + sA;          // this lane's entry of the sparse commit log
+        const uint4 *rec_ptr = recs + (sA + 480);   // the record this lane copies into the ring at its next promotion
         // Commit the round described by the p_* values, slide the window and fetch the states of the next round:
         // permutation stores, at once the next round's loads, then the lane state.
         auto commit = [&]() {
             if (p_swaps) {   // replica i takes state sj: its new diagonal value is the off-diagonal one just read
-                *(uint2 *)&s_rep[iA] = make_uint2(ej.x, __float_as_uint(f_ij));
-                *(uint2 *)&s_rep[jA] = make_uint2(ei.x, __float_as_uint(f_ji));
+                w2_sts64(rep_base + (iA << 3), ej.x, __float_as_uint(f_ij));
+                w2_sts64(rep_base + (jA << 3), ei.x, __float_as_uint(f_ji));
             }
             __syncwarp();
-            const uint4 eiA = *(const uint4 *)&s_rep[iA], ejA = *(const uint4 *)&s_rep[jA];
-            const uint4 eiB = *(const uint4 *)&s_rep[iB], ejB = *(const uint4 *)&s_rep[jB];
-            // `z` is the entries' padding word: always zero, but only known once the loads above have returned.  Every
-            // piece of book-keeping below is made to depend on it, which keeps the instruction scheduler from issuing it
-            // ahead of the stores and loads that head the dependent chain (a warp issues in order).
-#if W2_ZDEP
-            z = eiA.w;
-#endif
-            const unsigned adv = p_advance + z;
-            if (p_mine) slot_log[sA + z] = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
+            // the states of the next round: of the slot one window later for the lanes that leave the window
+            const uint2 ein = w2_lds64(rep_base + ((p_promoted ? iB : iA) << 3)), ejn = w2_lds64(rep_base + ((p_promoted ? jB : jA) << 3));
+            const unsigned adv = p_advance;
+            if (p_mine) *log_ptr = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
             h += adv;
             r = (r + adv) & 31u;
-            rem -= p_n + z;
-            if (p_promoted) { iA = iB; jA = jB; bmA = bmB; luA = luB; sA += 32; }
-            ei = p_promoted ? eiB : eiA;
-            ej = p_promoted ? ejB : ejA;
+            rem -= p_n;
+            if (p_promoted) {
+                iA = iB; jA = jB; bmA = bmB; luA = luB; epsA = epsB; sA += 32; log_ptr += 32; rec_ptr += 32;
+                w2_cp_async16(ring_base + (((sA + 480u) & (W2_RING - 1)) << 4), rec_ptr);   // over the entry of the slot just left
+            }
+            w2_cp_async_commit();
+            // the record one window later: the lanes that stay re-read the one they hold (no dependence on a predicate)
+            qB = w2_lds128(ring_base + (((sA + 32u) & (W2_RING - 1)) << 4));
+            ei = ein;
+            ej = ejn;
             w = (w - adv) & 31u;
+        };
+        // a copy is used 15 of the lane's promotions (at least 15 rounds) after it was issued
+        auto fetch = [&]() {
+            w2_cp_async_wait<8>();
+            unpack(qB, iB, jB, bmB, luB);   // the slot one window later
+            epsB = eps_of(iB, jB);
         };
         for (;;) {
             // ---------------- fast rounds.  The loop is rotated: an iteration COMMITS the round resolved by the previous
@@ -202,20 +255,17 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                 commit();
                 rounds++;
                 const unsigned si = ei.x, sj = ej.x;
-                f_ij = w2_image(s_qhi, s_qlo, (iA << logK) | sj);
-                f_ji = w2_image(s_qhi, s_qlo, (jA << logK) | si);
-                // the record of the slot one window later: the lanes that stay re-read the one they hold; the lines were
-                // brought into L1 two windows ahead and into L2 1024 slots ahead
-                const unsigned sZ = sA + z;
-                qB = __ldg(recs + (sZ + 32));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + (sZ + 96)));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + min(sZ + 1024u, nslots - 1u)));
+                {
+                    const unsigned a_ij = (iA << logK) | sj, a_ji = (jA << logK) | si;
+                    f_ij = w2_image_at(qhi_base + 2u * a_ij, qlo_base + a_ij);
+                    f_ji = w2_image_at(qhi_base + 2u * a_ji, qlo_base + a_ji);
+                }
+                fetch();
                 // the budget and the end of the pass: the round being resolved now commits at most 32 attempts and
                 // advances at most 33 slots, and one more round may follow it before the next test
                 go = rem >= 97u && h + 66u <= h_end;
-                const float eps0 = (__uint_as_float(ei.z) + __uint_as_float(ej.z)) + 1e-9f;
                 bool ge0, acc, undecided;
-                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, eps0, luA, iA == jA, ge0, acc, undecided);
+                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, epsA, luA, iA == jA, ge0, acc, undecided);
                 const unsigned und = undecided ? 1u : 0u;
                 const bool changes = acc && iA != jA;
                 const unsigned G = __ballot_sync(0xffffffffu, ge0);
@@ -245,21 +295,21 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                 adv33 = (Cw == 0u && sumO < X) ? 1u : 0u;
                 p_advance = Cw ? (unsigned)__popc(below) : 32u + adv33;
                 p_n = __popc(cm);
-                unpack(qB, iB, jB, bmB, luB);   // the next commit's "one window later" context (the load above has landed)
             } while (go && cm != 0u && adv33 == 0u);
             commit();   // the round resolved last
-            qB = __ldg(recs + (sA + 32));
-            unpack(qB, iB, jB, bmB, luB);
+            fetch();
             // ---------------- rare events
             if (adv33) {
                 // the slot after the window is a uniform's slot: the lane that is now at window position 31 holds slot
                 // h - 1 (skipped) and moves on by another window
                 if (w == 31u) {
-                    sA += 32;
-                    unpack(recs[sA], iA, jA, bmA, luA);
-                    qB = recs[sA + 32];
+                    sA += 32; log_ptr += 32; rec_ptr += 32;
+                    w2_cp_async16(ring_base + (((sA + 480u) & (W2_RING - 1)) << 4), rec_ptr);
+                    unpack(w2_lds128(ring_base + ((sA & (W2_RING - 1)) << 4)), iA, jA, bmA, luA);
+                    qB = w2_lds128(ring_base + (((sA + 32u) & (W2_RING - 1)) << 4));
                     unpack(qB, iB, jB, bmB, luB);
-                    ei = *(const uint4 *)&s_rep[iA]; ej = *(const uint4 *)&s_rep[jA];
+                    epsA = eps_of(iA, jA); epsB = eps_of(iB, jB);
+                    ei = w2_lds64(rep_base + (iA << 3)); ej = w2_lds64(rep_base + (jA << 3));
                 }
                 __syncwarp();
             }
@@ -294,8 +344,7 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                 p_promoted = w < p_advance;
                 p_entry = si | (sj << LOG_STATE_BITS) | ((acc ? 1u : 0u) << LOG_ACC_BIT) | (1u << 31);
                 commit();
-                qB = __ldg(recs + (sA + 32));
-                unpack(qB, iB, jB, bmB, luB);
+                fetch();
                 if (rem < 130u || h + 99u > h_end) break;
             }
         }
