@@ -275,3 +275,25 @@ def test_graft_entry_smoke_runs():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_nan_restart_retries_only_the_failed_replica_from_the_iteration_start():
+    """Restart policy of mcmc.py:706-759: a replica whose propagation went NaN is retried from the state it had when the
+    iteration began (device-side snapshot), the others keep their result (they are not propagated twice, and nobody is
+    rewound to an older host copy).  Replica 2 is given absurd velocities after two clean iterations, so that every
+    attempt fails and the run ends with SimulationNaNError; the healthy replicas must equal those of a clean run."""
+    from openmmtools_b200.multistate.utils import SimulationNaNError
+    K = 8
+    clean, _, _ = lj_sampler(K=K, seed=21, scheme=None)
+    sick, _, _ = lj_sampler(K=K, seed=21, scheme=None)
+    clean.run(3)
+    sick.run(2)
+    v = sick._engine.get_velocities()
+    v[2] = 1e30
+    sick._engine.set_velocities(v[2:3], first=2)
+    with pytest.raises(SimulationNaNError):
+        sick.run(1)
+    xs, xc = sick._engine.get_positions(), clean._engine.get_positions()
+    for k in range(K):
+        if k != 2:
+            assert np.array_equal(xs[k], xc[k]), k        # propagated exactly once, from the right state
