@@ -74,20 +74,25 @@ __global__ void __launch_bounds__(256) k_slots_build2(const uint32_t *__restrict
     rec[s] = r;
 }
 
-// The filter's decision for one (i, j, si, sj): image values f_xy = image of u[x, s_y] - rowmin_x.  Same arithmetic as
-// k_mix_walk_pow2<U_FILTER24> (see the bound's derivation there); eps0 = rowabs[i] + rowabs[j] + 1e-9.
-__device__ __forceinline__ void w2_filter(float f_ii, float f_ij, float f_jj, float f_ji, float eps0, float lu, bool i_eq_j,
+// The filter's decision for one (i, j, si, sj): image values d_x = image of u[x, s_x] - rowmin_x (the maintained diagonal)
+// and f_xy = image of u[x, s_y] - rowmin_x.  Same rigorous bound as k_mix_walk_pow2<U_FILTER24> (see its derivation there;
+// the factor 3.2e-5 leaves 5 % over the 2^-15 + 2^-23 the roundings need, far more than the re-association below costs):
+//   e0  = 3.2e-5 (|d_i| + |d_j|) + eps0        as soon as the states are known (before the image loads return),
+//   eps = 3.2e-5 (|f_ij| + |f_ji|) + e0,       lp = (d_i - f_ij) + (d_j - f_ji),
+//   log_p >= 0 is certain iff lp > eps; it is certainly < 0 iff lp < -eps; the comparison with the uniform is certain
+//   iff |lp - lu| > mar = 1.3e-7 (|lp| + |lu|) + eps.
+// eps0 = rowabs[i] + rowabs[j] + 1e-9, or -1e30 for a slot with i == j: the reference's log_p is then exactly 0 for finite
+// energies (accepted without a draw) and lp is exactly 0 > eps; non-finite energies give lp = NaN (undecided: exact path).
+__device__ __forceinline__ void w2_filter(float d_i, float f_ij, float d_j, float f_ji, float e0, float lu,
                                           bool &ge0, bool &acc, bool &undecided) {
-    const float lp = (f_ii - f_ij) + (f_jj - f_ji);
-    const float mag = (fabsf(f_ii) + fabsf(f_ij)) + (fabsf(f_jj) + fabsf(f_ji));
-    const float eps = fmaf(mag, 3.2e-5f, eps0);
+    const float lp = (d_i - f_ij) + (d_j - f_ji);
+    const float eps = fmaf(fabsf(f_ij) + fabsf(f_ji), 3.2e-5f, e0);
+    ge0 = lp > eps;
     const float d = lp - lu;
     const float mar = fmaf(fabsf(lp) + fabsf(lu), 1.3e-7f, eps);
-    const bool dec_lp = fabsf(lp) > eps, dec_d = fabsf(d) > mar;
-    const bool same = i_eq_j && (fabsf(f_ii) <= 3.0e38f);
-    ge0 = (dec_lp && lp > 0.f) || same;
-    acc = ge0 || (dec_lp && dec_d && d > 0.f);
-    undecided = !(ge0 || (dec_lp && dec_d));
+    const bool dec_lp = fabsf(lp) > eps;
+    acc = ge0 || (dec_lp && d > mar);
+    undecided = !(ge0 || (dec_lp && fabsf(d) > mar));
 }
 
 // One entry per replica k: the walker's view of the permutation.  `diag` is the image value of u[k, state] - rowmin_k, so
@@ -185,6 +190,7 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
         // slot contexts: A = current, B = the slot one window later (raw record qB, loaded a round ahead)
         unsigned iA, jA, bmA, iB, jB, bmB;
         float luA, luB, epsA, epsB;
+        unsigned hiA_i, loA_i, hiA_j, loA_j, hiB_i, loB_i, hiB_j, loB_j;   // shared addresses of the image rows of i and j
         auto unpack = [&](const uint4 q, unsigned &i, unsigned &j, unsigned &bm, float &lu) {
             i = q.x & 0xffffu; j = q.x >> 16; bm = q.y; lu = __uint_as_float(q.z);
         };
@@ -202,19 +208,29 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
         const unsigned qhi_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_qhi), 0);
         const unsigned qlo_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_qlo), 0);
         const unsigned rowabs_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_rowabs), 0);
-        auto eps_of = [&](unsigned i, unsigned j) { return (w2_lds_f32(rowabs_base + (i << 2)) + w2_lds_f32(rowabs_base + (j << 2))) + 1e-9f; };
+        auto eps_of = [&](unsigned i, unsigned j) {
+            const float e = (w2_lds_f32(rowabs_base + (i << 2)) + w2_lds_f32(rowabs_base + (j << 2))) + 1e-9f;
+            return i == j ? -1e30f : e;
+        };
+        auto rows_of = [&](unsigned i, unsigned j, unsigned &hi_i, unsigned &lo_i, unsigned &hi_j, unsigned &lo_j) {
+            hi_i = qhi_base + ((i << logK) << 1); lo_i = qlo_base + (i << logK);
+            hi_j = qhi_base + ((j << logK) << 1); lo_j = qlo_base + (j << logK);
+        };
         epsA = eps_of(iA, jA); epsB = eps_of(iB, jB);
+        rows_of(iA, jA, hiA_i, loA_i, hiA_j, loA_j); rows_of(iB, jB, hiB_i, loB_i, hiB_j, loB_j);
         uint2 ei = w2_lds64(rep_base + (iA << 3)), ej = w2_lds64(rep_base + (jA << 3));   // {state, diag} of both replicas
-        // what the round resolved last leaves to the next block (predicates are computed where their inputs appear, so
-        // that their latency overlaps the loop branch): this lane commits / swaps / leaves the window
-        bool p_mine = false, p_swaps = false, p_promoted = false;
-        unsigned p_entry = 0, p_advance = 0, p_n = 0;
+        // what the round resolved last leaves to the next block: the committed window positions, the positions that leave
+        // the window, whether this lane's attempt changes the permutation, its log entry
+        unsigned p_cm = 0, p_below = 0, p_chg = 0, p_entry = 0, p_advance = 0;
         float f_ij = 0.f, f_ji = 0.f;
         uint32_t *log_ptr = slot_log + sA;          // this lane's entry of the sparse commit log
         const uint4 *rec_ptr = recs + (sA + 480);   // the record this lane copies into the ring at its next promotion
         // Commit the round described by the p_* values, slide the window and fetch the states of the next round:
         // permutation stores, at once the next round's loads, then the lane state.
         auto commit = [&]() {
+            const bool p_mine = (p_cm >> w) & 1u;
+            const bool p_swaps = ((p_cm >> w) & p_chg) != 0u;
+            const bool p_promoted = (p_below >> w) & 1u;
             if (p_swaps) {   // replica i takes state sj: its new diagonal value is the off-diagonal one just read
                 w2_sts64(rep_base + (iA << 3), ej.x, __float_as_uint(f_ij));
                 w2_sts64(rep_base + (jA << 3), ei.x, __float_as_uint(f_ji));
@@ -226,9 +242,10 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
             if (p_mine) *log_ptr = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
             h += adv;
             r = (r + adv) & 31u;
-            rem -= p_n;
+            rem -= __popc(p_cm);
             if (p_promoted) {
                 iA = iB; jA = jB; bmA = bmB; luA = luB; epsA = epsB; sA += 32; log_ptr += 32; rec_ptr += 32;
+                hiA_i = hiB_i; loA_i = loB_i; hiA_j = hiB_j; loA_j = loB_j;
                 w2_cp_async16(ring_base + (((sA + 480u) & (W2_RING - 1)) << 4), rec_ptr);   // over the entry of the slot just left
             }
             w2_cp_async_commit();
@@ -243,6 +260,7 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
             w2_cp_async_wait<8>();
             unpack(qB, iB, jB, bmB, luB);   // the slot one window later
             epsB = eps_of(iB, jB);
+            rows_of(iB, jB, hiB_i, loB_i, hiB_j, loB_j);
         };
         for (;;) {
             // ---------------- fast rounds.  The loop is rotated: an iteration COMMITS the round resolved by the previous
@@ -250,22 +268,20 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
             // state loads -> image loads -> filter -> ballots); no data-dependent branch besides the loop's.
             bool go;
             unsigned cm = 0, adv33 = 0;
-            p_mine = p_swaps = p_promoted = false; p_advance = 0; p_n = 0;   // nothing to commit on entry
+            p_cm = p_below = p_advance = 0;   // nothing to commit on entry
             do {
                 commit();
                 rounds++;
                 const unsigned si = ei.x, sj = ej.x;
-                {
-                    const unsigned a_ij = (iA << logK) | sj, a_ji = (jA << logK) | si;
-                    f_ij = w2_image_at(qhi_base + 2u * a_ij, qlo_base + a_ij);
-                    f_ji = w2_image_at(qhi_base + 2u * a_ji, qlo_base + a_ji);
-                }
+                f_ij = w2_image_at(hiA_i + 2u * sj, loA_i + sj);
+                f_ji = w2_image_at(hiA_j + 2u * si, loA_j + si);
+                const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, epsA);
                 fetch();
                 // the budget and the end of the pass: the round being resolved now commits at most 32 attempts and
                 // advances at most 33 slots, and one more round may follow it before the next test
                 go = rem >= 97u && h + 66u <= h_end;
                 bool ge0, acc, undecided;
-                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, epsA, luA, iA == jA, ge0, acc, undecided);
+                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, e0, luA, ge0, acc, undecided);
                 const unsigned und = undecided ? 1u : 0u;
                 const bool changes = acc && iA != jA;
                 const unsigned G = __ballot_sync(0xffffffffu, ge0);
@@ -287,14 +303,11 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                 const unsigned low = Cw & (0u - Cw);
                 const unsigned below = low - 1u;       // low == 0 -> all lanes
                 cm = V & below;
-                p_mine = (cm >> w) & 1u;
-                p_swaps = p_mine && changes;
-                p_promoted = (below >> w) & 1u;
+                p_cm = cm; p_below = below; p_chg = changes ? 1u : 0u;
                 p_entry = si | (sj << LOG_STATE_BITS) | ((acc ? 1u : 0u) << LOG_ACC_BIT) | (1u << 31);
                 // bit 32 (even position) of the skip word can only be set by the carry of an odd-start run
                 adv33 = (Cw == 0u && sumO < X) ? 1u : 0u;
                 p_advance = Cw ? (unsigned)__popc(below) : 32u + adv33;
-                p_n = __popc(cm);
             } while (go && cm != 0u && adv33 == 0u);
             commit();   // the round resolved last
             fetch();
@@ -309,6 +322,7 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                     qB = w2_lds128(ring_base + (((sA + 32u) & (W2_RING - 1)) << 4));
                     unpack(qB, iB, jB, bmB, luB);
                     epsA = eps_of(iA, jA); epsB = eps_of(iB, jB);
+                    rows_of(iA, jA, hiA_i, loA_i, hiA_j, loA_j); rows_of(iB, jB, hiB_i, loB_i, hiB_j, loB_j);
                     ei = w2_lds64(rep_base + (iA << 3)); ej = w2_lds64(rep_base + (jA << 3));
                 }
                 __syncwarp();
@@ -338,10 +352,9 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                 __syncwarp();
                 const bool first_ge0 = __ballot_sync(0xffffffffu, ge0) != 0u;
                 p_advance = first_ge0 ? 1u : 2u;   // log_p < 0: the next slot is this attempt's uniform
-                p_n = 1u;
-                p_mine = (w == 0u);
-                p_swaps = p_mine && acc && iA != jA;
-                p_promoted = w < p_advance;
+                p_cm = 1u;                         // window position 0 commits; positions 0 .. advance-1 leave the window
+                p_below = first_ge0 ? 1u : 3u;
+                p_chg = (acc && iA != jA) ? 1u : 0u;
                 p_entry = si | (sj << LOG_STATE_BITS) | ((acc ? 1u : 0u) << LOG_ACC_BIT) | (1u << 31);
                 commit();
                 fetch();
