@@ -102,6 +102,12 @@ RX_API int rx_set_velocities(rx_engine *h, int32_t first, int32_t count, const d
 RX_API int rx_get_positions(rx_engine *h, int32_t first, int32_t count, double *xyz);
 RX_API int rx_get_velocities(rx_engine *h, int32_t first, int32_t count, double *xyz);
 /* potential (kJ/mol, in the replica's current state) and kinetic energy after the last propagate.       */
+/* Page-lock a caller buffer so that rx_set_* / rx_get_* on (parts of) it copy directly, without the engine's staging
+ * buffer (the host-resident SamplerState arrays of MultiStateSampler, multistatesampler.py:1296-1337 keeps them on the
+ * host between iterations).  Unregistered by rx_unpin_host_memory or rx_destroy.                                  */
+RX_API int rx_pin_host_memory(rx_engine *h, void *buffer, uint64_t bytes);
+RX_API int rx_unpin_host_memory(rx_engine *h, void *buffer);
+
 RX_API int rx_get_replica_energies(rx_engine *h, double *potential /*[K] or NULL*/, double *kinetic /*[K] or NULL*/);
 /* context.setVelocitiesToTemperature (mcmc.py:711): v = sqrt(kB T/m) N(0,1) for every owned replica.     */
 RX_API int rx_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream);

@@ -114,19 +114,36 @@ class Engine:
         xyz = _c64(xyz)
         self._check(self._lib.rx_set_velocities(self._h, first, xyz.shape[0], _ptr(xyz)))
 
-    def get_positions(self, first=None, count=None):
+    def _out(self, out, count):
+        if out is None:
+            return np.empty((count, self.N, 3))
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.shape != (count, self.N, 3):
+            raise ValueError('out must be a C-contiguous float64 array of shape %s' % ((count, self.N, 3),))
+        return out
+
+    def get_positions(self, first=None, count=None, out=None):
         first = self.k0 if first is None else first
         count = (self.k1 - first) if count is None else count
-        out = np.zeros((count, self.N, 3))
+        out = self._out(out, count)
         self._check(self._lib.rx_get_positions(self._h, first, count, _ptr(out)))
         return out
 
-    def get_velocities(self, first=None, count=None):
+    def get_velocities(self, first=None, count=None, out=None):
         first = self.k0 if first is None else first
         count = (self.k1 - first) if count is None else count
-        out = np.zeros((count, self.N, 3))
+        out = self._out(out, count)
         self._check(self._lib.rx_get_velocities(self._h, first, count, _ptr(out)))
         return out
+
+    def pinned_array(self, shape):
+        """A page-aligned float64 array registered with the engine (rx_pin_host_memory): set_*/get_* on it copy directly."""
+        n = int(np.prod(shape)) * 8
+        raw = np.empty(n + 4096, np.uint8)
+        off = (-raw.ctypes.data) % 4096
+        a = raw[off:off + n].view(np.float64).reshape(shape)
+        self._check(self._lib.rx_pin_host_memory(self._h, _ptr(a), n))
+        self._pinned = getattr(self, '_pinned', []) + [raw]     # keeps the allocation alive as long as the engine
+        return a
 
     def get_replica_energies(self):
         pot, kin = np.zeros(self.K), np.zeros(self.K)

@@ -18,7 +18,7 @@ RX_STREAM_NUMBA, RX_STREAM_NUMPY = 0, 1
 SYMBOLS = [
     'rx_create', 'rx_destroy', 'rx_last_error', 'rx_abi_version', 'rx_set_particles', 'rx_set_states',
     'rx_set_integrator', 'rx_set_positions', 'rx_set_velocities', 'rx_get_positions', 'rx_get_velocities',
-    'rx_get_replica_energies', 'rx_randomize_velocities', 'rx_minimize', 'rx_set_replica_states', 'rx_get_replica_states',
+    'rx_get_replica_energies', 'rx_pin_host_memory', 'rx_unpin_host_memory', 'rx_randomize_velocities', 'rx_minimize', 'rx_set_replica_states', 'rx_get_replica_states',
     'rx_propagate', 'rx_propagate_retry', 'rx_compute_energies', 'rx_compute_energies_at', 'rx_set_energies', 'rx_get_energies', 'rx_mix_seed',
     'rx_mix_skip', 'rx_mix_swap_all', 'rx_mix_swap_neighbors', 'rx_get_mix_counts', 'rx_mix_stream_position',
     'rx_run_iterations', 'rx_get_phase_times', 'rx_timer_mark', 'rx_timer_elapsed', 'rx_get_mix_stats', 'rx_comm_unique_id', 'rx_comm_init',
@@ -64,6 +64,8 @@ def load():
     for name in ('rx_set_positions', 'rx_set_velocities', 'rx_get_positions', 'rx_get_velocities'):
         getattr(lib, name).argtypes = [vp, i32, i32, vp]
     lib.rx_get_replica_energies.argtypes = [vp, vp, vp]
+    lib.rx_pin_host_memory.argtypes = [vp, vp, u64]
+    lib.rx_unpin_host_memory.argtypes = [vp, vp]
     lib.rx_randomize_velocities.argtypes = [vp, u64, u64]
     lib.rx_minimize.argtypes = [vp, dbl, i32, vp, vp]
     lib.rx_set_replica_states.argtypes = [vp, vp]

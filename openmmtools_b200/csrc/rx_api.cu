@@ -118,6 +118,7 @@ extern "C" void rx_destroy(rx_engine *h) {
     for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; i++) if (h->ev_user[i]) cudaEventDestroy(h->ev_user[i]);
     for (int i = 0; i < 2; i++) if (h->ev_walk[i]) cudaEventDestroy(h->ev_walk[i]);
+    for (const auto &r : h->pinned) cudaHostUnregister((void *)r.first);
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_rng) cudaStreamDestroy(h->stream_rng);
@@ -258,6 +259,35 @@ extern "C" int rx_get_positions(rx_engine *h, int32_t first, int32_t count, doub
 extern "C" int rx_get_velocities(rx_engine *h, int32_t first, int32_t count, double *xyz) {
     ENTER(h);
     return get_xyz(h, h->d_vel, first, count, xyz, false, "rx_get_velocities");
+}
+
+bool rxi_is_pinned(const rx_engine *h, const void *p, size_t bytes) {
+    const char *c = (const char *)p;
+    for (const auto &r : h->pinned)
+        if (c >= r.first && c + bytes <= r.first + r.second) return true;
+    return false;
+}
+
+/* Page-lock a caller buffer (cudaHostRegister) so that rx_set_* / rx_get_* copy straight between it and the device instead
+ * of staging through the engine's own pinned buffer: the host-resident SamplerStates of MultiStateSampler live in one
+ * such buffer.  The engine unregisters what is still registered when it is destroyed. */
+extern "C" int rx_pin_host_memory(rx_engine *h, void *ptr, uint64_t bytes) {
+    ENTER(h);
+    if (!ptr || !bytes) RX_FAIL(h, RX_ERR_INVALID, "rx_pin_host_memory: null buffer");
+    RX_CHECK_CUDA(h, cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    h->pinned.push_back(std::make_pair((const char *)ptr, (size_t)bytes));
+    return RX_OK;
+}
+extern "C" int rx_unpin_host_memory(rx_engine *h, void *ptr) {
+    ENTER(h);
+    for (size_t q = 0; q < h->pinned.size(); q++)
+        if (h->pinned[q].first == (const char *)ptr) {
+            RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+            cudaHostUnregister(ptr);
+            h->pinned.erase(h->pinned.begin() + q);
+            return RX_OK;
+        }
+    RX_FAIL(h, RX_ERR_INVALID, "rx_unpin_host_memory: buffer was not registered");
 }
 
 extern "C" int rx_get_replica_energies(rx_engine *h, double *potential, double *kinetic) {

@@ -599,8 +599,12 @@ __global__ void k_unpack(const float4 *__restrict__ in, double *__restrict__ out
 int rxi_convert_in(rx_engine *h, float4 *dst, int first_local, int count, const double *host_xyz, bool) {
     const long long n = (long long)count * h->cfg.n_atoms;
     if (n == 0) return RX_OK;
-    memcpy(h->h_io, host_xyz, n * 3 * sizeof(double));  // through pinned staging
-    RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_io, h->h_io, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const double *src = host_xyz;
+    if (!rxi_is_pinned(h, host_xyz, n * 3 * sizeof(double))) {   // pageable caller memory goes through the pinned staging buffer
+        memcpy(h->h_io, host_xyz, n * 3 * sizeof(double));
+        src = h->h_io;
+    }
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_io, src, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     k_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_io, dst + (size_t)first_local * h->cfg.n_atoms, n);
     RX_CHECK_CUDA(h, cudaGetLastError());
     RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -613,9 +617,10 @@ int rxi_convert_out(rx_engine *h, const float4 *src, int first_local, int count,
     k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(src + (size_t)first_local * h->cfg.n_atoms, h->d_io, n,
                                                                  wrap ? 1 : 0, h->cfg.box[0], h->cfg.box[1], h->cfg.box[2]);
     RX_CHECK_CUDA(h, cudaGetLastError());
-    RX_CHECK_CUDA(h, cudaMemcpyAsync(h->h_io, h->d_io, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const bool direct = rxi_is_pinned(h, host_xyz, n * 3 * sizeof(double));
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(direct ? host_xyz : h->h_io, h->d_io, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
-    memcpy(host_xyz, h->h_io, n * 3 * sizeof(double));
+    if (!direct) memcpy(host_xyz, h->h_io, n * 3 * sizeof(double));
     return RX_OK;
 }
 

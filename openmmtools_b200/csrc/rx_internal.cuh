@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <utility>
 #include "../../include/rx_b200.h"
 
 #define RX_KB 8.31446261815324e-3 /* kJ/mol/K, openmmtools/constants.py:7 with OpenMM >= 7.6 CODATA-2018 values */
@@ -70,6 +71,7 @@ struct rx_engine {
     bool have_snapshot = false;
     double *d_io = nullptr;                     // staging for set/get: [kloc][N][3]
     double *h_io = nullptr;                     // pinned host staging of the same size
+    std::vector<std::pair<const char *, size_t>> pinned;   // caller buffers registered with rx_pin_host_memory
     int *d_perm = nullptr;                      // [K] replica -> state
     double *d_u = nullptr;                      // [K][M]
     unsigned long long *d_nacc = nullptr, *d_nprop = nullptr;  // [M][M]
@@ -158,5 +160,6 @@ int rxi_convert_in(rx_engine *h, float4 *dst, int first_local, int count, const 
 int rxi_convert_out(rx_engine *h, const float4 *src, int first_local, int count, double *host_xyz, bool wrap);
 
 // ---- implemented in rx_api.cu ----
+bool rxi_is_pinned(const rx_engine *h, const void *p, size_t bytes);
 int rxi_allgather_energies(rx_engine *h);
 int rxi_allgather_rows(rx_engine *h, double *d_matrix, int n_cols);

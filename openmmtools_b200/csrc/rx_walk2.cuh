@@ -10,9 +10,8 @@
 //     exact path needs is recomputed from the two words of the stream (same log() as the pre-pass, same value);
 //   * the commit's bookkeeping (log entry, counters, promotion of the lanes that left the window) is issued after the
 //     next round's permutation loads, in their latency shadow;
-//   * there is no producer warp (v1's ring was synchronised by volatile flags only): every lane keeps the records of its
-//     own slot class in a small shared-memory ring that it fills itself with cp.async, 15 windows ahead of use;
-//     completion is tracked by the hardware (cp.async.wait_group), no flags, no fences.
+//   * a second warp turns the records into ready-to-use slot contexts in a shared-memory ring (release/acquire fence
+//     patterns on its two control words): the walker's round is bound by its instruction count, not by latency.
 // The kernel runs the bulk of a pass; the last < 600 slots / < 130 attempts of a pass are left to
 // k_mix_walk_pow2<U_FILTER24, true>, which reads the same records.
 #pragma once
@@ -127,16 +126,11 @@ __device__ __forceinline__ uint4 w2_lds128(unsigned a) {
 __device__ __forceinline__ void w2_sts64(unsigned a, unsigned x, unsigned y) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
-// The walker's record ring: 16 entries per lane (= per slot class mod 32), filled by the lane itself with asynchronous
-// global->shared copies 15 windows ahead of use (no register, no scoreboard wait; DRAM latency is far below that).
-#define W2_RING 512
-__device__ __forceinline__ void w2_cp_async16(unsigned dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ unsigned w2_lds32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
 }
-__device__ __forceinline__ void w2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void w2_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 __device__ __forceinline__ float w2_image_at(unsigned a_hi, unsigned a_lo) {   // the image is read-only while the walker runs
     unsigned hi, lo;
     asm("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(a_hi));
@@ -144,146 +138,195 @@ __device__ __forceinline__ float w2_image_at(unsigned a_hi, unsigned a_lo) {   /
     return __uint_as_float(__byte_perm(hi, lo, 0x1045));
 }
 
-__global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ rec, const uint32_t *__restrict__ words,
+// The walker warp issues about one instruction every two cycles (one warp, dependent code): what limits a round is the
+// NUMBER of instructions it executes, so everything that does not depend on the permutation is done by a second warp.
+// That warp turns the slot records into ready-to-use contexts in a shared-memory ring, far ahead of the walker (8 words):
+//   0: back-mask   1: f32 log-uniform of the next slot   2: eps0 (the filter bound's share of rows i and j; -1e30 when
+//   i == j)   3: 1 if i != j   4, 5: shared addresses of the image rows of i and j   6, 7: shared addresses of the
+//   replica entries of i and j of the slot ONE WINDOW LATER (the lane's next slot: its states are fetched a round ahead).
+// The image is re-laid out row by row in shared memory -- u16 plane of the row (2K bytes), then its u8 plane (K bytes) --
+// so that one address per row serves both planes.
+#define W2_RING 512
+struct W2Shared {   // cross-warp words: volatile (= relaxed, strong) accesses paired with fence.acq_rel.cta
+    volatile unsigned prod;   // contexts of the slots [.., prod) are in the ring        (producer: fence, then store)
+    volatile unsigned head;   // the walker no longer reads ring entries of slots < head   (walker: fence, then store)
+    volatile unsigned done;
+};
+
+__global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ rec, const uint32_t *__restrict__ words,
                                                   unsigned nslots, const double *__restrict__ u, int K, int logK,
                                                   int *__restrict__ perm_g, uint32_t *__restrict__ slot_log,
                                                   const unsigned char *__restrict__ filt,
                                                   const double *__restrict__ filt_rowabs, MixCtl *ctl) {
     extern __shared__ uint4 s_w2[];
-    uint4 *s_ring = s_w2;                                  // [W2_RING] slot records
-    W2Replica *s_rep = (W2Replica *)(s_ring + W2_RING);    // [K]
+    __shared__ W2Shared sh;
+    uint4 *s_ring = s_w2;                                  // [W2_RING][2] slot contexts
+    W2Replica *s_rep = (W2Replica *)(s_ring + 2 * W2_RING);  // [K]
     float *s_rowabs = (float *)(s_rep + K);                // [K] the row's share of the filter's rounding bound
     unsigned char *s_q = (unsigned char *)(s_rowabs + K);  // image: u16 plane [K*K], then u8 plane [K*K] (16-byte aligned for K >= 4)
-    const unsigned short *s_qhi = (const unsigned short *)s_q;
-    const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;
-    const int lane = threadIdx.x;
-    {
-        const uint4 *src = (const uint4 *)filt;   // (cudaMalloc alignment; 3 K^2 is a multiple of 16 for K >= 4, K = 2 has 12 bytes)
-        uint4 *dst = (uint4 *)s_q;
-        const int n16 = (3 * K * K) / 16;
-        for (int q = lane; q < n16; q += 32) dst[q] = src[q];
-        for (int q = n16 * 16 + lane; q < 3 * K * K; q += 32) s_q[q] = filt[q];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {   // image, row by row: [u16 plane of the row | u8 plane of the row], 3K bytes per row
+        const unsigned short *ghi = (const unsigned short *)filt;
+        const unsigned char *glo = filt + 2 * (size_t)K * K;
+        for (int q = tid; q < K * K; q += 64) {
+            const int row = q >> logK, col = q & (K - 1);
+            unsigned char *rowp = s_q + (size_t)3 * K * row;
+            ((unsigned short *)rowp)[col] = ghi[q];
+            rowp[2 * K + col] = glo[q];
+        }
     }
-    __syncwarp();
-    for (int q = lane; q < K; q += 32) {
+    const unsigned head0 = (unsigned)ctl->head;
+    if (tid == 0) { sh.prod = head0; sh.head = head0; sh.done = 0; }
+    __syncthreads();
+    for (int q = tid; q < K; q += 64) {
         W2Replica e;
         e.state = perm_g[q];
-        e.diag = w2_image(s_qhi, s_qlo, ((unsigned)q << logK) | (unsigned)e.state);
+        const unsigned char *rowp = s_q + (size_t)3 * K * q;
+        e.diag = __uint_as_float(__byte_perm((unsigned)((const unsigned short *)rowp)[e.state], (unsigned)rowp[2 * K + e.state], 0x1045));
         s_rep[q] = e;
         s_rowabs[q] = __fmul_ru(1.6e-14f, __fadd_ru(__double2float_ru(filt_rowabs[q]), 0.5f));
     }
-    const unsigned head0 = (unsigned)ctl->head;
-    __syncwarp();
+    __syncthreads();
     const uint4 *__restrict__ recs = (const uint4 *)rec;
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared((const void *)s_ring);
+    const unsigned img_base = (unsigned)__cvta_generic_to_shared((const void *)s_q);
+    const unsigned rep_base0 = (unsigned)__cvta_generic_to_shared((const void *)s_rep);
 
+    if (warp == 1) {
+        // ---------------- context producer: the ring holds the slots [head, head + W2_RING - 64) at most
+        unsigned prod = head0;
+        while (!sh.done) {
+            const unsigned head = sh.head;
+            __threadfence_block();   // acquire: the walker's reads of the entries below `head` are complete
+            unsigned limit = head + W2_RING - 64;
+            if (limit > nslots) limit = nslots;
+            if (prod < limit) {
+                unsigned cnt = limit - prod;
+                if (cnt > 64) cnt = 64;
+                uint4 q[2];
+                uint32_t nx[2];
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    const unsigned o = b * 32 + lane;
+                    if (o < cnt) { q[b] = __ldg(recs + (prod + o)); nx[b] = __ldg(&rec[min(prod + o + 32u, nslots - 1u)].ij); }
+                }
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    const unsigned o = b * 32 + lane;
+                    if (o < cnt) {
+                        const unsigned i = q[b].x & 0xffffu, j = q[b].x >> 16;
+                        const float eps0 = (i == j) ? -1e30f : (s_rowabs[i] + s_rowabs[j]) + 1e-9f;
+                        uint4 *dst = s_ring + 2 * ((prod + o) & (W2_RING - 1));
+                        dst[0] = make_uint4(q[b].y, q[b].z, __float_as_uint(eps0), i != j ? 1u : 0u);
+                        dst[1] = make_uint4(img_base + 3u * ((unsigned)K * i), img_base + 3u * ((unsigned)K * j),
+                                            rep_base0 + ((nx[b] & 0xffffu) << 3), rep_base0 + ((nx[b] >> 16) << 3));
+                    }
+                }
+                prod += cnt;
+                __threadfence_block();   // release: the contexts above are visible before `prod` moves
+                __syncwarp();
+                if (lane == 0) sh.prod = prod;
+            } else {
+                __nanosleep(100);
+            }
+        }
+        return;
+    }
+
+    // ---------------- walker (warp 0)
     unsigned h = head0;
     const long long remaining0 = ctl->remaining;
     unsigned rem = remaining0 > 0x7fffffffLL ? 0x7fffffffu : (unsigned)remaining0;
     const unsigned rem0 = rem;
     unsigned rounds = 0, slow = 0;
-    // a round may start while h <= h_end: its lanes copy the records of slots up to h + 33 + 31 + 480 into the ring
-    const unsigned h_end = nslots >= 1200u ? nslots - 560u : 0u;
-    if (rem >= 130 && nslots >= 1200u && h + 99u <= h_end) {
+    // The fast loop is entered when the contexts of [h, h + 196) are in the ring; it then runs a quota of rounds that cannot
+    // outrun the ring (a round advances at most 33 slots and reads the contexts of the 32 slots of its window).
+    unsigned prod_seen = head0;
+    auto ring_ready = [&]() -> bool {
+        if (h + 196u > nslots) return false;
+        if (prod_seen < h + 196u) {
+            __threadfence_block();            // release: this warp no longer reads ring entries of slots below h
+            if (lane == 0) sh.head = h;
+            while (prod_seen < h + 196u) prod_seen = sh.prod;
+        }
+        __threadfence_block();   // acquire: the contexts below `prod_seen` are visible
+        return true;
+    };
+    if (rem >= 130 && ring_ready()) {
+        // 32-bit shared addresses (through a shuffle, so that they live in registers instead of being re-derived)
+        const unsigned rep_base = __shfl_sync(0xffffffffu, rep_base0, 0);
+        const unsigned rg_base = __shfl_sync(0xffffffffu, ring_base, 0);
+        const unsigned a_head = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)&sh.head), 0);
+        const unsigned lo_off = 2u * (unsigned)K;       // the u8 plane of an image row
         unsigned r = h & 31u;                           // lane of window position 0
         unsigned w = ((unsigned)lane - h) & 31u;        // this lane's window position
         unsigned sA = h + w;                            // this lane's slot
-        // slot contexts: A = current, B = the slot one window later (raw record qB, loaded a round ahead)
-        unsigned iA, jA, bmA, iB, jB, bmB;
-        float luA, luB, epsA, epsB;
-        unsigned hiA_i, loA_i, hiA_j, loA_j, hiB_i, loB_i, hiB_j, loB_j;   // shared addresses of the image rows of i and j
-        auto unpack = [&](const uint4 q, unsigned &i, unsigned &j, unsigned &bm, float &lu) {
-            i = q.x & 0xffffu; j = q.x >> 16; bm = q.y; lu = __uint_as_float(q.z);
-        };
-        const unsigned ring_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_ring), 0);
-        // ring entry of slot s: s mod W2_RING; this lane owns the entries of its class (s mod 32)
-        for (unsigned k = 0; k < 16u; k++) w2_cp_async16(ring_base + (((sA + 32u * k) & (W2_RING - 1)) << 4), recs + (sA + 32u * k));
-        w2_cp_async_commit();
-        w2_cp_async_wait<0>();
-        __syncwarp();
-        unpack(w2_lds128(ring_base + ((sA & (W2_RING - 1)) << 4)), iA, jA, bmA, luA);
-        uint4 qB = w2_lds128(ring_base + (((sA + 32u) & (W2_RING - 1)) << 4));   // raw record one window later
-        unpack(qB, iB, jB, bmB, luB);
-        // 32-bit shared addresses (through a shuffle, so that they live in registers instead of being re-derived)
-        const unsigned rep_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_rep), 0);
-        const unsigned qhi_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_qhi), 0);
-        const unsigned qlo_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_qlo), 0);
-        const unsigned rowabs_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_rowabs), 0);
-        auto eps_of = [&](unsigned i, unsigned j) {
-            const float e = (w2_lds_f32(rowabs_base + (i << 2)) + w2_lds_f32(rowabs_base + (j << 2))) + 1e-9f;
-            return i == j ? -1e30f : e;
-        };
-        auto rows_of = [&](unsigned i, unsigned j, unsigned &hi_i, unsigned &lo_i, unsigned &hi_j, unsigned &lo_j) {
-            hi_i = qhi_base + ((i << logK) << 1); lo_i = qlo_base + (i << logK);
-            hi_j = qhi_base + ((j << logK) << 1); lo_j = qlo_base + (j << logK);
-        };
-        epsA = eps_of(iA, jA); epsB = eps_of(iB, jB);
-        rows_of(iA, jA, hiA_i, loA_i, hiA_j, loA_j); rows_of(iB, jB, hiB_i, loB_i, hiB_j, loB_j);
-        uint2 ei = w2_lds64(rep_base + (iA << 3)), ej = w2_lds64(rep_base + (jA << 3));   // {state, diag} of both replicas
+        unsigned ridx = sA & (W2_RING - 1);             // its ring entry
+        uint4 c0 = w2_lds128(rg_base + (ridx << 5));    // its context: back-mask, lu, eps0, i != j
+        uint4 c1 = w2_lds128(rg_base + (ridx << 5) + 16);   // image rows of i and j, replica entries of the next slot's i and j
+        unsigned aiA, ajA;                              // shared addresses of the replica entries of i and j
+        {
+            const unsigned ij = rec[sA].ij;
+            aiA = rep_base + ((ij & 0xffffu) << 3); ajA = rep_base + ((ij >> 16) << 3);
+        }
+        uint2 ei = w2_lds64(aiA), ej = w2_lds64(ajA);   // {state, diag} of both replicas
         // what the round resolved last leaves to the next block: the committed window positions, the positions that leave
-        // the window, whether this lane's attempt changes the permutation, its log entry
+        // the window, all-ones if this lane's attempt changes the permutation, its log entry
         unsigned p_cm = 0, p_below = 0, p_chg = 0, p_entry = 0, p_advance = 0;
         float f_ij = 0.f, f_ji = 0.f;
-        uint32_t *log_ptr = slot_log + sA;          // this lane's entry of the sparse commit log
-        const uint4 *rec_ptr = recs + (sA + 480);   // the record this lane copies into the ring at its next promotion
         // Commit the round described by the p_* values, slide the window and fetch the states of the next round:
         // permutation stores, at once the next round's loads, then the lane state.
         auto commit = [&]() {
-            const bool p_mine = (p_cm >> w) & 1u;
-            const bool p_swaps = ((p_cm >> w) & p_chg) != 0u;
-            const bool p_promoted = (p_below >> w) & 1u;
+            const unsigned bit = 1u << w;
+            const bool p_mine = (p_cm & bit) != 0u;
+            const bool p_swaps = (p_cm & bit & p_chg) != 0u;
+            const bool p_promoted = (p_below & bit) != 0u;
             if (p_swaps) {   // replica i takes state sj: its new diagonal value is the off-diagonal one just read
-                w2_sts64(rep_base + (iA << 3), ej.x, __float_as_uint(f_ij));
-                w2_sts64(rep_base + (jA << 3), ei.x, __float_as_uint(f_ji));
+                w2_sts64(aiA, ej.x, __float_as_uint(f_ij));
+                w2_sts64(ajA, ei.x, __float_as_uint(f_ji));
             }
             __syncwarp();
             // the states of the next round: of the slot one window later for the lanes that leave the window
-            const uint2 ein = w2_lds64(rep_base + ((p_promoted ? iB : iA) << 3)), ejn = w2_lds64(rep_base + ((p_promoted ? jB : jA) << 3));
-            const unsigned adv = p_advance;
-            if (p_mine) *log_ptr = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
-            h += adv;
-            r = (r + adv) & 31u;
+            aiA = p_promoted ? c1.z : aiA;
+            ajA = p_promoted ? c1.w : ajA;
+            const uint2 ein = w2_lds64(aiA), ejn = w2_lds64(ajA);
+            if (p_mine) slot_log[sA] = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
+            h += p_advance;
+            r = (r + p_advance) & 31u;
             rem -= __popc(p_cm);
-            if (p_promoted) {
-                iA = iB; jA = jB; bmA = bmB; luA = luB; epsA = epsB; sA += 32; log_ptr += 32; rec_ptr += 32;
-                hiA_i = hiB_i; loA_i = loB_i; hiA_j = hiB_j; loA_j = loB_j;
-                w2_cp_async16(ring_base + (((sA + 480u) & (W2_RING - 1)) << 4), rec_ptr);   // over the entry of the slot just left
-            }
-            w2_cp_async_commit();
-            // the record one window later: the lanes that stay re-read the one they hold (no dependence on a predicate)
-            qB = w2_lds128(ring_base + (((sA + 32u) & (W2_RING - 1)) << 4));
+            if (p_promoted) { sA += 32; ridx = (ridx + 32u) & (W2_RING - 1); }
+            // the context of this lane's (possibly new) slot: the lanes that stay re-read the one they hold
+            c0 = w2_lds128(rg_base + (ridx << 5));
+            c1 = w2_lds128(rg_base + (ridx << 5) + 16);
             ei = ein;
             ej = ejn;
-            w = (w - adv) & 31u;
-        };
-        // a copy is used 15 of the lane's promotions (at least 15 rounds) after it was issued
-        auto fetch = [&]() {
-            w2_cp_async_wait<8>();
-            unpack(qB, iB, jB, bmB, luB);   // the slot one window later
-            epsB = eps_of(iB, jB);
-            rows_of(iB, jB, hiB_i, loB_i, hiB_j, loB_j);
+            w = (w - p_advance) & 31u;
         };
         for (;;) {
             // ---------------- fast rounds.  The loop is rotated: an iteration COMMITS the round resolved by the previous
             // one and then evaluates and resolves the next, so that the block begins with the dependent chain (stores ->
             // state loads -> image loads -> filter -> ballots); no data-dependent branch besides the loop's.
-            bool go;
-            unsigned cm = 0, adv33 = 0;
+            unsigned cm = 0;
+            bool adv33 = false;
             p_cm = p_below = p_advance = 0;   // nothing to commit on entry
+            // rounds that can certainly still be started: each commits at most 32 attempts and advances at most 33 slots
+            // (the budget, the end of the pass and the ring are looked at again when this count runs out)
+            int quota = (int)min((rem - 97u) >> 5, (prod_seen - 163u - h) / 33u);
             do {
                 commit();
                 rounds++;
                 const unsigned si = ei.x, sj = ej.x;
-                f_ij = w2_image_at(hiA_i + 2u * sj, loA_i + sj);
-                f_ji = w2_image_at(hiA_j + 2u * si, loA_j + si);
-                const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, epsA);
-                fetch();
-                // the budget and the end of the pass: the round being resolved now commits at most 32 attempts and
-                // advances at most 33 slots, and one more round may follow it before the next test
-                go = rem >= 97u && h + 66u <= h_end;
+                f_ij = w2_image_at(c1.x + 2u * sj, c1.x + lo_off + sj);
+                f_ji = w2_image_at(c1.y + 2u * si, c1.y + lo_off + si);
+                const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, __uint_as_float(c0.z));
+                // release (every 8 rounds, one predicated instruction pair, no branch): the warp's reads of the ring entries
+                // below h -- ordered before this lane's store by the __syncwarp() of the commit -- are complete
+                if ((rounds & 7u) == 0u && lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a_head), "r"(h) : "memory");
+                quota--;
                 bool ge0, acc, undecided;
-                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, e0, luA, ge0, acc, undecided);
+                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, e0, __uint_as_float(c0.y), ge0, acc, undecided);
                 const unsigned und = undecided ? 1u : 0u;
-                const bool changes = acc && iA != jA;
+                const bool changes = acc && c0.w != 0u;
                 const unsigned G = __ballot_sync(0xffffffffu, ge0);
                 const unsigned A = __ballot_sync(0xffffffffu, changes);
                 const unsigned Gw = __funnelshift_r(G, G, r), Aw = __funnelshift_r(A, A, r);   // window order
@@ -298,45 +341,43 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                 unsigned earlier;   // bit 31-b: window position w-1-b is a visited state-changing swap
                 asm("shl.b32 %0, %1, %2;" : "=r"(earlier) : "r"(VA), "r"(32u - w));
                 // a round ends before the first visited lane that is stale -- or that the filter could not decide
-                const unsigned C = __ballot_sync(0xffffffffu, ((earlier & bmA) | und) != 0u);
+                const unsigned C = __ballot_sync(0xffffffffu, ((earlier & c0.x) | und) != 0u);
                 const unsigned Cw = __funnelshift_r(C, C, r) & V;
                 const unsigned low = Cw & (0u - Cw);
                 const unsigned below = low - 1u;       // low == 0 -> all lanes
                 cm = V & below;
-                p_cm = cm; p_below = below; p_chg = changes ? 1u : 0u;
-                p_entry = si | (sj << LOG_STATE_BITS) | ((acc ? 1u : 0u) << LOG_ACC_BIT) | (1u << 31);
-                // bit 32 (even position) of the skip word can only be set by the carry of an odd-start run
-                adv33 = (Cw == 0u && sumO < X) ? 1u : 0u;
-                p_advance = Cw ? (unsigned)__popc(below) : 32u + adv33;
-            } while (go && cm != 0u && adv33 == 0u);
+                p_cm = cm; p_below = below; p_chg = changes ? 0xffffffffu : 0u;
+                p_entry = (sj * (1u << LOG_STATE_BITS) + si) | (acc ? (1u << 31) | (1u << LOG_ACC_BIT) : (1u << 31));
+                p_advance = (unsigned)__popc(below);   // 32 when no lane is stale
+                // bit 32 (even position) of the skip word can only be set by the carry of an odd-start run: the slot after
+                // the window is then a uniform's slot (handled outside the loop)
+                adv33 = Cw == 0u && sumO < X;
+            } while (quota > 0 && cm != 0u && !adv33);
+            if (adv33) p_advance = 33u;
             commit();   // the round resolved last
-            fetch();
             // ---------------- rare events
             if (adv33) {
-                // the slot after the window is a uniform's slot: the lane that is now at window position 31 holds slot
-                // h - 1 (skipped) and moves on by another window
+                // the lane that is now at window position 31 holds slot h - 1 (skipped) and moves on by another window
                 if (w == 31u) {
-                    sA += 32; log_ptr += 32; rec_ptr += 32;
-                    w2_cp_async16(ring_base + (((sA + 480u) & (W2_RING - 1)) << 4), rec_ptr);
-                    unpack(w2_lds128(ring_base + ((sA & (W2_RING - 1)) << 4)), iA, jA, bmA, luA);
-                    qB = w2_lds128(ring_base + (((sA + 32u) & (W2_RING - 1)) << 4));
-                    unpack(qB, iB, jB, bmB, luB);
-                    epsA = eps_of(iA, jA); epsB = eps_of(iB, jB);
-                    rows_of(iA, jA, hiA_i, loA_i, hiA_j, loA_j); rows_of(iB, jB, hiB_i, loB_i, hiB_j, loB_j);
-                    ei = w2_lds64(rep_base + (iA << 3)); ej = w2_lds64(rep_base + (jA << 3));
+                    sA += 32; ridx = (ridx + 32u) & (W2_RING - 1);
+                    aiA = c1.z; ajA = c1.w;
+                    c0 = w2_lds128(rg_base + (ridx << 5)); c1 = w2_lds128(rg_base + (ridx << 5) + 16);
+                    ei = w2_lds64(aiA); ej = w2_lds64(ajA);
                 }
                 __syncwarp();
             }
-            if (rem < 130u || h + 99u > h_end) break;
+            if (rem < 130u) break;
+            if (prod_seen < h + 196u && !ring_ready()) break;
             if (cm == 0u) {
                 // the first lane of the window is undecided: one exact attempt, exactly what the reference does
                 rounds++;
                 bool ge0 = false, acc = false;
                 const unsigned si = ei.x, sj = ej.x;
-                f_ij = w2_image(s_qhi, s_qlo, (iA << logK) | sj);
-                f_ji = w2_image(s_qhi, s_qlo, (jA << logK) | si);
+                f_ij = w2_image_at(c1.x + 2u * sj, c1.x + lo_off + sj);
+                f_ji = w2_image_at(c1.y + 2u * si, c1.y + lo_off + si);
                 if (w == 0u) {
-                    const unsigned rowi = iA << logK, rowj = jA << logK;
+                    const unsigned ij = rec[sA].ij;
+                    const unsigned rowi = (ij & 0xffffu) << logK, rowj = (ij >> 16) << logK;
                     const double logp = swap_logp(u[rowi | sj], u[rowj | si], u[rowi | si], u[rowj | sj]);
                     ge0 = logp >= 0.0;
                     acc = ge0;
@@ -354,16 +395,17 @@ __global__ void __launch_bounds__(32) k_mix_walk2(const SlotRec2 *__restrict__ r
                 p_advance = first_ge0 ? 1u : 2u;   // log_p < 0: the next slot is this attempt's uniform
                 p_cm = 1u;                         // window position 0 commits; positions 0 .. advance-1 leave the window
                 p_below = first_ge0 ? 1u : 3u;
-                p_chg = (acc && iA != jA) ? 1u : 0u;
-                p_entry = si | (sj << LOG_STATE_BITS) | ((acc ? 1u : 0u) << LOG_ACC_BIT) | (1u << 31);
+                p_chg = (acc && c0.w != 0u) ? 0xffffffffu : 0u;
+                p_entry = (sj * (1u << LOG_STATE_BITS) + si) | (acc ? (1u << 31) | (1u << LOG_ACC_BIT) : (1u << 31));
                 commit();
-                fetch();
-                if (rem < 130u || h + 99u > h_end) break;
+                if (rem < 130u) break;
+                if (prod_seen < h + 196u && !ring_ready()) break;
             }
         }
         __syncwarp();
         for (int q = lane; q < K; q += 32) perm_g[q] = s_rep[q].state;
     }
+    if (lane == 0) sh.done = 1;
     slow = __reduce_add_sync(0xffffffffu, slow);
     if (lane == 0) {
         const long long remaining = remaining0 - (long long)(rem0 - rem);

@@ -77,6 +77,7 @@ class MultiStateSampler:
         self._unsampled_table = None
         self._engine = None
         self._states_stale = False     # host copies of sampler states are behind the device
+        self._host_x = self._host_v = None   # page-locked backing store of the owned sampler states
         self._seed = seed
         self._communicator = communicator
         self._rank = int(os.environ.get('RANK', '0')) if communicator is None else communicator.rank
@@ -351,6 +352,40 @@ class MultiStateSampler:
             comm = self._communicator = default_communicator()
         return int.from_bytes(comm.bcast_bytes(int(v).to_bytes(8, 'little') if self._rank == 0 else None, 8), 'little')
 
+    def _attach_host_store(self):
+        """One page-locked (K_loc, N, 3) pair is the backing store of the owned SamplerStates: their position / velocity
+        arrays are views into it, so that the per-iteration exchange with the device is one copy each way and no
+        per-replica work on the host."""
+        e = self._engine
+        n = e.k1 - e.k0
+        if n == 0 or self._host_x is not None:
+            return
+        N = self._sampler_states[0].n_particles
+        self._host_x = e.pinned_array((n, N, 3))
+        self._host_v = e.pinned_array((n, N, 3))
+        self._host_v[:] = 0.0
+        for r, k in enumerate(range(e.k0, e.k1)):
+            s = self._sampler_states[k]
+            self._host_x[r] = s._positions
+            s._positions = self._host_x[r]
+            if s._velocities is not None:
+                self._host_v[r] = s._velocities
+                s._velocities = self._host_v[r]
+
+    def _collect_host_store(self):
+        """Positions / velocities a caller replaced on a SamplerState go back into the backing store."""
+        e = self._engine
+        for r, k in enumerate(range(e.k0, e.k1)):
+            s = self._sampler_states[k]
+            if s._positions.base is not self._host_x.base:
+                self._host_x[r] = s._positions
+                s._positions = self._host_x[r]
+            if s._velocities is None:
+                raise RuntimeError('host-resident sampler state %d has no velocities' % k)
+            if s._velocities.base is not self._host_v.base:
+                self._host_v[r] = s._velocities
+                s._velocities = self._host_v[r]
+
     def _upload_sampler_states(self):
         e = self._engine
         K = len(self._sampler_states)
@@ -377,10 +412,21 @@ class MultiStateSampler:
         if self._engine is None or not self._states_stale:
             return
         e = self._engine
-        x, v = e.get_positions(), e.get_velocities()
+        self._attach_host_store()
+        if e.k1 > e.k0:
+            e.get_positions(out=self._host_x)
+            e.get_velocities(out=self._host_v)
         pot, kin = e.get_replica_energies()
+        pot, kin = pot.tolist(), kin.tolist()
+        hx, hv = self._host_x, self._host_v
         for r, k in enumerate(range(e.k0, e.k1)):
-            self._sampler_states[k]._update(x[r], v[r], pot[k], kin[k])
+            s = self._sampler_states[k]
+            if s._positions.base is not hx.base:
+                s._positions = hx[r]
+            if s._velocities is None or s._velocities.base is not hv.base:
+                s._velocities = hv[r]
+            s._potential_energy = pot[k]
+            s._kinetic_energy = kin[k]
         self._states_stale = False
 
     # ------------------------------------------------------------------ run (multistatesampler.py:724-804)
@@ -475,10 +521,11 @@ class MultiStateSampler:
             # reference semantics: sampler states live on the host and are pushed to the device every iteration
             # (SamplerState.apply_to_context, mcmc.py:709)
             self._sync_sampler_states()
-            x = np.stack([s._positions for s in self._sampler_states[e.k0:e.k1]])
-            v = np.stack([s._velocities for s in self._sampler_states[e.k0:e.k1]])
-            e.set_positions(x, first=e.k0)
-            e.set_velocities(v, first=e.k0)
+            self._attach_host_store()
+            if e.k1 > e.k0:
+                self._collect_host_store()
+                e.set_positions(self._host_x, first=e.k0)
+                e.set_velocities(self._host_v, first=e.k0)
         it = self._iteration if iteration is None else iteration
         n_restart = self._mcmc_moves[0].n_restart_attempts
         re = self._reassign if reassign is None else reassign
