@@ -81,7 +81,9 @@ class SocketCommunicator:
         self.bcast_bytes(b'x', 1)
 
     def gather_object(self, obj):
-        import pickle
+        """Gather every rank's sampler-state shard -- a list of (replica index, positions, velocities | None, potential |
+        None, kinetic | None) -- on rank 0.  The wire format is a fixed binary layout of numbers and raw float64 buffers
+        (no pickle: nothing that arrives on the socket is ever executed), sizes and the sender's rank are validated."""
         import struct
         if self.world_size == 1:
             return [obj]
@@ -94,18 +96,17 @@ class SocketCommunicator:
             out[0] = obj
             for _ in range(self.world_size - 1):
                 c, _a = srv.accept()
-                hdr = b''
-                while len(hdr) < 12:
-                    hdr += c.recv(12 - len(hdr))
-                r, n = struct.unpack('<iq', hdr)
-                buf = b''
-                while len(buf) < n:
-                    buf += c.recv(min(1 << 20, n - len(buf)))
-                out[r] = pickle.loads(buf)
+                c.settimeout(60)
+                r, n = struct.unpack('<iq', _recv_exact(c, 12))
+                if not (1 <= r < self.world_size) or out[r] is not None or not (0 <= n <= _MAX_SHARD_BYTES):
+                    c.close()
+                    srv.close()
+                    raise RuntimeError('gather: malformed header from a peer (rank %d, %d bytes)' % (r, n))
+                out[r] = _decode_shard(_recv_exact(c, n))
                 c.close()
             srv.close()
             return out
-        payload = pickle.dumps(obj)
+        payload = _encode_shard(obj)
         for _ in range(600):
             try:
                 c = socket.create_connection((self.addr, self.port + 1), timeout=5)
@@ -117,6 +118,62 @@ class SocketCommunicator:
         c.sendall(struct.pack('<iq', self.rank, len(payload)) + payload)
         c.close()
         return None
+
+
+_MAX_SHARD_BYTES = 1 << 34
+
+
+def _recv_exact(c, n):
+    buf = bytearray()
+    while len(buf) < n:
+        chunk = c.recv(min(1 << 20, n - len(buf)))
+        if not chunk:
+            raise RuntimeError('gather: connection closed after %d of %d bytes' % (len(buf), n))
+        buf += chunk
+    return bytes(buf)
+
+
+def _encode_shard(shard):
+    """[(k, x[N,3], v[N,3] | None, pe | None, ke | None), ...] -> bytes: count, then per item
+    <i k><i n_atoms><B has_v><B has_pe><B has_ke><d pe><d ke> + x (+ v) as little-endian float64."""
+    import struct
+    import numpy as np
+    parts = [struct.pack('<i', len(shard))]
+    for k, x, v, pe, ke in shard:
+        x = np.ascontiguousarray(x, dtype='<f8')
+        parts.append(struct.pack('<iiBBBdd', int(k), x.shape[0], v is not None, pe is not None, ke is not None,
+                                 0.0 if pe is None else float(pe), 0.0 if ke is None else float(ke)))
+        parts.append(x.tobytes())
+        if v is not None:
+            parts.append(np.ascontiguousarray(v, dtype='<f8').tobytes())
+    return b''.join(parts)
+
+
+def _decode_shard(buf):
+    import struct
+    import numpy as np
+    if len(buf) < 4:
+        raise RuntimeError('gather: malformed shard')
+    (count,), off = struct.unpack_from('<i', buf, 0), 4
+    if count < 0 or count > 1 << 24:
+        raise RuntimeError('gather: malformed shard')
+    out = []
+    for _ in range(count):
+        if off + struct.calcsize('<iiBBBdd') > len(buf):
+            raise RuntimeError('gather: malformed shard')
+        k, n, hv, hp, hk, pe, ke = struct.unpack_from('<iiBBBdd', buf, off)
+        off += struct.calcsize('<iiBBBdd')
+        nb = n * 24
+        if n < 0 or off + nb * (2 if hv else 1) > len(buf):
+            raise RuntimeError('gather: malformed shard')
+        x = np.frombuffer(buf, dtype='<f8', count=3 * n, offset=off).reshape(n, 3).copy()
+        off += nb
+        v = None
+        if hv:
+            v = np.frombuffer(buf, dtype='<f8', count=3 * n, offset=off).reshape(n, 3).copy()
+            off += nb
+        out.append((k, x, v, pe if hp else None, ke if hk else None))
+    return out
 
 
 def default_communicator():

@@ -177,7 +177,7 @@ class MultiStateReporter:
 
     def read_thermodynamic_states(self):
         with open(os.path.join(self._storage, 'objects_states.pkl'), 'rb') as f:
-            return pickle.load(f)
+            return _restricted_load(f)
 
     def write_mcmc_moves(self, mcmc_moves):
         with open(os.path.join(self._storage, 'objects_moves.pkl'), 'wb') as f:
@@ -185,7 +185,7 @@ class MultiStateReporter:
 
     def read_mcmc_moves(self):
         with open(os.path.join(self._storage, 'objects_moves.pkl'), 'rb') as f:
-            return pickle.load(f)
+            return _restricted_load(f)
 
     def write_dict(self, name, data, fixed_dimension=False):
         self._meta['dicts'][name] = _jsonable(data)
@@ -394,6 +394,35 @@ class MultiStateReporter:
         d = os.path.join(self._storage, 'checkpoint')
         its = sorted(int(f[5:14]) for f in os.listdir(d) if f.startswith('ckpt_') and f.endswith('.npz') and '.tmp' not in f)
         return its
+
+
+class _RestrictedUnpickler(pickle.Unpickler):
+    """The object files of a storage directory hold thermodynamic states and MCMC moves of THIS package (plus numpy arrays
+    and plain containers).  Nothing else is ever constructed while reading them: a storage directory that names any other
+    class is rejected instead of executed (the reference serialises through YAML for the same reason)."""
+    _NUMPY_OK = {('numpy.core.multiarray', '_reconstruct'), ('numpy._core.multiarray', '_reconstruct'),
+                 ('numpy', 'ndarray'), ('numpy', 'dtype'), ('numpy.core.multiarray', 'scalar'),
+                 ('numpy._core.multiarray', 'scalar'), ('numpy._core.numeric', '_frombuffer'),
+                 ('numpy.core.numeric', '_frombuffer')}
+    _BUILTINS_OK = {'set', 'frozenset', 'tuple', 'list', 'dict', 'complex', 'slice', 'range', 'bytearray', 'object'}
+
+    def find_class(self, module, name):
+        if module == 'openmmtools_b200' or module.startswith('openmmtools_b200.'):
+            return super().find_class(module, name)
+        if (module, name) in self._NUMPY_OK:
+            return super().find_class(module, name)
+        if module == 'builtins' and name in self._BUILTINS_OK:
+            return super().find_class(module, name)
+        if module == 'collections' and name in ('OrderedDict', 'defaultdict'):
+            return super().find_class(module, name)
+        if module == 'copyreg' and name == '_reconstructor':
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError('storage object file refers to %s.%s, which is not part of a sampler description'
+                                     % (module, name))
+
+
+def _restricted_load(f):
+    return _RestrictedUnpickler(f).load()
 
 
 def _jsonable(x):

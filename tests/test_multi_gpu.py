@@ -93,3 +93,37 @@ def test_two_gpus_reproduce_single_gpu(tmp_path):
         assert np.array_equal(d['u'], u1)
         k0 = int(d['k0'])
         assert np.array_equal(d['x'], x1[k0:k0 + d['x'].shape[0]])
+
+
+SOCKET_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+from openmmtools_b200._dist import SocketCommunicator
+c = SocketCommunicator()
+rng = np.random.default_rng(c.rank)
+shard = [(2 * c.rank + q, rng.random((7, 3)), None if q else rng.random((7, 3)), float(q), None) for q in range(2)]
+g = c.gather_object(shard)
+if c.rank == 0:
+    assert len(g) == 2 and [it[0] for part in g for it in part] == [0, 1, 2, 3]
+    r1 = np.random.default_rng(1)
+    x, v = r1.random((7, 3)), r1.random((7, 3))
+    assert np.array_equal(g[1][0][1], x) and np.array_equal(g[1][0][2], v) and g[1][1][2] is None and g[1][1][3] == 1.0 and g[1][0][4] is None
+print('ok', c.rank)
+'''
+
+
+def test_socket_communicator_gathers_shards_without_pickle(tmp_path):
+    """The fallback communicator (no torch.distributed): raw numeric wire format, validated sizes (ADVICE r1)."""
+    script = tmp_path / 's.py'
+    script.write_text(SOCKET_WORKER % {'root': ROOT})
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1', MASTER_PORT='29561')
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert sum(o.count('ok') for o in outs) == 2
+    from openmmtools_b200._dist import _decode_shard
+    with pytest.raises(RuntimeError):
+        _decode_shard(b'\x05\x00\x00\x00' + b'\x00' * 10)
