@@ -52,8 +52,14 @@ extern "C" int rx_create(const rx_config *cfg, rx_engine **out) {
     const int K = cfg->n_replicas, M = cfg->n_states, N = cfg->n_atoms, W = cfg->world_size, R = cfg->rank;
     h->k0 = (int)(((long long)R * K) / W);
     h->kloc = (int)(((long long)(R + 1) * K) / W) - h->k0;
-    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream_rng, cudaStreamNonBlocking));
+    {
+        // The side stream prepares the NEXT mixing call (random words, slot records) while the replicas propagate on the main
+        // stream: it gets the lowest priority, so that its thread blocks only fill what k_propagate leaves free.
+        int prio_lo = 0, prio_hi = 0;
+        CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CREATE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+        CREATE_CUDA(cudaStreamCreateWithPriority(&h->stream_rng, cudaStreamNonBlocking, prio_lo));
+    }
     for (int i = 0; i < 8; i++) CREATE_CUDA(cudaEventCreate(&h->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&h->ev_user[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&h->ev_walk[i]));

@@ -11,6 +11,8 @@
 // Energy function: alchemy/alchemy.py:1379-1388 (soft-core sterics), :1723-1750 / :1903-1919 (which pairs go
 // to which force), testsystems.py:1956-1997 (switched LJ, cutoff-periodic).
 #include "rx_internal.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -173,11 +175,11 @@ __device__ __forceinline__ void pair_term(const DynParams &p, const PairCtx &c, 
 // Force on one atom from the inner part of its neighbour list or, in the fallback, from all other atoms.
 template <bool C6, bool SW, bool ENERGY>
 __device__ __forceinline__ void lj_forces(const DynParams &p, const PairCtx &c, unsigned pos_base, int par_off,
-                                          unsigned nb_t, int N, int a, bool use_list, int n_inner,
+                                          unsigned nb_t, int N, int ncol, int a, bool use_list, int n_inner,
                                           float &fx, float &fy, float &fz, float &en) {
     float ax = 0.f, ay = 0.f, az = 0.f, e = 0.f;
     if (use_list) {
-        const unsigned stride = 2u * (unsigned)N;
+        const unsigned stride = 2u * (unsigned)ncol;
         unsigned q = nb_t;
         for (int n = 0; n < n_inner; n++, q += stride)
             pair_term<C6, SW, ENERGY>(p, c, pos_base, par_off, lds_u16(q), ax, ay, az, e);
@@ -207,7 +209,13 @@ __device__ __forceinline__ void lj_forces(const DynParams &p, const PairCtx &c, 
 //
 // Positions are double buffered: a force evaluation writes the moved positions into the buffer the previous
 // evaluation did not read, and the displacement vote (__syncthreads_or) is the only barrier of the step.
-template <bool C6, bool SW>
+// A replica may be split over a cluster of CL thread blocks (CL = 1, 2 or 4; chosen when there are fewer replicas than SMs):
+// block q of the cluster owns the atoms [q Nq, (q+1) Nq), every block keeps ALL positions in its own shared memory -- a block
+// writes the new positions of its atoms into every block's buffer through distributed shared memory -- and the step's only
+// barrier becomes a cluster barrier.  The displacement votes are cluster wide, so the lists are rebuilt at the same steps and
+// with the same contents as in one block: trajectories do not depend on CL (each atom sums its own list in list order, noise
+// is keyed by atom id).
+template <bool C6, bool SW, int CL>
 __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *__restrict__ atom,
                                                     const StateDev *__restrict__ states, const int *__restrict__ perm,
                                                     float4 *__restrict__ pos, float4 *__restrict__ vel, int k0,
@@ -215,14 +223,34 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
                                                     double *__restrict__ pot, double *__restrict__ kin,
                                                     int *__restrict__ nan_flag, const int *__restrict__ only) {
     extern __shared__ float4 s_dyn[];
-    if (only && !only[k0 + blockIdx.x]) return;   // a retry launch propagates the replicas that failed, nothing else
+    // (the whole cluster takes this exit together: `only` is indexed by replica)
+    if (only && !only[k0 + blockIdx.x / CL]) return;   // a retry launch propagates the replicas that failed, nothing else
     float4 *s_par = s_dyn + RX_MAX_ATOMS;  // [RX_MAX_ATOMS] (sqrt_eps, alch, -, -); s_dyn[0..] / s_dyn[2*MAX..]: positions
     float4 *s_ref = s_dyn + 3 * RX_MAX_ATOMS;                  // [nthr] the thread's position at the last outer build
-    unsigned short *s_nb = (unsigned short *)(s_ref + blockDim.x);  // [maxnb][N] lists, slot-major (conflict free)
+    unsigned short *s_nb = (unsigned short *)(s_ref + blockDim.x);  // [maxnb][nthr] lists, slot-major (conflict free)
     __shared__ double s_red[32];
-    const int r = blockIdx.x, k = k0 + r, t = threadIdx.x, nthr = blockDim.x;
-    const bool active = t < p.N;   // threads beyond N own no atom (they keep a >= N through every re-assignment)
-    int a = t;                     // the atom this thread owns
+    __shared__ int s_vote[2];            // cluster-wide votes (alternating words)
+    __shared__ double s_part[3 * 4];     // per-block partial sums, gathered in block 0 of the cluster
+    const int r = blockIdx.x / CL, q = blockIdx.x % CL, k = k0 + r, t = threadIdx.x, nthr = blockDim.x;
+    const int Nq = (p.N + CL - 1) / CL, a_base = q * Nq;
+    const int n_own = min(Nq, p.N - a_base);
+    const bool active = t < n_own;   // threads beyond the block's atoms own none (they keep an id past the block's range)
+    int a = a_base + t;              // the atom this thread owns
+    unsigned vote_id = 0;
+    if (t < 2) s_vote[t] = 0;
+    // OR of `flag` over all threads of the cluster (of the block when CL == 1), doubling as the step's barrier
+    auto cluster_or = [&](bool flag) -> bool {
+        if (CL == 1) return __syncthreads_or(flag ? 1 : 0) != 0;
+        vote_id++;
+        int *word = &s_vote[vote_id & 1u];
+        if (flag) {
+            cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+            for (int c = 0; c < CL; c++) *cl.map_shared_rank(word, c) = (int)vote_id;   // every voter writes the same value
+        }
+        cg::this_cluster().sync();   // release / acquire: the positions and the votes written before it are visible
+        return *(volatile int *)word == (int)vote_id;
+    };
     const StateDev st = states[perm[k]];
     const PairLam lam = {(float)st.la, (float)st.ob};
     float sig_i, se_i, inv_m, sigma_v;
@@ -233,14 +261,18 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         sigma_v = sqrtf((float)st.kT * inv_m);  // sqrt(kT/m), integrators.py:1314
     };
     load_atom();
-    float4 x4 = active ? pos[(size_t)r * p.N + t] : make_float4(0, 0, 0, 0);
-    float4 v4 = active ? vel[(size_t)r * p.N + t] : make_float4(0, 0, 0, 0);
+    float4 x4 = active ? pos[(size_t)r * p.N + a] : make_float4(0, 0, 0, 0);
+    float4 v4 = active ? vel[(size_t)r * p.N + a] : make_float4(0, 0, 0, 0);
     float x = x4.x, y = x4.y, z = x4.z, vx = v4.x, vy = v4.y, vz = v4.z;
     if (reassign && active) {  // context.setVelocitiesToTemperature, mcmc.py:711
-        const float3 g = philox_normal3(philox4x32_10(make_uint4(t, 0x80000000u, k, iteration), key));
+        const float3 g = philox_normal3(philox4x32_10(make_uint4(a, 0x80000000u, k, iteration), key));
         vx = sigma_v * g.x; vy = sigma_v * g.y; vz = sigma_v * g.z;
     }
-    if (active) s_par[t] = make_float4(se_i, alch_i ? 1.f : 0.f, 0.f, 0.f);
+    for (int j = t; j < p.N; j += nthr) {   // parameter records of ALL atoms (the pair loop reads those of its partners)
+        const float4 a4 = atom[j];
+        s_par[j] = make_float4(a4.y, a4.w != 0.f ? 1.f : 0.f, 0.f, 0.f);
+    }
+    if (CL > 1) cg::this_cluster().sync();   // every block of the cluster is resident and has cleared its vote words
     float fx = 0, fy = 0, fz = 0;
     bool f_valid = false;
     const float hx0 = (float)st.ho_x0[0], hx1 = (float)st.ho_x0[1], hx2 = (float)st.ho_x0[2], hK = (float)st.ho_K;
@@ -253,7 +285,7 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     int cur = 1;                   // position buffer of the latest force evaluation (0: s_dyn, 1: s_dyn + 2*MAX)
     const unsigned dyn_base = (unsigned)__cvta_generic_to_shared(s_dyn);
     const unsigned nb_t = (unsigned)__cvta_generic_to_shared(s_nb + t);
-    const unsigned stride = 2u * (unsigned)p.N;
+    const unsigned stride = 2u * (unsigned)nthr;
 
     // Deal the atoms to the threads again, sorted by (inner neighbour count, atom's previous thread): a stable
     // counting sort through scratch space in the (dead) list area.
@@ -266,7 +298,7 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         const int bin = active ? min(n_inner, RX_SORT_BINS - 2) : RX_SORT_BINS - 1;
         __syncthreads();  // every thread is done with its column (a partition may just have run)
         for (int q = t; q < nw * RX_SORT_BINS; q += nthr) x_cnt[q] = 0;
-        x_v[a] = make_float4(vx, vy, vz, 0.f);
+        x_v[a - a_base] = make_float4(vx, vy, vz, 0.f);
         __syncthreads();
         const unsigned m = __match_any_sync(0xffffffffu, bin);
         if (lane == __ffs(m) - 1) x_cnt[w * RX_SORT_BINS + bin] = (unsigned short)__popc(m);
@@ -286,7 +318,7 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         x_order[rank] = (unsigned short)a;
         __syncthreads();
         a = x_order[t];
-        const float4 vv = x_v[a];
+        const float4 vv = x_v[a - a_base];
         vx = vv.x; vy = vv.y; vz = vv.z;
         load_atom();
         if (active) { const float4 pa = s_pos[a]; x = pa.x; y = pa.y; z = pa.z; }
@@ -324,7 +356,7 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
                             dz = min_image_f(z - pj.z, p.Lz, p.iLz);
                 const float r2 = dx * dx + dy * dy + dz * dz;
                 if (r2 < p.rl2 && j != a) {
-                    if (cnt < p.maxnb) s_nb[cnt * p.N + t] = (unsigned short)j;
+                    if (cnt < p.maxnb) s_nb[cnt * nthr + t] = (unsigned short)j;
                     cnt++;
                 }
             }
@@ -332,14 +364,14 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         s_ref[t] = make_float4(x, y, z, 0.f);
         n_all = cnt;
         have_list = true;
-        if (__syncthreads_or(cnt > p.maxnb ? 1 : 0)) use_list = false;  // denser than the capacity: all-pairs from now on
+        if (cluster_or(cnt > p.maxnb)) use_list = false;  // denser than the capacity: all-pairs from now on (the whole cluster)
     };
     // Make the list valid for the positions in buffer s_pos (all threads call this together).
     auto refresh_list = [&](const float4 *s_pos) {
         const float4 rf = s_ref[t];
         const float mx = x - rf.x, my = y - rf.y, mz = z - rf.z;
         const bool far = !have_list || (active && mx * mx + my * my + mz * mz > p.half_out2);
-        if (__syncthreads_or(far ? 1 : 0)) {
+        if (cluster_or(far)) {
             const bool first = !have_list;
             build_outer(s_pos);
             if (use_list) partition(s_pos);
@@ -360,10 +392,18 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     auto publish = [&]() {
         cur ^= 1;
         float4 *s_pos = s_dyn + (cur ? 2 * RX_MAX_ATOMS : 0);
-        if (active) s_pos[a] = make_float4(x, y, z, sig_i);
+        if (active) {
+            const float4 me = make_float4(x, y, z, sig_i);
+            if (CL == 1) s_pos[a] = me;
+            else {
+                cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+                for (int c = 0; c < CL; c++) cl.map_shared_rank(s_pos, c)[a] = me;
+            }
+        }
         const float mx = x - xi, my = y - yi, mz = z - zi;
         const bool moved = use_list && (!have_list || (active && mx * mx + my * my + mz * mz > p.half_in2));
-        if (__syncthreads_or(moved ? 1 : 0)) refresh_list(s_pos);
+        if (cluster_or(moved)) refresh_list(s_pos);
     };
     auto compute_forces = [&](bool want_energy, float &e_out) {
         if (!lj) {
@@ -376,8 +416,8 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
             pc.x = x; pc.y = y; pc.z = z; pc.sig_i = sig_i; pc.se_i = se_i; pc.alch_i = alch_i;
             const unsigned pos_base = dyn_base + (cur ? 2u * 16u * RX_MAX_ATOMS : 0u);
             const int par_off = cur ? -16 * RX_MAX_ATOMS : 16 * RX_MAX_ATOMS;
-            if (want_energy) lj_forces<C6, SW, true>(p, pc, pos_base, par_off, nb_t, N, a, use_list, n_inner, fx, fy, fz, e_out);
-            else lj_forces<C6, SW, false>(p, pc, pos_base, par_off, nb_t, N, a, use_list, n_inner, fx, fy, fz, e_out);
+            if (want_energy) lj_forces<C6, SW, true>(p, pc, pos_base, par_off, nb_t, N, nthr, a, use_list, n_inner, fx, fy, fz, e_out);
+            else lj_forces<C6, SW, false>(p, pc, pos_base, par_off, nb_t, N, nthr, a, use_list, n_inner, fx, fy, fz, e_out);
         } else {
             fx = fy = fz = 0.f; e_out = 0.f;
         }
@@ -411,14 +451,26 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     compute_forces(true, e_i);
     __syncthreads();  // the list is dead from here: its area carries the per-atom terms
     double2 *x_e = (double2 *)s_nb;
-    x_e[a] = make_double2((double)e_i, active ? 0.5 * (double)(vx * vx + vy * vy + vz * vz) / (double)inv_m : 0.0);
+    x_e[a - a_base] = make_double2((double)e_i, active ? 0.5 * (double)(vx * vx + vy * vy + vz * vz) / (double)inv_m : 0.0);
     __syncthreads();
     const double2 et = x_e[t];
-    const double U = block_reduce_sum(active ? et.x : 0.0, s_red);
-    const double KE = block_reduce_sum(active ? et.y : 0.0, s_red);
+    double U = block_reduce_sum(t < n_own ? et.x : 0.0, s_red);
+    double KE = block_reduce_sum(t < n_own ? et.y : 0.0, s_red);
     const bool bad = active && !(isfinite(x) && isfinite(y) && isfinite(z) && isfinite(vx) && isfinite(vy) && isfinite(vz));
-    const int any_bad = __syncthreads_or(bad ? 1 : 0);
-    if (t == 0) {
+    int any_bad = __syncthreads_or(bad ? 1 : 0);
+    if (CL > 1) {   // block 0 of the cluster adds the partial sums in block order
+        cg::cluster_group cl = cg::this_cluster();
+        if (t == 0) {
+            double *dst = cl.map_shared_rank(s_part, 0);
+            dst[3 * q] = U; dst[3 * q + 1] = KE; dst[3 * q + 2] = any_bad ? 1.0 : 0.0;
+        }
+        cl.sync();
+        if (q == 0 && t == 0) {
+            U = 0; KE = 0; any_bad = 0;
+            for (int c = 0; c < CL; c++) { U += s_part[3 * c]; KE += s_part[3 * c + 1]; any_bad |= s_part[3 * c + 2] != 0.0; }
+        }
+    }
+    if (t == 0 && q == 0) {
         pot[k] = U + st.offset;
         kin[k] = KE;
         nan_flag[k] = (any_bad || !isfinite(U)) ? 1 : 0;
@@ -430,6 +482,7 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
         pos[(size_t)r * p.N + a] = make_float4(x, y, z, 0.f);
         vel[(size_t)r * p.N + a] = make_float4(vx, vy, vz, 0.f);
     }
+    if (CL > 1) cg::this_cluster().sync();   // no block leaves while another may still write into its shared memory
 }
 
 __global__ void k_randomize_velocities(int N, const float4 *__restrict__ atom, const StateDev *__restrict__ states,
@@ -652,7 +705,18 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     fill_dyn(h, p);
     const int N = h->cfg.n_atoms;
     if (N > 1024) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: more than 1024 atoms per replica is not supported yet");
-    const int threads = ((N + 31) / 32) * 32;
+    // Blocks per replica (a thread-block cluster): with fewer replicas than SMs a replica is split over 2 or 4 blocks, so that
+    // the launch still fills the GPU and a step is shorter (RX_CLUSTER = 1 | 2 | 4 overrides).
+    int cl = 1;
+    if (h->cfg.system_kind == RX_SYSTEM_LJ_ALCH && N >= 256) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+        if (h->kloc * 2 <= sms) cl = 4;
+        else if (h->kloc <= sms) cl = 2;
+        if (const char *e = getenv("RX_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cl = v; }
+    }
+    const int n_per = (N + cl - 1) / cl;
+    const int threads = ((n_per + 31) / 32) * 32;
     // shared memory: two position buffers + the parameter records + per-thread reference positions + the list area
     const size_t atoms_bytes = (size_t)3 * RX_MAX_ATOMS * sizeof(float4) + (size_t)threads * sizeof(float4);
     size_t area = (size_t)threads * sizeof(double2);  // the list area doubles as scratch for the final reductions
@@ -670,7 +734,7 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
         if (skin_in > eff_out / 3.0) skin_in = eff_out / 3.0;
         if (eff_out > 0.03) {
             const size_t budget = (threads > 512 ? 200 : 112) * 1024;
-            int cap = (int)((budget - atoms_bytes) / ((size_t)N * sizeof(unsigned short)));
+            int cap = (int)((budget - atoms_bytes) / ((size_t)threads * sizeof(unsigned short)));
             if (cap > 128) cap = 128;
             if (cap >= 8) {
                 p.maxnb = cap;
@@ -678,7 +742,7 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
                 p.rin2 = (float)((h->cfg.r_cutoff + skin_in) * (h->cfg.r_cutoff + skin_in));
                 p.half_in2 = (float)(0.25 * skin_in * skin_in);
                 p.half_out2 = (float)(0.25 * (eff_out - skin_in) * (eff_out - skin_in));
-                const size_t list_bytes = (((size_t)cap * N * sizeof(unsigned short)) + 15) / 16 * 16;
+                const size_t list_bytes = (((size_t)cap * threads * sizeof(unsigned short)) + 15) / 16 * 16;
                 // scratch of the atom re-assignment: velocities, order, per-warp bin counts, bin bases
                 const size_t sort_bytes = (size_t)threads * (sizeof(float4) + 2) + (size_t)(threads / 32 + 1) * RX_SORT_BINS * 2;
                 p.sort_atoms = (list_bytes >= sort_bytes && !getenv("RX_NO_SORT")) ? 1 : 0;
@@ -688,16 +752,33 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     }
     const size_t smem = atoms_bytes + area;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
-#define RX_LAUNCH_PROPAGATE(C6, SW)                                                                                        \
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(h->kloc * cl));
+    lc.blockDim = dim3((unsigned)threads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    const uint32_t it32 = (uint32_t)iteration;
+#define RX_LAUNCH_PROPAGATE(C6, SW, CL)                                                                                   \
     do {                                                                                                                   \
         if (smem > 48 * 1024)                                                                                              \
-            RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate<C6, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_propagate<C6, SW><<<h->kloc, threads, smem, h->stream>>>(p, h->d_atom, h->d_states, h->d_perm, h->d_pos, h->d_vel, \
-                                                                   h->k0, key, (uint32_t)iteration, reassign, h->d_pot,    \
-                                                                   h->d_kin, h->d_nan, d_only);                            \
+            RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate<C6, SW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        RX_CHECK_CUDA(h, cudaLaunchKernelEx(&lc, k_propagate<C6, SW, CL>, p, (const float4 *)h->d_atom, (const StateDev *)h->d_states, \
+                                            (const int *)h->d_perm, h->d_pos, h->d_vel, h->k0, key, it32, reassign, h->d_pot, \
+                                            h->d_kin, h->d_nan, d_only));                                                 \
     } while (0)
-    if (p.c_is_6) { if (p.use_switch) RX_LAUNCH_PROPAGATE(true, true); else RX_LAUNCH_PROPAGATE(true, false); }
-    else { if (p.use_switch) RX_LAUNCH_PROPAGATE(false, true); else RX_LAUNCH_PROPAGATE(false, false); }
+#define RX_LAUNCH_PROPAGATE_CL(C6, SW)                                                                                    \
+    do {                                                                                                                   \
+        if (cl == 4) RX_LAUNCH_PROPAGATE(C6, SW, 4); else if (cl == 2) RX_LAUNCH_PROPAGATE(C6, SW, 2);                    \
+        else RX_LAUNCH_PROPAGATE(C6, SW, 1);                                                                               \
+    } while (0)
+    if (p.c_is_6) { if (p.use_switch) RX_LAUNCH_PROPAGATE_CL(true, true); else RX_LAUNCH_PROPAGATE_CL(true, false); }
+    else { if (p.use_switch) RX_LAUNCH_PROPAGATE_CL(false, true); else RX_LAUNCH_PROPAGATE_CL(false, false); }
+#undef RX_LAUNCH_PROPAGATE_CL
 #undef RX_LAUNCH_PROPAGATE
     RX_CHECK_CUDA(h, cudaGetLastError());
     (*launches)++;
@@ -784,7 +865,7 @@ __global__ void __launch_bounds__(1024) k_minimize(DynParams p, const float4 *__
         if (p.kind == RX_SYSTEM_HARMONIC) { fx = -hK * (x - hx0); fy = -hK * (y - hx1); fz = -hK * (z - hx2); }
         else if (active) {
             pc.x = x; pc.y = y; pc.z = z;
-            lj_forces<C6, SW, false>(p, pc, pos_base, 16 * RX_MAX_ATOMS, 0u, p.N, t, false, 0, fx, fy, fz, e);
+            lj_forces<C6, SW, false>(p, pc, pos_base, 16 * RX_MAX_ATOMS, 0u, p.N, p.N, t, false, 0, fx, fy, fz, e);
         }
         if (!active) { fx = fy = fz = 0.f; }
         // block sums of F.F, F.v, v.v (fixed order: deterministic)

@@ -123,6 +123,11 @@ __device__ __forceinline__ uint4 w2_lds128(unsigned a) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ uint4 w2_lds128_ctx(unsigned a) {   // ring contexts inside the round loop: published before the loop
+    uint4 v;                                                    // was (re-)entered, not written again while they are in use
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ void w2_sts64(unsigned a, unsigned x, unsigned y) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
@@ -143,7 +148,7 @@ __device__ __forceinline__ float w2_image_at(unsigned a_hi, unsigned a_lo) {   /
 // That warp turns the slot records into ready-to-use contexts in a shared-memory ring, far ahead of the walker (8 words):
 //   0: back-mask   1: f32 log-uniform of the next slot   2: eps0 (the filter bound's share of rows i and j; -1e30 when
 //   i == j)   3: 1 if i != j   4, 5: shared addresses of the image rows of i and j   6, 7: shared addresses of the
-//   replica entries of i and j of the slot ONE WINDOW LATER (the lane's next slot: its states are fetched a round ahead).
+//   replica entries of i and j.  A lane holds the context of its slot and, loaded a round ahead, that of its next slot.
 // The image is re-laid out row by row in shared memory -- u16 plane of the row (2K bytes), then its u8 plane (K bytes) --
 // so that one address per row serves both planes.
 #define W2_RING 512
@@ -164,7 +169,9 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
     W2Replica *s_rep = (W2Replica *)(s_ring + 2 * W2_RING);  // [K]
     float *s_rowabs = (float *)(s_rep + K);                // [K] the row's share of the filter's rounding bound
     unsigned char *s_q = (unsigned char *)(s_rowabs + K);  // image: u16 plane [K*K], then u8 plane [K*K] (16-byte aligned for K >= 4)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (the warp index through a shuffle: the compiler then knows that it is the same in all lanes, and neither guards the
+    // walker's ballots against divergence nor builds its loop with divergence-capable -- slowly resolved -- branches)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     {   // image, row by row: [u16 plane of the row | u8 plane of the row], 3K bytes per row
         const unsigned short *ghi = (const unsigned short *)filt;
         const unsigned char *glo = filt + 2 * (size_t)K * K;
@@ -197,18 +204,17 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
         unsigned prod = head0;
         while (!sh.done) {
             const unsigned head = sh.head;
-            __threadfence_block();   // acquire: the walker's reads of the entries below `head` are complete
             unsigned limit = head + W2_RING - 64;
             if (limit > nslots) limit = nslots;
             if (prod < limit) {
+                __threadfence_block();   // acquire: the walker's reads of the entries below `head` are complete
                 unsigned cnt = limit - prod;
                 if (cnt > 64) cnt = 64;
                 uint4 q[2];
-                uint32_t nx[2];
 #pragma unroll
                 for (int b = 0; b < 2; b++) {
                     const unsigned o = b * 32 + lane;
-                    if (o < cnt) { q[b] = __ldg(recs + (prod + o)); nx[b] = __ldg(&rec[min(prod + o + 32u, nslots - 1u)].ij); }
+                    if (o < cnt) q[b] = __ldg(recs + (prod + o));
                 }
 #pragma unroll
                 for (int b = 0; b < 2; b++) {
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
                         uint4 *dst = s_ring + 2 * ((prod + o) & (W2_RING - 1));
                         dst[0] = make_uint4(q[b].y, q[b].z, __float_as_uint(eps0), i != j ? 1u : 0u);
                         dst[1] = make_uint4(img_base + 3u * ((unsigned)K * i), img_base + 3u * ((unsigned)K * j),
-                                            rep_base0 + ((nx[b] & 0xffffu) << 3), rep_base0 + ((nx[b] >> 16) << 3));
+                                            rep_base0 + (i << 3), rep_base0 + (j << 3));
                     }
                 }
                 prod += cnt;
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
                 __syncwarp();
                 if (lane == 0) sh.prod = prod;
             } else {
-                __nanosleep(100);
+                __nanosleep(800);   // (a poll is a shared-memory load next to the walker's: keep them rare)
             }
         }
         return;
@@ -239,94 +245,92 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
     unsigned rem = remaining0 > 0x7fffffffLL ? 0x7fffffffu : (unsigned)remaining0;
     const unsigned rem0 = rem;
     unsigned rounds = 0, slow = 0;
-    // The fast loop is entered when the contexts of [h, h + 196) are in the ring; it then runs a quota of rounds that cannot
-    // outrun the ring (a round advances at most 33 slots and reads the contexts of the 32 slots of its window).
     unsigned prod_seen = head0;
-    auto ring_ready = [&]() -> bool {
-        if (h + 196u > nslots) return false;
-        if (prod_seen < h + 196u) {
-            __threadfence_block();            // release: this warp no longer reads ring entries of slots below h
-            if (lane == 0) sh.head = h;
-            while (prod_seen < h + 196u) prod_seen = sh.prod;
-        }
-        __threadfence_block();   // acquire: the contexts below `prod_seen` are visible
-        return true;
-    };
-    if (rem >= 130 && ring_ready()) {
+    if (rem >= 130 && h + 162u <= nslots) {
+        while (sh.prod < h + 64u) { }   // the contexts of the first two windows
+        __threadfence_block();
         // 32-bit shared addresses (through a shuffle, so that they live in registers instead of being re-derived)
         const unsigned rep_base = __shfl_sync(0xffffffffu, rep_base0, 0);
         const unsigned rg_base = __shfl_sync(0xffffffffu, ring_base, 0);
         const unsigned a_head = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)&sh.head), 0);
+        const unsigned a_prod = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)&sh.prod), 0);
         const unsigned lo_off = 2u * (unsigned)K;       // the u8 plane of an image row
         unsigned r = h & 31u;                           // lane of window position 0
         unsigned w = ((unsigned)lane - h) & 31u;        // this lane's window position
         unsigned sA = h + w;                            // this lane's slot
-        unsigned ridx = sA & (W2_RING - 1);             // its ring entry
-        uint4 c0 = w2_lds128(rg_base + (ridx << 5));    // its context: back-mask, lu, eps0, i != j
-        uint4 c1 = w2_lds128(rg_base + (ridx << 5) + 16);   // image rows of i and j, replica entries of the next slot's i and j
-        unsigned aiA, ajA;                              // shared addresses of the replica entries of i and j
-        {
-            const unsigned ij = rec[sA].ij;
-            aiA = rep_base + ((ij & 0xffffu) << 3); ajA = rep_base + ((ij >> 16) << 3);
-        }
-        uint2 ei = w2_lds64(aiA), ej = w2_lds64(ajA);   // {state, diag} of both replicas
+        unsigned ridxB = (sA + 32u) & (W2_RING - 1);    // ring entry of its next slot (one window later)
+        // contexts: A = the lane's slot, B = its next slot (loaded a round before it can be needed)
+        uint4 cA0 = w2_lds128(rg_base + ((sA & (W2_RING - 1)) << 5)), cA1 = w2_lds128(rg_base + ((sA & (W2_RING - 1)) << 5) + 16);
+        uint4 cB0 = w2_lds128(rg_base + (ridxB << 5)), cB1 = w2_lds128(rg_base + (ridxB << 5) + 16);
+        uint2 ei = w2_lds64(cA1.z), ej = w2_lds64(cA1.w);   // {state, diag} of both replicas
         // what the round resolved last leaves to the next block: the committed window positions, the positions that leave
         // the window, all-ones if this lane's attempt changes the permutation, its log entry
-        unsigned p_cm = 0, p_below = 0, p_chg = 0, p_entry = 0, p_advance = 0;
+        unsigned p_cm = 0, p_below = 0, p_chg = 0, p_entry = 0;
         float f_ij = 0.f, f_ji = 0.f;
         // Commit the round described by the p_* values, slide the window and fetch the states of the next round:
         // permutation stores, at once the next round's loads, then the lane state.
         auto commit = [&]() {
+            unsigned sA_next = sA;
+            // the window advances by the number of positions that leave it (computed here rather than where `below` appears,
+            // at the end of the previous block: a population count is a long-latency operation whose scoreboard slot would
+            // otherwise be waited for at the loop's back edge)
+            const unsigned p_advance = (unsigned)__popc(p_below);
             const unsigned bit = 1u << w;
             const bool p_mine = (p_cm & bit) != 0u;
             const bool p_swaps = (p_cm & bit & p_chg) != 0u;
             const bool p_promoted = (p_below & bit) != 0u;
             if (p_swaps) {   // replica i takes state sj: its new diagonal value is the off-diagonal one just read
-                w2_sts64(aiA, ej.x, __float_as_uint(f_ij));
-                w2_sts64(ajA, ei.x, __float_as_uint(f_ji));
+                w2_sts64(cA1.z, ej.x, __float_as_uint(f_ij));
+                w2_sts64(cA1.w, ei.x, __float_as_uint(f_ji));
             }
             __syncwarp();
-            // the states of the next round: of the slot one window later for the lanes that leave the window
-            aiA = p_promoted ? c1.z : aiA;
-            ajA = p_promoted ? c1.w : ajA;
-            const uint2 ein = w2_lds64(aiA), ejn = w2_lds64(ajA);
+            // the states of the next round: of the next slot for the lanes that leave the window
+            const uint2 ein = w2_lds64(p_promoted ? cB1.z : cA1.z), ejn = w2_lds64(p_promoted ? cB1.w : cA1.w);
+            if (p_promoted) { cA0 = cB0; cA1 = cB1; sA_next = sA + 32; ridxB = (ridxB + 32u) & (W2_RING - 1); }
+            // the context of the (possibly new) next slot: the lanes that stay re-read the one they hold.  (Volatile like
+            // the loads above, so that they are issued right behind them, in their latency shadow, and not where the
+            // scheduler would otherwise sink them: in front of the round's last ballot.)
+            cB0 = w2_lds128(rg_base + (ridxB << 5));
+            cB1 = w2_lds128(rg_base + (ridxB << 5) + 16);
             if (p_mine) slot_log[sA] = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
+            sA = sA_next;
             h += p_advance;
             r = (r + p_advance) & 31u;
             rem -= __popc(p_cm);
-            if (p_promoted) { sA += 32; ridx = (ridx + 32u) & (W2_RING - 1); }
-            // the context of this lane's (possibly new) slot: the lanes that stay re-read the one they hold
-            c0 = w2_lds128(rg_base + (ridx << 5));
-            c1 = w2_lds128(rg_base + (ridx << 5) + 16);
             ei = ein;
             ej = ejn;
             w = (w - p_advance) & 31u;
         };
+        unsigned cm = 0, Cw = 0;
+        p_cm = p_below = 0;
         for (;;) {
+            // ---------------- every 8 rounds at most: the walker's position goes to the producer (release: this warp no
+            // longer reads ring entries of slots below h), the producer's comes back (acquire: the contexts below it are
+            // visible) and with it the number of rounds that can certainly be started now -- a round commits at most 32
+            // attempts and advances at most 32 slots; the lanes read the contexts of their slots in the next two windows.
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a_head), "r"(h) : "memory");
+            if (rem < 130u || h + 162u > nslots) break;
+            do {   // (the producer is never more than a burst away: it may fill the ring up to the position just published)
+                asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(prod_seen) : "r"(a_prod) : "memory");
+                prod_seen = __shfl_sync(0xffffffffu, prod_seen, 0);   // (warp-uniform for the compiler: see the warp index above)
+            } while (prod_seen < h + 162u);
+            unsigned quota = min(min((rem - 97u) >> 5, ((prod_seen - h - 97u) * 1985u) >> 16), 8u);
             // ---------------- fast rounds.  The loop is rotated: an iteration COMMITS the round resolved by the previous
             // one and then evaluates and resolves the next, so that the block begins with the dependent chain (stores ->
-            // state loads -> image loads -> filter -> ballots); no data-dependent branch besides the loop's.
-            unsigned cm = 0;
-            bool adv33 = false;
-            p_cm = p_below = p_advance = 0;   // nothing to commit on entry
-            // rounds that can certainly still be started: each commits at most 32 attempts and advances at most 33 slots
-            // (the budget, the end of the pass and the ring are looked at again when this count runs out)
-            int quota = (int)min((rem - 97u) >> 5, (prod_seen - 163u - h) / 33u);
+            // state loads -> image loads -> filter -> ballots); no data-dependent branch besides the loop's.  The round
+            // resolved last stays pending across the maintenance step above.
             do {
                 commit();
                 rounds++;
                 const unsigned si = ei.x, sj = ej.x;
-                f_ij = w2_image_at(c1.x + 2u * sj, c1.x + lo_off + sj);
-                f_ji = w2_image_at(c1.y + 2u * si, c1.y + lo_off + si);
-                const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, __uint_as_float(c0.z));
-                // release (every 8 rounds, one predicated instruction pair, no branch): the warp's reads of the ring entries
-                // below h -- ordered before this lane's store by the __syncwarp() of the commit -- are complete
-                if ((rounds & 7u) == 0u && lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a_head), "r"(h) : "memory");
-                quota--;
+                f_ij = w2_image_at(cA1.x + 2u * sj, cA1.x + lo_off + sj);
+                f_ji = w2_image_at(cA1.y + 2u * si, cA1.y + lo_off + si);
+                const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, __uint_as_float(cA0.z));
                 bool ge0, acc, undecided;
-                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, e0, __uint_as_float(c0.y), ge0, acc, undecided);
+                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, e0, __uint_as_float(cA0.y), ge0, acc, undecided);
                 const unsigned und = undecided ? 1u : 0u;
-                const bool changes = acc && c0.w != 0u;
+                const bool changes = acc && cA0.w != 0u;
                 const unsigned G = __ballot_sync(0xffffffffu, ge0);
                 const unsigned A = __ballot_sync(0xffffffffu, changes);
                 const unsigned Gw = __funnelshift_r(G, G, r), Aw = __funnelshift_r(A, A, r);   // window order
@@ -340,41 +344,30 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
                 const unsigned VA = V & Aw;
                 unsigned earlier;   // bit 31-b: window position w-1-b is a visited state-changing swap
                 asm("shl.b32 %0, %1, %2;" : "=r"(earlier) : "r"(VA), "r"(32u - w));
-                // a round ends before the first visited lane that is stale -- or that the filter could not decide
-                const unsigned C = __ballot_sync(0xffffffffu, ((earlier & c0.x) | und) != 0u);
-                const unsigned Cw = __funnelshift_r(C, C, r) & V;
+                // A round ends before the first visited lane that is stale -- or that the filter could not decide -- and
+                // before the last window position when its attempt draws a uniform (log_p < 0): that uniform's slot lies
+                // beyond the window, and committing it here would make the window advance by 33 (the lane of the skipped
+                // slot would have to move on by two windows at once); the attempt simply opens the next round instead.
+                const unsigned C = __ballot_sync(0xffffffffu, ((earlier & cA0.x) | und) != 0u);
+                Cw = (__funnelshift_r(C, C, r) | (X & 0x80000000u)) & V;
                 const unsigned low = Cw & (0u - Cw);
                 const unsigned below = low - 1u;       // low == 0 -> all lanes
                 cm = V & below;
                 p_cm = cm; p_below = below; p_chg = changes ? 0xffffffffu : 0u;
                 p_entry = (sj * (1u << LOG_STATE_BITS) + si) | (acc ? (1u << 31) | (1u << LOG_ACC_BIT) : (1u << 31));
-                p_advance = (unsigned)__popc(below);   // 32 when no lane is stale
-                // bit 32 (even position) of the skip word can only be set by the carry of an odd-start run: the slot after
-                // the window is then a uniform's slot (handled outside the loop)
-                adv33 = Cw == 0u && sumO < X;
-            } while (quota > 0 && cm != 0u && !adv33);
-            if (adv33) p_advance = 33u;
-            commit();   // the round resolved last
-            // ---------------- rare events
-            if (adv33) {
-                // the lane that is now at window position 31 holds slot h - 1 (skipped) and moves on by another window
-                if (w == 31u) {
-                    sA += 32; ridx = (ridx + 32u) & (W2_RING - 1);
-                    aiA = c1.z; ajA = c1.w;
-                    c0 = w2_lds128(rg_base + (ridx << 5)); c1 = w2_lds128(rg_base + (ridx << 5) + 16);
-                    ei = w2_lds64(aiA); ej = w2_lds64(ajA);
-                }
-                __syncwarp();
-            }
-            if (rem < 130u) break;
-            if (prod_seen < h + 196u && !ring_ready()) break;
-            if (cm == 0u) {
-                // the first lane of the window is undecided: one exact attempt, exactly what the reference does
+                // (position 0 is always visited: nothing commits iff it is itself the lane that ends the round)
+            } while (--quota != 0u && (Cw & 1u) == 0u);
+            if ((Cw & 1u) == 0u) continue;
+            commit();   // (nothing to commit: positions the lanes on the round that could not start)
+            // ---------------- rare: the first lane of the window is undecided: one exact attempt, exactly what the reference
+            // does (window position 0 commits; positions 0 .. advance-1 leave the window; log_p < 0: the next slot is this
+            // attempt's uniform)
+            {
                 rounds++;
                 bool ge0 = false, acc = false;
                 const unsigned si = ei.x, sj = ej.x;
-                f_ij = w2_image_at(c1.x + 2u * sj, c1.x + lo_off + sj);
-                f_ji = w2_image_at(c1.y + 2u * si, c1.y + lo_off + si);
+                f_ij = w2_image_at(cA1.x + 2u * sj, cA1.x + lo_off + sj);
+                f_ji = w2_image_at(cA1.y + 2u * si, cA1.y + lo_off + si);
                 if (w == 0u) {
                     const unsigned ij = rec[sA].ij;
                     const unsigned rowi = (ij & 0xffffu) << logK, rowj = (ij >> 16) << logK;
@@ -392,16 +385,15 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
                 }
                 __syncwarp();
                 const bool first_ge0 = __ballot_sync(0xffffffffu, ge0) != 0u;
-                p_advance = first_ge0 ? 1u : 2u;   // log_p < 0: the next slot is this attempt's uniform
-                p_cm = 1u;                         // window position 0 commits; positions 0 .. advance-1 leave the window
+                p_cm = 1u;
                 p_below = first_ge0 ? 1u : 3u;
-                p_chg = (acc && c0.w != 0u) ? 0xffffffffu : 0u;
+                p_chg = (acc && cA0.w != 0u) ? 0xffffffffu : 0u;
                 p_entry = (sj * (1u << LOG_STATE_BITS) + si) | (acc ? (1u << 31) | (1u << LOG_ACC_BIT) : (1u << 31));
                 commit();
-                if (rem < 130u) break;
-                if (prod_seen < h + 196u && !ring_ready()) break;
+                p_cm = p_below = 0;
             }
         }
+        commit();   // the round resolved last, if one is pending
         __syncwarp();
         for (int q = lane; q < K; q += 32) perm_g[q] = s_rep[q].state;
     }

@@ -188,3 +188,28 @@ def test_pair_kernel_variants_match_oracle(use_switch, annihilate, alpha, a, b, 
         assert np.abs(vg[k] - v).max() < 3e-4, (k, np.abs(vg[k] - v).max())
         assert abs(pot[k] - U) < 2e-3 * max(1.0, abs(U)), (pot[k], U)
     e.close()
+
+
+@pytest.mark.parametrize('cl', [2, 4])
+def test_cluster_split_replica_reproduces_single_block_trajectory(monkeypatch, cl):
+    """A replica split over a thread-block cluster (atoms partitioned over 2 or 4 blocks, positions exchanged through
+    distributed shared memory, cluster-wide displacement votes) must give the SAME trajectory as one block per replica:
+    lists are rebuilt at the same steps with the same contents, every atom sums its own list in list order, noise is
+    keyed by atom id.  200 hot steps cross several re-partitions and at least one outer rebuild."""
+    N, K = 512, 3
+    s = lj_setup(N=N, n_alch=10, seed=51)
+    lambdas = np.array([1.0, 0.5, 0.0]); temps = np.array([500.0, 500.0, 500.0])
+    rng = np.random.default_rng(15)
+    v0 = rng.normal(scale=0.3, size=(K, N, 3)).astype(np.float32).astype(np.float64)
+    out = []
+    for c in (1, cl):
+        monkeypatch.setenv('RX_CLUSTER', str(c))
+        e = make_engine(s, K, K, lambdas, temps, 0.002, 1.0, 200, 'V R O R V')
+        e.set_positions(np.stack([s['x']] * K)); e.set_velocities(v0)
+        e.set_replica_states(np.array([1, 2, 0]))
+        e.propagate(1234, 9)
+        out.append((e.get_positions(), e.get_velocities(), e.get_replica_energies()))
+        e.close()
+    (xa, va, (pa, ka)), (xb, vb, (pb, kb)) = out
+    assert np.array_equal(xa, xb) and np.array_equal(va, vb)
+    assert np.allclose(pa, pb, rtol=1e-12, atol=1e-9) and np.allclose(ka, kb, rtol=1e-12, atol=1e-9)   # other summation order

@@ -62,7 +62,7 @@ class _Stub:
 
 def fixture_forces(c):
     out = []
-    for d in FIXTURE['config%d' % c]:
+    for d in json.loads(json.dumps(FIXTURE['config%d' % c])):   # a private copy: a test may edit it
         f = type(d['type'], (_Stub,), {})(d)     # the adapter dispatches on the class NAME
         out.append(f)
     return lj_setup(N=N, n_alch=N_ALCH, reduced_density=0.4, seed=77), out

@@ -92,9 +92,11 @@ def run(K, nswap, model, seed, p_und=0.0):
             for l in lanes:
                 sh = 32 - w[l]; earlier = (VA << sh) & M32 if sh < 32 else 0
                 if ((earlier & A[l][2]) | und[l]) != 0: Cb |= 1 << l
-            Cw = rotr(Cb, r) & V; low = Cw & (-Cw & M32); below = (low - 1) & M32; cm = V & below
-            adv33 = 1 if (Cw == 0 and carryO) else 0
-            adv = popc(below) if Cw else 32 + adv33
+            # (the last window position does not commit an attempt whose uniform lies beyond the window)
+            Cw = (rotr(Cb, r) | (X & 0x80000000)) & V; low = Cw & (-Cw & M32); below = (low - 1) & M32; cm = V & below
+            adv33 = 0
+            adv = popc(below)
+            assert not (Cw == 0 and carryO)
             for l in lanes:
                 P['mine'][l] = bool((cm >> w[l]) & 1)
                 P['swaps'][l] = P['mine'][l] and ac[l] and A[l][0] != A[l][1]
