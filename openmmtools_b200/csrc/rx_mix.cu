@@ -759,7 +759,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     // filter mode: 16-byte SlotRec2 records, k_mix_walk2 for the bulk of a pass and k_mix_walk_pow2<U_FILTER24, true> for its tail
     const bool rec2 = (umode == U_FILTER24);
     const bool walk2 = rec2 && !getenv("RX_WALK_V1");
-    const size_t smem_w2 = (size_t)W2_RING * 32 + (size_t)K * 12 + (size_t)3 * K * K + 32;
+    const size_t smem_w2 = (size_t)W2_RING * 16 + (size_t)K * 8 + (size_t)3 * K * K;
     size_t smem = !fast ? smem_small : (umode == U_F64_SMEM ? smem_f64 : (umode == U_FILTER24 ? smem_f24 : smem_base));
     // The walker is one latency-bound CTA: claim (almost) a whole SM's shared memory so that no other CTA -- in particular
     // the stream generator that runs concurrently on the side stream -- is scheduled onto the same SM and steals issue slots.
@@ -836,7 +836,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
                     if (smem_w2 > smem) RX_FAIL(h, RX_ERR_INVALID, "internal: k_mix_walk2 shared memory");
                     // sparse commit log: one word per slot, zero = no attempt started there
                     RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_slotlog, 0, (size_t)nslots * sizeof(uint32_t), h->stream));
-                    k_mix_walk2<<<1, 64, smem, h->stream>>>((const SlotRec2 *)h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_slotlog, h->d_filt, h->d_filt_scale, h->d_ctl);
+                    k_mix_walk2<<<1, W2_THREADS, smem, h->stream>>>((const SlotRec2 *)h->d_slots, S.d_words, (unsigned)nslots, h->d_u, K, logK, h->d_perm, h->d_slotlog, h->d_filt, h->d_filt_scale, h->d_ctl);
                     RX_CHECK_CUDA(h, cudaGetLastError());
                     *launches += 1;
                 }

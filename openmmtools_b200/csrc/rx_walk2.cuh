@@ -143,134 +143,125 @@ __device__ __forceinline__ float w2_image_at(unsigned a_hi, unsigned a_lo) {   /
     return __uint_as_float(__byte_perm(hi, lo, 0x1045));
 }
 
-// The walker warp issues about one instruction every two cycles (one warp, dependent code): what limits a round is the
-// NUMBER of instructions it executes, so everything that does not depend on the permutation is done by a second warp.
-// That warp turns the slot records into ready-to-use contexts in a shared-memory ring, far ahead of the walker (8 words):
-//   0: back-mask   1: f32 log-uniform of the next slot   2: eps0 (the filter bound's share of rows i and j; -1e30 when
-//   i == j)   3: 1 if i != j   4, 5: shared addresses of the image rows of i and j   6, 7: shared addresses of the
-//   replica entries of i and j.  A lane holds the context of its slot and, loaded a round ahead, that of its next slot.
+// The walker's record ring: 16 entries per lane (= per slot class mod 32), filled by the lane itself with asynchronous
+// global->shared copies 15 windows ahead of use (no register, no scoreboard wait; DRAM latency is far below that);
+// completion is tracked by the hardware (cp.async.wait_group): no flags, no fences, no second warp in the loop.
+// (A producer warp that prepared ready-to-use contexts was tried: 106 instead of 125 instructions per round for the
+// walker, but its shared-memory traffic and the acquire/release pairs made the walker's own loads wait twice as long --
+// 210-260 ns per round against 177 ns for this organisation.)
+#define W2_RING 512
+__device__ __forceinline__ void w2_cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void w2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void w2_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // The image is re-laid out row by row in shared memory -- u16 plane of the row (2K bytes), then its u8 plane (K bytes) --
 // so that one address per row serves both planes.
-#define W2_RING 512
-struct W2Shared {   // cross-warp words: volatile (= relaxed, strong) accesses paired with fence.acq_rel.cta
-    volatile unsigned prod;   // contexts of the slots [.., prod) are in the ring        (producer: fence, then store)
-    volatile unsigned head;   // the walker no longer reads ring entries of slots < head   (walker: fence, then store)
-    volatile unsigned done;
-};
-
-__global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ rec, const uint32_t *__restrict__ words,
+#define W2_THREADS 128   // warps 1.. only help with the prologue
+__global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__restrict__ rec, const uint32_t *__restrict__ words,
                                                   unsigned nslots, const double *__restrict__ u, int K, int logK,
                                                   int *__restrict__ perm_g, uint32_t *__restrict__ slot_log,
                                                   const unsigned char *__restrict__ filt,
                                                   const double *__restrict__ filt_rowabs, MixCtl *ctl) {
     extern __shared__ uint4 s_w2[];
-    __shared__ W2Shared sh;
-    uint4 *s_ring = s_w2;                                  // [W2_RING][2] slot contexts
-    W2Replica *s_rep = (W2Replica *)(s_ring + 2 * W2_RING);  // [K]
-    float *s_rowabs = (float *)(s_rep + K);                // [K] the row's share of the filter's rounding bound
-    unsigned char *s_q = (unsigned char *)(s_rowabs + K);  // image: u16 plane [K*K], then u8 plane [K*K] (16-byte aligned for K >= 4)
+    uint4 *s_ring = s_w2;                                  // [W2_RING] slot records
+    W2Replica *s_rep = (W2Replica *)(s_ring + W2_RING);    // [K]
+    unsigned char *s_q = (unsigned char *)(s_rep + K);     // image rows, 3K bytes each
     // (the warp index through a shuffle: the compiler then knows that it is the same in all lanes, and neither guards the
     // walker's ballots against divergence nor builds its loop with divergence-capable -- slowly resolved -- branches)
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    {   // image, row by row: [u16 plane of the row | u8 plane of the row], 3K bytes per row
+    {
         const unsigned short *ghi = (const unsigned short *)filt;
         const unsigned char *glo = filt + 2 * (size_t)K * K;
-        for (int q = tid; q < K * K; q += 64) {
-            const int row = q >> logK, col = q & (K - 1);
-            unsigned char *rowp = s_q + (size_t)3 * K * row;
-            ((unsigned short *)rowp)[col] = ghi[q];
-            rowp[2 * K + col] = glo[q];
+        if (K >= 16) {   // 16-byte pieces: 8 values of the u16 plane, 16 of the u8 plane, never across a row
+            const uint4 *ghi4 = (const uint4 *)ghi, *glo4 = (const uint4 *)glo;   // (cudaMalloc alignment, 2 K^2 % 16 == 0)
+            for (int q = tid; q < (K * K) / 8; q += W2_THREADS) {
+                const int e = q * 8, row = e >> logK, col = e & (K - 1);
+                *(uint4 *)(s_q + (size_t)3 * K * row + 2 * col) = ghi4[q];
+            }
+            for (int q = tid; q < (K * K) / 16; q += W2_THREADS) {
+                const int e = q * 16, row = e >> logK, col = e & (K - 1);
+                *(uint4 *)(s_q + (size_t)3 * K * row + 2 * K + col) = glo4[q];
+            }
+        } else {
+            for (int q = tid; q < K * K; q += W2_THREADS) {
+                const int row = q >> logK, col = q & (K - 1);
+                unsigned char *rowp = s_q + (size_t)3 * K * row;
+                ((unsigned short *)rowp)[col] = ghi[q];
+                rowp[2 * K + col] = glo[q];
+            }
         }
     }
-    const unsigned head0 = (unsigned)ctl->head;
-    if (tid == 0) { sh.prod = head0; sh.head = head0; sh.done = 0; }
     __syncthreads();
-    for (int q = tid; q < K; q += 64) {
+    float rowabs_max = 0.f;
+    for (int q = tid; q < K; q += W2_THREADS) {
         W2Replica e;
         e.state = perm_g[q];
         const unsigned char *rowp = s_q + (size_t)3 * K * q;
         e.diag = __uint_as_float(__byte_perm((unsigned)((const unsigned short *)rowp)[e.state], (unsigned)rowp[2 * K + e.state], 0x1045));
         s_rep[q] = e;
-        s_rowabs[q] = __fmul_ru(1.6e-14f, __fadd_ru(__double2float_ru(filt_rowabs[q]), 0.5f));
     }
+    // the rows' share of the filter's rounding bound, the largest of all rows (rounded up; K values, read by every warp)
+    for (int q = lane; q < K; q += 32)
+        rowabs_max = fmaxf(rowabs_max, __fmul_ru(1.6e-14f, __fadd_ru(__double2float_ru(fabs(filt_rowabs[q])), 0.5f)));
+    for (int o = 16; o; o >>= 1) rowabs_max = fmaxf(rowabs_max, __shfl_xor_sync(0xffffffffu, rowabs_max, o));
+    const float eps_rows = __fadd_ru(__fadd_ru(rowabs_max, rowabs_max), 1e-9f);
     __syncthreads();
+    if (warp != 0) return;
     const uint4 *__restrict__ recs = (const uint4 *)rec;
-    const unsigned ring_base = (unsigned)__cvta_generic_to_shared((const void *)s_ring);
-    const unsigned img_base = (unsigned)__cvta_generic_to_shared((const void *)s_q);
-    const unsigned rep_base0 = (unsigned)__cvta_generic_to_shared((const void *)s_rep);
 
-    if (warp == 1) {
-        // ---------------- context producer: the ring holds the slots [head, head + W2_RING - 64) at most
-        unsigned prod = head0;
-        while (!sh.done) {
-            const unsigned head = sh.head;
-            unsigned limit = head + W2_RING - 64;
-            if (limit > nslots) limit = nslots;
-            if (prod < limit) {
-                __threadfence_block();   // acquire: the walker's reads of the entries below `head` are complete
-                unsigned cnt = limit - prod;
-                if (cnt > 64) cnt = 64;
-                uint4 q[2];
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    const unsigned o = b * 32 + lane;
-                    if (o < cnt) q[b] = __ldg(recs + (prod + o));
-                }
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    const unsigned o = b * 32 + lane;
-                    if (o < cnt) {
-                        const unsigned i = q[b].x & 0xffffu, j = q[b].x >> 16;
-                        const float eps0 = (i == j) ? -1e30f : (s_rowabs[i] + s_rowabs[j]) + 1e-9f;
-                        uint4 *dst = s_ring + 2 * ((prod + o) & (W2_RING - 1));
-                        dst[0] = make_uint4(q[b].y, q[b].z, __float_as_uint(eps0), i != j ? 1u : 0u);
-                        dst[1] = make_uint4(img_base + 3u * ((unsigned)K * i), img_base + 3u * ((unsigned)K * j),
-                                            rep_base0 + (i << 3), rep_base0 + (j << 3));
-                    }
-                }
-                prod += cnt;
-                __threadfence_block();   // release: the contexts above are visible before `prod` moves
-                __syncwarp();
-                if (lane == 0) sh.prod = prod;
-            } else {
-                __nanosleep(800);   // (a poll is a shared-memory load next to the walker's: keep them rare)
-            }
-        }
-        return;
-    }
-
-    // ---------------- walker (warp 0)
+    const unsigned head0 = (unsigned)ctl->head;
     unsigned h = head0;
     const long long remaining0 = ctl->remaining;
     unsigned rem = remaining0 > 0x7fffffffLL ? 0x7fffffffu : (unsigned)remaining0;
     const unsigned rem0 = rem;
     unsigned rounds = 0, slow = 0;
-    unsigned prod_seen = head0;
-    if (rem >= 130 && h + 162u <= nslots) {
-        while (sh.prod < h + 64u) { }   // the contexts of the first two windows
-        __threadfence_block();
+    // a round may start while h + 99 <= h_end: its lanes copy the records of slots up to h + 31 + 32 + 480 into the ring
+    const unsigned h_end = nslots >= 1200u ? nslots - 560u : 0u;
+    if (rem >= 130 && nslots >= 1200u && h + 99u <= h_end) {
         // 32-bit shared addresses (through a shuffle, so that they live in registers instead of being re-derived)
-        const unsigned rep_base = __shfl_sync(0xffffffffu, rep_base0, 0);
-        const unsigned rg_base = __shfl_sync(0xffffffffu, ring_base, 0);
-        const unsigned a_head = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)&sh.head), 0);
-        const unsigned a_prod = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)&sh.prod), 0);
-        const unsigned lo_off = 2u * (unsigned)K;       // the u8 plane of an image row
+        const unsigned ring_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_ring), 0);
+        const unsigned rep_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_rep), 0);
+        const unsigned img_base = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_q), 0);
+        const unsigned row_bytes = 3u * (unsigned)K, lo_off = 2u * (unsigned)K;
         unsigned r = h & 31u;                           // lane of window position 0
         unsigned w = ((unsigned)lane - h) & 31u;        // this lane's window position
-        unsigned sA = h + w;                            // this lane's slot
-        unsigned ridxB = (sA + 32u) & (W2_RING - 1);    // ring entry of its next slot (one window later)
-        // contexts: A = the lane's slot, B = its next slot (loaded a round before it can be needed)
-        uint4 cA0 = w2_lds128(rg_base + ((sA & (W2_RING - 1)) << 5)), cA1 = w2_lds128(rg_base + ((sA & (W2_RING - 1)) << 5) + 16);
-        uint4 cB0 = w2_lds128(rg_base + (ridxB << 5)), cB1 = w2_lds128(rg_base + (ridxB << 5) + 16);
-        uint2 ei = w2_lds64(cA1.z), ej = w2_lds64(cA1.w);   // {state, diag} of both replicas
+        const unsigned sA = h + w;                      // this lane's first slot
+        // slot contexts: A = the lane's slot, B = its next slot, one window later (its raw record is loaded a round ahead):
+        // back-mask, f32 log-uniform of the following slot, the filter bound's constant term (-1e30 when i == j),
+        // all-ones if i != j, shared addresses of the image rows and of the replica entries of i and j
+        unsigned bmA, neqA, rowiA, rowjA, repiA, repjA, bmB, neqB, rowiB, rowjB, repiB, repjB;
+        float luA, epsA, luB, epsB;
+        auto derive = [&](const uint4 q, unsigned &bm, float &lu, float &eps, unsigned &neq, unsigned &rowi, unsigned &rowj,
+                          unsigned &repi, unsigned &repj) {
+            const unsigned i = q.x & 0xffffu, j = q.x >> 16;
+            bm = q.y; lu = __uint_as_float(q.z);
+            neq = i != j ? 0xffffffffu : 0u;
+            eps = i != j ? eps_rows : -1e30f;
+            rowi = img_base + i * row_bytes; rowj = img_base + j * row_bytes;
+            repi = rep_base + (i << 3); repj = rep_base + (j << 3);
+        };
+        // ring entry of slot s: s mod W2_RING; this lane owns the entries of its class (s mod 32)
+        for (unsigned k = 0; k < 16u; k++) w2_cp_async16(ring_base + (((sA + 32u * k) & (W2_RING - 1)) << 4), recs + (sA + 32u * k));
+        w2_cp_async_commit();
+        w2_cp_async_wait<0>();
+        __syncwarp();
+        derive(w2_lds128(ring_base + ((sA & (W2_RING - 1)) << 4)), bmA, luA, epsA, neqA, rowiA, rowjA, repiA, repjA);
+        unsigned ridxB = (sA + 32u) & (W2_RING - 1);   // ring entry of the next slot
+        uint4 qB = w2_lds128(ring_base + (ridxB << 4));
+        derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
+        uint2 ei = w2_lds64(repiA), ej = w2_lds64(repjA);   // {state, diag} of both replicas
         // what the round resolved last leaves to the next block: the committed window positions, the positions that leave
         // the window, all-ones if this lane's attempt changes the permutation, its log entry
         unsigned p_cm = 0, p_below = 0, p_chg = 0, p_entry = 0;
         float f_ij = 0.f, f_ji = 0.f;
+        uint32_t *log_ptr = slot_log + sA;          // this lane's entry of the sparse commit log
+        const uint4 *rec_ptr = recs + (sA + 480);   // the record this lane copies into the ring at its next promotion
         // Commit the round described by the p_* values, slide the window and fetch the states of the next round:
         // permutation stores, at once the next round's loads, then the lane state.
         auto commit = [&]() {
-            unsigned sA_next = sA;
             // the window advances by the number of positions that leave it (computed here rather than where `below` appears,
             // at the end of the previous block: a population count is a long-latency operation whose scoreboard slot would
             // otherwise be waited for at the loop's back edge)
@@ -280,20 +271,22 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
             const bool p_swaps = (p_cm & bit & p_chg) != 0u;
             const bool p_promoted = (p_below & bit) != 0u;
             if (p_swaps) {   // replica i takes state sj: its new diagonal value is the off-diagonal one just read
-                w2_sts64(cA1.z, ej.x, __float_as_uint(f_ij));
-                w2_sts64(cA1.w, ei.x, __float_as_uint(f_ji));
+                w2_sts64(repiA, ej.x, __float_as_uint(f_ij));
+                w2_sts64(repjA, ei.x, __float_as_uint(f_ji));
             }
             __syncwarp();
             // the states of the next round: of the next slot for the lanes that leave the window
-            const uint2 ein = w2_lds64(p_promoted ? cB1.z : cA1.z), ejn = w2_lds64(p_promoted ? cB1.w : cA1.w);
-            if (p_promoted) { cA0 = cB0; cA1 = cB1; sA_next = sA + 32; ridxB = (ridxB + 32u) & (W2_RING - 1); }
-            // the context of the (possibly new) next slot: the lanes that stay re-read the one they hold.  (Volatile like
-            // the loads above, so that they are issued right behind them, in their latency shadow, and not where the
-            // scheduler would otherwise sink them: in front of the round's last ballot.)
-            cB0 = w2_lds128(rg_base + (ridxB << 5));
-            cB1 = w2_lds128(rg_base + (ridxB << 5) + 16);
-            if (p_mine) slot_log[sA] = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
-            sA = sA_next;
+            const uint2 ein = w2_lds64(p_promoted ? repiB : repiA), ejn = w2_lds64(p_promoted ? repjB : repjA);
+            if (p_mine) *log_ptr = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
+            if (p_promoted) {
+                bmA = bmB; luA = luB; epsA = epsB; neqA = neqB; rowiA = rowiB; rowjA = rowjB; repiA = repiB; repjA = repjB;
+                log_ptr += 32; rec_ptr += 32;
+                w2_cp_async16(ring_base + (((ridxB - 32u) & (W2_RING - 1)) << 4), rec_ptr);   // over the entry of the slot just left
+                ridxB = (ridxB + 32u) & (W2_RING - 1);
+            }
+            w2_cp_async_commit();
+            // the record of the (possibly new) next slot: the lanes that stay re-read the one they hold
+            qB = w2_lds128(ring_base + (ridxB << 4));
             h += p_advance;
             r = (r + p_advance) & 31u;
             rem -= __popc(p_cm);
@@ -301,36 +294,28 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
             ej = ejn;
             w = (w - p_advance) & 31u;
         };
-        unsigned cm = 0, Cw = 0;
-        p_cm = p_below = 0;
+        unsigned Cw = 0;
         for (;;) {
-            // ---------------- every 8 rounds at most: the walker's position goes to the producer (release: this warp no
-            // longer reads ring entries of slots below h), the producer's comes back (acquire: the contexts below it are
-            // visible) and with it the number of rounds that can certainly be started now -- a round commits at most 32
-            // attempts and advances at most 32 slots; the lanes read the contexts of their slots in the next two windows.
-            __syncwarp();
-            if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a_head), "r"(h) : "memory");
-            if (rem < 130u || h + 162u > nslots) break;
-            do {   // (the producer is never more than a burst away: it may fill the ring up to the position just published)
-                asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(prod_seen) : "r"(a_prod) : "memory");
-                prod_seen = __shfl_sync(0xffffffffu, prod_seen, 0);   // (warp-uniform for the compiler: see the warp index above)
-            } while (prod_seen < h + 162u);
-            unsigned quota = min(min((rem - 97u) >> 5, ((prod_seen - h - 97u) * 1985u) >> 16), 8u);
+            // ---------------- the budget and the end of the pass, every 64 rounds at most: a round commits at most 32
+            // attempts and advances at most 32 slots (the round resolved last stays pending across this step)
+            if (rem < 130u || h + 99u > h_end) break;
+            unsigned quota = min(min((rem - 97u) >> 5, (h_end - h - 66u) >> 5), 64u);
             // ---------------- fast rounds.  The loop is rotated: an iteration COMMITS the round resolved by the previous
             // one and then evaluates and resolves the next, so that the block begins with the dependent chain (stores ->
-            // state loads -> image loads -> filter -> ballots); no data-dependent branch besides the loop's.  The round
-            // resolved last stays pending across the maintenance step above.
+            // state loads -> image loads -> filter -> ballots); no data-dependent branch besides the loop's.
             do {
                 commit();
                 rounds++;
                 const unsigned si = ei.x, sj = ej.x;
-                f_ij = w2_image_at(cA1.x + 2u * sj, cA1.x + lo_off + sj);
-                f_ji = w2_image_at(cA1.y + 2u * si, cA1.y + lo_off + si);
-                const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, __uint_as_float(cA0.z));
+                f_ij = w2_image_at(rowiA + 2u * sj, rowiA + lo_off + sj);
+                f_ji = w2_image_at(rowjA + 2u * si, rowjA + lo_off + si);
+                const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, epsA);
+                w2_cp_async_wait<8>();   // a copy is used 15 of the lane's promotions (at least 15 rounds) after it was issued
+                derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
                 bool ge0, acc, undecided;
-                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, e0, __uint_as_float(cA0.y), ge0, acc, undecided);
+                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, e0, luA, ge0, acc, undecided);
                 const unsigned und = undecided ? 1u : 0u;
-                const bool changes = acc && cA0.w != 0u;
+                const bool changes = acc && neqA != 0u;
                 const unsigned G = __ballot_sync(0xffffffffu, ge0);
                 const unsigned A = __ballot_sync(0xffffffffu, changes);
                 const unsigned Gw = __funnelshift_r(G, G, r), Aw = __funnelshift_r(A, A, r);   // window order
@@ -348,17 +333,18 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
                 // before the last window position when its attempt draws a uniform (log_p < 0): that uniform's slot lies
                 // beyond the window, and committing it here would make the window advance by 33 (the lane of the skipped
                 // slot would have to move on by two windows at once); the attempt simply opens the next round instead.
-                const unsigned C = __ballot_sync(0xffffffffu, ((earlier & cA0.x) | und) != 0u);
+                const unsigned C = __ballot_sync(0xffffffffu, ((earlier & bmA) | und) != 0u);
                 Cw = (__funnelshift_r(C, C, r) | (X & 0x80000000u)) & V;
                 const unsigned low = Cw & (0u - Cw);
                 const unsigned below = low - 1u;       // low == 0 -> all lanes
-                cm = V & below;
-                p_cm = cm; p_below = below; p_chg = changes ? 0xffffffffu : 0u;
+                p_cm = V & below; p_below = below; p_chg = changes ? 0xffffffffu : 0u;
                 p_entry = (sj * (1u << LOG_STATE_BITS) + si) | (acc ? (1u << 31) | (1u << LOG_ACC_BIT) : (1u << 31));
                 // (position 0 is always visited: nothing commits iff it is itself the lane that ends the round)
             } while (--quota != 0u && (Cw & 1u) == 0u);
             if ((Cw & 1u) == 0u) continue;
             commit();   // (nothing to commit: positions the lanes on the round that could not start)
+            w2_cp_async_wait<8>();
+            derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
             // ---------------- rare: the first lane of the window is undecided: one exact attempt, exactly what the reference
             // does (window position 0 commits; positions 0 .. advance-1 leave the window; log_p < 0: the next slot is this
             // attempt's uniform)
@@ -366,9 +352,10 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
                 rounds++;
                 bool ge0 = false, acc = false;
                 const unsigned si = ei.x, sj = ej.x;
-                f_ij = w2_image_at(cA1.x + 2u * sj, cA1.x + lo_off + sj);
-                f_ji = w2_image_at(cA1.y + 2u * si, cA1.y + lo_off + si);
+                f_ij = w2_image_at(rowiA + 2u * sj, rowiA + lo_off + sj);
+                f_ji = w2_image_at(rowjA + 2u * si, rowjA + lo_off + si);
                 if (w == 0u) {
+                    const unsigned sA = (unsigned)(log_ptr - slot_log);   // this lane's slot
                     const unsigned ij = rec[sA].ij;
                     const unsigned rowi = (ij & 0xffffu) << logK, rowj = (ij >> 16) << logK;
                     const double logp = swap_logp(u[rowi | sj], u[rowj | si], u[rowi | si], u[rowj | sj]);
@@ -387,17 +374,19 @@ __global__ void __launch_bounds__(64) k_mix_walk2(const SlotRec2 *__restrict__ r
                 const bool first_ge0 = __ballot_sync(0xffffffffu, ge0) != 0u;
                 p_cm = 1u;
                 p_below = first_ge0 ? 1u : 3u;
-                p_chg = (acc && cA0.w != 0u) ? 0xffffffffu : 0u;
+                p_chg = (acc && neqA != 0u) ? 0xffffffffu : 0u;
                 p_entry = (sj * (1u << LOG_STATE_BITS) + si) | (acc ? (1u << 31) | (1u << LOG_ACC_BIT) : (1u << 31));
                 commit();
+                w2_cp_async_wait<8>();
+                derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
                 p_cm = p_below = 0;
             }
         }
         commit();   // the round resolved last, if one is pending
+        w2_cp_async_wait<0>();
         __syncwarp();
         for (int q = lane; q < K; q += 32) perm_g[q] = s_rep[q].state;
     }
-    if (lane == 0) sh.done = 1;
     slow = __reduce_add_sync(0xffffffffu, slow);
     if (lane == 0) {
         const long long remaining = remaining0 - (long long)(rem0 - rem);
