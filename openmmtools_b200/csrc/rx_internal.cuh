@@ -95,7 +95,7 @@ struct rx_engine {
     uint32_t *d_slotlog = nullptr;   // sparse commit log of k_mix_walk2: one word per slot
     unsigned char *d_filt = nullptr;   // 24-bit row image of u for the K=256 walker
     double *d_filt_scale = nullptr;    // [K] scales + [K] row abs-max
-    bool prepared_rec2 = false;   // ... as SlotRec2 records (filter mode)
+    int prepared_kind = 0;        // ... with these records (REC_* of rx_mix.cu)
     bool prepared = false;        // words + slot records for the next swap-all call were produced on stream_rng
     size_t last_consumed = 0;     // words the previous swap-all call consumed (sizes the generate-ahead)
     size_t slots_for_avail = 0;   // S.avail the slot records were built for

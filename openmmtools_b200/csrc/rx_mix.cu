@@ -168,6 +168,7 @@ struct WalkShared {     // control words shared by the two warps
     volatile unsigned head;   // walker position
     volatile unsigned done;
 };
+#include "rx_walk_any.cuh"
 
 // REC2: the records are SlotRec2 (rx_walk2.cuh); only with U_FILTER24, where this kernel finishes the passes of k_mix_walk2.
 template <int UMODE, bool REC2 = false>
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             unsigned limit = head + RING - 64;   // `head` may lag the walker by 8 rounds; it only ever lags (safe)
             if (limit > nslots) limit = nslots;
             if (prod < limit) {
+                __threadfence_block();   // acquire: the walker is done with the entries below `head`
                 SlotRec r[4];
                 unsigned cnt = limit - prod;
                 if (cnt > 128) cnt = 128;
@@ -390,13 +392,18 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         h += advance;
         wpos = (wpos + advance) & (RING - 1);
         rem -= n;
-        if ((rounds & 7u) == 0u && lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a_head), "r"(h) : "memory");
         __syncwarp();
+        // release: every lane's ring reads of this and earlier rounds (ordered before lane 0 by the warp barrier) precede
+        // the new head, behind which the producer may overwrite
+        if ((rounds & 7u) == 0u && lane == 0) {
+            __threadfence_block();
+            asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a_head), "r"(h) : "memory");
+        }
     };
     while (rem > 0 && h + 33 <= nslots) {
         if (prod_seen < h + 33) {
             do { prod_seen = sh.prod; } while (prod_seen < h + 33);   // the producer is behind (start of a pass)
-            asm volatile("" ::: "memory");
+            __threadfence_block();   // acquire: the records below the position just read are visible
         }
         if (rem >= 33) {
             // main loop: a round commits at most 32 attempts, so the budget cannot end inside it, and the slots
@@ -679,8 +686,10 @@ struct MixTrace {   // RX_TRACE_MIX=1: device-time breakdown of one swap-all cal
 
 static inline bool is_pow2(int k) { return k >= 2 && (k & (k - 1)) == 0; }
 
-static inline size_t pass_need(long long remaining, bool fast) {
-    const size_t chunk_words = (size_t)1 << 26;  // 64 Mi words per pass
+enum { REC_NONE = 0, REC_SLOT = 1, REC_SLOT2 = 2, REC_WORD = 3 };   // what prepare_pass builds from the stream
+
+static inline size_t pass_need(long long remaining, bool fast, bool anyk = false) {
+    const size_t chunk_words = anyk ? (size_t)1 << 25 : (size_t)1 << 26;  // words per pass (any K: 16 bytes of records per word)
     size_t need = fast ? (size_t)(4 * remaining + 160) : (size_t)(8 * remaining + 512);
     if (need > chunk_words) need = chunk_words;
     if (need < 512) need = 512;
@@ -690,18 +699,19 @@ static inline size_t pass_need(long long remaining, bool fast) {
 // Top the stream up to what a pass over `remaining` attempts may consume and (fast path) build its slot records,
 // on stream `st`.  Both are state independent, so for the NEXT mixing call this runs on the side stream while the
 // replicas are being propagated.
-static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fast, bool rec2, int K, cudaStream_t st, int *launches) {
-    const size_t need = pass_need(remaining, fast);
+static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fast, int kind, int K, cudaStream_t st, int *launches) {
+    const bool rec2 = kind == REC_SLOT2, anyk = kind == REC_WORD;
+    const size_t need = pass_need(remaining, fast, anyk);
     int rc = stream_reserve(h, S, 2 * need + 1024);   // room for the words generated ahead while the walker runs
     if (rc) return rc;
     rc = stream_fill(h, S, need, launches, st);
     if (rc) return rc;
-    if (fast) {
-        const long long nslots = (long long)(S.avail / 2);
+    if (fast || anyk) {
+        const long long nslots = anyk ? (long long)S.avail : (long long)(S.avail / 2);   // records: per slot, or per word
         if ((size_t)nslots > h->slots_cap) {
             // size for the largest stream the buffer can ever hold (2 * need + 1024 words), so that the slightly different
             // `avail` of every iteration never triggers another cudaFree/cudaMalloc (tens of ms each, device-synchronising)
-            size_t want = (S.cap + 1) / 2;
+            size_t want = anyk ? S.cap : (S.cap + 1) / 2;
             if (want < (size_t)nslots) want = (size_t)nslots;
             RX_CHECK_CUDA(h, cudaDeviceSynchronize());
             cudaFree(h->d_slots);
@@ -715,7 +725,12 @@ static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fas
             RX_CHECK_CUDA(h, cudaMalloc(&h->d_slotlog, want * sizeof(uint32_t)));
             h->slots_cap = want;
         }
-        if (rec2)
+        if (anyk) {
+            static_assert(sizeof(WordRec) == sizeof(SlotRec), "all record formats share the d_slots buffer");
+            int nbits = 0;
+            for (unsigned m = (unsigned)(K - 1); m; m >>= 1) nbits++;
+            k_words_build<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, nslots, K, 0xffffffffu >> (32 - nbits), (WordRec *)h->d_slots);
+        } else if (rec2)
             k_slots_build2<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, nslots, (uint32_t)(K - 1), (SlotRec2 *)h->d_slots);
         else
             k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, nslots, (uint32_t)(K - 1), h->d_slots);
@@ -745,6 +760,8 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         return RX_OK;
     }
     const bool fast = is_pow2(K) && K <= (1 << LOG_STATE_BITS);
+    // any other K up to 4095: the speculative walker over word positions (rx_walk_any.cuh); RX_WALK_SERIAL=1: the plain loop
+    const bool anyk = !fast && K >= 3 && K <= ANY_MAX_K && !getenv("RX_WALK_SERIAL");
     int logK = 0;
     while ((1 << logK) < K) logK++;
     const size_t smem_small = (size_t)K * sizeof(int);
@@ -759,6 +776,9 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     // filter mode: 16-byte SlotRec2 records, k_mix_walk2 for the bulk of a pass and k_mix_walk_pow2<U_FILTER24, true> for its tail
     const bool rec2 = (umode == U_FILTER24);
     const bool walk2 = rec2 && !getenv("RX_WALK_V1");
+    const int kind = anyk ? REC_WORD : (!fast ? REC_NONE : (rec2 ? REC_SLOT2 : REC_SLOT));
+    const size_t smem_any_f64 = smem_base + (size_t)K * K * sizeof(double);
+    const bool any_smem = anyk && smem_any_f64 <= 200 * 1024;
     const size_t smem_w2 = (size_t)W2_RING * 16 + (size_t)K * 8 + (size_t)3 * K * K;
     size_t smem = !fast ? smem_small : (umode == U_F64_SMEM ? smem_f64 : (umode == U_FILTER24 ? smem_f24 : smem_base));
     // The walker is one latency-bound CTA: claim (almost) a whole SM's shared memory so that no other CTA -- in particular
@@ -771,6 +791,10 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     }
     if (!fast) {
         if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (anyk) {
+            RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_any<U_F64_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_any<U_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        }
     } else {
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_F64_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_FILTER24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -795,9 +819,9 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     const uint64_t consumed0 = S.consumed;
     const size_t chunk_words = (size_t)1 << 26;
     while (remaining > 0) {
-        const size_t need = pass_need(remaining, fast);
+        const size_t need = pass_need(remaining, fast, anyk);
         int rc;
-        if (h->prepared && h->prepared_rec2 == rec2 && S.avail >= need && h->slots_for_avail == S.avail) {
+        if (h->prepared && h->prepared_kind == kind && S.avail >= need && h->slots_for_avail == S.avail) {
             // produced on the side stream while the replicas were propagating
             RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_prepared, 0));
             float ms = 0;
@@ -807,7 +831,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             h->mix_stats[5] += (long long)(rx_wall_us() - tw0);
         } else {
             if (h->prepared) RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream_rng));
-            rc = prepare_pass(h, S, remaining, fast, rec2, K, h->stream, launches);
+            rc = prepare_pass(h, S, remaining, fast, kind, K, h->stream, launches);
             if (rc) return rc;
         }
         h->prepared = false;
@@ -872,6 +896,18 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             }
             tr.mark("adopt-ahead + count");
         } else {
+            if (anyk) {
+                // bulk of the pass: speculative walker over word positions (claims the SM like the power-of-two walkers);
+                // what it leaves -- the last words of the pass -- is finished by the plain loop below
+                RX_CHECK_CUDA(h, cudaEventRecord(h->ev_walk[0], h->stream));
+                if (any_smem)
+                    k_mix_walk_any<U_F64_SMEM><<<1, 64, 226 * 1024, h->stream>>>((const WordRec *)h->d_slots, S.d_words, (unsigned)S.avail, h->d_u, K, h->d_perm, h->d_log, h->d_ctl);
+                else
+                    k_mix_walk_any<U_GLOBAL><<<1, 64, 226 * 1024, h->stream>>>((const WordRec *)h->d_slots, S.d_words, (unsigned)S.avail, h->d_u, K, h->d_perm, h->d_log, h->d_ctl);
+                RX_CHECK_CUDA(h, cudaGetLastError());
+                RX_CHECK_CUDA(h, cudaEventRecord(h->ev_walk[1], h->stream));
+                *launches += 1;
+            }
             k_mix_walk_serial<<<1, 32, smem, h->stream>>>(S.d_words, (long long)S.avail, h->d_u, K, M, h->d_perm, h->d_nacc,
                                                         h->d_nprop, h->d_ctl);
             RX_CHECK_CUDA(h, cudaGetLastError());
@@ -879,6 +915,17 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             RX_CHECK_CUDA(h, cudaMemcpyAsync(&ctl, h->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
             RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
             consumed_words = (size_t)ctl.head;
+            if (anyk) {
+                float wms = 0;
+                if (cudaEventElapsedTime(&wms, h->ev_walk[0], h->ev_walk[1]) == cudaSuccess) h->mix_stats[4] += (long long)(wms * 1e3f);
+                if (ctl.log_count > 0) {
+                    long long nb = (ctl.log_count + 255) / 256;
+                    if (nb > 148 * 16) nb = 148 * 16;
+                    k_mix_count<<<(unsigned)nb, 256, 0, h->stream>>>(h->d_log, ctl.log_count, M, h->d_nacc, h->d_nprop);
+                    RX_CHECK_CUDA(h, cudaGetLastError());
+                    *launches += 1;
+                }
+            }
         }
         if (ctl.remaining == remaining && consumed_words == 0 && need >= chunk_words)
             RX_FAIL(h, RX_ERR_INVALID, "internal: mixing made no progress");
@@ -899,8 +946,8 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         RX_CHECK_CUDA(h, cudaStreamWaitEvent(h->stream_rng, h->ev_consumed, 0));
         RX_CHECK_CUDA(h, cudaEventRecord(h->ev[6], h->stream_rng));
         int l2 = 0;
-        int rc2 = prepare_pass(h, S, nswap, fast, rec2, K, h->stream_rng, &l2);
-        h->prepared_rec2 = rec2;
+        int rc2 = prepare_pass(h, S, nswap, fast, kind, K, h->stream_rng, &l2);
+        h->prepared_kind = kind;
         if (rc2) return rc2;
         RX_CHECK_CUDA(h, cudaEventRecord(h->ev[7], h->stream_rng));
         RX_CHECK_CUDA(h, cudaEventRecord(h->ev_prepared, h->stream_rng));

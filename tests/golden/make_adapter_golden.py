@@ -11,6 +11,9 @@ from openmmtools_b200 import unit as u
 from helpers import lj_setup
 
 
+GPU_RC, GPU_RS = 0.75, 0.68   # nm; L = 1.578 nm for 40 particles at reduced density 0.4
+
+
 def dump(f):
     d = {'type': type(f).__name__, 'globals': dict(f.globals)}
     if isinstance(f, g.NonbondedForce):
@@ -36,6 +39,22 @@ if __name__ == '__main__':
                         softcore_a=a, softcore_b=b, softcore_c=cc)
         forces = factory._alchemically_modify_NonbondedForce(g.reference_force(s), [region], frozenset())
         out['config%d' % c] = [dump(f) for v in forces.values() for f in v]
+        # The same forces with a cutoff the engine (like OpenMM) accepts in this small box (r_c <= L/2): the energies the
+        # GPU test compares with, again evaluated from the reference-emitted expressions inside the cutoff.
+        U = []
+        for lam in g.LAMBDAS:
+            e = 0.0
+            for v in forces.values():
+                for f in v:
+                    f.cutoff = GPU_RC * u.nanometer
+                    if isinstance(f, g.NonbondedForce):
+                        e += g.nonbonded_energy(f, s['x'], s['L'])
+                    elif isinstance(f, g.CustomNonbondedForce):
+                        e += g.custom_nonbonded_energy(f, s['x'], s['L'], {'lambda_sterics': lam, 'lambda_electrostatics': lam})
+            U.append(e)
+        out['config%d_U_gpu' % c] = U
+    out['gpu_rc'] = GPU_RC
+    out['gpu_rs'] = GPU_RS
     dst = os.path.join(HERE, 'adapter_forces.json')
     json.dump(out, open(dst, 'w'))
     print('wrote', dst, os.path.getsize(dst))

@@ -85,6 +85,47 @@ def test_swap_all_full_size_vs_oracle(K, model, seed):
     e.close()
 
 
+@pytest.mark.parametrize('K,model,nswap,seed', [(3, 'flat', 200_000, 31), (5, 'normal', 200_000, 32), (12, 'flat', 300_000, 33),
+                                                (65, 'flat', 65 ** 3, 34), (100, 'normal', 100 ** 3, 35),
+                                                (127, 'ladder', 500_000, 36), (129, 'normal', 500_000, 37),
+                                                (200, 'normal', 2_000_000, 38), (1000, 'flat', 1_000_000, 39)])
+@pytest.mark.parametrize('serial', [False, True])
+def test_swap_all_any_k_vs_oracle(monkeypatch, K, model, nswap, seed, serial):
+    """K that is not a power of two: the speculative walker over word positions (k_mix_walk_any, the f64 matrix in shared
+    memory up to K ~ 150, from L2 above) and, with RX_WALK_SERIAL=1, the plain loop; three iterations each."""
+    from oracle import oracle
+    if serial:
+        if nswap > 300_000: pytest.skip('the plain loop takes 0.6 us per attempt')
+        monkeypatch.setenv('RX_WALK_SERIAL', '1')
+    u = energies(model, K, 777 + K)
+    e = gpu_engine(0, K, K)
+    e.set_energies(u)
+    e.set_replica_states(np.arange(K))
+    e.mix_seed(seed, 0)
+    mt = oracle.MT(seed)
+    st_o = np.arange(K, dtype=np.int64)
+    for it in range(3):
+        st, nacc, nprop = e.mix_swap_all(nswap)
+        na = np.zeros((K, K), np.int64); npr = np.zeros((K, K), np.int64)
+        oracle.mix_swap_all(mt, nswap, st_o, u, na, npr)
+        assert np.array_equal(st, st_o), it
+        assert np.array_equal(nacc, na) and np.array_equal(nprop, npr), it
+    stats = e.mix_stats()
+    if serial:
+        assert stats['rounds'] == 0
+    else:
+        assert 0 < stats['rounds'] < nswap   # the walker ran and committed several attempts per round
+    # the stream position: the next word both generators produce is the same one
+    e2 = gpu_engine(0, K, K); e2.mix_seed(seed, 0); e2.mix_skip(e.mix_stream_position(0), 0)
+    e2.set_energies(u); e2.set_replica_states(np.arange(K))
+    st2, _, _ = e2.mix_swap_all(1000)
+    st_o2 = np.arange(K, dtype=np.int64)
+    oracle.mix_swap_all(mt, 1000, st_o2, u, np.zeros((K, K), np.int64), np.zeros((K, K), np.int64))
+    assert np.array_equal(st2, st_o2)
+    e2.close()
+    e.close()
+
+
 def test_unseeded_stream_is_an_error():
     from openmmtools_b200._engine import EngineError
     e = gpu_engine(0, 4, 4)

@@ -60,9 +60,11 @@ class _Stub:
     def getUseDispersionCorrection(self): return self.d['dispersion']
 
 
-def fixture_forces(c):
+def fixture_forces(c, cutoff=None, switch=None):
     out = []
     for d in json.loads(json.dumps(FIXTURE['config%d' % c])):   # a private copy: a test may edit it
+        if cutoff is not None and 'cutoff' in d:
+            d['cutoff'], d['switch_distance'] = cutoff, switch
         f = type(d['type'], (_Stub,), {})(d)     # the adapter dispatches on the class NAME
         out.append(f)
     return lj_setup(N=N, n_alch=N_ALCH, reduced_density=0.4, seed=77), out
@@ -114,8 +116,10 @@ def test_plain_lj_force_and_refusals():
 @pytest.mark.gpu
 @pytest.mark.parametrize('c', [0, 1, 2])
 def test_engine_from_adapter_reproduces_reference_energies(c):
-    s, forces = fixture_forces(c)
+    # (the factory's forces with a cutoff the engine -- like OpenMM -- accepts in this small box: r_c <= L/2)
+    s, forces = fixture_forces(c, FIXTURE['gpu_rc'], FIXTURE['gpu_rs'])
     rec = adapter.system_from_openmm(StandInSystem(s), forces)
+    assert rec.cutoff == FIXTURE["gpu_rc"]
     # the golden numbers are the reference-emitted expressions inside the cutoff: no long-range corrections
     rec.use_dispersion_correction = False
     rec.alchemical_dispersion_correction = False
@@ -125,5 +129,5 @@ def test_engine_from_adapter_reproduces_reference_energies(c):
     eng.set_positions(G['x'][None])
     u_row = eng.compute_energies()[0] * (KB * 300.0)
     eng.close()
-    ref = G['config%d_U' % c]
+    ref = np.array(FIXTURE['config%d_U_gpu' % c])
     assert np.abs(u_row - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (u_row, ref)
