@@ -705,14 +705,16 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     fill_dyn(h, p);
     const int N = h->cfg.n_atoms;
     if (N > 1024) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: more than 1024 atoms per replica is not supported yet");
-    // Blocks per replica (a thread-block cluster): with fewer replicas than SMs a replica is split over 2 or 4 blocks, so that
-    // the launch still fills the GPU and a step is shorter (RX_CLUSTER = 1 | 2 | 4 overrides).
+    // Blocks per replica (a thread-block cluster; RX_CLUSTER = 1 | 2 | 4 overrides).  Measured on the 512-atom fluid (500
+    // steps, in the iteration loop): 32 replicas 2.27-2.36 ms in one block, 2.30-2.59 in two, 2.20-2.29 in four; 64 replicas
+    // 2.28-2.37 / 2.31-2.41 / 2.31-2.39.  A block of 128 threads leaves ONE warp per scheduler, which runs the step's
+    // ~1100 dependent instructions no faster than four warps sharing a scheduler do: the split only pays for the few
+    // replicas that would otherwise leave three quarters of the GPU idle, so that is the only case it is chosen for.
     int cl = 1;
     if (h->cfg.system_kind == RX_SYSTEM_LJ_ALCH && N >= 256) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-        if (h->kloc * 2 <= sms) cl = 4;
-        else if (h->kloc <= sms) cl = 2;
+        if (h->kloc * 4 <= sms) cl = 4;
         if (const char *e = getenv("RX_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cl = v; }
     }
     const int n_per = (N + cl - 1) / cl;

@@ -157,6 +157,24 @@ __device__ __forceinline__ void w2_cp_async_commit() { asm volatile("cp.async.co
 template <int N>
 __device__ __forceinline__ void w2_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// The exact decision for the attempt of slot s under the states (si, sj): bit 0 = log_p >= 0, bit 1 = accepted.  f64
+// energies from L2, the reference's own arithmetic; the uniform is compared in the log domain outside a 1e-9 band and as
+// U < exp(log_p) inside it.
+__device__ __noinline__ unsigned w2_exact_decision(const SlotRec2 *__restrict__ rec, const uint32_t *__restrict__ words,
+                                                   const double *__restrict__ u, unsigned s, unsigned si, unsigned sj, int logK) {
+    const unsigned ij = rec[s].ij;
+    const unsigned rowi = (ij & 0xffffu) << logK, rowj = (ij >> 16) << logK;
+    const double logp = swap_logp(u[rowi | sj], u[rowj | si], u[rowi | si], u[rowj | sj]);
+    if (logp >= 0.0) return 3u;
+    const unsigned s1 = s + 1;
+    const double dd = logp - slot_logU(words, s1);
+    bool acc;
+    if (dd > 1e-9) acc = true;
+    else if (dd < -1e-9) acc = false;
+    else acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp);
+    return acc ? 2u : 0u;
+}
+
 // The image is re-laid out row by row in shared memory -- u16 plane of the row (2K bytes), then its u8 plane (K bytes) --
 // so that one address per row serves both planes.
 #define W2_THREADS 128   // warps 1.. only help with the prologue
@@ -295,11 +313,15 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
             w = (w - p_advance) & 31u;
         };
         unsigned Cw = 0;
+        // Exact decisions injected into ONE fast round (see the rare path below): `bias` joins the lane's log_p, `luA` is
+        // replaced, so that the filter reproduces the exact answer; both are restored when that round has been resolved.
+        float bias = 0.f, lu_saved = 0.f;
+        bool injected = false;
         for (;;) {
             // ---------------- the budget and the end of the pass, every 64 rounds at most: a round commits at most 32
             // attempts and advances at most 32 slots (the round resolved last stays pending across this step)
             if (rem < 130u || h + 99u > h_end) break;
-            unsigned quota = min(min((rem - 97u) >> 5, (h_end - h - 66u) >> 5), 64u);
+            unsigned quota = min(min((rem - 97u) >> 5, (h_end - h - 66u) >> 5), injected ? 1u : 64u);
             // ---------------- fast rounds.  The loop is rotated: an iteration COMMITS the round resolved by the previous
             // one and then evaluates and resolves the next, so that the block begins with the dependent chain (stores ->
             // state loads -> image loads -> filter -> ballots); no data-dependent branch besides the loop's.
@@ -313,7 +335,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
                 w2_cp_async_wait<8>();   // a copy is used 15 of the lane's promotions (at least 15 rounds) after it was issued
                 derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
                 bool ge0, acc, undecided;
-                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y), f_ji, e0, luA, ge0, acc, undecided);
+                w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y) + bias, f_ji, e0, luA, ge0, acc, undecided);
                 const unsigned und = undecided ? 1u : 0u;
                 const bool changes = acc && neqA != 0u;
                 const unsigned G = __ballot_sync(0xffffffffu, ge0);
@@ -341,13 +363,42 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
                 p_entry = (sj * (1u << LOG_STATE_BITS) + si) | (acc ? (1u << 31) | (1u << LOG_ACC_BIT) : (1u << 31));
                 // (position 0 is always visited: nothing commits iff it is itself the lane that ends the round)
             } while (--quota != 0u && (Cw & 1u) == 0u);
+            // (a no-op unless the round just resolved ran alone, with injected decisions: see below)
+            const bool was_injected = injected;
+            luA = was_injected ? lu_saved : luA;
+            bias = 0.f;
+            injected = false;
             if ((Cw & 1u) == 0u) continue;
             commit();   // (nothing to commit: positions the lanes on the round that could not start)
             w2_cp_async_wait<8>();
             derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
-            // ---------------- rare: the first lane of the window is undecided: one exact attempt, exactly what the reference
-            // does (window position 0 commits; positions 0 .. advance-1 leave the window; log_p < 0: the next slot is this
-            // attempt's uniform)
+            // ---------------- rare: the filter could not decide the window's first lane (nothing was committed: the states
+            // are those the round was evaluated with).  Every undecided lane takes the exact decision for its slot and
+            // injects it into the next fast round -- a bias of +-1e20..1e30 on its log_p and a matching log-uniform make
+            // the filter reproduce it -- which is run alone (quota 1) and then resolves and commits like any other round.
+            // (One exact attempt per rare event would cost 0.4 us per attempt on a degenerate matrix: at iteration 0 all
+            // replicas are in the same configuration and every log_p is a rounding error around 0.)
+            if (!was_injected) {
+                const unsigned si = ei.x, sj = ej.x;
+                const float f1 = w2_image_at(rowiA + 2u * sj, rowiA + lo_off + sj);
+                const float f2 = w2_image_at(rowjA + 2u * si, rowjA + lo_off + si);
+                const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, epsA);
+                bool ge0, acc, undecided;
+                w2_filter(__uint_as_float(ei.y), f1, __uint_as_float(ej.y), f2, e0, luA, ge0, acc, undecided);
+                lu_saved = luA;
+                if (undecided) {
+                    const unsigned d = w2_exact_decision(rec, words, u, (unsigned)(log_ptr - slot_log), si, sj, logK);
+                    bias = (d & 1u) ? 1e30f : -1e20f;
+                    if (!(d & 1u)) luA = (d & 2u) ? -1e30f : 0.f;
+                    slow++;
+                }
+                __syncwarp();
+                injected = true;
+                continue;
+            }
+            // ---------------- rarer still: undecided WITH the exact decision injected (non-finite energies make log_p a NaN
+            // whatever the bias): one exact attempt, exactly what the reference does (window position 0 commits; positions
+            // 0 .. advance-1 leave the window; log_p < 0: the next slot is this attempt's uniform)
             {
                 rounds++;
                 bool ge0 = false, acc = false;

@@ -78,6 +78,7 @@ class MultiStateSampler:
         self._engine = None
         self._states_stale = False     # host copies of sampler states are behind the device
         self._host_x = self._host_v = None   # page-locked backing store of the owned sampler states
+        self._host_store = None
         self._seed = seed
         self._communicator = communicator
         self._rank = int(os.environ.get('RANK', '0')) if communicator is None else communicator.rank
@@ -352,10 +353,21 @@ class MultiStateSampler:
             comm = self._communicator = default_communicator()
         return int.from_bytes(comm.bcast_bytes(int(v).to_bytes(8, 'little') if self._rank == 0 else None, 8), 'little')
 
+    class _HostStore:
+        """Page-locked backing store of the owned SamplerStates: positions, velocities (K_loc, N, 3) and the energies the
+        engine reported last; `dirty` is set by a SamplerState whose arrays were replaced (states.py)."""
+
+        def __init__(self, x, v):
+            self.x, self.v = x, v
+            self.pot = np.zeros(len(x))
+            self.kin = np.zeros(len(x))
+            self.dirty = True   # states not attached yet
+
     def _attach_host_store(self):
         """One page-locked (K_loc, N, 3) pair is the backing store of the owned SamplerStates: their position / velocity
-        arrays are views into it, so that the per-iteration exchange with the device is one copy each way and no
-        per-replica work on the host."""
+        arrays are views into it and their energies are read from it, so that the per-iteration exchange with the device
+        is one copy each way and NO per-replica work on the host (the loops below only run when a caller assigned new
+        arrays to a state)."""
         e = self._engine
         n = e.k1 - e.k0
         if n == 0 or self._host_x is not None:
@@ -364,6 +376,7 @@ class MultiStateSampler:
         self._host_x = e.pinned_array((n, N, 3))
         self._host_v = e.pinned_array((n, N, 3))
         self._host_v[:] = 0.0
+        self._host_store = self._HostStore(self._host_x, self._host_v)
         for r, k in enumerate(range(e.k0, e.k1)):
             s = self._sampler_states[k]
             self._host_x[r] = s._positions
@@ -371,12 +384,18 @@ class MultiStateSampler:
             if s._velocities is not None:
                 self._host_v[r] = s._velocities
                 s._velocities = self._host_v[r]
+            s._store, s._store_index = self._host_store, r
 
     def _collect_host_store(self):
         """Positions / velocities a caller replaced on a SamplerState go back into the backing store."""
         e = self._engine
+        st = self._host_store
+        if st is None or not st.dirty:
+            return
         for r, k in enumerate(range(e.k0, e.k1)):
             s = self._sampler_states[k]
+            if s._store is not st:
+                s._store, s._store_index = st, r
             if s._positions.base is not self._host_x.base:
                 self._host_x[r] = s._positions
                 s._positions = self._host_x[r]
@@ -385,6 +404,7 @@ class MultiStateSampler:
             if s._velocities.base is not self._host_v.base:
                 self._host_v[r] = s._velocities
                 s._velocities = self._host_v[r]
+        # (the dirty flag is cleared by _sync_sampler_states, which also re-attaches the energies)
 
     def _upload_sampler_states(self):
         e = self._engine
@@ -417,16 +437,23 @@ class MultiStateSampler:
             e.get_positions(out=self._host_x)
             e.get_velocities(out=self._host_v)
         pot, kin = e.get_replica_energies()
-        pot, kin = pot.tolist(), kin.tolist()
-        hx, hv = self._host_x, self._host_v
-        for r, k in enumerate(range(e.k0, e.k1)):
-            s = self._sampler_states[k]
-            if s._positions.base is not hx.base:
-                s._positions = hx[r]
-            if s._velocities is None or s._velocities.base is not hv.base:
-                s._velocities = hv[r]
-            s._potential_energy = pot[k]
-            s._kinetic_energy = kin[k]
+        st = self._host_store
+        if st is not None:
+            st.pot[:] = pot[e.k0:e.k1]
+            st.kin[:] = kin[e.k0:e.k1]
+        if st is not None and st.dirty:
+            from ..states import _FROM_STORE
+            hx, hv = self._host_x, self._host_v
+            for r, k in enumerate(range(e.k0, e.k1)):
+                s = self._sampler_states[k]
+                s._store, s._store_index = st, r
+                if s._positions.base is not hx.base:
+                    s._positions = hx[r]
+                if s._velocities is None or s._velocities.base is not hv.base:
+                    s._velocities = hv[r]
+                s._potential_energy = _FROM_STORE
+                s._kinetic_energy = _FROM_STORE
+            st.dirty = False
         self._states_stale = False
 
     # ------------------------------------------------------------------ run (multistatesampler.py:724-804)
@@ -635,13 +662,14 @@ class MultiStateSampler:
         if comm is None:
             from .._dist import default_communicator
             comm = self._communicator = default_communicator()
-        shard = [(k, s._positions, s._velocities, s._potential_energy, s._kinetic_energy)
+        shard = [(k, s._positions, s._velocities) + s._energies_md()
                  for k, s in zip(range(e.k0, e.k1), self._sampler_states[e.k0:e.k1])]
         gathered = comm.gather_object(shard)
         if self._rank == 0:
             for part in gathered:
                 for k, x, v, pe, ke in part:
-                    self._sampler_states[k]._update(x, v, pe, ke)
+                    if not (e.k0 <= k < e.k1):   # (this rank's own states are already current)
+                        self._sampler_states[k]._update(x, v, pe, ke)
 
     # ------------------------------------------------------------------ online analysis (multistatesampler.py:1625-1695)
     @staticmethod

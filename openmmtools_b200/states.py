@@ -209,10 +209,25 @@ class ThermodynamicState:
 
 
 # ------------------------------------------------------------------------------------------------------
+class _FromStore:
+    """Marker: the energy of an attached SamplerState is read from its sampler's host store (multistatesampler.py)."""
+
+    def __repr__(self):
+        return '<energy in the host store>'
+
+
+_FROM_STORE = _FromStore()
+
+
 class SamplerState:
     """Positions, velocities and box vectors of one replica (states.py:1933-2520)."""
 
     def __init__(self, positions, velocities=None, box_vectors=None):
+        # a sampler with host-resident states keeps the arrays of all its replicas in one page-locked store and attaches
+        # the states to it (positions/velocities are views, energies are read through `_store`); assigning new arrays
+        # marks the store dirty so that the sampler picks them up
+        self._store = None
+        self._store_index = -1
         self._positions = None
         self._velocities = None
         self._box_vectors = None
@@ -247,6 +262,8 @@ class SamplerState:
         if self._positions is not None and a.shape != self._positions.shape:
             raise SamplerStateError(SamplerStateError.INCONSISTENT_POSITIONS)
         self._positions = a
+        if self._store is not None:
+            self._store.dirty = True
         # new positions invalidate the cached potential energy (states.py:2386-2390)
         self._potential_energy = None
         self._collective_variables = None
@@ -264,6 +281,8 @@ class SamplerState:
             if a.shape != self._positions.shape:
                 raise SamplerStateError(SamplerStateError.INCONSISTENT_VELOCITIES)
             self._velocities = a
+        if self._store is not None:
+            self._store.dirty = True
         self._kinetic_energy = None
 
     @property
@@ -279,9 +298,12 @@ class SamplerState:
 
     @property
     def potential_energy(self):
-        if self._potential_energy is None:
+        pe = self._potential_energy
+        if pe is _FROM_STORE:
+            pe = float(self._store.pot[self._store_index])
+        if pe is None:
             return None
-        return self._potential_energy * unit.kilojoule_per_mole
+        return pe * unit.kilojoule_per_mole
 
     @potential_energy.setter
     def potential_energy(self, value):
@@ -291,9 +313,12 @@ class SamplerState:
 
     @property
     def kinetic_energy(self):
-        if self._kinetic_energy is None:
+        ke = self._kinetic_energy
+        if ke is _FROM_STORE:
+            ke = float(self._store.kin[self._store_index])
+        if ke is None:
             return None
-        return self._kinetic_energy * unit.kilojoule_per_mole
+        return ke * unit.kilojoule_per_mole
 
     @kinetic_energy.setter
     def kinetic_energy(self, value):
@@ -351,6 +376,8 @@ class SamplerState:
         ss._box_vectors = copy.deepcopy(self._box_vectors)
         ss._potential_energy = None
         ss._kinetic_energy = None
+        ss._store = None
+        ss._store_index = -1
         return ss
 
     def __getstate__(self, ignore_velocities=False):
@@ -361,6 +388,8 @@ class SamplerState:
                     collective_variables=self.collective_variables)
 
     def __setstate__(self, serialization, ignore_velocities=False):
+        self._store = getattr(self, '_store', None)
+        self._store_index = getattr(self, '_store_index', -1)
         self._positions = None
         self._velocities = getattr(self, '_velocities', None)
         self._unitless_positions_cache = None
@@ -379,7 +408,14 @@ class SamplerState:
         return copy.deepcopy(self)
 
     # -- engine-side update (what update_from_context does in the reference, states.py:2215-2255)
+    def _energies_md(self):
+        """(potential, kinetic) as plain floats in kJ/mol, or None."""
+        pe, ke = self.potential_energy, self.kinetic_energy
+        return (None if pe is None else float(unit.to_md(pe)), None if ke is None else float(unit.to_md(ke)))
+
     def _update(self, positions, velocities, potential, kinetic):
+        if self._store is not None:
+            self._store.dirty = True
         self._positions = np.array(positions, dtype=np.float64)
         self._velocities = None if velocities is None else np.array(velocities, dtype=np.float64)
         self._potential_energy = None if potential is None else float(potential)

@@ -1,7 +1,8 @@
 """Lane-level CPU model of k_mix_walk2's control logic (openmmtools_b200/csrc/rx_walk2.cuh): fixed lane <-> slot mapping,
 window rotated over the lanes, visited-chain bit arithmetic, conflict ballot with undecided lanes folded in, deferred
-(rotated) commit with promotion of the lanes that left the window, the 33-slot advance and the exact single-attempt
-round.  The model must reproduce the sequential reference loop (replicaexchange.py:321-349) attempt by attempt; the
+(rotated) commit with promotion of the lanes that left the window, no 33-slot advance, and the exact re-evaluation of a
+round whose first lane the filter could not decide (on the device the undecided lanes take the exact decision and inject it
+into the next fast round, run alone: the same decisions, resolved by the same arithmetic).  The model must reproduce the sequential reference loop (replicaexchange.py:321-349) attempt by attempt; the
 filter's 'undecided' answers are injected at random (a decision is then arbitrary, as on the device)."""
 import sys, math, random, os
 import numpy as np
@@ -68,6 +69,28 @@ def run(K, nswap, model, seed, p_und=0.0):
             st[l] = (perm[A[l][0]], perm[A[l][1]])
             w[l] = (w[l] - P['adv']) & 31
             B[l] = rec(sA[l] + 32)
+    def resolve(ge, ac, und):
+        G = sum(1 << l for l in lanes if ge[l]); Am = sum(1 << l for l in lanes if ac[l] and A[l][0] != A[l][1])
+        Gw, Aw = rotr(G, r), rotr(Am, r)
+        X = ~Gw & M32; starts = X & ~(X << 1) & M32; SE = starts & 0x55555555; SO = starts & 0xAAAAAAAA
+        sumE = (X + SE); sumO = (X + SO); carryO = sumO > M32; sumE &= M32; sumO &= M32
+        skip = (((sumE ^ X) & ~SE) & 0xAAAAAAAA) | (((sumO ^ X) & ~SO) & 0x55555555)
+        V = ~skip & M32; VA = V & Aw
+        Cb = 0
+        for l in lanes:
+            sh = 32 - w[l]; earlier = (VA << sh) & M32 if sh < 32 else 0
+            if ((earlier & A[l][2]) | und[l]) != 0: Cb |= 1 << l
+        # (the last window position does not commit an attempt whose uniform lies beyond the window)
+        Cw = (rotr(Cb, r) | (X & 0x80000000)) & V; low = Cw & (-Cw & M32); below = (low - 1) & M32; cm = V & below
+        adv = popc(below)
+        assert not (Cw == 0 and carryO)
+        for l in lanes:
+            P['mine'][l] = bool((cm >> w[l]) & 1)
+            P['swaps'][l] = P['mine'][l] and ac[l] and A[l][0] != A[l][1]
+            P['prom'][l] = bool((below >> w[l]) & 1)
+            P['entry'][l] = (sA[l], st[l][0], st[l][1], ac[l])
+        P['adv'] = adv; P['n'] = popc(cm)
+        return cm
     rounds = 0
     while True:
         P.update(mine=[False]*32, swaps=[False]*32, prom=[False]*32, adv=0, n=0)
@@ -82,27 +105,8 @@ def run(K, nswap, model, seed, p_und=0.0):
                 assert (i, j) == ij[sA[l]]
                 ge[l], ac[l] = evaluate(sA[l], i, j, si, sj)
                 if rng.random() < p_und: und[l] = 1; ge[l] = rng.random() < .5; ac[l] = rng.random() < .5
-            G = sum(1 << l for l in lanes if ge[l]); Am = sum(1 << l for l in lanes if ac[l] and A[l][0] != A[l][1])
-            Gw, Aw = rotr(G, r), rotr(Am, r)
-            X = ~Gw & M32; starts = X & ~(X << 1) & M32; SE = starts & 0x55555555; SO = starts & 0xAAAAAAAA
-            sumE = (X + SE); sumO = (X + SO); carryO = sumO > M32; sumE &= M32; sumO &= M32
-            skip = (((sumE ^ X) & ~SE) & 0xAAAAAAAA) | (((sumO ^ X) & ~SO) & 0x55555555)
-            V = ~skip & M32; VA = V & Aw
-            Cb = 0
-            for l in lanes:
-                sh = 32 - w[l]; earlier = (VA << sh) & M32 if sh < 32 else 0
-                if ((earlier & A[l][2]) | und[l]) != 0: Cb |= 1 << l
-            # (the last window position does not commit an attempt whose uniform lies beyond the window)
-            Cw = (rotr(Cb, r) | (X & 0x80000000)) & V; low = Cw & (-Cw & M32); below = (low - 1) & M32; cm = V & below
+            cm = resolve(ge, ac, und)
             adv33 = 0
-            adv = popc(below)
-            assert not (Cw == 0 and carryO)
-            for l in lanes:
-                P['mine'][l] = bool((cm >> w[l]) & 1)
-                P['swaps'][l] = P['mine'][l] and ac[l] and A[l][0] != A[l][1]
-                P['prom'][l] = bool((below >> w[l]) & 1)
-                P['entry'][l] = (sA[l], st[l][0], st[l][1], ac[l])
-            P['adv'] = adv; P['n'] = popc(cm)
             if not (go and cm != 0 and adv33 == 0): break
         commit()
         if adv33:
@@ -111,15 +115,15 @@ def run(K, nswap, model, seed, p_und=0.0):
                     sA[l] += 32; A[l] = rec(sA[l]); B[l] = rec(sA[l] + 32); st[l] = (perm[A[l][0]], perm[A[l][1]])
         if rem < 130 or h + 99 > h_end: break
         if cm == 0:
+            # the window's first lane is undecided: every lane is evaluated exactly (under the same states) and the round is
+            # resolved again -- now it commits at least the first attempt
             rounds += 1
-            l0 = [l for l in lanes if w[l] == 0][0]
-            i, j, _ = A[l0]; si, sj = st[l0]
-            g, a = evaluate(sA[l0], i, j, si, sj)
-            adv = 1 if g else 2
+            ge = [False]*32; ac = [False]*32
             for l in lanes:
-                P['mine'][l] = (l == l0); P['swaps'][l] = (l == l0) and a and i != j; P['prom'][l] = w[l] < adv
-                P['entry'][l] = (sA[l], st[l][0], st[l][1], a)
-            P['adv'] = adv; P['n'] = 1
+                i, j, bm = A[l]; si, sj = st[l]
+                ge[l], ac[l] = evaluate(sA[l], i, j, si, sj)
+            cm = resolve(ge, ac, [0]*32)
+            assert cm & 1
             commit()
             P.update(mine=[False]*32, swaps=[False]*32, prom=[False]*32, adv=0, n=0)
             if rem < 130 or h + 99 > h_end: break
