@@ -135,12 +135,12 @@ class Engine:
         self._check(self._lib.rx_get_velocities(self._h, first, count, _ptr(out)))
         return out
 
-    def pinned_array(self, shape):
-        """A page-aligned float64 array registered with the engine (rx_pin_host_memory): set_*/get_* on it copy directly."""
-        n = int(np.prod(shape)) * 8
-        raw = np.empty(n + 4096, np.uint8)
+    def pinned_array(self, shape, dtype=np.float64):
+        """A page-aligned array registered with the engine (rx_pin_host_memory): copies to and from it are direct DMA."""
+        n = max(int(np.prod(shape)) * np.dtype(dtype).itemsize, 8)
+        raw = np.zeros(n + 4096, np.uint8)
         off = (-raw.ctypes.data) % 4096
-        a = raw[off:off + n].view(np.float64).reshape(shape)
+        a = raw[off:off + int(np.prod(shape)) * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
         self._check(self._lib.rx_pin_host_memory(self._h, _ptr(a), n))
         self._pinned = getattr(self, '_pinned', []) + [raw]     # keeps the allocation alive as long as the engine
         return a
@@ -193,10 +193,24 @@ class Engine:
         self._check(rc)
         return flags
 
-    def compute_energies(self, fetch=True):
-        u = np.zeros((self.K, self.M)) if fetch else None
+    def compute_energies(self, fetch=True, out=None):
+        """`out`: a C-contiguous float64 (K, M) array to receive the matrix (page-locked: a direct DMA copy)."""
+        u = (self._result(out, (self.K, self.M), np.float64) if out is not None else np.zeros((self.K, self.M))) if fetch else None
         self._check(self._lib.rx_compute_energies(self._h, _ptr(u)))
         return u
+
+    @staticmethod
+    def _result(a, shape, dtype):
+        if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.shape == tuple(shape) and a.flags.c_contiguous):
+            raise ValueError('out must be a C-contiguous %s array of shape %s' % (np.dtype(dtype).name, tuple(shape)))
+        return a
+
+    def _mix_out(self, out):
+        if out is None:
+            return (np.zeros(self.K, np.int64), np.zeros((self.M, self.M), np.int64), np.zeros((self.M, self.M), np.int64))
+        st, nacc, nprop = out
+        return (self._result(st, (self.K,), np.int64), self._result(nacc, (self.M, self.M), np.int64),
+                self._result(nprop, (self.M, self.M), np.int64))
 
     def set_energies(self, u):
         u = _c64(u, (self.K, self.M))
@@ -213,19 +227,18 @@ class Engine:
     def mix_skip(self, n_words, stream=_lib.RX_STREAM_NUMBA):
         self._check(self._lib.rx_mix_skip(self._h, stream, int(n_words)))
 
-    def mix_swap_all(self, nswap_attempts=None, fetch=True):
+    def mix_swap_all(self, nswap_attempts=None, fetch=True, out=None):
+        """`out`: (states int64 (K,), n_accepted int64 (M, M), n_proposed int64 (M, M)) to receive the results."""
         n = self.K ** 3 if nswap_attempts is None else int(nswap_attempts)
         if not fetch:
             self._check(self._lib.rx_mix_swap_all(self._h, n, None, None, None))
             return None
-        st = np.zeros(self.K, np.int64)
-        nacc = np.zeros((self.M, self.M), np.int64); nprop = np.zeros((self.M, self.M), np.int64)
+        st, nacc, nprop = self._mix_out(out)
         self._check(self._lib.rx_mix_swap_all(self._h, n, _ptr(st), _ptr(nacc), _ptr(nprop)))
         return st, nacc, nprop
 
-    def mix_swap_neighbors(self):
-        st = np.zeros(self.K, np.int64)
-        nacc = np.zeros((self.M, self.M), np.int64); nprop = np.zeros((self.M, self.M), np.int64)
+    def mix_swap_neighbors(self, out=None):
+        st, nacc, nprop = self._mix_out(out)
         self._check(self._lib.rx_mix_swap_neighbors(self._h, _ptr(st), _ptr(nacc), _ptr(nprop)))
         return st, nacc, nprop
 

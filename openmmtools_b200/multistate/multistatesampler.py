@@ -330,6 +330,20 @@ class MultiStateSampler:
         self._engine.set_replica_states(self._replica_thermodynamic_states)
         self._seed_mixing_streams()
         self._upload_sampler_states()
+        self._pin_result_arrays()
+
+    def _pin_result_arrays(self):
+        """The matrices the engine writes every iteration (energies, swap statistics, permutation) move into page-locked
+        memory, so that the engine's results land in them by direct DMA (no staging, no intermediate arrays)."""
+        e = self._engine
+        for name in ('_energy_thermodynamic_states', '_n_accepted_matrix', '_n_proposed_matrix'):
+            a = getattr(self, name)
+            b = e.pinned_array(a.shape, a.dtype)
+            b[...] = a
+            setattr(self, name, b)
+        st = np.asarray(self._replica_thermodynamic_states, dtype=np.int64)
+        self._replica_thermodynamic_states = e.pinned_array(st.shape, np.int64)
+        self._replica_thermodynamic_states[...] = st
 
     def _seed_mixing_streams(self):
         # the reference never seeds numba's / numpy's generators (os.urandom); a user seed makes runs reproducible
@@ -579,11 +593,12 @@ class MultiStateSampler:
 
     def _compute_energies(self):
         """u[k, l] for all replicas and states in one launch (+ NCCL all-gather) (multistatesampler.py:1436-1494)."""
-        u = self._engine.compute_energies()
         if self.locality is None:
+            self._engine.compute_energies(out=self._energy_thermodynamic_states)
             self._neighborhoods[:, :] = 1
-            self._energy_thermodynamic_states[:, :] = u
+            u = self._energy_thermodynamic_states
         else:
+            u = self._engine.compute_energies()
             # only the states within `locality` of each replica's current state are (re)written, the rest keeps its old
             # value exactly as in the reference (multistatesampler.py:1263-1281,1441-1456); the device matrix is complete,
             # and swap-neighbors (forced by locality, replicaexchange.py:228-230) only reads entries inside the band
@@ -682,13 +697,14 @@ class MultiStateSampler:
         st = np.asarray(replica_states)
         logZ = -np.asarray(f_k, dtype=np.float64)
         if locality is None:
-            mask = np.ones((K, M), dtype=bool)
+            log_p = -u                      # (every state is in every replica's neighbourhood: no mask to build)
         else:
             l = np.arange(M)[None, :]
             mask = (l >= st[:, None] - locality) & (l <= st[:, None] + locality)
-        log_p = np.where(mask, -u, -np.inf)
+            log_p = np.where(mask, -u, -np.inf)
         top = log_p.max(axis=1, keepdims=True)
-        p = np.exp(log_p - top)
+        p = log_p - top
+        np.exp(p, out=p)
         p /= p.sum(axis=1, keepdims=True)
         logZ = logZ + (gamma0 / float(iteration + 1)) * p.sum(axis=0)
         return -(logZ - logZ[0])

@@ -45,18 +45,16 @@ class ReplicaExchangeSampler(MultiStateSampler):
     def _mix_replicas(self):
         """Attempt to swap replicas according to the scheme; uses the energies of the previous iteration."""
         e = self._engine
+        # the engine writes straight into the sampler's (page-locked) matrices
+        out = (self._replica_thermodynamic_states, self._n_accepted_matrix, self._n_proposed_matrix)
         if self.replica_mixing_scheme == 'swap-neighbors':
-            st, nacc, nprop = e.mix_swap_neighbors()
+            e.mix_swap_neighbors(out=out)
         elif self.replica_mixing_scheme == 'swap-all':
-            st, nacc, nprop = e.mix_swap_all(self.n_replicas ** 3)
+            e.mix_swap_all(self.n_replicas ** 3, out=out)
         else:
             assert self.replica_mixing_scheme is None
             self._n_accepted_matrix[:, :] = 0
             self._n_proposed_matrix[:, :] = 0
-            return self._replica_thermodynamic_states
-        self._n_accepted_matrix[:, :] = nacc
-        self._n_proposed_matrix[:, :] = nprop
-        self._replica_thermodynamic_states[:] = st
         return self._replica_thermodynamic_states
 
     # reference-compatible static kernel entry point (called directly by the reference's tests/test_mixing.py:41-43)
