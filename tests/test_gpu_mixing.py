@@ -126,6 +126,31 @@ def test_swap_all_any_k_vs_oracle(monkeypatch, K, model, nswap, seed, serial):
     e.close()
 
 
+@pytest.mark.parametrize('K,kind', [(100, 'equal_rows'), (100, 'nonfinite'), (37, 'equal_rows')])
+def test_swap_all_any_k_hard_matrices(K, kind):
+    """Identical rows (iteration 0 of a run whose replicas start from one configuration: every log_p is a rounding error
+    around 0) and non-finite entries."""
+    from oracle import oracle
+    rng = np.random.default_rng(5)
+    if kind == 'equal_rows':
+        u = np.tile(rng.normal(0, 30, K)[None, :], (K, 1))
+    else:
+        u = rng.normal(0, 3, (K, K)); u[3, 5] = np.inf; u[7, :] = np.nan; u[11, 2] = -np.inf; u[20, 20] = 1e300
+    u = np.ascontiguousarray(u)
+    nswap = 200_000
+    e = gpu_engine(0, K, K)
+    e.set_energies(u); e.set_replica_states(np.arange(K)); e.mix_seed(77, 0)
+    mt = oracle.MT(77); st_o = np.arange(K, dtype=np.int64)
+    with np.errstate(all='ignore'):
+        for it in range(2):
+            st, nacc, nprop = e.mix_swap_all(nswap)
+            na = np.zeros((K, K), np.int64); npr = np.zeros((K, K), np.int64)
+            oracle.mix_swap_all(mt, nswap, st_o, u, na, npr)
+            assert np.array_equal(st, st_o), (kind, it)
+            assert np.array_equal(nacc, na) and np.array_equal(nprop, npr), (kind, it)
+    e.close()
+
+
 def test_unseeded_stream_is_an_error():
     from openmmtools_b200._engine import EngineError
     e = gpu_engine(0, 4, 4)
