@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
                                                   const unsigned char *__restrict__ filt,
                                                   const double *__restrict__ filt_rowabs, MixCtl *ctl) {
     extern __shared__ uint4 s_w2[];
+    __shared__ unsigned long long s_ptrs[2];               // global base pointers of the round loop (see there)
     uint4 *s_ring = s_w2;                                  // [W2_RING] slot records
     W2Replica *s_rep = (W2Replica *)(s_ring + W2_RING);    // [K]
     unsigned char *s_q = (unsigned char *)(s_rep + K);     // image rows, 3K bytes each
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
             }
         }
     }
+    if (tid == 0) { s_ptrs[0] = (unsigned long long)__cvta_generic_to_global(slot_log); s_ptrs[1] = (unsigned long long)rec; }
     __syncthreads();
     float rowabs_max = 0.f;
     for (int q = tid; q < K; q += W2_THREADS) {
@@ -246,12 +248,26 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
         const unsigned row_bytes = 3u * (unsigned)K, lo_off = 2u * (unsigned)K;
         unsigned r = h & 31u;                           // lane of window position 0
         unsigned w = ((unsigned)lane - h) & 31u;        // this lane's window position
-        const unsigned sA = h + w;                      // this lane's first slot
+        unsigned sA = h + w;                            // this lane's slot
+        // (the two global base pointers of the loop as opaque register values: taken from the constant bank where they are
+        // used, each use would wait for an LDC)
+        // (read back from shared memory by a volatile load: nothing the compiler can re-derive)
+        const uint2 pl = w2_lds64((unsigned)__cvta_generic_to_shared((const void *)&s_ptrs[0]));
+        const uint2 pr = w2_lds64((unsigned)__cvta_generic_to_shared((const void *)&s_ptrs[1]));
+        const unsigned long long slot_log_r = ((unsigned long long)pl.y << 32) | pl.x;
+        const uint4 *recs_r = (const uint4 *)(((unsigned long long)pr.y << 32) | pr.x);
         // slot contexts: A = the lane's slot, B = its next slot, one window later (its raw record is loaded a round ahead):
         // back-mask, f32 log-uniform of the following slot, the filter bound's constant term (-1e30 when i == j),
         // all-ones if i != j, shared addresses of the image rows and of the replica entries of i and j
-        unsigned bmA, neqA, rowiA, rowjA, repiA, repjA, bmB, neqB, rowiB, rowjB, repiB, repjB;
-        float luA, epsA, luB, epsB;
+        unsigned bmA, neqA, rowiA, rowjA, repiA, repjA;
+        float luA, epsA;
+        // of the next slot only what the commit needs at once is prepared a round ahead: its indices and the addresses of
+        // its replica entries; the rest of its context is derived when (and only in the lanes where) the slot is entered
+        unsigned iB, jB, repiB, repjB;
+        auto ahead = [&](const uint4 q) {
+            iB = q.x & 0xffffu; jB = q.x >> 16;
+            repiB = rep_base + (iB << 3); repjB = rep_base + (jB << 3);
+        };
         auto derive = [&](const uint4 q, unsigned &bm, float &lu, float &eps, unsigned &neq, unsigned &rowi, unsigned &rowj,
                           unsigned &repi, unsigned &repj) {
             const unsigned i = q.x & 0xffffu, j = q.x >> 16;
@@ -269,14 +285,12 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
         derive(w2_lds128(ring_base + ((sA & (W2_RING - 1)) << 4)), bmA, luA, epsA, neqA, rowiA, rowjA, repiA, repjA);
         unsigned ridxB = (sA + 32u) & (W2_RING - 1);   // ring entry of the next slot
         uint4 qB = w2_lds128(ring_base + (ridxB << 4));
-        derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
+        ahead(qB);
         uint2 ei = w2_lds64(repiA), ej = w2_lds64(repjA);   // {state, diag} of both replicas
         // what the round resolved last leaves to the next block: the committed window positions, the positions that leave
         // the window, all-ones if this lane's attempt changes the permutation, its log entry
         unsigned p_cm = 0, p_below = 0, p_chg = 0, p_entry = 0;
         float f_ij = 0.f, f_ji = 0.f;
-        uint32_t *log_ptr = slot_log + sA;          // this lane's entry of the sparse commit log
-        const uint4 *rec_ptr = recs + (sA + 480);   // the record this lane copies into the ring at its next promotion
         // Commit the round described by the p_* values, slide the window and fetch the states of the next round:
         // permutation stores, at once the next round's loads, then the lane state.
         auto commit = [&]() {
@@ -295,11 +309,16 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
             __syncwarp();
             // the states of the next round: of the next slot for the lanes that leave the window
             const uint2 ein = w2_lds64(p_promoted ? repiB : repiA), ejn = w2_lds64(p_promoted ? repjB : repjA);
-            if (p_mine) *log_ptr = p_entry;     // sparse commit log, indexed by slot (zero = no attempt)
+            if (p_mine)   // sparse commit log, indexed by slot (zero = no attempt)
+                asm volatile("st.global.u32 [%0], %1;" ::"l"(slot_log_r + 4ull * sA), "r"(p_entry) : "memory");
             if (p_promoted) {
-                bmA = bmB; luA = luB; epsA = epsB; neqA = neqB; rowiA = rowiB; rowjA = rowjB; repiA = repiB; repjA = repjB;
-                log_ptr += 32; rec_ptr += 32;
-                w2_cp_async16(ring_base + (((ridxB - 32u) & (W2_RING - 1)) << 4), rec_ptr);   // over the entry of the slot just left
+                bmA = qB.y; luA = __uint_as_float(qB.z);
+                neqA = iB != jB ? 0xffffffffu : 0u;
+                epsA = iB != jB ? eps_rows : -1e30f;
+                rowiA = img_base + iB * row_bytes; rowjA = img_base + jB * row_bytes;
+                repiA = repiB; repjA = repjB;
+                sA += 32u;
+                w2_cp_async16(ring_base + (((ridxB - 32u) & (W2_RING - 1)) << 4), recs_r + (sA + 480u));   // over the entry of the slot just left
                 ridxB = (ridxB + 32u) & (W2_RING - 1);
             }
             w2_cp_async_commit();
@@ -333,7 +352,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
                 f_ji = w2_image_at(rowjA + 2u * si, rowjA + lo_off + si);
                 const float e0 = fmaf(fabsf(__uint_as_float(ei.y)) + fabsf(__uint_as_float(ej.y)), 3.2e-5f, epsA);
                 w2_cp_async_wait<8>();   // a copy is used 15 of the lane's promotions (at least 15 rounds) after it was issued
-                derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
+                ahead(qB);
                 bool ge0, acc, undecided;
                 w2_filter(__uint_as_float(ei.y), f_ij, __uint_as_float(ej.y) + bias, f_ji, e0, luA, ge0, acc, undecided);
                 const unsigned und = undecided ? 1u : 0u;
@@ -371,7 +390,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
             if ((Cw & 1u) == 0u) continue;
             commit();   // (nothing to commit: positions the lanes on the round that could not start)
             w2_cp_async_wait<8>();
-            derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
+            ahead(qB);
             // ---------------- rare: the filter could not decide the window's first lane (nothing was committed: the states
             // are those the round was evaluated with).  Every undecided lane takes the exact decision for its slot and
             // injects it into the next fast round -- a bias of +-1e20..1e30 on its log_p and a matching log-uniform make
@@ -387,7 +406,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
                 w2_filter(__uint_as_float(ei.y), f1, __uint_as_float(ej.y), f2, e0, luA, ge0, acc, undecided);
                 lu_saved = luA;
                 if (undecided) {
-                    const unsigned d = w2_exact_decision(rec, words, u, (unsigned)(log_ptr - slot_log), si, sj, logK);
+                    const unsigned d = w2_exact_decision(rec, words, u, sA, si, sj, logK);
                     bias = (d & 1u) ? 1e30f : -1e20f;
                     if (!(d & 1u)) luA = (d & 2u) ? -1e30f : 0.f;
                     slow++;
@@ -406,7 +425,6 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
                 f_ij = w2_image_at(rowiA + 2u * sj, rowiA + lo_off + sj);
                 f_ji = w2_image_at(rowjA + 2u * si, rowjA + lo_off + si);
                 if (w == 0u) {
-                    const unsigned sA = (unsigned)(log_ptr - slot_log);   // this lane's slot
                     const unsigned ij = rec[sA].ij;
                     const unsigned rowi = (ij & 0xffffu) << logK, rowj = (ij >> 16) << logK;
                     const double logp = swap_logp(u[rowi | sj], u[rowj | si], u[rowi | si], u[rowj | sj]);
@@ -429,7 +447,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
                 p_entry = (sj * (1u << LOG_STATE_BITS) + si) | (acc ? (1u << 31) | (1u << LOG_ACC_BIT) : (1u << 31));
                 commit();
                 w2_cp_async_wait<8>();
-                derive(qB, bmB, luB, epsB, neqB, rowiB, rowjB, repiB, repjB);
+                ahead(qB);
                 p_cm = p_below = 0;
             }
         }
