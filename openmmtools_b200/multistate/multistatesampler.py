@@ -74,6 +74,7 @@ class MultiStateSampler:
         self.energy_context_cache = ContextCache()
         self.sampler_context_cache = ContextCache()
         self._reporter = None
+        self._want_async_reporting = False
         self._unsampled_table = None
         self._engine = None
         self._states_stale = False     # host copies of sampler states are behind the device
@@ -219,6 +220,7 @@ class MultiStateSampler:
         if isinstance(self._mcmc_moves, mcmc.MCMCMove):
             self._mcmc_moves = [copy.deepcopy(self._mcmc_moves) for _ in thermodynamic_states]
         self._reporter = reporter
+        self._wrap_reporter()
         extra = reporter.read_checkpoint_extra(checkpoint)
         if self._seed is None:
             self._seed = extra.get('seed')
@@ -237,6 +239,7 @@ class MultiStateSampler:
                unsampled_thermodynamic_states=None, metadata=None):
         if storage is not None:
             self._reporter = storage if isinstance(storage, MultiStateReporter) else MultiStateReporter(storage)
+            self._wrap_reporter()
         if self._thermodynamic_states is not None:
             raise RuntimeError('Cannot initialize the same sampler twice (create() was already called).')
         # multistatesampler.py:586-589: an existing storage is never overwritten
@@ -366,6 +369,28 @@ class MultiStateSampler:
             from .._dist import default_communicator
             comm = self._communicator = default_communicator()
         return int.from_bytes(comm.bcast_bytes(int(v).to_bytes(8, 'little') if self._rank == 0 else None, 8), 'little')
+
+    @property
+    def asynchronous_reporting(self):
+        """True: the records of an iteration are written to storage by a writer thread while the next iteration runs
+        (multistate/_async_writer.py); run() returns with everything on storage.  Default False (the reference's behaviour)."""
+        return self._want_async_reporting
+
+    @asynchronous_reporting.setter
+    def asynchronous_reporting(self, on):
+        self._want_async_reporting = bool(on)
+        self._wrap_reporter()
+
+    def _wrap_reporter(self):
+        from ._async_writer import AsyncReporter
+        r = self._reporter
+        if r is None:
+            return
+        if self._want_async_reporting and not isinstance(r, AsyncReporter):
+            self._reporter = AsyncReporter(r)
+        elif not self._want_async_reporting and isinstance(r, AsyncReporter):
+            r.shutdown()
+            self._reporter = r._reporter
 
     class _HostStore:
         """Page-locked backing store of the owned SamplerStates: positions, velocities (K_loc, N, 3) and the energies the
@@ -500,6 +525,8 @@ class MultiStateSampler:
             self._update_timing(t3 - t0, time.time() - timer_start, run_initial_iteration, iteration_limit,
                                 phases=(t1 - t0, t2 - t1, t3 - t2))
             self._check_nan_energy()
+        if self._want_async_reporting and self._reporter is not None:
+            self._reporter.drain()     # run() returns with every record on storage
 
     def extend(self, n_iterations):
         if self._iteration + n_iterations > self.number_of_iterations:

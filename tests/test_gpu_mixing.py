@@ -151,6 +151,35 @@ def test_swap_all_any_k_hard_matrices(K, kind):
     e.close()
 
 
+@pytest.mark.parametrize('nswap', [40, 6000])
+def test_swap_all_tie_break_inside_the_guard_band(nswap):
+    """The one place where the decision is not taken in the log domain: |log_p - log U| <= 1e-9, where the kernels fall back to
+    the reference's own test U < exp(log_p).  K = 2 matrices are built so that the first attempt with i != j lands inside
+    the band (log_p = log U to a relative 0, 1e-14, 1e-12, 1e-10 on either side), for 60 seeds; nswap = 40 runs in the
+    pass-tail kernel (k_mix_walk_pow2), 6000 in k_mix_walk2."""
+    from oracle import oracle
+    hits = 0
+    for seed in range(60):
+        mt = oracle.MT(seed)
+        while True:
+            i, j = mt.randint(2), mt.randint(2)
+            if i != j: break
+        U = mt.rand()
+        for rel in (0.0, 1e-14, -1e-14, 1e-12, -1e-12, 1e-10, -1e-10):
+            lp = np.log(U) * (1.0 + rel)
+            u = np.array([[0.0, -0.5 * lp], [-0.5 * lp, 0.0]])      # log_p(0, 1) = -(u01 + u10) + u00 + u11 = lp
+            e = gpu_engine(0, 2, 2)
+            e.set_energies(u); e.set_replica_states(np.arange(2)); e.mix_seed(seed, 0)
+            st, nacc, nprop = e.mix_swap_all(nswap)
+            hits += e.mix_stats()['exact_exp'] > 0
+            e.close()
+            mo = oracle.MT(seed); st_o = np.arange(2, dtype=np.int64)
+            na = np.zeros((2, 2), np.int64); npr = np.zeros((2, 2), np.int64)
+            oracle.mix_swap_all(mo, nswap, st_o, u, na, npr)
+            assert np.array_equal(st, st_o) and np.array_equal(nacc, na) and np.array_equal(nprop, npr), (seed, rel)
+    assert hits > 100   # the exact path really ran
+
+
 def test_unseeded_stream_is_an_error():
     from openmmtools_b200._engine import EngineError
     e = gpu_engine(0, 4, 4)
