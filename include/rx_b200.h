@@ -95,6 +95,15 @@ RX_API int rx_set_states(rx_engine *h, const rx_state_params *states /* [n_state
 RX_API int rx_set_integrator(rx_engine *h, double timestep, double collision_rate, int32_t n_steps,
                       const char *splitting);
 
+/* One move per thermodynamic state: a replica is propagated with the move of the state it is in.
+ * Replaces: the per-state mcmc_moves list of MultiStateSampler, openmmtools/multistate/multistatesampler.py:906-910 (one deep
+ * copy per state) and its use in _propagate_replica, :1311-1322 (mcmc_move = self._mcmc_moves[thermodynamic_state_id]).
+ * Call after rx_set_integrator (the move of every state not set here), once per state whose move differs;
+ * reassign_velocities is that move's flag (the `reassign_velocities` argument of rx_propagate is then ignored).
+ * rx_set_integrator again returns to one move for all states. */
+RX_API int rx_set_state_integrator(rx_engine *h, int32_t state, double timestep, double collision_rate, int32_t n_steps,
+                                   const char *splitting, int32_t reassign_velocities);
+
 /* ---- replica state I/O (SamplerState.apply_to_context / update_from_context, states.py:2215-2279) -- */
 /* xyz: [count][N][3] doubles, global replica indices; replicas not owned by this engine are skipped.    */
 RX_API int rx_set_positions(rx_engine *h, int32_t first, int32_t count, const double *xyz);

@@ -105,6 +105,11 @@ class Engine:
         self._check(self._lib.rx_set_integrator(self._h, float(timestep), float(collision_rate), int(n_steps),
                                                 splitting.replace(' ', '').encode()))
 
+    def set_state_integrator(self, state, timestep, collision_rate, n_steps, splitting='V R O R V', reassign_velocities=False):
+        """The move of one thermodynamic state where the states carry different moves (after set_integrator)."""
+        self._check(self._lib.rx_set_state_integrator(self._h, int(state), float(timestep), float(collision_rate), int(n_steps),
+                                                      splitting.replace(' ', '').encode(), int(bool(reassign_velocities))))
+
     # -- replica state
     def set_positions(self, xyz, first=0):
         xyz = _c64(xyz)

@@ -125,6 +125,7 @@ extern "C" void rx_destroy(rx_engine *h) {
     for (int i = 0; i < 2; i++) if (h->ev_user[i]) cudaEventDestroy(h->ev_user[i]);
     for (int i = 0; i < 2; i++) if (h->ev_walk[i]) cudaEventDestroy(h->ev_walk[i]);
     for (const auto &r : h->pinned) cudaHostUnregister((void *)r.first);
+    cudaFree(h->d_moves);
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_rng) cudaStreamDestroy(h->stream_rng);
@@ -220,6 +221,41 @@ extern "C" int rx_set_integrator(rx_engine *h, double timestep, double collision
     memset(h->program, 0, sizeof(h->program));
     memcpy(h->program, splitting, n);
     h->have_integrator = true;
+    h->state_moves.clear();   // one move for every state again
+    return RX_OK;
+}
+
+/* One MCMCMove per thermodynamic state (openmmtools/multistate/multistatesampler.py:906-910; a replica is propagated with
+ * the move of the state it is in, :1311-1322).  Call after rx_set_integrator (which provides the move of every state not
+ * set here) for each state whose move differs; rx_set_integrator again returns to one move for all states. */
+extern "C" int rx_set_state_integrator(rx_engine *h, int32_t state, double timestep, double collision_rate, int32_t n_steps,
+                                       const char *splitting, int32_t reassign_velocities) {
+    ENTER(h);
+    if (!h->have_integrator) RX_FAIL(h, RX_ERR_INVALID, "rx_set_state_integrator: rx_set_integrator must be called first");
+    if (state < 0 || state >= h->cfg.n_states) RX_FAIL(h, RX_ERR_INVALID, "rx_set_state_integrator: state out of range");
+    if (!(timestep > 0) || collision_rate < 0 || n_steps < 0) RX_FAIL(h, RX_ERR_INVALID, "rx_set_state_integrator: bad timestep/collision_rate/n_steps");
+    if (!splitting) RX_FAIL(h, RX_ERR_INVALID, "rx_set_state_integrator: null splitting");
+    const size_t n = strlen(splitting);
+    if (n == 0 || n >= RX_MAX_PROGRAM) RX_FAIL(h, RX_ERR_INVALID, "rx_set_state_integrator: splitting must have 1..31 substeps");
+    bool hasV = false, hasR = false, hasO = false;
+    for (size_t i = 0; i < n; i++) {
+        const char c = splitting[i];
+        if (c == 'V') hasV = true; else if (c == 'R') hasR = true; else if (c == 'O') hasO = true;
+        else RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_set_state_integrator: only R, V and O substeps are supported");
+    }
+    if (!(hasV && hasR && hasO)) RX_FAIL(h, RX_ERR_INVALID, "rx_set_state_integrator: splitting must contain R, V and O");
+    if (h->state_moves.empty()) {   // start from the common move
+        h->state_moves.resize((size_t)h->cfg.n_states);
+        for (auto &m : h->state_moves) {
+            m.dt = h->dt; m.gamma = h->gamma; m.n_steps = h->n_steps; m.reassign = 0;
+            memcpy(m.program, h->program, sizeof(m.program));
+        }
+    }
+    rx_state_move &m = h->state_moves[(size_t)state];
+    m.dt = timestep; m.gamma = collision_rate; m.n_steps = n_steps; m.reassign = reassign_velocities ? 1 : 0; m.set = true;
+    memset(m.program, 0, sizeof(m.program));
+    memcpy(m.program, splitting, n);
+    h->state_moves_dirty = true;
     return RX_OK;
 }
 

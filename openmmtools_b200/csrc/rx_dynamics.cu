@@ -70,6 +70,14 @@ struct DynParams {
     char prog[RX_MAX_PROGRAM];
 };
 
+// One entry per thermodynamic state when the states carry different moves (multistatesampler.py:906-910: one MCMCMove per
+// state); a replica is propagated with the move of the state it is in.
+struct MoveDev {
+    float dt, a, b;
+    int n_steps, n_prog, nV, nR, nO, reassign;
+    char prog[RX_MAX_PROGRAM];
+};
+
 struct PairLam { float la, ob; };
 
 // Pair interaction in float: returns -dU/dr / r (so f_i += ret * (xi - xj)) and optionally the energy.
@@ -215,13 +223,15 @@ __device__ __forceinline__ void lj_forces(const DynParams &p, const PairCtx &c, 
 // barrier becomes a cluster barrier.  The displacement votes are cluster wide, so the lists are rebuilt at the same steps and
 // with the same contents as in one block: trajectories do not depend on CL (each atom sums its own list in list order, noise
 // is keyed by atom id).
-template <bool C6, bool SW, int CL>
+// PS: per-state moves (the integrator parameters come from `moves[state]` instead of `p`).
+template <bool C6, bool SW, int CL, bool PS = false>
 __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *__restrict__ atom,
                                                     const StateDev *__restrict__ states, const int *__restrict__ perm,
                                                     float4 *__restrict__ pos, float4 *__restrict__ vel, int k0,
                                                     uint2 key, uint32_t iteration, int reassign,
                                                     double *__restrict__ pot, double *__restrict__ kin,
-                                                    int *__restrict__ nan_flag, const int *__restrict__ only) {
+                                                    int *__restrict__ nan_flag, const int *__restrict__ only,
+                                                    const MoveDev *__restrict__ moves) {
     extern __shared__ float4 s_dyn[];
     // (the whole cluster takes this exit together: `only` is indexed by replica)
     if (only && !only[k0 + blockIdx.x / CL]) return;   // a retry launch propagates the replicas that failed, nothing else
@@ -253,6 +263,12 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     };
     const StateDev st = states[perm[k]];
     const PairLam lam = {(float)st.la, (float)st.ob};
+    // the move: the launch's, or the one of this replica's state
+    const MoveDev *mv = PS ? moves + perm[k] : nullptr;
+    const float m_dt = PS ? mv->dt : p.dt, m_a = PS ? mv->a : p.a, m_b = PS ? mv->b : p.b;
+    const int m_steps = PS ? mv->n_steps : p.n_steps, m_nprog = PS ? mv->n_prog : p.n_prog, m_nV = PS ? mv->nV : p.nV,
+              m_nR = PS ? mv->nR : p.nR;
+    if (PS) reassign = mv->reassign;
     float sig_i, se_i, inv_m, sigma_v;
     bool alch_i;
     auto load_atom = [&]() {
@@ -425,23 +441,23 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
 
     uint32_t ocount = 0;
     float dummy;
-    for (int s = 0; s < p.n_steps; s++) {
-        for (int q = 0; q < p.n_prog; q++) {
-            const char op = p.prog[q];
+    for (int s = 0; s < m_steps; s++) {
+        for (int q = 0; q < m_nprog; q++) {
+            const char op = PS ? mv->prog[q] : p.prog[q];
             if (op == 'V') {
                 if (!f_valid) { compute_forces(false, dummy); f_valid = true; }
-                const float h = p.dt / (float)p.nV;
+                const float h = m_dt / (float)m_nV;
                 vx += h * fx * inv_m; vy += h * fy * inv_m; vz += h * fz * inv_m;
             } else if (op == 'R') {
-                const float h = p.dt / (float)p.nR;
+                const float h = m_dt / (float)m_nR;
                 x += h * vx; y += h * vy; z += h * vz;
                 f_valid = false;
             } else {  // 'O'
                 const float3 g = philox_normal3(philox4x32_10(make_uint4(a, ocount, k, iteration), key));
                 ocount++;
-                vx = p.a * vx + p.b * sigma_v * g.x;
-                vy = p.a * vy + p.b * sigma_v * g.y;
-                vz = p.a * vz + p.b * sigma_v * g.z;
+                vx = m_a * vx + m_b * sigma_v * g.x;
+                vy = m_a * vy + m_b * sigma_v * g.y;
+                vz = m_a * vz + m_b * sigma_v * g.z;
             }
         }
     }
@@ -699,6 +715,30 @@ static int fill_dyn(rx_engine *h, DynParams &p) {
     return RX_OK;
 }
 
+// The per-state move table (rx_set_state_integrator), uploaded when it changed.
+int rxi_upload_state_moves(rx_engine *h) {
+    if (!h->state_moves_dirty) return RX_OK;
+    const int M = h->cfg.n_states;
+    std::vector<MoveDev> tab((size_t)M);
+    for (int l = 0; l < M; l++) {
+        const rx_state_move &m = h->state_moves[(size_t)l];
+        MoveDev &d = tab[(size_t)l];
+        memset(&d, 0, sizeof(d));
+        int n = 0, nV = 0, nR = 0, nO = 0;
+        for (const char *q = m.program; *q; q++, n++) { if (*q == 'V') nV++; else if (*q == 'R') nR++; else nO++; d.prog[n] = *q; }
+        d.n_prog = n; d.nV = nV; d.nR = nR; d.nO = nO;
+        d.dt = (float)m.dt; d.n_steps = m.n_steps; d.reassign = m.reassign;
+        const double hO = m.dt / (nO > 0 ? nO : 1);   // integrators.py:1141-1146
+        d.a = (float)exp(-m.gamma * hO);
+        d.b = (float)sqrt(1.0 - exp(-2.0 * m.gamma * hO));
+    }
+    if (!h->d_moves) RX_CHECK_CUDA(h, cudaMalloc(&h->d_moves, sizeof(MoveDev) * (size_t)M));
+    RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_moves, tab.data(), sizeof(MoveDev) * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));   // (tab is a stack object)
+    h->state_moves_dirty = false;
+    return RX_OK;
+}
+
 int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches, const int *d_only) {
     if (h->kloc == 0) return RX_OK;
     DynParams p;
@@ -716,6 +756,12 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
         if (h->kloc * 4 <= sms) cl = 4;
         if (const char *e = getenv("RX_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cl = v; }
+    }
+    const bool per_state = !h->state_moves.empty();
+    if (per_state) {
+        cl = 1;
+        int rcm = rxi_upload_state_moves(h);
+        if (rcm) return rcm;
     }
     const int n_per = (N + cl - 1) / cl;
     const int threads = ((n_per + 31) / 32) * 32;
@@ -765,18 +811,19 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     lc.attrs = at;
     lc.numAttrs = 1;
     const uint32_t it32 = (uint32_t)iteration;
-#define RX_LAUNCH_PROPAGATE(C6, SW, CL)                                                                                   \
+#define RX_LAUNCH_PROPAGATE(C6, SW, CL, PS)                                                                               \
     do {                                                                                                                   \
         if (smem > 48 * 1024)                                                                                              \
-            RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate<C6, SW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        RX_CHECK_CUDA(h, cudaLaunchKernelEx(&lc, k_propagate<C6, SW, CL>, p, (const float4 *)h->d_atom, (const StateDev *)h->d_states, \
+            RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_propagate<C6, SW, CL, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        RX_CHECK_CUDA(h, cudaLaunchKernelEx(&lc, k_propagate<C6, SW, CL, PS>, p, (const float4 *)h->d_atom, (const StateDev *)h->d_states, \
                                             (const int *)h->d_perm, h->d_pos, h->d_vel, h->k0, key, it32, reassign, h->d_pot, \
-                                            h->d_kin, h->d_nan, d_only));                                                 \
+                                            h->d_kin, h->d_nan, d_only, (const MoveDev *)h->d_moves));                    \
     } while (0)
 #define RX_LAUNCH_PROPAGATE_CL(C6, SW)                                                                                    \
     do {                                                                                                                   \
-        if (cl == 4) RX_LAUNCH_PROPAGATE(C6, SW, 4); else if (cl == 2) RX_LAUNCH_PROPAGATE(C6, SW, 2);                    \
-        else RX_LAUNCH_PROPAGATE(C6, SW, 1);                                                                               \
+        if (per_state) RX_LAUNCH_PROPAGATE(C6, SW, 1, true);                                                               \
+        else if (cl == 4) RX_LAUNCH_PROPAGATE(C6, SW, 4, false); else if (cl == 2) RX_LAUNCH_PROPAGATE(C6, SW, 2, false); \
+        else RX_LAUNCH_PROPAGATE(C6, SW, 1, false);                                                                        \
     } while (0)
     if (p.c_is_6) { if (p.use_switch) RX_LAUNCH_PROPAGATE_CL(true, true); else RX_LAUNCH_PROPAGATE_CL(true, false); }
     else { if (p.use_switch) RX_LAUNCH_PROPAGATE_CL(false, true); else RX_LAUNCH_PROPAGATE_CL(false, false); }

@@ -48,6 +48,13 @@ struct MixCtl {          // device-resident control block of the resumable mixin
     long long log_count; // entries written to the commit log by this launch
 };
 
+struct rx_state_move {
+    double dt = 0, gamma = 0;
+    int n_steps = 0, reassign = 0;
+    char program[RX_MAX_PROGRAM] = {0};
+    bool set = false;
+};
+
 struct rx_engine {
     rx_config cfg;
     int k0 = 0, kloc = 0;  // owned replicas [k0, k0+kloc)
@@ -85,6 +92,9 @@ struct rx_engine {
     double dt = 0, gamma = 0;
     int n_steps = 0;
     char program[RX_MAX_PROGRAM] = {0};
+    std::vector<rx_state_move> state_moves;   // per-state moves (empty: one move for all states)
+    bool state_moves_dirty = false;
+    void *d_moves = nullptr;
     // mixing
     MTStream streams[2];
     SlotRec *d_slots = nullptr;
@@ -150,6 +160,7 @@ void rxi_mix_free(rx_engine *h);
 
 // ---- implemented in rx_dynamics.cu ----
 int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches, const int *d_only = nullptr);
+int rxi_upload_state_moves(rx_engine *h);
 int rxi_snapshot_state(rx_engine *h);   // positions + velocities at the start of a propagation
 int rxi_restore_failed(rx_engine *h);   // replicas with a NaN flag go back to the snapshot; d_retry = the flags
 int rxi_compute_energy_rows(rx_engine *h, int *launches);  // fills d_u rows [k0, k0+kloc)

@@ -290,10 +290,7 @@ class MultiStateSampler:
         elif len(self._mcmc_moves) != M:
             raise RuntimeError('The number of MCMCMoves ({}) and ThermodynamicStates ({}) must be the same.'.format(
                 len(self._mcmc_moves), M))
-        for mv in self._mcmc_moves[1:]:
-            if not mcmc.same_integrator(mv, self._mcmc_moves[0]):
-                raise NotImplementedError('per-state moves with different integrator parameters are not provided '
-                                          '(one fused kernel propagates all replicas)')
+        # (moves that differ between states are handed to the engine one by one: _apply_moves)
         self._n_accepted_matrix = np.zeros([M, M], np.int64)
         self._n_proposed_matrix = np.zeros([M, M], np.int64)
         self._energy_thermodynamic_states = np.zeros([K, M], np.float64)
@@ -323,9 +320,7 @@ class MultiStateSampler:
                                              world_size=self._world_size)
         if self._world_size > 1:
             self._init_communicator()
-        dt, gamma, n_steps, splitting = self._mcmc_moves[0]._integrator_parameters()
-        self._engine.set_integrator(dt, gamma, n_steps, splitting)
-        self._reassign = bool(self._mcmc_moves[0].reassign_velocities)
+        self._apply_moves()
         if self._seed is None:
             self._seed = int(np.random.SeedSequence().entropy & 0x7FFFFFFFFFFFFFFF)
             if self._world_size > 1:
@@ -347,6 +342,19 @@ class MultiStateSampler:
         st = np.asarray(self._replica_thermodynamic_states, dtype=np.int64)
         self._replica_thermodynamic_states = e.pinned_array(st.shape, np.int64)
         self._replica_thermodynamic_states[...] = st
+
+    def _apply_moves(self):
+        """The moves go to the engine: one for all states, or -- when the states carry different moves
+        (multistatesampler.py:906-910) -- one per state; a replica is propagated with the move of the state it is in
+        (multistatesampler.py:1311-1322), inside the same fused launch."""
+        mv0 = self._mcmc_moves[0]
+        dt, gamma, n_steps, splitting = mv0._integrator_parameters()
+        self._engine.set_integrator(dt, gamma, n_steps, splitting)
+        self._reassign = bool(mv0.reassign_velocities)
+        if any(not mcmc.same_integrator(mv, mv0) for mv in self._mcmc_moves[1:]):
+            for l, mv in enumerate(self._mcmc_moves):
+                dt, gamma, n_steps, splitting = mv._integrator_parameters()
+                self._engine.set_state_integrator(l, dt, gamma, n_steps, splitting, bool(mv.reassign_velocities))
 
     def _seed_mixing_streams(self):
         # the reference never seeds numba's / numpy's generators (os.urandom); a user seed makes runs reproducible
@@ -550,7 +558,7 @@ class MultiStateSampler:
             self._compute_energies()
             self._replica_thermodynamic_states = self._mix_replicas()
         if mcmc_moves is not None:
-            self._engine.set_integrator(*self._mcmc_moves[0]._integrator_parameters())
+            self._apply_moves()
 
     def minimize(self, tolerance=1.0 * unit.kilojoules_per_mole / unit.nanometers, max_iterations=0):
         """Minimize all replicas, each in its current thermodynamic state (multistatesampler.py:611-647).

@@ -213,3 +213,37 @@ def test_cluster_split_replica_reproduces_single_block_trajectory(monkeypatch, c
     (xa, va, (pa, ka)), (xb, vb, (pb, kb)) = out
     assert np.array_equal(xa, xb) and np.array_equal(va, vb)
     assert np.allclose(pa, pb, rtol=1e-12, atol=1e-9) and np.allclose(ka, kb, rtol=1e-12, atol=1e-9)   # other summation order
+
+
+def test_per_state_moves_propagate_each_replica_with_the_move_of_its_state():
+    """One MCMCMove per thermodynamic state (multistatesampler.py:906-910, :1311-1322): in ONE launch the replicas in states
+    0, 1 run move A and those in states 2, 3 move B (other timestep, friction, step count, splitting, velocity
+    reassignment).  Each replica must come out exactly as from an engine where every state has that move."""
+    N, K = 256, 4
+    s = lj_setup(N=N, n_alch=8, seed=61)
+    lambdas = np.array([1.0, 0.7, 0.3, 0.0]); temps = np.array([300.0, 320.0, 340.0, 360.0])
+    A = (0.002, 1.0, 40, 'V R O R V', False)
+    B = (0.001, 5.0, 25, 'O V R V O', True)
+    rng = np.random.default_rng(16)
+    v0 = rng.normal(scale=0.3, size=(K, N, 3)).astype(np.float32).astype(np.float64)
+    perm = np.array([2, 0, 3, 1])            # replica -> state
+    def run(moves):
+        e = make_engine(s, K, K, lambdas, temps, *moves[0][:4])
+        if any(m != moves[0] for m in moves):
+            for l, m in enumerate(moves):
+                e.set_state_integrator(l, *m)
+        e.set_positions(np.stack([s['x']] * K)); e.set_velocities(v0)
+        e.set_replica_states(perm)
+        e.propagate(77, 3, moves[0][4] if all(m == moves[0] for m in moves) else False)
+        out = (e.get_positions(), e.get_velocities(), e.get_replica_energies())
+        e.close()
+        return out
+    xm, vm, (pm, km) = run([A, A, B, B])
+    xa, va, (pa, ka) = run([A] * 4)
+    xb, vb, (pb, kb) = run([B] * 4)
+    for k in range(K):
+        x_ref, v_ref, p_ref, k_ref = (xa, va, pa, ka) if perm[k] < 2 else (xb, vb, pb, kb)
+        assert np.array_equal(xm[k], x_ref[k]) and np.array_equal(vm[k], v_ref[k]), k
+        # (the two kernel instantiations may contract the f64 energy sums differently: last-bit differences)
+        assert np.isclose(pm[k], p_ref[k], rtol=1e-12, atol=1e-9) and np.isclose(km[k], k_ref[k], rtol=1e-12, atol=1e-9), k
+    assert not np.array_equal(xa[0], xb[0])   # the two moves really differ

@@ -297,3 +297,20 @@ def test_nan_restart_retries_only_the_failed_replica_from_the_iteration_start():
     for k in range(K):
         if k != 2:
             assert np.array_equal(xs[k], xc[k]), k        # propagated exactly once, from the right state
+
+
+@pytest.mark.gpu
+def test_sampler_accepts_one_move_per_state():
+    """mcmc_moves as a list with different moves (multistatesampler.py:906-910): the sampler hands them to the engine state
+    by state; the replicas in the hot, short-timestep states run their own move."""
+    from openmmtools_b200 import testsystems, states, mcmc, multistate, unit
+    ho = testsystems.HarmonicOscillator()
+    ts = [states.ThermodynamicState(ho.system, T * unit.kelvin) for T in (300, 400, 500)]
+    moves = [mcmc.LangevinSplittingDynamicsMove(timestep=2.0 * unit.femtosecond, n_steps=30),
+             mcmc.LangevinSplittingDynamicsMove(timestep=1.0 * unit.femtosecond, n_steps=60),
+             mcmc.LangevinSplittingDynamicsMove(timestep=0.5 * unit.femtosecond, n_steps=120, splitting='O V R V O')]
+    s = multistate.ReplicaExchangeSampler(mcmc_moves=moves, number_of_iterations=5, seed=3)
+    s.create(ts, [states.SamplerState(ho.positions)], storage=None)
+    s.run()
+    assert s.iteration == 5 and np.all(np.isfinite(s._energy_thermodynamic_states))
+    assert [m.n_steps for m in s.mcmc_moves] == [30, 60, 120]
