@@ -7,8 +7,8 @@ from energy_models import energies
 from openmmtools_b200 import testsystems, alchemy, states, mcmc, multistate, unit
 from openmmtools_b200._engine import Engine
 
-# mixing kernels: pow2 small (f64 smem), K=256 (row image), non-pow2 (serial), neighbours
-for K, n in ((16, 4096), (256, 60000), (12, 1728)):
+# mixing kernels: pow2 small, K=256 (row image, k_mix_walk2 + tail), K not a power of two (k_mix_walk_any + plain tail), neighbours
+for K, n in ((16, 4096), (256, 60000), (12, 1728), (100, 30000)):
     e = Engine(0, K, K)
     e.set_energies(energies('flat', K, 7)); e.set_replica_states(np.arange(K)); e.mix_seed(3, 0); e.mix_seed(4, 1)
     e.mix_swap_all(n); e.mix_swap_all(n); e.mix_swap_neighbors()
@@ -26,6 +26,11 @@ s.create(ts, [ss]); s.run(); s.sampler_states
 s._engine.run_iterations(2, 'swap-all', 1, 10)
 s._engine.set_integrator(0.002, 1.0, 150, 'V R O R V')  # long enough for list re-partitions and an outer rebuild
 s._engine.run_iterations(1, 'swap-all', 1, 12)
+# one move per state (k_propagate<.., PS>), the NaN restart path
+s._engine.set_state_integrator(3, 0.001, 5.0, 20, 'O V R V O', True)
+s._engine.run_iterations(1, 'swap-all', 1, 13)
+s._engine.set_integrator(0.002, 1.0, 12, 'V R O R V')
+s._engine.propagate(1, 14); s._engine.propagate_retry(2, 14)
 ho = testsystems.HarmonicOscillator()
 hs = multistate.ReplicaExchangeSampler(mcmc_moves=mcmc.LangevinSplittingDynamicsMove(n_steps=20), number_of_iterations=2, seed=2,
                                        replica_mixing_scheme='swap-neighbors')
