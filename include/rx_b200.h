@@ -47,7 +47,11 @@ enum rx_system_kind {
     RX_SYSTEM_LJ_ALCH = 1,  /* testsystems.LennardJonesFluid (testsystems.py:1872-2030) through
                                alchemy.AbsoluteAlchemicalFactory (alchemy.py:1539-2038): switched LJ +
                                soft-core sterics, cubic periodic box                                   */
-    RX_SYSTEM_HARMONIC = 2  /* testsystems.HarmonicOscillator (testsystems.py:761-788), per-state K/x0/U0 */
+    RX_SYSTEM_HARMONIC = 2, /* testsystems.HarmonicOscillator (testsystems.py:761-788), per-state K/x0/U0 */
+    RX_SYSTEM_MOLECULE = 3  /* a small molecule in vacuum (<= 32 atoms), e.g. testsystems.AlanineDipeptideVacuum
+                               (testsystems.py:3352-3388): harmonic bonds and angles, periodic torsions, all-pairs
+                               Coulomb + Lennard-Jones with exclusions and scaled 1-4 pairs, distance constraints;
+                               states differ in temperature only (ParallelTemperingSampler)                  */
 };
 
 typedef struct {
@@ -85,11 +89,35 @@ RX_API void rx_destroy(rx_engine *h);
 RX_API const char *rx_last_error(const rx_engine *h);
 RX_API int rx_abi_version(void);
 
+/* The force field of a RX_SYSTEM_MOLECULE engine, in md units (nm, kJ/mol, amu, e, rad), as
+ * openmm.app.AmberPrmtopFile.createSystem(implicitSolvent=None, nonbondedCutoff=None, constraints=...) defines it for
+ * testsystems.AlanineDipeptideVacuum (openmmtools/testsystems.py:3375-3388).  Arrays are caller-owned and copied.
+ *   bonds[n][4]       i, j, K, r0            1/2 K (r - r0)^2        (constrained bonds are NOT listed here)
+ *   angles[n][5]      i, j, k, K, theta0     1/2 K (theta - theta0)^2
+ *   torsions[n][7]    i, j, k, l, n, phase, k    k (1 + cos(n phi - phase))
+ *   exclusions[n][2]  pairs without nonbonded interaction (1-2, 1-3)
+ *   exceptions[n][5]  i, j, q_i q_j, sigma, epsilon   replacing the pair's interaction (scaled 1-4 pairs)
+ *   constraints[n][3] i, j, distance
+ * All other pairs interact by 138.935456 q_i q_j / r + 4 eps_ij ((s_ij/r)^12 - (s_ij/r)^6), Lorentz-Berthelot s_ij, eps_ij.
+ * remove_cm_motion: the centre-of-mass velocity is removed at the start of every integration step (CMMotionRemover).
+ * constraint_tolerance: relative tolerance of the constraint solvers (integrators.py: constraint_tolerance, 1e-8). */
+typedef struct {
+    int32_t n_bonds, n_angles, n_torsions, n_exclusions, n_exceptions, n_constraints, remove_cm_motion, reserved;
+    double constraint_tolerance;
+    const double *mass, *charge, *sigma, *epsilon;   /* [n_atoms] */
+    const double *bonds, *angles, *torsions;
+    const int64_t *exclusions;
+    const double *exceptions, *constraints;
+} rx_molecule;
+
 /* ---- static tables -------------------------------------------------------------------------------- */
 /* per-atom sigma (nm), epsilon (kJ/mol), mass (amu), alchemical mask; for RX_SYSTEM_HARMONIC only mass. */
 RX_API int rx_set_particles(rx_engine *h, const double *sigma, const double *epsilon, const double *mass,
                      const uint8_t *alchemical_mask);
 RX_API int rx_set_states(rx_engine *h, const rx_state_params *states /* [n_states] */);
+/* RX_SYSTEM_MOLECULE: the particles and the force field at once (instead of rx_set_particles).
+ * Replaces: the System built by AmberPrmtopFile.createSystem for AlanineDipeptideVacuum, testsystems.py:3375-3388. */
+RX_API int rx_set_molecule(rx_engine *h, const rx_molecule *molecule);
 /* LangevinSplittingDynamicsMove parameters (mcmc.py:1280-1291) / LangevinIntegrator (integrators.py:1071-1158):
  * timestep (ps), collision_rate (1/ps), n_steps, splitting with the spaces removed, e.g. "VRORV".        */
 RX_API int rx_set_integrator(rx_engine *h, double timestep, double collision_rate, int32_t n_steps,

@@ -11,7 +11,7 @@
 import numpy as np
 from . import _lib
 from ._engine import Engine
-from .system import LJ, HARMONIC
+from .system import MOLECULE, LJ, HARMONIC
 
 _GL_X, _GL_W = np.polynomial.legendre.leggauss(64)
 
@@ -138,6 +138,8 @@ def engine_tables(thermodynamic_states):
             if lam[l] not in cache:
                 cache[lam[l]] = alchemical_dispersion_correction(sys0, lam[l])
             off[l] = base_lrc + cache[lam[l]]
+        elif sys0.kind == MOLECULE:
+            pass      # the states of a molecule differ in temperature only
         else:
             so = s._standard_system
             hoK[l] = so.ho_K
@@ -168,6 +170,9 @@ def build_engine(thermodynamic_states, n_replicas, device=0, rank=0, world_size=
                      softcore_alpha=sys0.softcore_alpha, softcore_a=sys0.softcore_a, softcore_b=sys0.softcore_b,
                      softcore_c=sys0.softcore_c)
         eng.set_particles(sys0.sigma, sys0.epsilon, sys0.masses, sys0.alchemical_mask())
+    elif sys0.kind == MOLECULE:
+        eng = Engine(_lib.RX_SYSTEM_MOLECULE, n_replicas, M, N, device=device, rank=rank, world_size=world_size)
+        eng.set_molecule(sys0)
     else:
         eng = Engine(_lib.RX_SYSTEM_HARMONIC, n_replicas, M, N, device=device, rank=rank, world_size=world_size)
         eng.set_particles(None, None, sys0.masses, None)

@@ -105,6 +105,21 @@ class Engine:
         self._check(self._lib.rx_set_integrator(self._h, float(timestep), float(collision_rate), int(n_steps),
                                                 splitting.replace(' ', '').encode()))
 
+    def set_molecule(self, system, constraint_tolerance=1e-8):
+        """Particles and force field of a RX_SYSTEM_MOLECULE engine from a system.System of kind 'molecule'."""
+        f = lambda a, w: np.ascontiguousarray(np.asarray(a if a is not None else np.zeros((0, w)), np.float64).reshape(-1, w))
+        arrs = dict(mass=np.ascontiguousarray(system.masses, np.float64), charge=np.ascontiguousarray(system.charge, np.float64),
+                    sigma=np.ascontiguousarray(system.sigma, np.float64), epsilon=np.ascontiguousarray(system.epsilon, np.float64),
+                    bonds=f(system.bonds, 4), angles=f(system.angles, 5), torsions=f(system.torsions, 7),
+                    exclusions=np.ascontiguousarray(np.asarray(system.exclusions if system.exclusions is not None else np.zeros((0, 2)), np.int64).reshape(-1, 2)),
+                    exceptions=f(system.exceptions, 5), constraints=f(system.constraints, 3))
+        m = _lib.RxMolecule(len(arrs['bonds']), len(arrs['angles']), len(arrs['torsions']), len(arrs['exclusions']),
+                            len(arrs['exceptions']), len(arrs['constraints']), int(bool(system.remove_cm_motion)), 0,
+                            float(constraint_tolerance), *[arrs[k].ctypes.data for k in
+                                                           ('mass', 'charge', 'sigma', 'epsilon', 'bonds', 'angles', 'torsions',
+                                                            'exclusions', 'exceptions', 'constraints')])
+        self._check(self._lib.rx_set_molecule(self._h, C.byref(m)))
+
     def set_state_integrator(self, state, timestep, collision_rate, n_steps, splitting='V R O R V', reassign_velocities=False):
         """The move of one thermodynamic state where the states carry different moves (after set_integrator)."""
         self._check(self._lib.rx_set_state_integrator(self._h, int(state), float(timestep), float(collision_rate), int(n_steps),

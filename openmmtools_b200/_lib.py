@@ -11,13 +11,13 @@ LIB_PATH = os.environ.get('RX_B200_LIB') or os.path.join(_HERE, 'csrc', 'librx_b
 
 RX_ABI_VERSION = 1
 RX_OK, RX_ERR_INVALID, RX_ERR_CUDA, RX_ERR_NAN, RX_ERR_UNSUPPORTED, RX_ERR_COMM, RX_ERR_CAPACITY = 0, -1, -2, -3, -4, -5, -6
-RX_SYSTEM_NONE, RX_SYSTEM_LJ_ALCH, RX_SYSTEM_HARMONIC = 0, 1, 2
+RX_SYSTEM_NONE, RX_SYSTEM_LJ_ALCH, RX_SYSTEM_HARMONIC, RX_SYSTEM_MOLECULE = 0, 1, 2, 3
 RX_STREAM_NUMBA, RX_STREAM_NUMPY = 0, 1
 
 # every symbol include/rx_b200.h declares
 SYMBOLS = [
     'rx_create', 'rx_destroy', 'rx_last_error', 'rx_abi_version', 'rx_set_particles', 'rx_set_states',
-    'rx_set_integrator', 'rx_set_state_integrator', 'rx_set_positions', 'rx_set_velocities', 'rx_get_positions', 'rx_get_velocities',
+    'rx_set_integrator', 'rx_set_state_integrator', 'rx_set_molecule', 'rx_set_positions', 'rx_set_velocities', 'rx_get_positions', 'rx_get_velocities',
     'rx_get_replica_energies', 'rx_pin_host_memory', 'rx_unpin_host_memory', 'rx_randomize_velocities', 'rx_minimize', 'rx_set_replica_states', 'rx_get_replica_states',
     'rx_propagate', 'rx_propagate_retry', 'rx_compute_energies', 'rx_compute_energies_at', 'rx_set_energies', 'rx_get_energies', 'rx_mix_seed',
     'rx_mix_skip', 'rx_mix_swap_all', 'rx_mix_swap_neighbors', 'rx_get_mix_counts', 'rx_mix_stream_position',
@@ -37,6 +37,15 @@ class RxConfig(C.Structure):
 class RxStateParams(C.Structure):
     _fields_ = [('temperature', C.c_double), ('lambda_sterics', C.c_double), ('energy_offset', C.c_double),
                 ('ho_K', C.c_double), ('ho_x0', C.c_double * 3)]
+
+
+class RxMolecule(C.Structure):
+    _fields_ = [('n_bonds', C.c_int32), ('n_angles', C.c_int32), ('n_torsions', C.c_int32), ('n_exclusions', C.c_int32),
+                ('n_exceptions', C.c_int32), ('n_constraints', C.c_int32), ('remove_cm_motion', C.c_int32), ('reserved', C.c_int32),
+                ('constraint_tolerance', C.c_double),
+                ('mass', C.c_void_p), ('charge', C.c_void_p), ('sigma', C.c_void_p), ('epsilon', C.c_void_p),
+                ('bonds', C.c_void_p), ('angles', C.c_void_p), ('torsions', C.c_void_p), ('exclusions', C.c_void_p),
+                ('exceptions', C.c_void_p), ('constraints', C.c_void_p)]
 
 
 _lib = None
@@ -62,6 +71,7 @@ def load():
     lib.rx_set_states.argtypes = [vp, vp]
     lib.rx_set_integrator.argtypes = [vp, dbl, dbl, i32, C.c_char_p]
     lib.rx_set_state_integrator.argtypes = [vp, i32, dbl, dbl, i32, C.c_char_p, i32]
+    lib.rx_set_molecule.argtypes = [vp, C.POINTER(RxMolecule)]
     for name in ('rx_set_positions', 'rx_set_velocities', 'rx_get_positions', 'rx_get_velocities'):
         getattr(lib, name).argtypes = [vp, i32, i32, vp]
     lib.rx_get_replica_energies.argtypes = [vp, vp, vp]

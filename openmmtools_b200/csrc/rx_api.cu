@@ -30,8 +30,9 @@ extern "C" int rx_create(const rx_config *cfg, rx_engine **out) {
     if (!cfg || !out) CREATE_FAIL(RX_ERR_INVALID, "rx_create: null argument");
     if (cfg->abi_version != RX_ABI_VERSION) CREATE_FAIL(RX_ERR_INVALID, "rx_create: ABI version mismatch");
     if (cfg->n_replicas < 1 || cfg->n_states < 1) CREATE_FAIL(RX_ERR_INVALID, "rx_create: n_replicas and n_states must be >= 1");
-    if (cfg->system_kind < RX_SYSTEM_NONE || cfg->system_kind > RX_SYSTEM_HARMONIC) CREATE_FAIL(RX_ERR_INVALID, "rx_create: unknown system_kind");
+    if (cfg->system_kind < RX_SYSTEM_NONE || cfg->system_kind > RX_SYSTEM_MOLECULE) CREATE_FAIL(RX_ERR_INVALID, "rx_create: unknown system_kind");
     if (cfg->system_kind != RX_SYSTEM_NONE && cfg->n_atoms < 1) CREATE_FAIL(RX_ERR_INVALID, "rx_create: n_atoms must be >= 1");
+    if (cfg->system_kind == RX_SYSTEM_MOLECULE && cfg->n_atoms > 32) CREATE_FAIL(RX_ERR_UNSUPPORTED, "rx_create: a molecule has at most 32 atoms");
     if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) CREATE_FAIL(RX_ERR_INVALID, "rx_create: bad rank/world_size");
     if (cfg->system_kind == RX_SYSTEM_LJ_ALCH) {
         for (int d = 0; d < 3; d++)
@@ -89,10 +90,12 @@ extern "C" int rx_create(const rx_config *cfg, rx_engine **out) {
     }
     if (cfg->system_kind != RX_SYSTEM_NONE) {
         const size_t n = (size_t)(h->kloc > 0 ? h->kloc : 1) * N;
-        CREATE_CUDA(cudaMalloc(&h->d_pos, sizeof(float4) * n));
-        CREATE_CUDA(cudaMalloc(&h->d_vel, sizeof(float4) * n));
-        CREATE_CUDA(cudaMemset(h->d_pos, 0, sizeof(float4) * n));
-        CREATE_CUDA(cudaMemset(h->d_vel, 0, sizeof(float4) * n));
+        // (a molecule keeps its state as double[3] per atom, the other systems as float4)
+        const size_t per_atom = cfg->system_kind == RX_SYSTEM_MOLECULE ? 3 * sizeof(double) : sizeof(float4);
+        CREATE_CUDA(cudaMalloc(&h->d_pos, per_atom * n));
+        CREATE_CUDA(cudaMalloc(&h->d_vel, per_atom * n));
+        CREATE_CUDA(cudaMemset(h->d_pos, 0, per_atom * n));
+        CREATE_CUDA(cudaMemset(h->d_vel, 0, per_atom * n));
         CREATE_CUDA(cudaMalloc(&h->d_io, sizeof(double) * 3 * n));
         CREATE_CUDA(cudaHostAlloc(&h->h_io, sizeof(double) * 3 * n, cudaHostAllocDefault));
         CREATE_CUDA(cudaMalloc(&h->d_atom, sizeof(float4) * N));
@@ -126,6 +129,7 @@ extern "C" void rx_destroy(rx_engine *h) {
     for (int i = 0; i < 2; i++) if (h->ev_walk[i]) cudaEventDestroy(h->ev_walk[i]);
     for (const auto &r : h->pinned) cudaHostUnregister((void *)r.first);
     cudaFree(h->d_moves);
+    rxi_free_molecule(h);
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_rng) cudaStreamDestroy(h->stream_rng);
@@ -141,6 +145,7 @@ extern "C" int rx_set_particles(rx_engine *h, const double *sigma, const double 
                                 const uint8_t *alch) {
     ENTER(h);
     if (h->cfg.system_kind == RX_SYSTEM_NONE) RX_FAIL(h, RX_ERR_INVALID, "rx_set_particles: engine has no particle system");
+    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) RX_FAIL(h, RX_ERR_INVALID, "rx_set_particles: use rx_set_molecule for RX_SYSTEM_MOLECULE");
     if (!mass) RX_FAIL(h, RX_ERR_INVALID, "rx_set_particles: mass is required");
     const int N = h->cfg.n_atoms;
     const bool lj = h->cfg.system_kind == RX_SYSTEM_LJ_ALCH;
@@ -171,6 +176,17 @@ extern "C" int rx_set_particles(rx_engine *h, const double *sigma, const double 
     RX_CHECK_CUDA(h, cudaMalloc(&h->d_pairs, sizeof(double2) * (size_t)cap * (h->kloc > 0 ? h->kloc : 1)));
     h->have_particles = true;
     return RX_OK;
+}
+
+extern "C" int rx_set_molecule(rx_engine *h, const rx_molecule *molecule) {
+    ENTER(h);
+    if (h->cfg.system_kind != RX_SYSTEM_MOLECULE) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: the engine was not created with RX_SYSTEM_MOLECULE");
+    if (!molecule) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: null");
+    if (molecule->n_bonds < 0 || molecule->n_angles < 0 || molecule->n_torsions < 0 || molecule->n_exclusions < 0 ||
+        molecule->n_exceptions < 0 || molecule->n_constraints < 0)
+        RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: negative count");
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return rxi_set_molecule(h, molecule);
 }
 
 static int convert_states(rx_engine *h, const rx_state_params *s, int n, std::vector<StateDev> &out, const char *who) {

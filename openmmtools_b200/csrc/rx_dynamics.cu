@@ -62,6 +62,7 @@ struct DynParams {
     int use_switch, annihilate, c_is_6;
     float sc_c;                 // softcore_c
     float dt, a, b;             // timestep, O-step coefficients exp(-gamma h), sqrt(1-exp(-2 gamma h))
+    double dt_d, a_d, b_d;      // the same in f64 (the molecule kernel)
     int n_steps, n_prog, nV, nR, nO;
     int maxnb;                  // Verlet-list capacity per atom (0: all-pairs only)
     int sort_atoms;             // re-deal atoms to threads by neighbour count at every list build
@@ -668,6 +669,12 @@ __global__ void k_unpack(const float4 *__restrict__ in, double *__restrict__ out
 int rxi_convert_in(rx_engine *h, float4 *dst, int first_local, int count, const double *host_xyz, bool) {
     const long long n = (long long)count * h->cfg.n_atoms;
     if (n == 0) return RX_OK;
+    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {   // the state of a molecule is kept in f64: a plain copy
+        double *d = (double *)dst + (size_t)first_local * h->cfg.n_atoms * 3;
+        RX_CHECK_CUDA(h, cudaMemcpyAsync(d, host_xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+        return RX_OK;
+    }
     const double *src = host_xyz;
     if (!rxi_is_pinned(h, host_xyz, n * 3 * sizeof(double))) {   // pageable caller memory goes through the pinned staging buffer
         memcpy(h->h_io, host_xyz, n * 3 * sizeof(double));
@@ -683,6 +690,12 @@ int rxi_convert_in(rx_engine *h, float4 *dst, int first_local, int count, const 
 int rxi_convert_out(rx_engine *h, const float4 *src, int first_local, int count, double *host_xyz, bool wrap) {
     const long long n = (long long)count * h->cfg.n_atoms;
     if (n == 0) return RX_OK;
+    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {
+        const double *d = (const double *)src + (size_t)first_local * h->cfg.n_atoms * 3;
+        RX_CHECK_CUDA(h, cudaMemcpyAsync(host_xyz, d, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+        return RX_OK;
+    }
     k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(src + (size_t)first_local * h->cfg.n_atoms, h->d_io, n,
                                                                  wrap ? 1 : 0, h->cfg.box[0], h->cfg.box[1], h->cfg.box[2]);
     RX_CHECK_CUDA(h, cudaGetLastError());
@@ -692,6 +705,8 @@ int rxi_convert_out(rx_engine *h, const float4 *src, int first_local, int count,
     if (!direct) memcpy(host_xyz, h->h_io, n * 3 * sizeof(double));
     return RX_OK;
 }
+
+#include "rx_molecule.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 static int fill_dyn(rx_engine *h, DynParams &p) {
@@ -712,6 +727,7 @@ static int fill_dyn(rx_engine *h, DynParams &p) {
     const double hO = h->dt / (nO > 0 ? nO : 1);   // integrators.py:1141-1146
     p.a = (float)exp(-h->gamma * hO);
     p.b = (float)sqrt(1.0 - exp(-2.0 * h->gamma * hO));
+    p.dt_d = h->dt; p.a_d = exp(-h->gamma * hO); p.b_d = sqrt(1.0 - exp(-2.0 * h->gamma * hO));
     return RX_OK;
 }
 
@@ -744,6 +760,16 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     DynParams p;
     fill_dyn(h, p);
     const int N = h->cfg.n_atoms;
+    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {
+        if (!h->state_moves.empty()) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: per-state moves are not provided for molecules");
+        const uint2 mkey = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
+        k_propagate_mol<<<h->kloc, 32, 0, h->stream>>>(*(const MolDev *)h->mol_dev, p, (const StateDev *)h->d_states, (const int *)h->d_perm,
+                                                      (double *)h->d_pos, (double *)h->d_vel, h->k0, mkey, (uint32_t)iteration, reassign,
+                                                      h->d_pot, h->d_kin, h->d_nan, d_only);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        (*launches)++;
+        return RX_OK;
+    }
     if (N > 1024) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: more than 1024 atoms per replica is not supported yet");
     // Blocks per replica (a thread-block cluster; RX_CLUSTER = 1 | 2 | 4 overrides).  Measured on the 512-atom fluid (500
     // steps, in the iteration loop): 32 replicas 2.27-2.36 ms in one block, 2.30-2.59 in two, 2.20-2.29 in four; 64 replicas
@@ -838,7 +864,7 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
 // from the state it had when the move began) and the restore of the replicas whose NaN flag is set.
 int rxi_snapshot_state(rx_engine *h) {
     if (h->kloc == 0) return RX_OK;
-    const size_t bytes = sizeof(float4) * (size_t)h->kloc * h->cfg.n_atoms;
+    const size_t bytes = (h->cfg.system_kind == RX_SYSTEM_MOLECULE ? 3 * sizeof(double) : sizeof(float4)) * (size_t)h->kloc * h->cfg.n_atoms;
     if (!h->d_pos_snap) {
         RX_CHECK_CUDA(h, cudaMalloc(&h->d_pos_snap, bytes));
         RX_CHECK_CUDA(h, cudaMalloc(&h->d_vel_snap, bytes));
@@ -866,6 +892,12 @@ __global__ void k_restore_failed(const int *__restrict__ nan_flag, int *__restri
 int rxi_restore_failed(rx_engine *h) {
     if (h->kloc == 0) return RX_OK;
     if (!h->have_snapshot) RX_FAIL(h, RX_ERR_INVALID, "rx_propagate_retry: no start-of-iteration snapshot (call rx_propagate first)");
+    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {
+        k_restore_failed_mol<<<h->kloc, 32, 0, h->stream>>>(h->d_nan, h->d_retry, h->k0, h->cfg.n_atoms, (const double *)h->d_pos_snap,
+                                                           (const double *)h->d_vel_snap, (double *)h->d_pos, (double *)h->d_vel);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        return RX_OK;
+    }
     k_restore_failed<<<h->kloc, 256, 0, h->stream>>>(h->d_nan, h->d_retry, h->k0, h->cfg.n_atoms, h->d_pos_snap, h->d_vel_snap,
                                                     h->d_pos, h->d_vel);
     RX_CHECK_CUDA(h, cudaGetLastError());
@@ -957,6 +989,7 @@ __global__ void __launch_bounds__(1024) k_minimize(DynParams p, const float4 *__
 
 int rxi_minimize(rx_engine *h, double tolerance, int max_iterations, double *d_rms, int *d_iters) {
     if (h->kloc == 0) return RX_OK;
+    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_minimize: not provided for molecules");
     DynParams p;
     fill_dyn(h, p);
     const int N = h->cfg.n_atoms;
@@ -976,6 +1009,13 @@ int rxi_minimize(rx_engine *h, double tolerance, int max_iterations, double *d_r
 int rxi_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream_id) {
     if (h->kloc == 0) return RX_OK;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {   // (k_propagate_mol projects incoming velocities onto the constraints)
+        k_randomize_velocities_mol<<<h->kloc, 32, 0, h->stream>>>(*(const MolDev *)h->mol_dev, (const StateDev *)h->d_states,
+                                                                 (const int *)h->d_perm, (double *)h->d_vel, h->k0, key, (uint32_t)stream_id);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+        return RX_OK;
+    }
     k_randomize_velocities<<<h->kloc, 256, 0, h->stream>>>(h->cfg.n_atoms, h->d_atom, h->d_states, h->d_perm, h->d_vel, h->k0,
                                                            key, (uint32_t)stream_id);
     RX_CHECK_CUDA(h, cudaGetLastError());
@@ -988,6 +1028,12 @@ int rxi_randomize_velocities(rx_engine *h, uint64_t seed, uint64_t stream_id) {
 int rxi_compute_energy_rows_at(rx_engine *h, const StateDev *d_states, int n_states, double *d_out, int *launches) {
     if (h->kloc == 0) return RX_OK;
     const rx_config &c = h->cfg;
+    if (c.system_kind == RX_SYSTEM_MOLECULE) {
+        k_energy_mol<<<h->kloc, 32, 0, h->stream>>>(*(const MolDev *)h->mol_dev, d_states, n_states, (const double *)h->d_pos, h->k0, d_out);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        (*launches)++;
+        return RX_OK;
+    }
     EnParams p;
     memset(&p, 0, sizeof(p));
     p.N = c.n_atoms; p.M = n_states; p.kind = c.system_kind; p.n_alch = h->n_alch;
@@ -1008,4 +1054,118 @@ int rxi_compute_energy_rows_at(rx_engine *h, const StateDev *d_states, int n_sta
 
 int rxi_compute_energy_rows(rx_engine *h, int *launches) {
     return rxi_compute_energy_rows_at(h, h->d_states, h->cfg.n_states, h->d_u, launches);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Molecule tables (rx_set_molecule): per-atom term lists, the pair mask, constraint clusters.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+static int mol_upload(rx_engine *h, const std::vector<T> &v, const T **out) {
+    void *d = nullptr;
+    const size_t bytes = sizeof(T) * (v.empty() ? 1 : v.size());
+    RX_CHECK_CUDA(h, cudaMalloc(&d, bytes));
+    if (!v.empty()) RX_CHECK_CUDA(h, cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    h->mol_allocs.push_back(d);
+    *out = (const T *)d;
+    return RX_OK;
+}
+
+int rxi_set_molecule(rx_engine *h, const rx_molecule *mol) {
+    const int n = h->cfg.n_atoms;
+    if (n > MOL_MAX_ATOMS) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_set_molecule: more than 32 atoms per molecule is not provided");
+    if (!mol->mass || !mol->charge || !mol->sigma || !mol->epsilon) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: null per-atom arrays");
+    auto atom_ok = [&](double v) { return v >= 0 && v < n && v == floor(v); };
+    for (void *d : h->mol_allocs) cudaFree(d);
+    h->mol_allocs.clear();
+    std::vector<double> mass(mol->mass, mol->mass + n), charge(mol->charge, mol->charge + n), sigma(mol->sigma, mol->sigma + n),
+        eps(mol->epsilon, mol->epsilon + n);
+    for (int i = 0; i < n; i++)
+        if (!(mass[i] > 0) || !(sigma[i] > 0) || eps[i] < 0) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: need mass > 0, sigma > 0, epsilon >= 0");
+    std::vector<std::vector<MolBond>> ba(n);
+    std::vector<std::vector<MolAngle>> aa(n);
+    std::vector<std::vector<MolTorsion>> ta(n);
+    std::vector<std::vector<MolExc>> xa(n);
+    std::vector<unsigned> mask(n);
+    for (int i = 0; i < n; i++) mask[i] = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) & ~(1u << i);
+    for (int b = 0; b < mol->n_bonds; b++) {
+        const double *q = mol->bonds + 4 * b;
+        if (!atom_ok(q[0]) || !atom_ok(q[1]) || q[0] == q[1]) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: bad bond");
+        const int i = (int)q[0], j = (int)q[1];
+        ba[i].push_back(MolBond{j, 0, q[2], q[3]});
+        ba[j].push_back(MolBond{i, 0, q[2], q[3]});
+    }
+    for (int a = 0; a < mol->n_angles; a++) {
+        const double *q = mol->angles + 5 * a;
+        if (!atom_ok(q[0]) || !atom_ok(q[1]) || !atom_ok(q[2])) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: bad angle");
+        const int id[3] = {(int)q[0], (int)q[1], (int)q[2]};
+        for (int role = 0; role < 3; role++) aa[id[role]].push_back(MolAngle{id[0], id[1], id[2], role, q[3], q[4]});
+    }
+    for (int t = 0; t < mol->n_torsions; t++) {
+        const double *q = mol->torsions + 7 * t;
+        if (!atom_ok(q[0]) || !atom_ok(q[1]) || !atom_ok(q[2]) || !atom_ok(q[3])) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: bad torsion");
+        const int id[4] = {(int)q[0], (int)q[1], (int)q[2], (int)q[3]};
+        for (int role = 0; role < 4; role++) ta[id[role]].push_back(MolTorsion{id[0], id[1], id[2], id[3], (int)q[4], role, q[5], q[6]});
+    }
+    for (int e = 0; e < mol->n_exclusions; e++) {
+        const int64_t i = mol->exclusions[2 * e], j = mol->exclusions[2 * e + 1];
+        if (i < 0 || i >= n || j < 0 || j >= n || i == j) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: bad exclusion");
+        mask[i] &= ~(1u << j); mask[j] &= ~(1u << i);
+    }
+    for (int e = 0; e < mol->n_exceptions; e++) {
+        const double *q = mol->exceptions + 5 * e;
+        if (!atom_ok(q[0]) || !atom_ok(q[1]) || q[0] == q[1]) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: bad exception");
+        const int i = (int)q[0], j = (int)q[1];
+        mask[i] &= ~(1u << j); mask[j] &= ~(1u << i);
+        xa[i].push_back(MolExc{j, 0, q[2], q[3], q[4]});
+        xa[j].push_back(MolExc{i, 0, q[2], q[3], q[4]});
+    }
+    // constraint clusters: connected components, constraints kept in list order inside a cluster
+    std::vector<int> comp(n);
+    for (int i = 0; i < n; i++) comp[i] = i;
+    auto find = [&](int x) { while (comp[x] != x) x = comp[x] = comp[comp[x]]; return x; };
+    for (int c = 0; c < mol->n_constraints; c++) {
+        const double *q = mol->constraints + 3 * c;
+        if (!atom_ok(q[0]) || !atom_ok(q[1]) || q[0] == q[1] || !(q[2] > 0)) RX_FAIL(h, RX_ERR_INVALID, "rx_set_molecule: bad constraint");
+        comp[find((int)q[0])] = find((int)q[1]);
+    }
+    std::vector<int> cluster_of(n, -1), c_off(1, 0);
+    std::vector<std::vector<MolCons>> cl;
+    for (int c = 0; c < mol->n_constraints; c++) {
+        const double *q = mol->constraints + 3 * c;
+        const int root = find((int)q[0]);
+        if (cluster_of[root] < 0) { cluster_of[root] = (int)cl.size(); cl.emplace_back(); }
+        cl[cluster_of[root]].push_back(MolCons{(int)q[0], (int)q[1], q[2]});
+    }
+    if ((int)cl.size() > 32) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_set_molecule: more than 32 constraint clusters");
+    std::vector<MolCons> cons;
+    for (auto &c : cl) { cons.insert(cons.end(), c.begin(), c.end()); c_off.push_back((int)cons.size()); }
+    auto flatten = [&](auto &per_atom, auto &flat, std::vector<int> &off) {
+        off.assign(1, 0);
+        for (int i = 0; i < n; i++) { flat.insert(flat.end(), per_atom[i].begin(), per_atom[i].end()); off.push_back((int)flat.size()); }
+    };
+    std::vector<MolBond> bonds; std::vector<MolAngle> angles; std::vector<MolTorsion> tors; std::vector<MolExc> exc;
+    std::vector<int> b_off, a_off, t_off, x_off;
+    flatten(ba, bonds, b_off); flatten(aa, angles, a_off); flatten(ta, tors, t_off); flatten(xa, exc, x_off);
+    MolDev *m = (MolDev *)h->mol_dev;
+    if (!m) { m = new MolDev(); h->mol_dev = m; }
+    memset(m, 0, sizeof(*m));
+    m->n = n; m->n_clusters = (int)cl.size(); m->remove_cm = mol->remove_cm_motion ? 1 : 0;
+    m->tol = mol->constraint_tolerance > 0 ? mol->constraint_tolerance : 1e-8;   // integrators.py constraint_tolerance default
+    int rc = 0;
+    if ((rc = mol_upload(h, mass, &m->mass)) || (rc = mol_upload(h, charge, &m->charge)) || (rc = mol_upload(h, sigma, &m->sigma)) ||
+        (rc = mol_upload(h, eps, &m->eps)) || (rc = mol_upload(h, b_off, &m->b_off)) || (rc = mol_upload(h, a_off, &m->a_off)) ||
+        (rc = mol_upload(h, t_off, &m->t_off)) || (rc = mol_upload(h, x_off, &m->x_off)) || (rc = mol_upload(h, c_off, &m->c_off)) ||
+        (rc = mol_upload(h, bonds, &m->bonds)) || (rc = mol_upload(h, angles, &m->angles)) || (rc = mol_upload(h, tors, &m->torsions)) ||
+        (rc = mol_upload(h, exc, &m->exc)) || (rc = mol_upload(h, cons, &m->cons)) || (rc = mol_upload(h, mask, &m->nb_mask)))
+        return rc;
+    h->have_particles = true;
+    return RX_OK;
+}
+
+void rxi_free_molecule(rx_engine *h) {
+    for (void *d : h->mol_allocs) cudaFree(d);
+    h->mol_allocs.clear();
+    delete (MolDev *)h->mol_dev;
+    h->mol_dev = nullptr;
 }

@@ -92,6 +92,8 @@ struct rx_engine {
     double dt = 0, gamma = 0;
     int n_steps = 0;
     char program[RX_MAX_PROGRAM] = {0};
+    void *mol_dev = nullptr;                 // MolDev (host copy of the device table of a RX_SYSTEM_MOLECULE engine)
+    std::vector<void *> mol_allocs;
     std::vector<rx_state_move> state_moves;   // per-state moves (empty: one move for all states)
     bool state_moves_dirty = false;
     void *d_moves = nullptr;
@@ -161,6 +163,8 @@ void rxi_mix_free(rx_engine *h);
 // ---- implemented in rx_dynamics.cu ----
 int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches, const int *d_only = nullptr);
 int rxi_upload_state_moves(rx_engine *h);
+int rxi_set_molecule(rx_engine *h, const rx_molecule *mol);
+void rxi_free_molecule(rx_engine *h);
 int rxi_snapshot_state(rx_engine *h);   // positions + velocities at the start of a propagation
 int rxi_restore_failed(rx_engine *h);   // replicas with a NaN flag go back to the snapshot; d_retry = the flags
 int rxi_compute_energy_rows(rx_engine *h, int *launches);  // fills d_u rows [k0, k0+kloc)

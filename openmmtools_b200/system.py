@@ -9,14 +9,14 @@ import copy
 import hashlib
 import numpy as np
 
-LJ, HARMONIC = 'lj', 'harmonic'
+LJ, HARMONIC, MOLECULE = 'lj', 'harmonic', 'molecule'
 
 
 class System:
     """Parameters of one of the supported systems (md units: nm, ps, dalton, kJ/mol)."""
 
     def __init__(self, kind, masses, box_vectors=None):
-        if kind not in (LJ, HARMONIC):
+        if kind not in (LJ, HARMONIC, MOLECULE):
             raise ValueError('unsupported system kind %r' % (kind,))
         self.kind = kind
         self.masses = np.array(masses, dtype=np.float64)
@@ -41,6 +41,15 @@ class System:
         self.ho_K = None
         self.ho_x0 = (0.0, 0.0, 0.0)
         self.ho_U0 = 0.0
+        # -- small molecule in vacuum (HarmonicBond/Angle, PeriodicTorsion, NonbondedForce NoCutoff + exceptions, HBonds
+        #    constraints, CMMotionRemover): what AmberPrmtopFile.createSystem builds for AlanineDipeptideVacuum
+        self.bonds = None          # float64[nb, 4]  i, j, K (kJ/mol/nm^2), r0 (nm)        1/2 K (r - r0)^2
+        self.angles = None         # float64[na, 5]  i, j, k, K (kJ/mol/rad^2), theta0     1/2 K (t - t0)^2
+        self.torsions = None       # float64[nt, 7]  i, j, k, l, n, phase, k (kJ/mol)      k (1 + cos(n phi - phase))
+        self.exclusions = None     # int[ne, 2]      pairs without any nonbonded interaction (1-2, 1-3)
+        self.exceptions = None     # float64[nx, 5]  i, j, q_i q_j (scaled), sigma, epsilon (scaled): the 1-4 pairs
+        self.constraints = None    # float64[nc, 3]  i, j, distance (nm)
+        self.remove_cm_motion = False
         # -- OpenMM-style global parameters with their defaults (read by GlobalParameterState.from_system)
         self.global_parameters = {}
 
@@ -64,7 +73,7 @@ class System:
         return self.kind == LJ
 
     def getNumConstraints(self):
-        return 0
+        return 0 if self.constraints is None else len(self.constraints)
 
     @property
     def n_particles(self):
@@ -98,6 +107,11 @@ class System:
                            self.use_dispersion_correction, self.alchemical_atoms, self.annihilate_sterics,
                            self.softcore_alpha, self.softcore_a, self.softcore_b, self.softcore_c,
                            self.alchemical_dispersion_correction)).encode())
+        if self.kind == MOLECULE:
+            for a in (self.sigma, self.epsilon, self.charge, self.bonds, self.angles, self.torsions, self.exclusions,
+                      self.exceptions, self.constraints):
+                h.update(np.asarray(a, dtype=np.float64).tobytes())
+            h.update(repr(self.remove_cm_motion).encode())
         return h.hexdigest()
 
     def __getstate__(self):

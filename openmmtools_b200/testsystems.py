@@ -3,12 +3,13 @@
 Mirrors /root/reference/openmmtools/testsystems.py: ``HarmonicOscillator`` (:685-840) and
 ``LennardJonesFluid`` (:1872-2030) with the same constructor arguments, defaults and derived quantities
 (box edge from the reduced density, cutoff 3 sigma, switching distance cutoff - switch_width, sub-random
-initial positions).  The other ~68 reference systems need OpenMM's app layer and are out of scope.
+initial positions), and ``AlanineDipeptideVacuum`` (:3352-3388) from the reference's AMBER input files (``amber.py``; the
+parsed parameters ship as data/alanine_dipeptide_vacuum.json).  The other reference systems are out of scope.
 """
 import numpy as np
 from . import unit
 from .constants import kB
-from .system import System, LJ, HARMONIC
+from .system import System, LJ, HARMONIC, MOLECULE
 from . import sobol
 
 
@@ -124,6 +125,38 @@ class LennardJonesFluid(TestSystem):
         self.positions = subrandom_particle_positions(nparticles, system.getDefaultPeriodicBoxVectors())
         self.nparticles = nparticles
         self.reduced_density = reduced_density
+
+
+class AlanineDipeptideVacuum(TestSystem):
+    """Alanine dipeptide (ff96) in vacuum (testsystems.py:3352-3388): what AmberPrmtopFile.createSystem(implicitSolvent=None,
+    constraints=constraints, nonbondedCutoff=None) builds from alanine-dipeptide.prmtop -- harmonic bonds and angles, periodic
+    torsions, Coulomb + Lennard-Jones over all pairs with 1-2/1-3 exclusions and scaled 1-4 pairs, constraints on the bonds
+    to hydrogen (their bond terms dropped), centre-of-mass motion removal -- and the positions of alanine-dipeptide.crd.
+
+    ``constraints``: 'HBonds' (the reference default, app.HBonds) or None."""
+
+    def __init__(self, constraints='HBonds', hydrogenMass=None, **kwargs):
+        TestSystem.__init__(self, **kwargs)
+        import json, os
+        if hydrogenMass is not None:
+            raise NotImplementedError('hydrogen mass repartitioning is not provided')
+        name = getattr(constraints, '__name__', constraints)
+        if name not in ('HBonds', None):
+            raise NotImplementedError("constraints must be 'HBonds' or None")
+        d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'alanine_dipeptide_vacuum.json')))
+        system = System(MOLECULE, d['mass'])
+        system.charge = np.array(d['charge']); system.sigma = np.array(d['sigma']); system.epsilon = np.array(d['epsilon'])
+        hb = name == 'HBonds'
+        system.bonds = np.array([[b[0], b[1], b[2], b[3]] for b in d['bonds'] if not (hb and b[4])], dtype=np.float64).reshape(-1, 4)
+        system.constraints = np.array([[b[0], b[1], b[3]] for b in d['bonds'] if hb and b[4]], dtype=np.float64).reshape(-1, 3)
+        system.angles = np.array(d['angles'], dtype=np.float64).reshape(-1, 5)
+        system.torsions = np.array(d['torsions'], dtype=np.float64).reshape(-1, 7)
+        system.exclusions = np.array(d['exclusions'], dtype=np.int64).reshape(-1, 2)
+        system.exceptions = np.array(d['exceptions'], dtype=np.float64).reshape(-1, 5)
+        system.remove_cm_motion = True     # createSystem(removeCMMotion=True) is the default
+        self.system = system
+        self.positions = unit.Quantity(np.array(d['positions'], dtype=np.float64), unit.nanometer)
+        self.atom_names = list(d['names'])
 
 
 class LennardJonesGrid(TestSystem):   # pragma: no cover

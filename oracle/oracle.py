@@ -13,8 +13,8 @@ _LIB = os.path.join(_HERE, 'liborc.so')
 
 
 def build(force=False):
-    src = os.path.join(_HERE, 'rx_oracle.c')
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ('rx_oracle.c', 'rx_oracle_mol.c'))
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
         subprocess.check_call(['make', '-C', _HERE, '-B', 'liborc.so'], stdout=subprocess.DEVNULL)
     return _LIB
 
@@ -48,6 +48,9 @@ def lib():
         _lib.orc_ho_energy.restype = C.c_double
         _lib.orc_mix_swap_all.restype = C.c_int64
         _lib.orc_mix_swap_neighbors.restype = C.c_int64
+        _lib.orc_mol_energy.restype = C.c_double
+        _lib.orc_mol_langevin.restype = C.c_double
+        _lib.orc_mol_kinetic.restype = C.c_double
     return _lib
 
 
@@ -172,3 +175,48 @@ def ho_langevin(x, v, mass, noise, K, x0, U0, kT, dt, gamma, n_steps, program='V
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+class _OrcMol(C.Structure):
+    _fields_ = [('n_atoms', C.c_int), ('n_bonds', C.c_int), ('n_angles', C.c_int), ('n_torsions', C.c_int), ('n_excl', C.c_int),
+                ('n_exc', C.c_int), ('n_cons', C.c_int), ('remove_cm', C.c_int),
+                ('mass', C.c_void_p), ('charge', C.c_void_p), ('sigma', C.c_void_p), ('eps', C.c_void_p),
+                ('bonds', C.c_void_p), ('angles', C.c_void_p), ('torsions', C.c_void_p), ('excl', C.c_void_p),
+                ('exc', C.c_void_p), ('cons', C.c_void_p)]
+
+
+class Molecule:
+    """A small molecule in vacuum (rx_oracle_mol.c): bonds/angles/torsions, all-pairs Coulomb + LJ with exclusions and 1-4
+    exceptions, distance constraints.  `system` is an openmmtools_b200.system.System of kind 'molecule' (plain arrays)."""
+
+    def __init__(self, system):
+        f = lambda a, w: np.ascontiguousarray(np.asarray(a, np.float64).reshape(-1, w))
+        self.mass = np.ascontiguousarray(system.masses, np.float64)
+        self.charge = np.ascontiguousarray(system.charge, np.float64)
+        self.sigma = np.ascontiguousarray(system.sigma, np.float64)
+        self.eps = np.ascontiguousarray(system.epsilon, np.float64)
+        self.bonds, self.angles, self.torsions = f(system.bonds, 4), f(system.angles, 5), f(system.torsions, 7)
+        self.excl = np.ascontiguousarray(np.asarray(system.exclusions, np.int64).reshape(-1, 2))
+        self.exc = f(system.exceptions, 5)
+        self.cons = f(system.constraints if system.constraints is not None else np.zeros((0, 3)), 3)
+        self.N = len(self.mass)
+        self.s = _OrcMol(self.N, len(self.bonds), len(self.angles), len(self.torsions), len(self.excl), len(self.exc),
+                         len(self.cons), int(bool(system.remove_cm_motion)), _p(self.mass).value, _p(self.charge).value,
+                         _p(self.sigma).value, _p(self.eps).value, _p(self.bonds).value, _p(self.angles).value,
+                         _p(self.torsions).value, _p(self.excl).value, _p(self.exc).value, _p(self.cons).value)
+
+    def energy(self, x, forces=False):
+        x = np.ascontiguousarray(x, np.float64)
+        f = np.zeros_like(x) if forces else None
+        U = lib().orc_mol_energy(C.byref(self.s), _p(x), _p(f) if forces else None)
+        return (U, f) if forces else U
+
+    def kinetic(self, v):
+        return lib().orc_mol_kinetic(C.byref(self.s), _p(np.ascontiguousarray(v, np.float64)))
+
+    def langevin(self, x, v, noise, kT, dt, gamma, n_steps, program='VRORV', tol=1e-10):
+        """In-place constrained V/R/O splitting steps with injected noise [n_steps*nO, N, 3]; returns the final potential."""
+        assert x.dtype == np.float64 and v.dtype == np.float64 and x.flags.c_contiguous and v.flags.c_contiguous
+        noise = np.ascontiguousarray(noise, np.float64)
+        return lib().orc_mol_langevin(C.byref(self.s), _p(x), _p(v), _p(noise), C.c_double(kT), C.c_double(dt), C.c_double(gamma),
+                                      C.c_int(n_steps), program.replace(' ', '').encode(), C.c_double(tol))

@@ -1,0 +1,127 @@
+"""RX_SYSTEM_MOLECULE on the GPU against the oracle (oracle/rx_oracle_mol.c): energies, constrained Langevin steps with the
+same noise, constraint satisfaction over a long launch, and config 4 of BASELINE.json -- ParallelTemperingSampler on
+testsystems.AlanineDipeptideVacuum (paralleltempering.py:109-237, testsystems.py:3352-3388) -- at reduced size."""
+import numpy as np
+import pytest
+from helpers import gpu_engine, KB, device_noise
+from openmmtools_b200 import testsystems, unit, _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def aladip(constraints='HBonds'):
+    a = testsystems.AlanineDipeptideVacuum(constraints=constraints)
+    return a, np.ascontiguousarray(a.positions.value_in_unit(unit.nanometer), np.float64)
+
+
+def make_engine(system, temps):
+    K = len(temps)
+    e = gpu_engine(_lib.RX_SYSTEM_MOLECULE, K, K, system.n_particles)
+    e.set_molecule(system, constraint_tolerance=1e-10)
+    e.set_states(np.asarray(temps, float), np.ones(K))
+    return e
+
+
+def test_energy_rows_match_the_oracle():
+    from oracle import oracle
+    for constraints in ('HBonds', None):
+        a, x = aladip(constraints)
+        temps = np.array([300.0, 350.0, 420.0, 600.0])
+        rng = np.random.default_rng(3)
+        xs = np.stack([x + rng.normal(0, 0.004, x.shape) for _ in temps])
+        e = make_engine(a.system, temps)
+        e.set_positions(xs)
+        u = e.compute_energies()
+        e.close()
+        m = oracle.Molecule(a.system)
+        U = np.array([m.energy(xk) for xk in xs])
+        ref = U[:, None] / (KB * temps)[None, :]
+        assert np.abs(u - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize('splitting,n_steps', [('V R O R V', 1), ('V R O R V', 25), ('O V R V O', 10), ('R V O', 7)])
+@pytest.mark.parametrize('constraints', ['HBonds', None])
+def test_constrained_steps_match_the_oracle_with_the_same_noise(splitting, n_steps, constraints):
+    from oracle import oracle
+    a, x = aladip(constraints)
+    temps = np.array([300.0, 450.0, 600.0])
+    K = len(temps)
+    rng = np.random.default_rng(8)
+    m = oracle.Molecule(a.system)
+    v0 = np.stack([rng.normal(size=x.shape) * np.sqrt(KB * T / m.mass)[:, None] for T in temps])
+    e = make_engine(a.system, temps)
+    dt, gamma = 0.001, 5.0
+    e.set_integrator(dt, gamma, n_steps, splitting)
+    e.set_positions(np.stack([x] * K)); e.set_velocities(v0)
+    e.set_replica_states(np.array([2, 0, 1]))
+    seed, it = 4242, 17
+    e.propagate(seed, it)
+    xg, vg = e.get_positions(), e.get_velocities()
+    pg, kg = e.get_replica_energies()
+    e.close()
+    nO = splitting.replace(' ', '').count('O')
+    perm = [2, 0, 1]
+    for k in range(K):
+        xo, vo = x.copy(), np.ascontiguousarray(v0[k])
+        # (the kernel first projects the incoming velocities onto the constraints: zero steps of the oracle do the same)
+        noise = device_noise(seed, it, k, 22, n_steps * nO)
+        kT = KB * temps[perm[k]]
+        U = oracle_run(m, xo, vo, noise, kT, dt, gamma, n_steps, splitting)
+        assert np.abs(xg[k] - xo).max() < 1e-8, (k, np.abs(xg[k] - xo).max())
+        assert np.abs(vg[k] - vo).max() < 1e-6, (k, np.abs(vg[k] - vo).max())
+        assert abs(pg[k] - U) < 1e-5 and abs(kg[k] - m.kinetic(vo)) < 1e-5
+
+
+def oracle_run(m, x, v, noise, kT, dt, gamma, n_steps, splitting):
+    """The oracle with the kernel's entry convention: incoming velocities are first made to obey the constraints."""
+    import ctypes as C
+    from oracle import oracle
+    if len(m.cons):
+        oracle.lib().orc_mol_rattle(C.byref(m.s), x.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_double(1e-10))
+    return m.langevin(x, v, noise, kT, dt, gamma, n_steps, splitting, tol=1e-10)
+
+
+def test_long_launch_keeps_constraints_and_is_reproducible():
+    a, x = aladip()
+    temps = np.linspace(300.0, 600.0, 8)
+    K = len(temps)
+    out = []
+    for rep in range(2):
+        e = make_engine(a.system, temps)
+        e.set_integrator(0.002, 5.0, 500, 'V R O R V')
+        e.set_positions(np.stack([x] * K)); e.randomize_velocities(11)
+        e.propagate(5, 1); e.propagate(5, 2)
+        out.append((e.get_positions(), e.get_velocities(), e.get_replica_energies()))
+        e.close()
+    (xa, va, (pa, ka)), (xb, vb, (pb, kb)) = out
+    assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(pa, pb)     # bit-reproducible
+    c = a.system.constraints
+    i, j = c[:, 0].astype(int), c[:, 1].astype(int)
+    d = np.linalg.norm(xa[:, i] - xa[:, j], axis=2)
+    assert np.abs(d - c[None, :, 2]).max() < 1e-9
+    assert np.all(np.isfinite(pa)) and np.all(ka > 0)
+    # hotter replicas have more kinetic energy on average (51 degrees of freedom each)
+    assert ka[-3:].mean() > ka[:3].mean()
+
+
+def test_parallel_tempering_on_alanine_dipeptide():
+    """BASELINE config 4 at reduced size: 12 temperatures 300-600 K, 5 iterations of 100 steps."""
+    from oracle import oracle
+    from openmmtools_b200 import states, mcmc, multistate
+    a, x = aladip()
+    ts = states.ThermodynamicState(a.system, 300.0 * unit.kelvin)
+    move = mcmc.LangevinSplittingDynamicsMove(timestep=2.0 * unit.femtosecond, collision_rate=5.0 / unit.picosecond, n_steps=100)
+    s = multistate.ParallelTemperingSampler(mcmc_moves=move, number_of_iterations=5, seed=9)
+    s.create(ts, [states.SamplerState(a.positions)], storage=None, min_temperature=300.0 * unit.kelvin,
+             max_temperature=600.0 * unit.kelvin, n_temperatures=12)
+    s.run()
+    assert s.iteration == 5
+    u = np.array(s._energy_thermodynamic_states)
+    m = oracle.Molecule(a.system)
+    T = np.array([st.temperature.value_in_unit(unit.kelvin) for st in s._thermodynamic_states])
+    assert abs(T[0] - 300.0) < 1e-9 and abs(T[-1] - 600.0) < 1e-9
+    for k, st in enumerate(s.sampler_states):
+        xk = np.ascontiguousarray(st.positions.value_in_unit(unit.nanometer), np.float64)
+        U = m.energy(xk)
+        assert np.abs(u[k] - U / (KB * T)).max() < 1e-8 * max(1.0, abs(U))
+    assert sorted(s._replica_thermodynamic_states.tolist()) == list(range(12))
