@@ -763,7 +763,7 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {
         if (!h->state_moves.empty()) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: per-state moves are not provided for molecules");
         const uint2 mkey = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
-        k_propagate_mol<<<h->kloc, 32, 0, h->stream>>>(*(const MolDev *)h->mol_dev, p, (const StateDev *)h->d_states, (const int *)h->d_perm,
+        k_propagate_mol<<<h->kloc, 32, ((const MolDev *)h->mol_dev)->shared_bytes, h->stream>>>(*(const MolDev *)h->mol_dev, p, (const StateDev *)h->d_states, (const int *)h->d_perm,
                                                       (double *)h->d_pos, (double *)h->d_vel, h->k0, mkey, (uint32_t)iteration, reassign,
                                                       h->d_pot, h->d_kin, h->d_nan, d_only);
         RX_CHECK_CUDA(h, cudaGetLastError());
@@ -1029,7 +1029,7 @@ int rxi_compute_energy_rows_at(rx_engine *h, const StateDev *d_states, int n_sta
     if (h->kloc == 0) return RX_OK;
     const rx_config &c = h->cfg;
     if (c.system_kind == RX_SYSTEM_MOLECULE) {
-        k_energy_mol<<<h->kloc, 32, 0, h->stream>>>(*(const MolDev *)h->mol_dev, d_states, n_states, (const double *)h->d_pos, h->k0, d_out);
+        k_energy_mol<<<h->kloc, 32, ((const MolDev *)h->mol_dev)->shared_bytes, h->stream>>>(*(const MolDev *)h->mol_dev, d_states, n_states, (const double *)h->d_pos, h->k0, d_out);
         RX_CHECK_CUDA(h, cudaGetLastError());
         (*launches)++;
         return RX_OK;
@@ -1147,14 +1147,24 @@ int rxi_set_molecule(rx_engine *h, const rx_molecule *mol) {
     std::vector<MolBond> bonds; std::vector<MolAngle> angles; std::vector<MolTorsion> tors; std::vector<MolExc> exc;
     std::vector<int> b_off, a_off, t_off, x_off;
     flatten(ba, bonds, b_off); flatten(aa, angles, a_off); flatten(ta, tors, t_off); flatten(xa, exc, x_off);
+    std::vector<double> seps(n);
+    for (int i = 0; i < n; i++) seps[i] = sqrt(eps[i]);
+    // (padding so that the 8-byte staging copies never read past an allocation)
+    b_off.push_back(0); a_off.push_back(0); t_off.push_back(0); x_off.push_back(0); mask.push_back(0);
     MolDev *m = (MolDev *)h->mol_dev;
     if (!m) { m = new MolDev(); h->mol_dev = m; }
     memset(m, 0, sizeof(*m));
+    for (int i = 0; i <= n; i++) { m->b_off_h[i] = b_off[i]; m->a_off_h[i] = a_off[i]; m->t_off_h[i] = t_off[i]; m->x_off_h[i] = x_off[i]; }
+    {
+        auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
+        m->shared_bytes = (int)(up(sizeof(MolBond) * bonds.size()) + up(sizeof(MolAngle) * angles.size()) + up(sizeof(MolTorsion) * tors.size()) +
+                                up(sizeof(MolExc) * exc.size()) + 4 * up(sizeof(int) * (n + 2)) + 3 * up(sizeof(double) * n) + up(sizeof(unsigned) * (n + 1)) + 64);
+    }
     m->n = n; m->n_clusters = (int)cl.size(); m->remove_cm = mol->remove_cm_motion ? 1 : 0;
     m->tol = mol->constraint_tolerance > 0 ? mol->constraint_tolerance : 1e-8;   // integrators.py constraint_tolerance default
     int rc = 0;
     if ((rc = mol_upload(h, mass, &m->mass)) || (rc = mol_upload(h, charge, &m->charge)) || (rc = mol_upload(h, sigma, &m->sigma)) ||
-        (rc = mol_upload(h, eps, &m->eps)) || (rc = mol_upload(h, b_off, &m->b_off)) || (rc = mol_upload(h, a_off, &m->a_off)) ||
+        (rc = mol_upload(h, eps, &m->eps)) || (rc = mol_upload(h, seps, &m->seps)) || (rc = mol_upload(h, b_off, &m->b_off)) || (rc = mol_upload(h, a_off, &m->a_off)) ||
         (rc = mol_upload(h, t_off, &m->t_off)) || (rc = mol_upload(h, x_off, &m->x_off)) || (rc = mol_upload(h, c_off, &m->c_off)) ||
         (rc = mol_upload(h, bonds, &m->bonds)) || (rc = mol_upload(h, angles, &m->angles)) || (rc = mol_upload(h, tors, &m->torsions)) ||
         (rc = mol_upload(h, exc, &m->exc)) || (rc = mol_upload(h, cons, &m->cons)) || (rc = mol_upload(h, mask, &m->nb_mask)))

@@ -27,8 +27,10 @@ struct MolCons { int i, j; double d; };
 struct MolDev {
     int n, n_clusters, remove_cm, pad;
     double tol;
-    const double *mass, *charge, *sigma, *eps;
+    const double *mass, *charge, *sigma, *eps, *seps;
     const int *b_off, *a_off, *t_off, *x_off, *c_off;
+    int b_off_h[MOL_MAX_ATOMS + 1], a_off_h[MOL_MAX_ATOMS + 1], t_off_h[MOL_MAX_ATOMS + 1], x_off_h[MOL_MAX_ATOMS + 1];   // (host copies: counts)
+    int shared_bytes;
     const MolBond *bonds;
     const MolAngle *angles;
     const MolTorsion *torsions;
@@ -42,35 +44,61 @@ __device__ __forceinline__ void mol_cross(const double *a, const double *b, doub
 }
 __device__ __forceinline__ double mol_dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
+template <typename R> __device__ __forceinline__ R mol_sqrt(R x);
+template <> __device__ __forceinline__ float mol_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double mol_sqrt<double>(double x) { return sqrt(x); }
+template <typename R> __device__ __forceinline__ R mol_acos(R x);
+template <> __device__ __forceinline__ float mol_acos<float>(float x) { return acosf(x); }
+template <> __device__ __forceinline__ double mol_acos<double>(double x) { return acos(x); }
+template <typename R> __device__ __forceinline__ R mol_atan2(R y, R x);
+template <> __device__ __forceinline__ float mol_atan2<float>(float y, float x) { return atan2f(y, x); }
+template <> __device__ __forceinline__ double mol_atan2<double>(double y, double x) { return atan2(y, x); }
+template <typename R> __device__ __forceinline__ void mol_sincos(R x, R *s, R *c);
+template <> __device__ __forceinline__ void mol_sincos<float>(float x, float *s, float *c) { sincosf(x, s, c); }
+template <> __device__ __forceinline__ void mol_sincos<double>(double x, double *s, double *c) { sincos(x, s, c); }
+
+// The term tables of one molecule in shared memory (a few KB: read every step by every lane).
+struct MolShared {
+    const MolBond *bonds; const MolAngle *angles; const MolTorsion *torsions; const MolExc *exc;
+    const int *b_off, *a_off, *t_off, *x_off;
+    const double *charge, *sigma, *seps;   // seps = sqrt(epsilon)
+    const unsigned *nb_mask;
+    int n;
+};
+
 // Force on atom a (ENERGY: instead the energy of the terms this atom owns: bonds/exceptions/pairs with the larger partner
-// index, angles and torsions in which it has role 0).  X: positions of all atoms in shared memory.
-template <bool ENERGY>
-__device__ double mol_atom(const MolDev &m, const double (*X)[3], int a, double *f) {
-    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+// index, angles and torsions in which it has role 0).  X: positions of all atoms in shared memory.  R: the arithmetic type --
+// float for the forces of the dynamics (as in k_propagate: f32 forces on f64-stored positions, differences taken in f64),
+// double for energies.
+template <bool ENERGY, typename R>
+__device__ double mol_atom(const MolShared &m, const double (*X)[3], int a, double *f) {
+    double e = 0.0;
+    R fx = 0, fy = 0, fz = 0;
     const double xa[3] = {X[a][0], X[a][1], X[a][2]};
     for (int q = m.b_off[a]; q < m.b_off[a + 1]; q++) {
         const MolBond b = m.bonds[q];
-        const double d[3] = {xa[0] - X[b.j][0], xa[1] - X[b.j][1], xa[2] - X[b.j][2]};
-        const double r = sqrt(mol_dot(d, d)), dr = r - b.r0;
-        if (ENERGY) { if (b.j > a) e += 0.5 * b.K * dr * dr; }
-        else { const double c = -b.K * dr / r; fx += c * d[0]; fy += c * d[1]; fz += c * d[2]; }
+        const R d[3] = {(R)(xa[0] - X[b.j][0]), (R)(xa[1] - X[b.j][1]), (R)(xa[2] - X[b.j][2])};
+        const R r = mol_sqrt<R>(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), dr = r - (R)b.r0;
+        if (ENERGY) { if (b.j > a) e += 0.5 * b.K * (double)dr * (double)dr; }
+        else { const R c = -(R)b.K * dr / r; fx += c * d[0]; fy += c * d[1]; fz += c * d[2]; }
     }
     for (int q = m.a_off[a]; q < m.a_off[a + 1]; q++) {
         const MolAngle g = m.angles[q];
-        double u[3], v[3];
-        for (int c = 0; c < 3; c++) { u[c] = X[g.i][c] - X[g.j][c]; v[c] = X[g.k][c] - X[g.j][c]; }
-        const double ru = sqrt(mol_dot(u, u)), rv = sqrt(mol_dot(v, v));
-        double cs = mol_dot(u, v) / (ru * rv);
-        cs = fmin(1.0, fmax(-1.0, cs));
-        const double dt = acos(cs) - g.t0;
-        if (ENERGY) { if (g.role == 0) e += 0.5 * g.K * dt * dt; }
+        R u[3], v[3];
+        for (int c = 0; c < 3; c++) { u[c] = (R)(X[g.i][c] - X[g.j][c]); v[c] = (R)(X[g.k][c] - X[g.j][c]); }
+        const R ru2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], rv2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        const R iruv = (R)1 / mol_sqrt<R>(ru2 * rv2);
+        R cs = (u[0] * v[0] + u[1] * v[1] + u[2] * v[2]) * iruv;
+        cs = cs > (R)1 ? (R)1 : (cs < (R)-1 ? (R)-1 : cs);
+        const R dt = mol_acos<R>(cs) - (R)g.t0;
+        if (ENERGY) { if (g.role == 0) e += 0.5 * g.K * (double)dt * (double)dt; }
         else {
-            const double sn = sqrt(1.0 - cs * cs);
-            const double gg = (sn > 1e-12) ? g.K * dt / sn : 0.0;
-            double o[3];
+            const R sn = mol_sqrt<R>((R)1 - cs * cs);
+            const R gg = (sn > (R)1e-6) ? (R)g.K * dt / sn : (R)0;
+            R o[3];
             for (int c = 0; c < 3; c++) {
-                const double fi = gg * (v[c] / (ru * rv) - cs * u[c] / (ru * ru));
-                const double fk = gg * (u[c] / (ru * rv) - cs * v[c] / (rv * rv));
+                const R fi = gg * (v[c] * iruv - cs * u[c] / ru2);
+                const R fk = gg * (u[c] * iruv - cs * v[c] / rv2);
                 o[c] = g.role == 0 ? fi : (g.role == 2 ? fk : -(fi + fk));
             }
             fx += o[0]; fy += o[1]; fz += o[2];
@@ -78,66 +106,215 @@ __device__ double mol_atom(const MolDev &m, const double (*X)[3], int a, double 
     }
     for (int q = m.t_off[a]; q < m.t_off[a + 1]; q++) {
         const MolTorsion t = m.torsions[q];
-        double rij[3], rkj[3], rkl[3], mm[3], nn[3];
-        for (int c = 0; c < 3; c++) { rij[c] = X[t.i][c] - X[t.j][c]; rkj[c] = X[t.k][c] - X[t.j][c]; rkl[c] = X[t.k][c] - X[t.l][c]; }
-        mol_cross(rij, rkj, mm); mol_cross(rkj, rkl, nn);
-        const double nrkj = sqrt(mol_dot(rkj, rkj));
-        const double phi = atan2(nrkj * mol_dot(rij, nn), mol_dot(mm, nn));
-        if (ENERGY) { if (t.role == 0) e += t.kk * (1.0 + cos((double)t.n * phi - t.phase)); }
+        R rij[3], rkj[3], rkl[3], mm[3], nn[3];
+        for (int c = 0; c < 3; c++) { rij[c] = (R)(X[t.i][c] - X[t.j][c]); rkj[c] = (R)(X[t.k][c] - X[t.j][c]); rkl[c] = (R)(X[t.k][c] - X[t.l][c]); }
+        mm[0] = rij[1] * rkj[2] - rij[2] * rkj[1]; mm[1] = rij[2] * rkj[0] - rij[0] * rkj[2]; mm[2] = rij[0] * rkj[1] - rij[1] * rkj[0];
+        nn[0] = rkj[1] * rkl[2] - rkj[2] * rkl[1]; nn[1] = rkj[2] * rkl[0] - rkj[0] * rkl[2]; nn[2] = rkj[0] * rkl[1] - rkj[1] * rkl[0];
+        const R rkj2 = rkj[0] * rkj[0] + rkj[1] * rkj[1] + rkj[2] * rkj[2], nrkj = mol_sqrt<R>(rkj2);
+        const R phi = mol_atan2<R>(nrkj * (rij[0] * nn[0] + rij[1] * nn[1] + rij[2] * nn[2]), mm[0] * nn[0] + mm[1] * nn[1] + mm[2] * nn[2]);
+        R sn, cs;
+        mol_sincos<R>((R)t.n * phi - (R)t.phase, &sn, &cs);
+        if (ENERGY) { if (t.role == 0) e += t.kk * (1.0 + (double)cs); }
         else {
-            const double dU = -t.kk * (double)t.n * sin((double)t.n * phi - t.phase);
-            const double m2 = mol_dot(mm, mm), n2 = mol_dot(nn, nn);
-            const double pp = mol_dot(rij, rkj) / (nrkj * nrkj), qq = mol_dot(rkl, rkj) / (nrkj * nrkj);
-            double o[3];
+            const R dU = -(R)t.kk * (R)t.n * sn;
+            const R m2 = mm[0] * mm[0] + mm[1] * mm[1] + mm[2] * mm[2], n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
+            const R pp = (rij[0] * rkj[0] + rij[1] * rkj[1] + rij[2] * rkj[2]) / rkj2, qq = (rkl[0] * rkj[0] + rkl[1] * rkj[1] + rkl[2] * rkj[2]) / rkj2;
+            const R ci = -dU * nrkj / m2, cl = dU * nrkj / n2;
+            R o[3];
             for (int c = 0; c < 3; c++) {
-                const double fi = -dU * nrkj / m2 * mm[c], fl = dU * nrkj / n2 * nn[c];
-                const double sv = pp * fi - qq * fl;
+                const R fi = ci * mm[c], fl = cl * nn[c];
+                const R sv = pp * fi - qq * fl;
                 o[c] = t.role == 0 ? fi : (t.role == 1 ? sv - fi : (t.role == 2 ? -sv - fl : fl));
             }
             fx += o[0]; fy += o[1]; fz += o[2];
         }
     }
     const unsigned mask = m.nb_mask[a];
-    const double qa = MOL_ONE_4PI_EPS0 * m.charge[a], sa = m.sigma[a], ea = m.eps[a];
+    const R qa = (R)(MOL_ONE_4PI_EPS0 * m.charge[a]), sa = (R)m.sigma[a], ea = (R)m.seps[a];
     for (int b = 0; b < m.n; b++) {
         if (!((mask >> b) & 1u)) continue;
         if (ENERGY && b < a) continue;
-        const double d[3] = {xa[0] - X[b][0], xa[1] - X[b][1], xa[2] - X[b][2]};
-        const double r2 = mol_dot(d, d), r = sqrt(r2);
-        const double qq = qa * m.charge[b], s = 0.5 * (sa + m.sigma[b]), ee = sqrt(ea * m.eps[b]);
-        const double s2 = s * s / r2, s6 = s2 * s2 * s2;
-        if (ENERGY) e += qq / r + 4.0 * ee * (s6 * s6 - s6);
-        else { const double c = (qq / r + 24.0 * ee * (2.0 * s6 * s6 - s6)) / r2; fx += c * d[0]; fy += c * d[1]; fz += c * d[2]; }
+        const R d[3] = {(R)(xa[0] - X[b][0]), (R)(xa[1] - X[b][1]), (R)(xa[2] - X[b][2])};
+        const R ir2 = (R)1 / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), ir = mol_sqrt<R>(ir2);
+        const R qq = qa * (R)m.charge[b], s = (R)0.5 * (sa + (R)m.sigma[b]), ee = ea * (R)m.seps[b];
+        const R s2 = s * s * ir2, s6 = s2 * s2 * s2;
+        if (ENERGY) e += (double)(qq * ir + (R)4 * ee * (s6 * s6 - s6));
+        else { const R c = (qq * ir + (R)24 * ee * ((R)2 * s6 * s6 - s6)) * ir2; fx += c * d[0]; fy += c * d[1]; fz += c * d[2]; }
     }
     for (int q = m.x_off[a]; q < m.x_off[a + 1]; q++) {
         const MolExc x = m.exc[q];
         if (ENERGY && x.j < a) continue;
-        const double d[3] = {xa[0] - X[x.j][0], xa[1] - X[x.j][1], xa[2] - X[x.j][2]};
-        const double r2 = mol_dot(d, d), r = sqrt(r2);
-        const double qq = MOL_ONE_4PI_EPS0 * x.qq;
-        const double s2 = x.sig * x.sig / r2, s6 = s2 * s2 * s2;
-        if (ENERGY) e += qq / r + 4.0 * x.eps * (s6 * s6 - s6);
-        else { const double c = (qq / r + 24.0 * x.eps * (2.0 * s6 * s6 - s6)) / r2; fx += c * d[0]; fy += c * d[1]; fz += c * d[2]; }
+        const R d[3] = {(R)(xa[0] - X[x.j][0]), (R)(xa[1] - X[x.j][1]), (R)(xa[2] - X[x.j][2])};
+        const R ir2 = (R)1 / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), ir = mol_sqrt<R>(ir2);
+        const R qq = (R)(MOL_ONE_4PI_EPS0 * x.qq);
+        const R s2 = (R)(x.sig * x.sig) * ir2, s6 = s2 * s2 * s2;
+        if (ENERGY) e += (double)(qq * ir + (R)4 * (R)x.eps * (s6 * s6 - s6));
+        else { const R c = (qq * ir + (R)24 * (R)x.eps * ((R)2 * s6 * s6 - s6)) * ir2; fx += c * d[0]; fy += c * d[1]; fz += c * d[2]; }
     }
-    if (!ENERGY) { f[0] = fx; f[1] = fy; f[2] = fz; }
+    if (!ENERGY) { f[0] = (double)fx; f[1] = (double)fy; f[2] = (double)fz; }
     return e;
 }
 
+// Copy the term tables into shared memory (all lanes of the warp; `buf` has room for mol_shared_bytes(m)).
+__device__ void mol_stage(const MolDev &m, unsigned char *buf, MolShared &s) {
+    const int n = m.n, lane = threadIdx.x;
+    auto put = [&](const void *src, size_t bytes) {
+        unsigned char *dst = buf;
+        for (size_t q = lane * 8; q < bytes; q += 32 * 8) *(unsigned long long *)(dst + q) = *(const unsigned long long *)((const unsigned char *)src + q);
+        buf += (bytes + 15) & ~(size_t)15;
+        return dst;
+    };
+    s.n = n;
+    const int nb = m.b_off_h[n], na = m.a_off_h[n], nt = m.t_off_h[n], nx = m.x_off_h[n];
+    s.bonds = (const MolBond *)put(m.bonds, sizeof(MolBond) * nb);
+    s.angles = (const MolAngle *)put(m.angles, sizeof(MolAngle) * na);
+    s.torsions = (const MolTorsion *)put(m.torsions, sizeof(MolTorsion) * nt);
+    s.exc = (const MolExc *)put(m.exc, sizeof(MolExc) * nx);
+    s.b_off = (const int *)put(m.b_off, sizeof(int) * (n + 2)); s.a_off = (const int *)put(m.a_off, sizeof(int) * (n + 2));
+    s.t_off = (const int *)put(m.t_off, sizeof(int) * (n + 2)); s.x_off = (const int *)put(m.x_off, sizeof(int) * (n + 2));
+    s.charge = (const double *)put(m.charge, sizeof(double) * n); s.sigma = (const double *)put(m.sigma, sizeof(double) * n);
+    s.seps = (const double *)put(m.seps, sizeof(double) * n);
+    s.nb_mask = (const unsigned *)put(m.nb_mask, sizeof(unsigned) * (n + 1));
+    __syncwarp();
+}
+
+// Constraints are solved per cluster (connected component of the constraint graph) by ONE lane.  Clusters of up to
+// MOL_MAXC constraints (a CH3 group has three) are solved as a whole: the velocity conditions are a linear system in the
+// multipliers (one solve), the position conditions are solved by Newton iterations on the same coupled system
+// (M-SHAKE: converges quadratically, 2-3 iterations where Gauss-Seidel sweeps need ~10).  Larger clusters fall back to
+// Gauss-Seidel sweeps.  Both reach the same constrained point to the tolerance (the oracle uses sweeps).
+#define MOL_MAXC 4
+
+struct MolCluster {       // one lane's cluster, in registers / local memory for the whole kernel
+    int nc;
+    int i[MOL_MAXC], j[MOL_MAXC];
+    double d2[MOL_MAXC], wi[MOL_MAXC], wj[MOL_MAXC];
+    double coup[MOL_MAXC][MOL_MAXC];   // mass coupling of constraints c and d (see mol_load_cluster)
+};
+
+__device__ __forceinline__ void mol_load_cluster(const MolDev &m, int c, MolCluster &k) {
+    const int q0 = m.c_off[c];
+    k.nc = m.c_off[c + 1] - q0;
+    // (static indices only, so that the whole record lives in registers)
+#pragma unroll
+    for (int a = 0; a < MOL_MAXC; a++) {
+        const bool on = a < k.nc && k.nc <= MOL_MAXC;
+        const MolCons s = on ? m.cons[q0 + a] : MolCons{0, 0, 1.0};
+        k.i[a] = s.i; k.j[a] = s.j; k.d2[a] = s.d * s.d;
+        k.wi[a] = on ? 1.0 / m.mass[s.i] : 0.0; k.wj[a] = on ? 1.0 / m.mass[s.j] : 0.0;
+    }
+    // a unit multiplier on constraint d moves x_i(d) by +w r_d and x_j(d) by -w r_d: its effect on the bond vector of c
+#pragma unroll
+    for (int a = 0; a < MOL_MAXC; a++)
+#pragma unroll
+        for (int b = 0; b < MOL_MAXC; b++) {
+            double v = 0.0;
+            if (k.i[a] == k.i[b]) v += k.wi[a];
+            if (k.i[a] == k.j[b]) v -= k.wi[a];
+            if (k.j[a] == k.i[b]) v -= k.wj[a];
+            if (k.j[a] == k.j[b]) v += k.wj[a];
+            k.coup[a][b] = v;
+        }
+}
+
+// solve A g = b in place (A: NC x NC, diagonally dominant here), result in b; fully unrolled: everything stays in registers
+template <int NC>
+__device__ __forceinline__ void mol_solve(double (*A)[MOL_MAXC], double *b) {
+#pragma unroll
+    for (int p = 0; p < NC; p++) {
+        const double ip = 1.0 / A[p][p];
+#pragma unroll
+        for (int r = p + 1; r < NC; r++) {
+            const double f = A[r][p] * ip;
+#pragma unroll
+            for (int c = p; c < NC; c++) A[r][c] -= f * A[p][c];
+            b[r] -= f * b[p];
+        }
+    }
+#pragma unroll
+    for (int p = NC - 1; p >= 0; p--) {
+        double v = b[p];
+#pragma unroll
+        for (int c = p + 1; c < NC; c++) v -= A[p][c] * b[c];
+        b[p] = v / A[p][p];
+    }
+}
+
+// SHAKE on a cluster of NC constraints: Newton iterations on the coupled system (M-SHAKE).
+template <int NC>
+__device__ __forceinline__ void mol_shake_n(const MolDev &m, const MolCluster &k, const double (*XO)[3], double (*X)[3]) {
+    double r0[MOL_MAXC][3];
+#pragma unroll
+    for (int a = 0; a < NC; a++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) r0[a][q] = XO[k.i[a]][q] - XO[k.j[a]][q];
+    for (int it = 0; it < 50; it++) {
+        double A[MOL_MAXC][MOL_MAXC], g[MOL_MAXC], r[MOL_MAXC][3];
+        bool done = true;
+#pragma unroll
+        for (int a = 0; a < NC; a++) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) r[a][q] = X[k.i[a]][q] - X[k.j[a]][q];
+            g[a] = k.d2[a] - mol_dot(r[a], r[a]);
+            if (fabs(g[a]) > m.tol * k.d2[a]) done = false;
+        }
+        if (done) break;
+#pragma unroll
+        for (int a = 0; a < NC; a++)
+#pragma unroll
+            for (int b = 0; b < NC; b++) A[a][b] = 2.0 * k.coup[a][b] * mol_dot(r[a], r0[b]);
+        mol_solve<NC>(A, g);
+#pragma unroll
+        for (int b = 0; b < NC; b++)
+#pragma unroll
+            for (int q = 0; q < 3; q++) { X[k.i[b]][q] += g[b] * k.wi[b] * r0[b][q]; X[k.j[b]][q] -= g[b] * k.wj[b] * r0[b][q]; }
+    }
+}
+
+// RATTLE on a cluster of NC constraints: one linear solve.
+template <int NC>
+__device__ __forceinline__ void mol_rattle_n(const MolCluster &k, const double (*X)[3], double (*V)[3]) {
+    double A[MOL_MAXC][MOL_MAXC], g[MOL_MAXC], r[MOL_MAXC][3];
+#pragma unroll
+    for (int a = 0; a < NC; a++) {
+        double dv[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) { r[a][q] = X[k.i[a]][q] - X[k.j[a]][q]; dv[q] = V[k.i[a]][q] - V[k.j[a]][q]; }
+        g[a] = mol_dot(r[a], dv);
+    }
+#pragma unroll
+    for (int a = 0; a < NC; a++)
+#pragma unroll
+        for (int b = 0; b < NC; b++) A[a][b] = k.coup[a][b] * mol_dot(r[a], r[b]);
+    mol_solve<NC>(A, g);
+#pragma unroll
+    for (int b = 0; b < NC; b++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) { V[k.i[b]][q] -= g[b] * k.wi[b] * r[b][q]; V[k.j[b]][q] += g[b] * k.wj[b] * r[b][q]; }
+}
+
 // SHAKE on one cluster: positions X moved so that its constraints have their lengths, along the bond vectors of XO.
-__device__ void mol_shake_cluster(const MolDev &m, int c, const double (*XO)[3], double (*X)[3]) {
+__device__ __forceinline__ void mol_shake_cluster(const MolDev &m, int c, const MolCluster &k, const double (*XO)[3], double (*X)[3]) {
+    switch (k.nc) {
+        case 1: mol_shake_n<1>(m, k, XO, X); return;
+        case 2: mol_shake_n<2>(m, k, XO, X); return;
+        case 3: mol_shake_n<3>(m, k, XO, X); return;
+        case 4: mol_shake_n<4>(m, k, XO, X); return;
+        default: break;
+    }
     for (int it = 0; it < 500; it++) {
         bool done = true;
         for (int q = m.c_off[c]; q < m.c_off[c + 1]; q++) {
-            const MolCons k = m.cons[q];
-            const double d2 = k.d * k.d;
+            const MolCons s = m.cons[q];
+            const double d2 = s.d * s.d;
             double r[3], r0[3];
-            for (int a = 0; a < 3; a++) { r[a] = X[k.i][a] - X[k.j][a]; r0[a] = XO[k.i][a] - XO[k.j][a]; }
+            for (int a = 0; a < 3; a++) { r[a] = X[s.i][a] - X[s.j][a]; r0[a] = XO[s.i][a] - XO[s.j][a]; }
             const double diff = d2 - mol_dot(r, r);
             if (fabs(diff) > m.tol * d2) {
                 done = false;
-                const double wi = 1.0 / m.mass[k.i], wj = 1.0 / m.mass[k.j];
+                const double wi = 1.0 / m.mass[s.i], wj = 1.0 / m.mass[s.j];
                 const double g = diff / (2.0 * (wi + wj) * mol_dot(r, r0));
-                for (int a = 0; a < 3; a++) { X[k.i][a] += g * wi * r0[a]; X[k.j][a] -= g * wj * r0[a]; }
+                for (int a = 0; a < 3; a++) { X[s.i][a] += g * wi * r0[a]; X[s.j][a] -= g * wj * r0[a]; }
             }
         }
         if (done) break;
@@ -145,19 +322,26 @@ __device__ void mol_shake_cluster(const MolDev &m, int c, const double (*XO)[3],
 }
 
 // RATTLE on one cluster: the velocity components along its constraints are removed.
-__device__ void mol_rattle_cluster(const MolDev &m, int c, const double (*X)[3], double (*V)[3]) {
+__device__ __forceinline__ void mol_rattle_cluster(const MolDev &m, int c, const MolCluster &k, const double (*X)[3], double (*V)[3]) {
+    switch (k.nc) {
+        case 1: mol_rattle_n<1>(k, X, V); return;
+        case 2: mol_rattle_n<2>(k, X, V); return;
+        case 3: mol_rattle_n<3>(k, X, V); return;
+        case 4: mol_rattle_n<4>(k, X, V); return;
+        default: break;
+    }
     for (int it = 0; it < 500; it++) {
         bool done = true;
         for (int q = m.c_off[c]; q < m.c_off[c + 1]; q++) {
-            const MolCons k = m.cons[q];
+            const MolCons s = m.cons[q];
             double r[3], dv[3];
-            for (int a = 0; a < 3; a++) { r[a] = X[k.i][a] - X[k.j][a]; dv[a] = V[k.i][a] - V[k.j][a]; }
+            for (int a = 0; a < 3; a++) { r[a] = X[s.i][a] - X[s.j][a]; dv[a] = V[s.i][a] - V[s.j][a]; }
             const double rv = mol_dot(r, dv), r2 = mol_dot(r, r);
             if (fabs(rv) > m.tol * r2) {
                 done = false;
-                const double wi = 1.0 / m.mass[k.i], wj = 1.0 / m.mass[k.j];
+                const double wi = 1.0 / m.mass[s.i], wj = 1.0 / m.mass[s.j];
                 const double g = rv / ((wi + wj) * r2);
-                for (int a = 0; a < 3; a++) { V[k.i][a] -= g * wi * r[a]; V[k.j][a] += g * wj * r[a]; }
+                for (int a = 0; a < 3; a++) { V[s.i][a] -= g * wi * r[a]; V[s.j][a] += g * wj * r[a]; }
             }
         }
         if (done) break;
@@ -176,8 +360,11 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
                                                       int reassign, double *__restrict__ pot, double *__restrict__ kin,
                                                       int *__restrict__ nan_flag, const int *__restrict__ only) {
     __shared__ double X[MOL_MAX_ATOMS][3], XO[MOL_MAX_ATOMS][3], V[MOL_MAX_ATOMS][3];
+    extern __shared__ unsigned long long mol_tab[];
     const int r = blockIdx.x, k = k0 + r, a = threadIdx.x, n = m.n;
     if (only && !only[k]) return;
+    MolShared ms;
+    mol_stage(m, (unsigned char *)mol_tab, ms);
     const bool active = a < n;
     const StateDev st = states[perm[k]];
     const double mass = active ? m.mass[a] : 1.0, sg = sqrt(st.kT / mass);
@@ -189,8 +376,11 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
             V[a][0] = sg * g.x; V[a][1] = sg * g.y; V[a][2] = sg * g.z;
         }
     }
+    MolCluster kc;
+    kc.nc = 0;
+    if (a < m.n_clusters) mol_load_cluster(m, a, kc);
     __syncwarp();
-    if (a < m.n_clusters) mol_rattle_cluster(m, a, X, V);   // incoming velocities obey the constraints
+    if (a < m.n_clusters) mol_rattle_cluster(m, a, kc, X, V);   // incoming velocities obey the constraints
     __syncwarp();
     int nV = p.nV, nR = p.nR;
     double f[3] = {0, 0, 0};
@@ -206,11 +396,11 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
         for (int q = 0; q < p.n_prog; q++) {
             const char op = p.prog[q];
             if (op == 'V') {
-                if (!f_valid) { if (active) mol_atom<false>(m, X, a, f); f_valid = true; }
+                if (!f_valid) { if (active) mol_atom<false, float>(ms, X, a, f); f_valid = true; }
                 const double h = (double)p.dt_d / nV;
                 if (active) for (int c = 0; c < 3; c++) V[a][c] += h * f[c] / mass;
                 __syncwarp();
-                if (a < m.n_clusters) mol_rattle_cluster(m, a, X, V);
+                if (a < m.n_clusters) mol_rattle_cluster(m, a, kc, X, V);
                 __syncwarp();
             } else if (op == 'R') {
                 const double h = (double)p.dt_d / nR;
@@ -218,11 +408,11 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
                 if (active) for (int c = 0; c < 3; c++) { XO[a][c] = X[a][c]; X[a][c] += h * V[a][c]; xu[c] = X[a][c]; }
                 __syncwarp();
                 if (m.n_clusters) {
-                    if (a < m.n_clusters) mol_shake_cluster(m, a, XO, X);
+                    if (a < m.n_clusters) mol_shake_cluster(m, a, kc, XO, X);
                     __syncwarp();
                     if (active) for (int c = 0; c < 3; c++) V[a][c] += (X[a][c] - xu[c]) / h;
                     __syncwarp();
-                    if (a < m.n_clusters) mol_rattle_cluster(m, a, X, V);
+                    if (a < m.n_clusters) mol_rattle_cluster(m, a, kc, X, V);
                     __syncwarp();
                 }
                 f_valid = false;
@@ -235,12 +425,12 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
                 }
                 ocount++;
                 __syncwarp();
-                if (a < m.n_clusters) mol_rattle_cluster(m, a, X, V);
+                if (a < m.n_clusters) mol_rattle_cluster(m, a, kc, X, V);
                 __syncwarp();
             }
         }
     }
-    const double U = mol_warp_sum(active ? mol_atom<true>(m, X, a, nullptr) : 0.0);
+    const double U = mol_warp_sum(active ? mol_atom<true, double>(ms, X, a, nullptr) : 0.0);
     const double KE = mol_warp_sum(active ? 0.5 * mass * (V[a][0] * V[a][0] + V[a][1] * V[a][1] + V[a][2] * V[a][2]) : 0.0);
     const bool bad = active && !(isfinite(X[a][0]) && isfinite(X[a][1]) && isfinite(X[a][2]) && isfinite(V[a][0]) &&
                                  isfinite(V[a][1]) && isfinite(V[a][2]));
@@ -255,11 +445,14 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
 __global__ void __launch_bounds__(32) k_energy_mol(MolDev m, const StateDev *__restrict__ states, int n_states,
                                                    const double *__restrict__ pos, int k0, double *__restrict__ u_out) {
     __shared__ double X[MOL_MAX_ATOMS][3];
+    extern __shared__ unsigned long long mol_tab[];
     const int r = blockIdx.x, k = k0 + r, a = threadIdx.x, n = m.n;
     const bool active = a < n;
+    MolShared ms;
+    mol_stage(m, (unsigned char *)mol_tab, ms);
     if (active) for (int c = 0; c < 3; c++) X[a][c] = pos[((size_t)r * n + a) * 3 + c];
     __syncwarp();
-    const double U = mol_warp_sum(active ? mol_atom<true>(m, X, a, nullptr) : 0.0);
+    const double U = mol_warp_sum(active ? mol_atom<true, double>(ms, X, a, nullptr) : 0.0);
     for (int l = a; l < n_states; l += 32) u_out[(size_t)k * n_states + l] = states[l].beta * (U + states[l].offset);
 }
 

@@ -67,11 +67,12 @@ def test_constrained_steps_match_the_oracle_with_the_same_noise(splitting, n_ste
         noise = device_noise(seed, it, k, 22, n_steps * nO)
         kT = KB * temps[perm[k]]
         U = oracle_run(m, xo, vo, noise, kT, dt, gamma, n_steps, splitting)
-        assert np.abs(xg[k] - xo).max() < 1e-8, (k, np.abs(xg[k] - xo).max())
+        # (the kernel evaluates forces in f32 -- as k_propagate does -- on f64 positions; energies and constraints in f64)
+        assert np.abs(xg[k] - xo).max() < 3e-7, (k, np.abs(xg[k] - xo).max())
         # (flexible bonds to hydrogen amplify rounding differences faster than the constrained system)
-        assert np.abs(vg[k] - vo).max() < (1e-6 if constraints else 2e-5), (k, np.abs(vg[k] - vo).max())
+        assert np.abs(vg[k] - vo).max() < 1e-4, (k, np.abs(vg[k] - vo).max())
         # (energies: a 1e-9 nm difference on an unconstrained 284512 kJ/mol/nm^2 bond is 1e-5 kJ/mol)
-        assert abs(pg[k] - U) < 1e-3 and abs(kg[k] - m.kinetic(vo)) < 1e-3
+        assert abs(pg[k] - U) < 2e-3 and abs(kg[k] - m.kinetic(vo)) < 2e-3
 
 
 def oracle_run(m, x, v, noise, kT, dt, gamma, n_steps, splitting):
