@@ -1063,8 +1063,10 @@ int rxi_compute_energy_rows(rx_engine *h, int *launches) {
 template <typename T>
 static int mol_upload(rx_engine *h, const std::vector<T> &v, const T **out) {
     void *d = nullptr;
-    const size_t bytes = sizeof(T) * (v.empty() ? 1 : v.size());
+    // (+16: the kernels stage these tables into shared memory in 8-byte pieces and may read up to the next multiple of 8)
+    const size_t bytes = sizeof(T) * (v.empty() ? 1 : v.size()) + 16;
     RX_CHECK_CUDA(h, cudaMalloc(&d, bytes));
+    RX_CHECK_CUDA(h, cudaMemset(d, 0, bytes));
     if (!v.empty()) RX_CHECK_CUDA(h, cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
     h->mol_allocs.push_back(d);
     *out = (const T *)d;

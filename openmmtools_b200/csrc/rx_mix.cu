@@ -133,13 +133,15 @@ __global__ void __launch_bounds__(256) k_slots_build(const uint32_t *__restrict_
 // ------------------------------------------------------------------------------------------------------
 // The speculative chain walker.  K must be a power of two <= 16384.
 //
-// CTA = 2 warps.  Warp 1 streams the slot records from global memory into a shared-memory ring far ahead of the
-// walker (the records come from DRAM: written once by k_slots_build, read once).  Warp 0 walks: per round it
-// (1) reads 32 records from the ring, (2) looks up the current states of both replicas, (3) fetches u[i,sj], u[j,si]
-// and the maintained diagonal d[k] = u[k, perm[k]], (4) evaluates log_p and the accept test, (5) resolves the
-// visited chain and staleness with ballots and bit tricks, (6) commits the valid prefix: permutation + diagonal
+// One warp walks (a second one only helps with the prologue).  The slot records come from DRAM (written once by the
+// pre-pass, read once) into a 1024-slot shared-memory ring by cp.async that the walker issues itself, 512 slots ahead.
+// Per round the warp (1) reads 32 records from the ring, (2) looks up the current states of both replicas, (3) fetches
+// u[i,sj], u[j,si] and the maintained diagonal d[k] = u[k, perm[k]], (4) evaluates log_p and the accept test, (5) resolves
+// the visited chain and staleness with ballots and bit tricks, (6) commits the valid prefix: permutation + diagonal
 // in shared memory and ONE coalesced store of packed (si, sj, accepted) entries into a commit log (the count
 // matrices are built from the log afterwards by k_mix_count, in parallel).
+// (Round 1 had a producer warp and a ring synchronised by fences and volatile flags; the single warp with hardware-tracked
+// copies is racecheck-clean and costs ~6 more instructions per round.)
 //
 // Where the energies live (UMODE):
 //   U_FILTER24   the default for K <= 256 (at K = 256 the 512 KB of f64 do not fit; at smaller K the f32 filter is
@@ -178,17 +180,15 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
                                                       const unsigned char *__restrict__ filt,
                                                       const double *__restrict__ filt_rowabs, MixCtl *ctl) {
     extern __shared__ double s_mix[];
-    __shared__ WalkShared sh;
-    // layout: ring_lu[RING] f64 | diag[K] f64 | (u f64 [K*K]) | ring_ij[RING] u32 | ring_bm[RING] u32 | perm[K] i32 | (image: u16[K*K] + u8[K*K])
-    double *ring_lu = s_mix;
-    double *s_diag = ring_lu + RING;
+    // layout: ring[RING] 16-byte records | diag[K] f64 | (rowabs[K]) | (u f64 [K*K]) | perm[K] i32 | (image: u16[K*K] + u8[K*K])
+    uint4 *s_ring = (uint4 *)s_mix;
+    double *s_diag = s_mix + 2 * RING;
     double *s_rowabs = s_diag + K;                                   // [K] |row minimum| (U_FILTER24 only)
     double *s_u = s_rowabs + (UMODE == U_FILTER24 ? K : 0);
-    uint32_t *ring_ij = (uint32_t *)(s_u + (UMODE == U_F64_SMEM ? (size_t)K * K : 0));
-    uint32_t *ring_bm = ring_ij + RING;
-    int *s_perm = (int *)(ring_bm + RING);
+    int *s_perm = (int *)(s_u + (UMODE == U_F64_SMEM ? (size_t)K * K : 0));
     unsigned char *s_q = (unsigned char *)(s_perm + K);   // 24-bit image: int16 high plane [K*K] then uint8 low plane [K*K]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (the warp index through a shuffle: warp-uniform for the compiler, see k_mix_walk2)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     for (int q = tid; q < K; q += 64) {
         const int st = perm_g[q];
         s_perm[q] = st;
@@ -204,51 +204,29 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         for (int q = tid; q < (3 * K * K) / 4; q += 64) dst[q] = src[q];
     }
     const unsigned head0 = (unsigned)ctl->head;
-    if (tid == 0) { sh.prod = head0; sh.head = head0; sh.done = 0; }
     __syncthreads();
+    if (warp != 0) return;   // (the second warp only helps with the prologue)
 
-    if (warp == 1) {
-        // ---------------- producer: keep the ring filled up to head + RING - 64
-        unsigned prod = head0;
-        while (!sh.done) {
-            const unsigned head = sh.head;
-            unsigned limit = head + RING - 64;   // `head` may lag the walker by 8 rounds; it only ever lags (safe)
-            if (limit > nslots) limit = nslots;
-            if (prod < limit) {
-                __threadfence_block();   // acquire: the walker is done with the entries below `head`
-                SlotRec r[4];
-                unsigned cnt = limit - prod;
-                if (cnt > 128) cnt = 128;
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const unsigned o = b * 32 + lane;
-                    if (o < cnt) r[b] = rec[prod + o];
-                }
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const unsigned o = b * 32 + lane;
-                    if (o < cnt) {
-                        const unsigned w = (prod + o) & (RING - 1);
-                        ring_ij[w] = r[b].ij; ring_bm[w] = r[b].backmask;
-                        if (REC2) {
-                            // SlotRec2: the third word is the f32 log-uniform of the NEXT slot, whose ring entry it is
-                            const uint4 q = *(const uint4 *)&r[b];
-                            ((float *)ring_lu)[(w + 1) & (RING - 1)] = __uint_as_float(q.z);
-                        }
-                        else if (UMODE == U_FILTER24) ((float *)ring_lu)[w] = (float)r[b].logU;   // the filter works in f32
-                        else ring_lu[w] = r[b].logU;
-                    }
-                }
-                prod += cnt;
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) sh.prod = prod;
-            } else {
-                __nanosleep(40);
-            }
+    // The records come into the ring by cp.async issued by the walker itself, 640 slots ahead, topped up every 8 rounds;
+    // completion is tracked by the hardware (cp.async.wait_group), the warp barrier at the end of a round makes the data
+    // visible to all lanes.  No second warp,
+    // no flags, no fences: nothing for racecheck to find.
+    // (32-bit shared address through a shuffle: it then lives in a register instead of being re-derived from SR_CgaCtaId
+    // every round)
+    const unsigned ring_addr = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)s_ring), 0);
+    const uint4 *recs = (const uint4 *)rec;
+    unsigned filled = head0;
+    auto refill = [&](unsigned h_now) {
+        while (filled < h_now + 640u && filled < nslots) {
+            if (filled + (unsigned)lane < nslots)
+                w2_cp_async16(ring_addr + (((filled + (unsigned)lane) & (RING - 1)) << 4), recs + (filled + lane));
+            filled += 32u;
         }
-        return;
-    }
+        w2_cp_async_commit();
+    };
+    refill(head0);
+    w2_cp_async_wait<0>();
+    __syncwarp();
 
     // ---------------- walker (warp 0).  The loop is latency bound (one warp, one dependent chain per round), so it is
     // written for a short instruction stream: 32-bit indices, cached producer position, head published every 8 rounds.
@@ -256,22 +234,25 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
     const long long remaining0 = ctl->remaining;
     unsigned rem = remaining0 > 0x7fffffffLL ? 0x7fffffffu : (unsigned)remaining0;   // attempts this launch may still do
     const unsigned rem0 = rem;
-    unsigned logpos = (unsigned)ctl->log_count, rounds = 0, slow = 0, prod_seen = head0;   // the log continues where k_mix_walk2 stopped
+    unsigned logpos = (unsigned)ctl->log_count, rounds = 0, slow = 0;   // the log continues where k_mix_walk2 stopped
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned sh_amt = 32u - (unsigned)lane;
     const unsigned short *s_qhi = (const unsigned short *)s_q;            // [K*K] sign, exponent, 7 mantissa bits
     const unsigned char *s_qlo = s_q + 2 * (size_t)K * K;                  // [K*K] next 8 mantissa bits
-    // (through a shuffle so that it stays in a register instead of being re-derived from SR_CgaCtaId every round)
-    const unsigned a_head = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared((const void *)&sh.head), 0);
     unsigned wpos = (h + (unsigned)lane) & (RING - 1);   // this lane's ring slot
     // One round.  TAIL = the launch's attempt budget may end inside the window (checked only in the last rounds).
     auto round = [&](auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
         rounds++;
         const unsigned w = wpos;   // (h + lane) & (RING - 1), carried from round to round
-        const uint32_t ij = ring_ij[w], backmask = ring_bm[w];
-        // the uniform an attempt here would draw belongs to the NEXT slot
-        const double logU_next = (UMODE == U_FILTER24) ? 0.0 : ring_lu[(w + 1) & (RING - 1)];
+        const uint4 rq = w2_lds128(ring_addr + (w << 4));
+        const uint32_t ij = rq.x, backmask = rq.y;
+        // the uniform an attempt here would draw belongs to the NEXT slot (SlotRec: its f64 logU is words z, w of the record)
+        double logU_next = 0.0;
+        if (UMODE != U_FILTER24 || !REC2) {
+            const uint2 lw = w2_lds64(ring_addr + (((w + 1) & (RING - 1)) << 4) + 8u);
+            logU_next = __hiloint2double((int)lw.y, (int)lw.x);
+        }
         const unsigned i = ij & 0xffffu, j = ij >> 16;
         const int si = s_perm[i], sj = s_perm[j];
         const unsigned a_ij = (i << logK) | (unsigned)sj, a_ji = (j << logK) | (unsigned)si;
@@ -294,7 +275,8 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             // 1.6e-14 mag is inside the slack of 3.2e-5
             const float eps = fmaf(mag, 3.2e-5f, (((const float *)s_rowabs)[i] + ((const float *)s_rowabs)[j]) + 1e-9f);
             // log of the uniform, rounded to f32 by the producer: |lu - logU| <= 2^-24 |lu|; d carries one more rounding
-            const float lu = ((const float *)ring_lu)[(w + 1) & (RING - 1)];
+            // (SlotRec2: the f32 log-uniform of the next slot is the third word of this slot's own record)
+            const float lu = REC2 ? __uint_as_float(rq.z) : (float)logU_next;
             const float d = lp - lu;
             const float mar = fmaf(fabsf(lp) + fabsf(lu), 1.3e-7f, eps);
             // |lp| > eps decides the sign of log_p, |d| > mar decides the comparison with the uniform (NaN: undecided)
@@ -392,29 +374,20 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
         h += advance;
         wpos = (wpos + advance) & (RING - 1);
         rem -= n;
+        // every 8 rounds (at most 264 slots): top the ring up to 640 slots ahead and wait for all copies but the ones just
+        // issued -- what the next 8 rounds read (< h + 298) was issued at the previous top-up or earlier (>= h + 376 then)
+        if ((rounds & 7u) == 0u) { refill(h); w2_cp_async_wait<1>(); }
         __syncwarp();
-        // release: every lane's ring reads of this and earlier rounds (ordered before lane 0 by the warp barrier) precede
-        // the new head, behind which the producer may overwrite
-        if ((rounds & 7u) == 0u && lane == 0) {
-            __threadfence_block();
-            asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a_head), "r"(h) : "memory");
-        }
     };
     while (rem > 0 && h + 33 <= nslots) {
-        if (prod_seen < h + 33) {
-            do { prod_seen = sh.prod; } while (prod_seen < h + 33);   // the producer is behind (start of a pass)
-            __threadfence_block();   // acquire: the records below the position just read are visible
-        }
         if (rem >= 33) {
-            // main loop: a round commits at most 32 attempts, so the budget cannot end inside it, and the slots
-            // [h, prod_seen) are in the ring: one loop condition covers the producer, the budget and the end of the pass
-            // rem >= 33 and h + 33 <= prod_seen in one signed test (all values are far below 2^31)
-            do { round(std::false_type()); } while ((int)((rem - 33u) | (prod_seen - 33u - h)) >= 0);
+            // main loop: a round commits at most 32 attempts, so the budget cannot end inside it
+            do { round(std::false_type()); } while (rem >= 33u && h + 33u <= nslots);
         } else {
             round(std::true_type());
         }
     }
-    if (lane == 0) sh.done = 1;
+    w2_cp_async_wait<0>();
     for (int q = lane; q < K; q += 32) perm_g[q] = s_perm[q];
     slow = __reduce_add_sync(0xffffffffu, slow);
     if (lane == 0) {
