@@ -989,7 +989,13 @@ __global__ void __launch_bounds__(1024) k_minimize(DynParams p, const float4 *__
 
 int rxi_minimize(rx_engine *h, double tolerance, int max_iterations, double *d_rms, int *d_iters) {
     if (h->kloc == 0) return RX_OK;
-    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_minimize: not provided for molecules");
+    if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {
+        const MolDev *m = (const MolDev *)h->mol_dev;
+        k_minimize_mol<<<h->kloc, 32, m->shared_bytes, h->stream>>>(*m, (double *)h->d_pos, h->k0, tolerance,
+                                                                   max_iterations > 0 ? max_iterations : 100000, d_rms, d_iters);
+        RX_CHECK_CUDA(h, cudaGetLastError());
+        return RX_OK;
+    }
     DynParams p;
     fill_dyn(h, p);
     const int N = h->cfg.n_atoms;

@@ -440,6 +440,82 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
         for (int c = 0; c < 3; c++) { pos[((size_t)r * n + a) * 3 + c] = X[a][c]; vel[((size_t)r * n + a) * 3 + c] = V[a][c]; }
 }
 
+// MultiStateSampler.minimize (multistatesampler.py:611-647) for a molecule: FIRE descent on the constraint manifold.  The
+// force is projected onto the manifold (components along the constrained bonds removed: the RATTLE solve with unit
+// weights), the move is followed by SHAKE, the FIRE velocity is kept tangent.  Converged when the RMS of the projected force
+// falls below tol_rms (kJ/mol/nm); f64 throughout.  (OpenMM's L-BFGS is not reproduced, as for the other systems.)
+__global__ void __launch_bounds__(32) k_minimize_mol(MolDev m, double *__restrict__ pos, int k0, double tol_rms, int max_iter,
+                                                     double *__restrict__ rms_out, int *__restrict__ iters_out) {
+    __shared__ double X[MOL_MAX_ATOMS][3], XO[MOL_MAX_ATOMS][3], V[MOL_MAX_ATOMS][3], F[MOL_MAX_ATOMS][3];
+    extern __shared__ unsigned long long mol_tab[];
+    const int r = blockIdx.x, k = k0 + r, a = threadIdx.x, n = m.n;
+    const bool active = a < n;
+    MolShared ms;
+    mol_stage(m, (unsigned char *)mol_tab, ms);
+    MolCluster kc, ku;   // the cluster with its masses (SHAKE) and with unit weights (projections)
+    kc.nc = ku.nc = 0;
+    if (a < m.n_clusters) {
+        mol_load_cluster(m, a, kc);
+        ku = kc;
+#pragma unroll
+        for (int c = 0; c < MOL_MAXC; c++) { const bool on = c < ku.nc; ku.wi[c] = on ? 1.0 : 0.0; ku.wj[c] = on ? 1.0 : 0.0; }
+#pragma unroll
+        for (int c = 0; c < MOL_MAXC; c++)
+#pragma unroll
+            for (int d = 0; d < MOL_MAXC; d++) {
+                double v = 0.0;
+                if (ku.i[c] == ku.i[d]) v += ku.wi[c];
+                if (ku.i[c] == ku.j[d]) v -= ku.wi[c];
+                if (ku.j[c] == ku.i[d]) v -= ku.wj[c];
+                if (ku.j[c] == ku.j[d]) v += ku.wj[c];
+                ku.coup[c][d] = v;
+            }
+    }
+    if (active) for (int c = 0; c < 3; c++) { X[a][c] = pos[((size_t)r * n + a) * 3 + c]; V[a][c] = 0.0; }
+    __syncwarp();
+    const double dt0 = 0.001, dt_max = 0.010, alpha0 = 0.1, max_move = 0.01;   // (as k_minimize)
+    double dt = dt0, alpha = alpha0, rms = 0.0;
+    int n_pos = 0, it = 0;
+    for (;; it++) {
+        double f[3] = {0, 0, 0};
+        if (active) mol_atom<false, double>(ms, X, a, f);
+        if (active) for (int c = 0; c < 3; c++) F[a][c] = f[c];
+        __syncwarp();
+        if (a < m.n_clusters && ku.nc <= MOL_MAXC) mol_rattle_cluster(m, a, ku, X, F);   // projected force
+        __syncwarp();
+        if (active) for (int c = 0; c < 3; c++) f[c] = F[a][c];
+        const double FF = mol_warp_sum(active ? f[0] * f[0] + f[1] * f[1] + f[2] * f[2] : 0.0);
+        rms = sqrt(FF / (3.0 * n));
+        if (!(rms > tol_rms) || it >= max_iter) break;   // converged, out of iterations, or NaN
+        double v[3] = {active ? V[a][0] : 0.0, active ? V[a][1] : 0.0, active ? V[a][2] : 0.0};
+        const double P = mol_warp_sum(f[0] * v[0] + f[1] * v[1] + f[2] * v[2]);
+        const double VV = mol_warp_sum(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (P > 0.0) {
+            const double mix = alpha * sqrt(VV / fmax(FF, 1e-300));
+            for (int c = 0; c < 3; c++) v[c] = (1.0 - alpha) * v[c] + mix * f[c];
+            if (++n_pos > 5) { dt = fmin(dt * 1.1, dt_max); alpha *= 0.99; }
+        } else {
+            v[0] = v[1] = v[2] = 0.0; dt *= 0.5; alpha = alpha0; n_pos = 0;
+        }
+        const double inv_m = active ? 1.0 / m.mass[a] : 0.0;
+        for (int c = 0; c < 3; c++) v[c] += dt * f[c] * inv_m;
+        double mv[3] = {dt * v[0], dt * v[1], dt * v[2]};
+        const double m2 = mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2];
+        if (m2 > max_move * max_move) {   // displacement cap: rescale this atom's velocity
+            const double sc = max_move / sqrt(m2);
+            for (int c = 0; c < 3; c++) { v[c] *= sc; mv[c] *= sc; }
+        }
+        if (active) for (int c = 0; c < 3; c++) { XO[a][c] = X[a][c]; X[a][c] += mv[c]; V[a][c] = v[c]; }
+        __syncwarp();
+        if (a < m.n_clusters) mol_shake_cluster(m, a, kc, XO, X);
+        __syncwarp();
+        if (a < m.n_clusters && ku.nc <= MOL_MAXC) mol_rattle_cluster(m, a, ku, X, V);   // velocity stays tangent
+        __syncwarp();
+    }
+    if (a == 0) { rms_out[k] = rms; iters_out[k] = it; }
+    if (active) for (int c = 0; c < 3; c++) pos[((size_t)r * n + a) * 3 + c] = X[a][c];
+}
+
 // u[k][l] = beta_l (U(x_k) + offset_l): the states of a molecule differ in temperature only (parallel tempering,
 // paralleltempering.py:175-237: one potential evaluation per replica, scaled by beta_l).
 __global__ void __launch_bounds__(32) k_energy_mol(MolDev m, const StateDev *__restrict__ states, int n_states,

@@ -128,3 +128,27 @@ def test_parallel_tempering_on_alanine_dipeptide():
         U = m.energy(xk)
         assert np.abs(u[k] - U / (KB * T)).max() < 1e-8 * max(1.0, abs(U))
     assert sorted(s._replica_thermodynamic_states.tolist()) == list(range(12))
+
+
+def test_minimize_descends_on_the_constraint_manifold():
+    """sampler.minimize() (multistatesampler.py:611-647) on the molecule: the energy goes down, the projected force falls
+    below the tolerance, the constrained bonds keep their lengths."""
+    from oracle import oracle
+    from openmmtools_b200 import states, mcmc, multistate
+    a, x = aladip()
+    m = oracle.Molecule(a.system)
+    ts = states.ThermodynamicState(a.system, 300.0 * unit.kelvin)
+    s = multistate.ParallelTemperingSampler(mcmc_moves=mcmc.LangevinSplittingDynamicsMove(n_steps=10), number_of_iterations=1, seed=2)
+    s.create(ts, [states.SamplerState(a.positions)], storage=None, min_temperature=300.0 * unit.kelvin,
+             max_temperature=400.0 * unit.kelvin, n_temperatures=4)
+    s.run()                                    # thermal configurations
+    before = [m.energy(np.ascontiguousarray(st.positions.value_in_unit(unit.nanometer), np.float64)) for st in s.sampler_states]
+    s.minimize(tolerance=5.0 * unit.kilojoules_per_mole / unit.nanometers, max_iterations=5000)
+    c = a.system.constraints
+    i, j = c[:, 0].astype(int), c[:, 1].astype(int)
+    for k, st in enumerate(s.sampler_states):
+        xk = np.ascontiguousarray(st.positions.value_in_unit(unit.nanometer), np.float64)
+        assert m.energy(xk) < before[k] - 1.0
+        assert np.abs(np.linalg.norm(xk[i] - xk[j], axis=1) - c[:, 2]).max() < 1e-8
+    assert np.all(s._last_minimization['rms_force'] <= 5.0)
+    assert np.all(s._last_minimization['iterations'] > 0)
