@@ -152,3 +152,30 @@ def test_minimize_descends_on_the_constraint_manifold():
         assert np.abs(np.linalg.norm(xk[i] - xk[j], axis=1) - c[:, 2]).max() < 1e-8
     assert np.all(s._last_minimization['rms_force'] <= 5.0)
     assert np.all(s._last_minimization['iterations'] > 0)
+
+
+def test_nan_restart_on_a_molecule_retries_only_the_failed_replica():
+    """The restart policy (mcmc.py:706-759) with the molecule's f64 state: the replica that went NaN restarts from the
+    device-side snapshot, the others keep their result."""
+    from openmmtools_b200 import states, mcmc, multistate
+    from openmmtools_b200.multistate.utils import SimulationNaNError
+    a, x = aladip()
+    def sampler():
+        ts = states.ThermodynamicState(a.system, 300.0 * unit.kelvin)
+        s = multistate.ParallelTemperingSampler(mcmc_moves=mcmc.LangevinSplittingDynamicsMove(n_steps=50), number_of_iterations=100,
+                                                seed=12, replica_mixing_scheme=None)
+        s.create(ts, [states.SamplerState(a.positions)], storage=None, min_temperature=300.0 * unit.kelvin,
+                 max_temperature=500.0 * unit.kelvin, n_temperatures=6)
+        return s
+    clean, sick = sampler(), sampler()
+    clean.run(3)
+    sick.run(2)
+    v = sick._engine.get_velocities()
+    v[2] = np.nan       # (f64 state: absurd but finite velocities would not overflow)
+    sick._engine.set_velocities(v[2:3], first=2)
+    with pytest.raises(SimulationNaNError):
+        sick.run(1)
+    xs, xc = sick._engine.get_positions(), clean._engine.get_positions()
+    for k in range(6):
+        if k != 2:
+            assert np.array_equal(xs[k], xc[k]), k
