@@ -763,7 +763,7 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {
         if (!h->state_moves.empty()) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: per-state moves are not provided for molecules");
         const uint2 mkey = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
-        k_propagate_mol<<<h->kloc, 32, ((const MolDev *)h->mol_dev)->shared_bytes, h->stream>>>(*(const MolDev *)h->mol_dev, p, (const StateDev *)h->d_states, (const int *)h->d_perm,
+        k_propagate_mol<<<h->kloc, 32, ((const MolDev *)h->mol_dev)->dyn_shared_bytes, h->stream>>>(*(const MolDev *)h->mol_dev, p, (const StateDev *)h->d_states, (const int *)h->d_perm,
                                                       (double *)h->d_pos, (double *)h->d_vel, h->k0, mkey, (uint32_t)iteration, reassign,
                                                       h->d_pot, h->d_kin, h->d_nan, d_only);
         RX_CHECK_CUDA(h, cudaGetLastError());
@@ -1170,6 +1170,80 @@ int rxi_set_molecule(rx_engine *h, const rx_molecule *mol) {
     }
     m->n = n; m->n_clusters = (int)cl.size(); m->remove_cm = mol->remove_cm_motion ? 1 : 0;
     m->tol = mol->constraint_tolerance > 0 ? mol->constraint_tolerance : 1e-8;   // integrators.py constraint_tolerance default
+    // ---- term tables of the dynamics (each term once) and the slots of their force contributions: atom by atom, in the
+    // order bonds, angles, torsions, pairs, each in list order
+    {
+        struct Contrib { int kind, term, role; };
+        std::vector<std::vector<Contrib>> per_atom(n);
+        std::vector<TBond> tb((size_t)mol->n_bonds);
+        std::vector<TAngle> tang((size_t)mol->n_angles);
+        std::vector<TTors> tt((size_t)mol->n_torsions);
+        std::vector<TPair> tp;
+        for (int b = 0; b < mol->n_bonds; b++) {
+            const double *q = mol->bonds + 4 * b;
+            tb[b] = TBond{(short)q[0], (short)q[1], 0, 0, (float)q[2], (float)q[3]};
+            per_atom[(int)q[0]].push_back({0, b, 0}); per_atom[(int)q[1]].push_back({0, b, 1});
+        }
+        for (int a = 0; a < mol->n_angles; a++) {
+            const double *q = mol->angles + 5 * a;
+            tang[a] = TAngle{(short)q[0], (short)q[1], (short)q[2], 0, 0, 0, (float)q[3], (float)q[4]};
+            for (int r = 0; r < 3; r++) per_atom[(int)q[r]].push_back({1, a, r});
+        }
+        for (int t = 0; t < mol->n_torsions; t++) {
+            const double *q = mol->torsions + 7 * t;
+            tt[t] = TTors{(short)q[0], (short)q[1], (short)q[2], (short)q[3], 0, 0, 0, 0, (float)q[4], (float)q[5], (float)q[6]};
+            for (int r = 0; r < 4; r++) per_atom[(int)q[r]].push_back({2, t, r});
+        }
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++)
+                if ((mask[i] >> j) & 1u) {
+                    tp.push_back(TPair{(short)i, (short)j, 0, 0, (float)(MOL_ONE_4PI_EPS0 * charge[i] * charge[j]),
+                                       (float)(0.5 * (sigma[i] + sigma[j])), (float)sqrt(eps[i] * eps[j])});
+                    per_atom[i].push_back({3, (int)tp.size() - 1, 0}); per_atom[j].push_back({3, (int)tp.size() - 1, 1});
+                }
+        for (int e = 0; e < mol->n_exceptions; e++) {
+            const double *q = mol->exceptions + 5 * e;
+            tp.push_back(TPair{(short)q[0], (short)q[1], 0, 0, (float)(MOL_ONE_4PI_EPS0 * q[2]), (float)q[3], (float)q[4]});
+            per_atom[(int)q[0]].push_back({3, (int)tp.size() - 1, 0}); per_atom[(int)q[1]].push_back({3, (int)tp.size() - 1, 1});
+        }
+        std::vector<int> goff(1, 0);
+        int slot = 0;
+        for (int i = 0; i < n; i++) {
+            for (const Contrib &c : per_atom[i]) {
+                short *dst = nullptr;
+                if (c.kind == 0) dst = c.role == 0 ? &tb[c.term].si : &tb[c.term].sj;
+                else if (c.kind == 1) dst = c.role == 0 ? &tang[c.term].si : (c.role == 1 ? &tang[c.term].sj : &tang[c.term].sk);
+                else if (c.kind == 2) dst = c.role == 0 ? &tt[c.term].si : (c.role == 1 ? &tt[c.term].sj : (c.role == 2 ? &tt[c.term].sk : &tt[c.term].sl));
+                else dst = c.role == 0 ? &tp[c.term].si : &tp[c.term].sj;
+                *dst = (short)slot++;
+            }
+            goff.push_back(slot);
+        }
+        goff.push_back(slot);   // (padding to an even count)
+        auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
+        MolTerms hd;
+        memset(&hd, 0, sizeof(hd));
+        size_t off = up(sizeof(MolTerms));
+        hd.o_bond = (int)off; off += up(sizeof(TBond) * tb.size());
+        hd.o_angle = (int)off; off += up(sizeof(TAngle) * tang.size());
+        hd.o_tors = (int)off; off += up(sizeof(TTors) * tt.size());
+        hd.o_pair = (int)off; off += up(sizeof(TPair) * tp.size());
+        hd.o_goff = (int)off; off += up(sizeof(int) * goff.size());
+        std::vector<unsigned char> blob(off, 0);
+        memcpy(blob.data(), &hd, sizeof(hd));
+        if (!tb.empty()) memcpy(blob.data() + hd.o_bond, tb.data(), sizeof(TBond) * tb.size());
+        if (!tang.empty()) memcpy(blob.data() + hd.o_angle, tang.data(), sizeof(TAngle) * tang.size());
+        if (!tt.empty()) memcpy(blob.data() + hd.o_tors, tt.data(), sizeof(TTors) * tt.size());
+        if (!tp.empty()) memcpy(blob.data() + hd.o_pair, tp.data(), sizeof(TPair) * tp.size());
+        memcpy(blob.data() + hd.o_goff, goff.data(), sizeof(int) * goff.size());
+        const unsigned char *d_blob = nullptr;
+        int rcb = mol_upload(h, blob, &d_blob);
+        if (rcb) return rcb;
+        m->terms = (const MolTerms *)d_blob;
+        m->terms_bytes = (int)off;
+        m->n_tb = (int)tb.size(); m->n_ta = (int)tang.size(); m->n_tt = (int)tt.size(); m->n_tp = (int)tp.size(); m->n_slots = slot;
+        m->dyn_shared_bytes = m->shared_bytes + (int)up(off) + (int)up(sizeof(float) * 3 * (size_t)(slot > 0 ? slot : 1));
+    }
     int rc = 0;
     if ((rc = mol_upload(h, mass, &m->mass)) || (rc = mol_upload(h, charge, &m->charge)) || (rc = mol_upload(h, sigma, &m->sigma)) ||
         (rc = mol_upload(h, eps, &m->eps)) || (rc = mol_upload(h, seps, &m->seps)) || (rc = mol_upload(h, b_off, &m->b_off)) || (rc = mol_upload(h, a_off, &m->a_off)) ||

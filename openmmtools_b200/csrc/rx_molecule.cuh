@@ -24,6 +24,18 @@ struct MolTorsion { int i, j, k, l, n, role; double phase, kk; };
 struct MolExc { int j, pad; double qq, sig, eps; };
 struct MolCons { int i, j; double d; };
 
+// Term tables of the dynamics' force evaluation: every bond / angle / torsion / interacting pair is evaluated ONCE, by
+// whichever lane its index falls to (t = lane, lane + 32, ...), in f32; its contributions go to fixed slots of a shared-memory
+// array and every atom then adds up ITS slots in slot order -- no atomics, the same bits every run.  (The per-atom
+// evaluation of mol_atom() runs each angle three and each torsion four times, with loops of unequal length per lane.)
+struct TBond { short i, j, si, sj; float K, r0; };
+struct TAngle { short i, j, k, si, sj, sk; float K, t0; };
+struct TTors { short i, j, k, l, si, sj, sk, sl; float n, phase, kk; };
+struct TPair { short i, j, si, sj; float qq, sig, eps; };   // qq = 138.935456 q_i q_j (exceptions: their own values)
+struct MolTerms {      // one contiguous blob: header, then the arrays (offsets in bytes from the blob's start)
+    int o_bond, o_angle, o_tors, o_pair, o_goff, pad[3];
+};
+
 struct MolDev {
     int n, n_clusters, remove_cm, pad;
     double tol;
@@ -37,6 +49,9 @@ struct MolDev {
     const MolExc *exc;
     const MolCons *cons;
     const unsigned *nb_mask;     // bit b of nb_mask[a]: the pair (a, b) has the plain Coulomb + LJ interaction
+    // term-parallel force evaluation of the dynamics (one entry per TERM, see mol_forces_terms)
+    const struct MolTerms *terms;
+    int terms_bytes, n_tb, n_ta, n_tt, n_tp, n_slots, dyn_shared_bytes;
 };
 
 __device__ __forceinline__ void mol_cross(const double *a, const double *b, double *c) {
@@ -153,6 +168,65 @@ __device__ double mol_atom(const MolShared &m, const double (*X)[3], int a, doub
     }
     if (!ENERGY) { f[0] = (double)fx; f[1] = (double)fy; f[2] = (double)fz; }
     return e;
+}
+
+// All terms, each once (see MolTerms).  FS: float[n_slots][3] in shared memory.
+__device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned char *tb, const double (*X)[3], float (*FS)[3]) {
+    const MolTerms *h = (const MolTerms *)tb;
+    const int lane = threadIdx.x;
+    const TBond *B = (const TBond *)(tb + h->o_bond);
+    for (int t = lane; t < m.n_tb; t += 32) {
+        const TBond b = B[t];
+        const float d[3] = {(float)(X[b.i][0] - X[b.j][0]), (float)(X[b.i][1] - X[b.j][1]), (float)(X[b.i][2] - X[b.j][2])};
+        const float r = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const float c = -b.K * (r - b.r0) / r;
+        for (int q = 0; q < 3; q++) { FS[b.si][q] = c * d[q]; FS[b.sj][q] = -c * d[q]; }
+    }
+    const TAngle *A = (const TAngle *)(tb + h->o_angle);
+    for (int t = lane; t < m.n_ta; t += 32) {
+        const TAngle g = A[t];
+        float u[3], v[3];
+        for (int c = 0; c < 3; c++) { u[c] = (float)(X[g.i][c] - X[g.j][c]); v[c] = (float)(X[g.k][c] - X[g.j][c]); }
+        const float ru2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], rv2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        const float iruv = rsqrtf(ru2 * rv2);
+        float cs = (u[0] * v[0] + u[1] * v[1] + u[2] * v[2]) * iruv;
+        cs = fminf(1.f, fmaxf(-1.f, cs));
+        const float dt = acosf(cs) - g.t0, sn = sqrtf(1.f - cs * cs);
+        const float gg = (sn > 1e-6f) ? g.K * dt / sn : 0.f;
+        for (int c = 0; c < 3; c++) {
+            const float fi = gg * (v[c] * iruv - cs * u[c] / ru2), fk = gg * (u[c] * iruv - cs * v[c] / rv2);
+            FS[g.si][c] = fi; FS[g.sk][c] = fk; FS[g.sj][c] = -(fi + fk);
+        }
+    }
+    const TTors *T = (const TTors *)(tb + h->o_tors);
+    for (int t = lane; t < m.n_tt; t += 32) {
+        const TTors w = T[t];
+        float rij[3], rkj[3], rkl[3], mm[3], nn[3];
+        for (int c = 0; c < 3; c++) { rij[c] = (float)(X[w.i][c] - X[w.j][c]); rkj[c] = (float)(X[w.k][c] - X[w.j][c]); rkl[c] = (float)(X[w.k][c] - X[w.l][c]); }
+        mm[0] = rij[1] * rkj[2] - rij[2] * rkj[1]; mm[1] = rij[2] * rkj[0] - rij[0] * rkj[2]; mm[2] = rij[0] * rkj[1] - rij[1] * rkj[0];
+        nn[0] = rkj[1] * rkl[2] - rkj[2] * rkl[1]; nn[1] = rkj[2] * rkl[0] - rkj[0] * rkl[2]; nn[2] = rkj[0] * rkl[1] - rkj[1] * rkl[0];
+        const float rkj2 = rkj[0] * rkj[0] + rkj[1] * rkj[1] + rkj[2] * rkj[2], nrkj = sqrtf(rkj2);
+        const float phi = atan2f(nrkj * (rij[0] * nn[0] + rij[1] * nn[1] + rij[2] * nn[2]), mm[0] * nn[0] + mm[1] * nn[1] + mm[2] * nn[2]);
+        float sn, cs;
+        sincosf(w.n * phi - w.phase, &sn, &cs);
+        const float dU = -w.kk * w.n * sn;
+        const float m2 = mm[0] * mm[0] + mm[1] * mm[1] + mm[2] * mm[2], n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
+        const float pp = (rij[0] * rkj[0] + rij[1] * rkj[1] + rij[2] * rkj[2]) / rkj2, qq = (rkl[0] * rkj[0] + rkl[1] * rkj[1] + rkl[2] * rkj[2]) / rkj2;
+        const float ci = -dU * nrkj / m2, cl = dU * nrkj / n2;
+        for (int c = 0; c < 3; c++) {
+            const float fi = ci * mm[c], fl = cl * nn[c], sv = pp * fi - qq * fl;
+            FS[w.si][c] = fi; FS[w.sj][c] = sv - fi; FS[w.sk][c] = -sv - fl; FS[w.sl][c] = fl;
+        }
+    }
+    const TPair *P = (const TPair *)(tb + h->o_pair);
+    for (int t = lane; t < m.n_tp; t += 32) {
+        const TPair p = P[t];
+        const float d[3] = {(float)(X[p.i][0] - X[p.j][0]), (float)(X[p.i][1] - X[p.j][1]), (float)(X[p.i][2] - X[p.j][2])};
+        const float ir2 = 1.f / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), ir = sqrtf(ir2);
+        const float s2 = p.sig * p.sig * ir2, s6 = s2 * s2 * s2;
+        const float c = (p.qq * ir + 24.f * p.eps * (2.f * s6 * s6 - s6)) * ir2;
+        for (int q = 0; q < 3; q++) { FS[p.si][q] = c * d[q]; FS[p.sj][q] = -c * d[q]; }
+    }
 }
 
 // Copy the term tables into shared memory (all lanes of the warp; `buf` has room for mol_shared_bytes(m)).
@@ -365,6 +439,12 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
     if (only && !only[k]) return;
     MolShared ms;
     mol_stage(m, (unsigned char *)mol_tab, ms);
+    // the dynamics' term tables and the slots of their force contributions, behind the other tables
+    unsigned char *tb = (unsigned char *)mol_tab + m.shared_bytes;
+    for (int q = threadIdx.x * 8; q < m.terms_bytes; q += 32 * 8) *(unsigned long long *)(tb + q) = *(const unsigned long long *)((const unsigned char *)m.terms + q);
+    float (*FS)[3] = (float (*)[3])(tb + ((m.terms_bytes + 15) & ~15));
+    __syncwarp();
+    const int *g_off = (const int *)(tb + ((const MolTerms *)tb)->o_goff);
     const bool active = a < n;
     const StateDev st = states[perm[k]];
     const double mass = active ? m.mass[a] : 1.0, sg = sqrt(st.kT / mass);
@@ -396,7 +476,17 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
         for (int q = 0; q < p.n_prog; q++) {
             const char op = p.prog[q];
             if (op == 'V') {
-                if (!f_valid) { if (active) mol_atom<false, float>(ms, X, a, f); f_valid = true; }
+                if (!f_valid) {
+                    mol_forces_terms(m, tb, X, FS);
+                    __syncwarp();
+                    if (active) {   // this atom's slots, in slot order
+                        float fx = 0.f, fy = 0.f, fz = 0.f;
+                        for (int q = g_off[a]; q < g_off[a + 1]; q++) { fx += FS[q][0]; fy += FS[q][1]; fz += FS[q][2]; }
+                        f[0] = fx; f[1] = fy; f[2] = fz;
+                    }
+                    __syncwarp();
+                    f_valid = true;
+                }
                 const double h = (double)p.dt_d / nV;
                 if (active) for (int c = 0; c < 3; c++) V[a][c] += h * f[c] / mass;
                 __syncwarp();
