@@ -216,6 +216,9 @@ RX_API int rx_timer_elapsed(rx_engine *h, double *ms);
 /* Mixing-kernel statistics of the last swap-all call: [0] speculation rounds, [1] exact-path fallbacks,
  * [2] passes, [3] MT words consumed, [4] walker kernel time (us), [5] host wait for the side-stream pre-pass (us). */
 RX_API int rx_get_mix_stats(rx_engine *h, int64_t out[6]);
+/* Diagnostic: y[t] = the device's correctly rounded exp(x[t]) (host arrays) -- the function behind the one decision the
+ * mixing kernels do not take in the log domain, `rand() < exp(log_p)` of replicaexchange.py:340 inside the 1e-9 guard band. */
+RX_API int rx_selftest_exp(rx_engine *h, const double *x, double *y, int32_t n);
 
 /* ---- multi-GPU ------------------------------------------------------------------------------------ */
 /* NCCL is loaded with dlopen(nccl_library_path).  Rank 0 creates an id (rx_comm_unique_id), the host code

@@ -292,6 +292,13 @@ class Engine:
         self._check(self._lib.rx_timer_elapsed(self._h, C.byref(v)))
         return v.value
 
+    def selftest_exp(self, x):
+        """The device's correctly rounded exp (the mixing kernels' tie-break function) of a float64 array."""
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.empty_like(x)
+        self._check(self._lib.rx_selftest_exp(self._h, _ptr(x), _ptr(y), C.c_int32(x.size)))
+        return y
+
     def mix_stats(self):
         out = np.zeros(6, np.int64)
         self._check(self._lib.rx_get_mix_stats(self._h, _ptr(out)))

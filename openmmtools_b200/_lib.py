@@ -21,7 +21,7 @@ SYMBOLS = [
     'rx_get_replica_energies', 'rx_pin_host_memory', 'rx_unpin_host_memory', 'rx_randomize_velocities', 'rx_minimize', 'rx_set_replica_states', 'rx_get_replica_states',
     'rx_propagate', 'rx_propagate_retry', 'rx_compute_energies', 'rx_compute_energies_at', 'rx_set_energies', 'rx_get_energies', 'rx_mix_seed',
     'rx_mix_skip', 'rx_mix_swap_all', 'rx_mix_swap_neighbors', 'rx_get_mix_counts', 'rx_mix_stream_position',
-    'rx_run_iterations', 'rx_get_phase_times', 'rx_timer_mark', 'rx_timer_elapsed', 'rx_get_mix_stats', 'rx_comm_unique_id', 'rx_comm_init',
+    'rx_run_iterations', 'rx_get_phase_times', 'rx_timer_mark', 'rx_timer_elapsed', 'rx_get_mix_stats', 'rx_selftest_exp', 'rx_comm_unique_id', 'rx_comm_init',
 ]
 
 
@@ -98,6 +98,7 @@ def load():
     lib.rx_timer_mark.argtypes = [vp, i32]
     lib.rx_timer_elapsed.argtypes = [vp, C.POINTER(dbl)]
     lib.rx_get_mix_stats.argtypes = [vp, vp]
+    lib.rx_selftest_exp.argtypes = [vp, vp, vp, C.c_int32]
     lib.rx_comm_unique_id.argtypes = [C.c_char_p, vp]
     lib.rx_comm_init.argtypes = [vp, C.c_char_p, vp]
     if lib.rx_abi_version() != RX_ABI_VERSION:

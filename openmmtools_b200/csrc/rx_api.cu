@@ -661,6 +661,13 @@ extern "C" int rx_timer_elapsed(rx_engine *h, double *ms) {
     *ms = f;
     return RX_OK;
 }
+extern "C" int rx_selftest_exp(rx_engine *h, const double *x, double *y, int32_t n) {
+    if (!h) return RX_ERR_INVALID;
+    if (n > 0 && (!x || !y)) RX_FAIL(h, RX_ERR_INVALID, "rx_selftest_exp: null array");
+    RX_CHECK_CUDA(h, cudaSetDevice(h->cfg.device));
+    return rxi_selftest_exp(h, x, y, n);
+}
+
 extern "C" int rx_get_mix_stats(rx_engine *h, int64_t out[6]) {
     ENTER(h);
     for (int i = 0; i < 6; i++) out[i] = h->mix_stats[i];

@@ -46,6 +46,7 @@ struct MixCtl {          // device-resident control block of the resumable mixin
     int rounds;          // statistics: speculation rounds executed
     long long slow_exp;  // statistics: exact exp() fallbacks
     long long log_count; // entries written to the commit log by this launch
+    long long aux;       // k_mix_walk2c: candidate index reached (extent of its sparse commit log)
 };
 
 struct rx_state_move {
@@ -105,6 +106,9 @@ struct rx_engine {
     uint32_t *d_log = nullptr;   // commit log of the walker: packed (si, sj, accepted)
     size_t log_cap = 0;
     uint32_t *d_slotlog = nullptr;   // sparse commit log of k_mix_walk2: one word per slot
+    uint32_t *d_cpos = nullptr;      // k_mix_walk2c: word position of every candidate of the pass
+    uint32_t *d_ctile = nullptr;     // ... candidates per tile / their exclusive scan, then [last] = number of candidates
+    size_t ctile_cap = 0;
     unsigned char *d_filt = nullptr;   // 24-bit row image of u for the K=256 walker
     double *d_filt_scale = nullptr;    // [K] scales + [K] row abs-max
     int prepared_kind = 0;        // ... with these records (REC_* of rx_mix.cu)
@@ -156,6 +160,7 @@ struct PhaseTimer {
 // ---- implemented in rx_mix.cu ----
 int rxi_mix_seed(rx_engine *h, int stream, uint32_t seed);
 int rxi_mix_skip(rx_engine *h, int stream, unsigned long long n);
+int rxi_selftest_exp(rx_engine *h, const double *x, double *y, int n);
 int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches);
 int rxi_mix_swap_neighbors(rx_engine *h, int *launches);
 void rxi_mix_free(rx_engine *h);

@@ -91,6 +91,83 @@ __device__ __forceinline__ double swap_logp(double e_ij, double e_ji, double e_i
     return __dadd_rn(__dadd_rn(-__dadd_rn(e_ij, e_ji), e_ii), e_jj);
 }
 
+// exp(x), correctly rounded (round to nearest) -- for the reference's own test `rand() < exp(log_p)` in the cases where
+// it is not decided in the log domain.  CUDA's exp() may be off by one ulp; the host libm the reference calls (numba -> libm
+// exp) is correctly rounded at all but ~1 % of the arguments: with a one-ulp error the decision differs from the
+// reference's whenever U is the double next to exp(log_p) (tests/test_gpu_mixing.py constructs such matrices).
+// Double-double evaluation: x = k ln2 + r (three-part ln 2, the first part fdlibm's ln2HI so that k ln2HI is exact),
+// expm1(r / 256) by its Taylor series to the 9th power, eight squarings in the form m <- m (m + 2), result (1 + m) 2^k;
+// relative error ~2^-95, so the rounding can only be wrong if exp(x) lies within ~2^-40 ulp of a midpoint between two doubles.
+// Rare path only (guard band, plain loop): its speed is irrelevant.
+struct rx_dd { double hi, lo; };
+__device__ __forceinline__ rx_dd dd_fast_two_sum(double a, double b) {
+    const double s = __dadd_rn(a, b);
+    return {s, __dadd_rn(b, -__dadd_rn(s, -a))};
+}
+__device__ __forceinline__ rx_dd dd_two_sum(double a, double b) {
+    const double s = __dadd_rn(a, b), bb = __dadd_rn(s, -a);
+    return {s, __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb))};
+}
+__device__ __forceinline__ rx_dd dd_add(rx_dd a, rx_dd b) {
+    rx_dd s = dd_two_sum(a.hi, b.hi);
+    const rx_dd t = dd_two_sum(a.lo, b.lo);
+    s = dd_fast_two_sum(s.hi, __dadd_rn(s.lo, t.hi));
+    return dd_fast_two_sum(s.hi, __dadd_rn(s.lo, t.lo));
+}
+__device__ __forceinline__ rx_dd dd_mul(rx_dd a, rx_dd b) {
+    const double p = __dmul_rn(a.hi, b.hi);
+    double e = __fma_rn(a.hi, b.hi, -p);
+    e = __fma_rn(a.hi, b.lo, e);
+    e = __fma_rn(a.lo, b.hi, e);
+    return dd_fast_two_sum(p, e);
+}
+__device__ __noinline__ double rx_exp_cr(double x) {
+    if (!(x == x)) return x;
+    if (x > 709.782712893384) return INFINITY;
+    if (x < -745.1332191019412) return 0.0;      // exp(x) <= 2^-1075 rounds to zero
+    const double kd = rint(__dmul_rn(x, 1.4426950408889634));
+    const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.9082149292705877e-10, ln2LL = 1.1612227229362532e-26;
+    const double r0 = __fma_rn(-kd, ln2HI, x);                  // exact
+    const double p = __dmul_rn(kd, ln2LO), pe = __fma_rn(kd, ln2LO, -p);
+    rx_dd r = dd_two_sum(r0, -p);
+    r = dd_fast_two_sum(r.hi, __dadd_rn(r.lo, -__dadd_rn(pe, __dmul_rn(kd, ln2LL))));
+    const rx_dd s = {__dmul_rn(r.hi, 0.00390625), __dmul_rn(r.lo, 0.00390625)};   // r / 256, exact
+    const rx_dd c[8] = {   // 1/2! .. 1/9!
+        {0.5, 0.0},
+        {0.16666666666666666, 9.25185853854297e-18},
+        {0.041666666666666664, 2.3129646346357427e-18},
+        {0.008333333333333333, 1.1564823173178714e-19},
+        {0.001388888888888889, -5.300543954373577e-20},
+        {0.0001984126984126984, 1.7209558293420705e-22},
+        {2.48015873015873e-05, 2.1511947866775882e-23},
+        {2.7557319223985893e-06, -1.858393274046472e-22}};
+    rx_dd acc = c[7];
+#pragma unroll
+    for (int n = 6; n >= 0; n--) acc = dd_add(c[n], dd_mul(s, acc));
+    rx_dd m = dd_add(s, dd_mul(dd_mul(s, s), acc));                  // expm1(r / 256)
+#pragma unroll
+    for (int q = 0; q < 8; q++) m = dd_mul(m, dd_add(m, rx_dd{2.0, 0.0}));     // expm1(2 t) = expm1(t) (expm1(t) + 2)
+    const rx_dd y = dd_add(rx_dd{1.0, 0.0}, m);
+    return ldexp(y.hi, (int)kd);
+}
+
+__global__ void k_selftest_exp(const double *__restrict__ x, double *__restrict__ y, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) y[t] = rx_exp_cr(x[t]);
+}
+int rxi_selftest_exp(rx_engine *h, const double *x, double *y, int n) {
+    double *d = nullptr;
+    if (n <= 0) return RX_OK;
+    RX_CHECK_CUDA(h, cudaMalloc(&d, 2 * (size_t)n * sizeof(double)));
+    RX_CHECK_CUDA(h, cudaMemcpy(d, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    k_selftest_exp<<<(n + 127) / 128, 128, 0, h->stream>>>(d, d + n, n);
+    RX_CHECK_CUDA(h, cudaGetLastError());
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    RX_CHECK_CUDA(h, cudaMemcpy(y, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return RX_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Slot records (state independent, fully parallel).
 // ------------------------------------------------------------------------------------------------------
@@ -171,6 +248,7 @@ struct WalkShared {     // control words shared by the two warps
     volatile unsigned done;
 };
 #include "rx_walk_any.cuh"
+#include "rx_walk2c.cuh"
 
 // REC2: the records are SlotRec2 (rx_walk2.cuh); only with U_FILTER24, where this kernel finishes the passes of k_mix_walk2.
 template <int UMODE, bool REC2 = false>
@@ -298,7 +376,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
             if (__any_sync(0xffffffffu, ambiguous)) {
                 if (ambiguous) {  // too close to call in the log domain: do exactly what the reference does
                     const unsigned s1 = h + lane + 1;
-                    acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp);
+                    acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < rx_exp_cr(logp);
                     slow++;
                 }
             }
@@ -345,7 +423,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_pow2(const SlotRec *__restrict_
                         const double dd = logp - (REC2 ? slot_logU(words, h + lane + 1) : rec[h + lane + 1].logU);
                         if (dd > 1e-9) acc = true;
                         else if (dd < -1e-9) acc = false;
-                        else { const unsigned s1 = h + lane + 1; acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp); }
+                        else { const unsigned s1 = h + lane + 1; acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < rx_exp_cr(logp); }
                     }
                     slow++;
                 }
@@ -486,7 +564,7 @@ __global__ void __launch_bounds__(32) k_mix_walk_serial(const uint32_t *__restri
                 if (q + 2 > nwords) break;
                 const double U = mt_double(words[q], words[q + 1]);
                 q += 2;
-                acc = U < exp(logp);
+                acc = U < rx_exp_cr(logp);
             }
             nprop[(size_t)si * M + sj] += 1;
             nprop[(size_t)sj * M + si] += 1;
@@ -530,7 +608,7 @@ __global__ void __launch_bounds__(32) k_mix_neighbors(const uint32_t *__restrict
             if (!acc) {
                 const double U = mt_double(words[p], words[p + 1]);
                 p += 2;
-                acc = U < exp(logp);
+                acc = U < rx_exp_cr(logp);
             }
             nprop[(size_t)si * M + sj] += 1;
             nprop[(size_t)sj * M + si] += 1;
@@ -659,7 +737,7 @@ struct MixTrace {   // RX_TRACE_MIX=1: device-time breakdown of one swap-all cal
 
 static inline bool is_pow2(int k) { return k >= 2 && (k & (k - 1)) == 0; }
 
-enum { REC_NONE = 0, REC_SLOT = 1, REC_SLOT2 = 2, REC_WORD = 3 };   // what prepare_pass builds from the stream
+enum { REC_NONE = 0, REC_SLOT = 1, REC_SLOT2 = 2, REC_WORD = 3, REC_CAND = 4 };   // what prepare_pass builds from the stream
 
 static inline size_t pass_need(long long remaining, bool fast, bool anyk = false) {
     const size_t chunk_words = anyk ? (size_t)1 << 25 : (size_t)1 << 26;  // words per pass (any K: 16 bytes of records per word)
@@ -673,7 +751,7 @@ static inline size_t pass_need(long long remaining, bool fast, bool anyk = false
 // on stream `st`.  Both are state independent, so for the NEXT mixing call this runs on the side stream while the
 // replicas are being propagated.
 static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fast, int kind, int K, cudaStream_t st, int *launches) {
-    const bool rec2 = kind == REC_SLOT2, anyk = kind == REC_WORD;
+    const bool rec2 = kind == REC_SLOT2, candk = kind == REC_CAND, anyk = kind == REC_WORD || candk;
     const size_t need = pass_need(remaining, fast, anyk);
     int rc = stream_reserve(h, S, 2 * need + 1024);   // room for the words generated ahead while the walker runs
     if (rc) return rc;
@@ -698,7 +776,27 @@ static int prepare_pass(rx_engine *h, MTStream &S, long long remaining, bool fas
             RX_CHECK_CUDA(h, cudaMalloc(&h->d_slotlog, want * sizeof(uint32_t)));
             h->slots_cap = want;
         }
-        if (anyk) {
+        if (candk && (!h->d_cpos || h->ctile_cap < h->slots_cap)) {
+            RX_CHECK_CUDA(h, cudaDeviceSynchronize());
+            cudaFree(h->d_cpos); cudaFree(h->d_ctile);
+            h->d_cpos = nullptr; h->d_ctile = nullptr;
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_cpos, (h->slots_cap + 8) * sizeof(uint32_t)));
+            RX_CHECK_CUDA(h, cudaMalloc(&h->d_ctile, (h->slots_cap / CAND_TILE + 8) * sizeof(uint32_t)));
+            h->ctile_cap = h->slots_cap;
+        }
+        if (candk) {
+            // candidate coordinates (rx_walk2c.cuh): flag + count per tile, scan, scatter, one record per candidate index
+            int nbits = 0;
+            for (unsigned m = (unsigned)(K - 1); m; m >>= 1) nbits++;
+            const uint32_t mask = 0xffffffffu >> (32 - nbits);
+            const int ntiles = (int)((nslots + CAND_TILE - 1) / CAND_TILE);
+            uint32_t *d_ncand = h->d_ctile + (h->ctile_cap / CAND_TILE + 4);
+            k_cand_count<<<ntiles, 256, 0, st>>>(S.d_words, nslots, K, mask, h->d_ctile);
+            k_cand_scan<<<1, 1024, 0, st>>>(h->d_ctile, ntiles, d_ncand);
+            k_cand_scatter<<<ntiles, 256, 0, st>>>(S.d_words, nslots, K, mask, h->d_ctile, h->d_cpos);
+            k_cand_records<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(S.d_words, h->d_cpos, d_ncand, mask, (SlotRec2 *)h->d_slots);
+            *launches += 3;
+        } else if (anyk) {
             static_assert(sizeof(WordRec) == sizeof(SlotRec), "all record formats share the d_slots buffer");
             int nbits = 0;
             for (unsigned m = (unsigned)(K - 1); m; m >>= 1) nbits++;
@@ -749,7 +847,11 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     // filter mode: 16-byte SlotRec2 records, k_mix_walk2 for the bulk of a pass and k_mix_walk_pow2<U_FILTER24, true> for its tail
     const bool rec2 = (umode == U_FILTER24);
     const bool walk2 = rec2 && !getenv("RX_WALK_V1");
-    const int kind = anyk ? REC_WORD : (!fast ? REC_NONE : (rec2 ? REC_SLOT2 : REC_SLOT));
+    // any K <= 256 whose row image fits: the walker of k_mix_walk2 in candidate coordinates (rx_walk2c.cuh);
+    // RX_WALK_ANY_V1=1 keeps the word-position walker (cross-check)
+    const size_t smem_w2c = (size_t)W2_RING * 16 + (size_t)K * 8 + (size_t)((3 * K + 1) & ~1) * K;
+    const bool candk = anyk && K <= 256 && smem_w2c <= 224 * 1024 && !getenv("RX_WALK_ANY_V1") && !getenv("RX_NO_FILTER");
+    const int kind = candk ? REC_CAND : (anyk ? REC_WORD : (!fast ? REC_NONE : (rec2 ? REC_SLOT2 : REC_SLOT)));
     const size_t smem_any_f64 = smem_base + (size_t)K * K * sizeof(double);
     const bool any_smem = anyk && smem_any_f64 <= 200 * 1024;
     const size_t smem_w2 = (size_t)W2_RING * 16 + (size_t)K * 8 + (size_t)3 * K * K;
@@ -764,6 +866,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
     }
     if (!fast) {
         if (smem > 48 * 1024) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (candk) RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk2c, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         if (anyk) {
             RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_any<U_F64_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_any<U_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -775,7 +878,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         RX_CHECK_CUDA(h, cudaFuncSetAttribute(k_mix_walk_pow2<U_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_base_launch));
     }
     tr.mark("func attributes");
-    if (umode == U_FILTER24) {
+    if (umode == U_FILTER24 || candk) {
         if (!h->d_filt) {
             RX_CHECK_CUDA(h, cudaMalloc(&h->d_filt, (size_t)3 * K * K + 16));
             RX_CHECK_CUDA(h, cudaMalloc(&h->d_filt_scale, sizeof(double) * 2 * K));
@@ -809,7 +912,7 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
         }
         h->prepared = false;
         tr.mark("prepared/built");
-        MixCtl ctl = {0, remaining, 0, 0, 0, 0};
+        MixCtl ctl = {0, remaining, 0, 0, 0, 0, 0};
         RX_CHECK_CUDA(h, cudaMemcpyAsync(h->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->stream));
         size_t consumed_words;
         if (fast) {
@@ -869,7 +972,17 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             }
             tr.mark("adopt-ahead + count");
         } else {
-            if (anyk) {
+            if (candk) {
+                // bulk of the pass: the walk2 organisation over candidate indices; the plain loop below finishes the pass
+                RX_CHECK_CUDA(h, cudaEventRecord(h->ev_walk[0], h->stream));
+                RX_CHECK_CUDA(h, cudaMemsetAsync(h->d_slotlog, 0, S.avail * sizeof(uint32_t), h->stream));
+                k_mix_walk2c<<<1, W2_THREADS, 226 * 1024, h->stream>>>((const SlotRec2 *)h->d_slots, S.d_words, h->d_cpos,
+                                                                        h->d_ctile + (h->ctile_cap / CAND_TILE + 4), h->d_u, K, h->d_perm,
+                                                                        h->d_slotlog, h->d_filt, h->d_filt_scale, h->d_ctl);
+                RX_CHECK_CUDA(h, cudaGetLastError());
+                RX_CHECK_CUDA(h, cudaEventRecord(h->ev_walk[1], h->stream));
+                *launches += 1;
+            } else if (anyk) {
                 // bulk of the pass: speculative walker over word positions (claims the SM like the power-of-two walkers);
                 // what it leaves -- the last words of the pass -- is finished by the plain loop below
                 RX_CHECK_CUDA(h, cudaEventRecord(h->ev_walk[0], h->stream));
@@ -891,7 +1004,14 @@ int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches) {
             if (anyk) {
                 float wms = 0;
                 if (cudaEventElapsedTime(&wms, h->ev_walk[0], h->ev_walk[1]) == cudaSuccess) h->mix_stats[4] += (long long)(wms * 1e3f);
-                if (ctl.log_count > 0) {
+                if (candk && ctl.aux > 0) {
+                    long long nb = (ctl.aux + 255) / 256;
+                    if (nb > 148 * 16) nb = 148 * 16;
+                    k_mix_count_slots<<<(unsigned)nb, 256, 0, h->stream>>>(h->d_slotlog, 0, ctl.aux, M, h->d_nacc, h->d_nprop);
+                    RX_CHECK_CUDA(h, cudaGetLastError());
+                    *launches += 1;
+                }
+                if (!candk && ctl.log_count > 0) {
                     long long nb = (ctl.log_count + 255) / 256;
                     if (nb > 148 * 16) nb = 148 * 16;
                     k_mix_count<<<(unsigned)nb, 256, 0, h->stream>>>(h->d_log, ctl.log_count, M, h->d_nacc, h->d_nprop);
@@ -963,6 +1083,8 @@ void rxi_mix_free(rx_engine *h) {
     cudaFree(h->d_slots);
     cudaFree(h->d_log);
     cudaFree(h->d_slotlog);
+    cudaFree(h->d_cpos);
+    cudaFree(h->d_ctile);
     cudaFree(h->d_filt);
     cudaFree(h->d_filt_scale);
     cudaFree(h->d_ctl);

@@ -171,7 +171,7 @@ __device__ __noinline__ unsigned w2_exact_decision(const SlotRec2 *__restrict__ 
     bool acc;
     if (dd > 1e-9) acc = true;
     else if (dd < -1e-9) acc = false;
-    else acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp);
+    else acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < rx_exp_cr(logp);
     return acc ? 2u : 0u;
 }
 
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2(const SlotRec2 *__rest
                         const double dd = logp - slot_logU(words, s1);
                         if (dd > 1e-9) acc = true;
                         else if (dd < -1e-9) acc = false;
-                        else acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < exp(logp);
+                        else acc = mt_double(words[2 * (size_t)s1], words[2 * (size_t)s1 + 1]) < rx_exp_cr(logp);
                     }
                     slow++;
                 }

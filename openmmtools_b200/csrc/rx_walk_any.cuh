@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(64) k_mix_walk_any(const WordRec *__restrict__
         if (__any_sync(0xffffffffu, ambiguous)) {
             if (ambiguous) {  // too close to call in the log domain: do exactly what the reference does
                 const size_t p1 = (size_t)h + lane + len;
-                acc = mt_double(words[p1], words[p1 + 1]) < exp(logp);
+                acc = mt_double(words[p1], words[p1 + 1]) < rx_exp_cr(logp);
                 slow++;
             }
         }

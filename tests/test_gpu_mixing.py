@@ -89,14 +89,19 @@ def test_swap_all_full_size_vs_oracle(K, model, seed):
                                                 (65, 'flat', 65 ** 3, 34), (100, 'normal', 100 ** 3, 35),
                                                 (127, 'ladder', 500_000, 36), (129, 'normal', 500_000, 37),
                                                 (200, 'normal', 2_000_000, 38), (1000, 'flat', 1_000_000, 39)])
-@pytest.mark.parametrize('serial', [False, True])
-def test_swap_all_any_k_vs_oracle(monkeypatch, K, model, nswap, seed, serial):
-    """K that is not a power of two: the speculative walker over word positions (k_mix_walk_any, the f64 matrix in shared
-    memory up to K ~ 150, from L2 above) and, with RX_WALK_SERIAL=1, the plain loop; three iterations each."""
+@pytest.mark.parametrize('path', ['default', 'serial', 'words'])
+def test_swap_all_any_k_vs_oracle(monkeypatch, K, model, nswap, seed, path):
+    """K that is not a power of two.  default: the walk2 organisation in candidate coordinates (k_mix_walk2c, K <= 256) or the
+    walker over word positions (k_mix_walk_any: above 256, or everywhere with RX_WALK_ANY_V1=1 -- the f64 matrix in shared
+    memory up to K ~ 150, from L2 above); with RX_WALK_SERIAL=1 the plain loop; three iterations each."""
     from oracle import oracle
+    serial = path == 'serial'
     if serial:
         if nswap > 300_000: pytest.skip('the plain loop takes 0.6 us per attempt')
         monkeypatch.setenv('RX_WALK_SERIAL', '1')
+    if path == 'words':
+        if K > 256: pytest.skip('already the default above K = 256')
+        monkeypatch.setenv('RX_WALK_ANY_V1', '1')
     u = energies(model, K, 777 + K)
     e = gpu_engine(0, K, K)
     e.set_energies(u)
@@ -151,6 +156,70 @@ def test_swap_all_any_k_hard_matrices(K, kind):
     e.close()
 
 
+def _exp_correctly_rounded(x):
+    """exp(x) rounded to nearest from 60-digit arithmetic (float(Decimal) rounds correctly)."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    return float(Decimal(float(x)).exp())
+
+
+def _libm_decides_like_exact_arithmetic(U, lp):
+    """The reference's test U < exp(lp) with the host libm's exp against the same test with the correctly rounded exp.  They
+    differ only where the libm is not correctly rounded AND U is the neighbouring double -- no implementation can then agree with
+    every libm (glibc's exp is wrong by one unit in ~1 % of the last places; its FMA and non-FMA variants differ too)."""
+    import math
+    return (U < math.exp(lp)) == (U < _exp_correctly_rounded(lp))     # math.exp: the C library's, like numba's and the oracle's
+
+
+def test_device_exp_is_correctly_rounded():
+    """rx_exp_cr (the tie-break's exp, double-double) against 60-digit arithmetic: random arguments over the range the
+    mixing kernels can meet, and the worst case for the decision: x = log(U), where exp(x) is within an ulp of U."""
+    rng = np.random.default_rng(11)
+    U = (rng.integers(1, 2 ** 53, 1500).astype(np.float64)) / 2.0 ** 53
+    x = np.concatenate([-40.0 * rng.random(1500), np.log(U), rng.uniform(-745.0, 709.0, 300),
+                        [0.0, -0.0, 1.0, -1.0, 709.78, -745.13, -745.14, -800.0, 710.0, -1e-300, 1e-17, -36.7368005696771]])
+    e = gpu_engine(0, 2, 2)
+    y = e.selftest_exp(x)
+    e.close()
+    with np.errstate(over='ignore'):
+        ref = np.array([_exp_correctly_rounded(v) if v < 709.79 else np.inf for v in x])
+    bad = np.flatnonzero(y != ref)
+    assert bad.size == 0, [(x[b], y[b], ref[b]) for b in bad[:5]]
+    # (for the record: how often the host libm itself is not correctly rounded on the same arguments)
+    import math
+    libm = np.array([math.exp(v) if v < 709.78 else np.inf for v in x])
+    print('libm exp differs from the correctly rounded value at %d of %d arguments' % (int(np.sum(libm != ref)), x.size))
+
+
+def test_swap_all_tie_break_inside_the_guard_band_any_k():
+    """The same for K = 3 (k_mix_walk2c: rejection-sampled indices, the exact decision of w2c_exact_decision)."""
+    from oracle import oracle
+    hits = 0; undecidable = 0
+    for seed in range(40):
+        mt = oracle.MT(seed)
+        while True:
+            i, j = mt.randint(3), mt.randint(3)
+            if i != j: break
+        U = mt.rand()
+        for rel in (0.0, 1e-14, -1e-14, 1e-12, -1e-12, 1e-10, -1e-10):
+            lp = np.log(U) * (1.0 + rel)
+            if not _libm_decides_like_exact_arithmetic(U, lp): undecidable += 1; continue
+            u = np.zeros((3, 3)); u[i, j] = u[j, i] = -0.5 * lp      # log_p(i, j) = lp under the identity permutation
+            e = gpu_engine(0, 3, 3)
+            e.set_energies(u); e.set_replica_states(np.arange(3)); e.mix_seed(seed, 0)
+            st, nacc, nprop = e.mix_swap_all(6000)
+            stats = e.mix_stats()
+            hits += stats['exact_exp'] > 0
+            assert stats['rounds'] > 0
+            e.close()
+            mo = oracle.MT(seed); st_o = np.arange(3, dtype=np.int64)
+            na = np.zeros((3, 3), np.int64); npr = np.zeros((3, 3), np.int64)
+            oracle.mix_swap_all(mo, 6000, st_o, u, na, npr)
+            assert np.array_equal(st, st_o) and np.array_equal(nacc, na) and np.array_equal(nprop, npr), (seed, rel)
+    assert hits > 100   # the exact path really ran
+    assert undecidable <= 6   # (cases where the host libm's exp is itself off by one in the last place and that decides)
+
+
 @pytest.mark.parametrize('nswap', [40, 6000])
 def test_swap_all_tie_break_inside_the_guard_band(nswap):
     """The one place where the decision is not taken in the log domain: |log_p - log U| <= 1e-9, where the kernels fall back to
@@ -158,7 +227,7 @@ def test_swap_all_tie_break_inside_the_guard_band(nswap):
     the band (log_p = log U to a relative 0, 1e-14, 1e-12, 1e-10 on either side), for 60 seeds; nswap = 40 runs in the
     pass-tail kernel (k_mix_walk_pow2), 6000 in k_mix_walk2."""
     from oracle import oracle
-    hits = 0
+    hits = 0; undecidable = 0
     for seed in range(60):
         mt = oracle.MT(seed)
         while True:
@@ -167,6 +236,7 @@ def test_swap_all_tie_break_inside_the_guard_band(nswap):
         U = mt.rand()
         for rel in (0.0, 1e-14, -1e-14, 1e-12, -1e-12, 1e-10, -1e-10):
             lp = np.log(U) * (1.0 + rel)
+            if not _libm_decides_like_exact_arithmetic(U, lp): undecidable += 1; continue
             u = np.array([[0.0, -0.5 * lp], [-0.5 * lp, 0.0]])      # log_p(0, 1) = -(u01 + u10) + u00 + u11 = lp
             e = gpu_engine(0, 2, 2)
             e.set_energies(u); e.set_replica_states(np.arange(2)); e.mix_seed(seed, 0)
@@ -178,6 +248,7 @@ def test_swap_all_tie_break_inside_the_guard_band(nswap):
             oracle.mix_swap_all(mo, nswap, st_o, u, na, npr)
             assert np.array_equal(st, st_o) and np.array_equal(nacc, na) and np.array_equal(nprop, npr), (seed, rel)
     assert hits > 100   # the exact path really ran
+    assert undecidable <= 8
 
 
 def test_unseeded_stream_is_an_error():

@@ -153,6 +153,59 @@ def test_alchemical_dispersion_correction_limits():
     assert _backend.alchemical_dispersion_correction(asys2, 0.3) == 0.0
 
 
+def test_dispersion_corrections_from_their_definition():
+    """Independent of the closed forms in _backend.py and oracle/rx_oracle.c: the correction is the mean-field energy of what
+    the cut-off removes, (2 pi N^2 / V) <int_0^inf r^2 [U(r) - U(r) S(r) theta(rc - r)] dr>, the average taken over all
+    N (N + 1) / 2 unordered particle pairs including i = j (OpenMM's pair-count convention for NonbondedForce; for a
+    CustomNonbondedForce with interaction groups the sum runs over the pairs of the groups, same normalisation).  Here:
+    explicit loops over particle pairs and scipy's adaptive quadrature of that integrand."""
+    from scipy.integrate import quad
+    fl, asys = make_alch(n=64, n_alch=3)
+    s = asys
+    N, V, rc, rs = s.n_particles, abs(np.linalg.det(s.box_vectors)), s.cutoff, s.switching_distance
+    sig, eps = np.asarray(s.sigma, float), np.asarray(s.epsilon, float)
+    alch = s.alchemical_mask().astype(bool)
+
+    def removed(U):   # int_0^inf r^2 [U - U S theta(rc - r)] dr = int_rs^rc r^2 U (1 - S) dr + int_rc^inf r^2 U dr
+        sw = lambda r: 1.0 - 6 * ((r - rs) / (rc - rs)) ** 5 + 15 * ((r - rs) / (rc - rs)) ** 4 - 10 * ((r - rs) / (rc - rs)) ** 3
+        a = quad(lambda r: r * r * U(r) * (1.0 - sw(r)), rs, rc, epsabs=0, epsrel=1e-12)[0]
+        b = quad(lambda r: r * r * U(r), rc, np.inf, epsabs=0, epsrel=1e-12)[0]
+        return a + b
+    cache = {}
+
+    def pair_term(sg, e, lam):
+        key = (sg, e, lam)
+        if key not in cache:
+            if lam is None:
+                U = lambda r: 4 * e * ((sg / r) ** 12 - (sg / r) ** 6)
+            else:
+                def U(r):
+                    x = 1.0 / (s.softcore_alpha * (1.0 - lam) ** s.softcore_b + (r / sg) ** s.softcore_c) ** (6.0 / s.softcore_c)
+                    return lam ** s.softcore_a * 4 * e * x * (x - 1.0)
+            cache[key] = removed(U) if e != 0.0 else 0.0
+        return cache[key]
+    # NonbondedForce: alchemical atoms carry eps = 0 (alchemy.py:1909)
+    e_nb = np.where(alch, 0.0, eps)
+    tot = 0.0
+    for i in range(N):
+        for j in range(i, N):
+            tot += pair_term(0.5 * (sig[i] + sig[j]), float(np.sqrt(e_nb[i] * e_nb[j])), None)
+    ref = 2 * np.pi * N * N / V * tot / (0.5 * N * (N + 1))
+    assert _backend.lj_dispersion_correction(s) == pytest.approx(ref, rel=1e-9)
+    # the two soft-core CustomNonbondedForces: environment x alchemical at lambda, alchemical x alchemical at lambda = 1
+    for lam in (1.0, 0.7, 0.25, 0.0):
+        tot = 0.0
+        for i in np.flatnonzero(alch):
+            for j in np.flatnonzero(~alch):
+                tot += pair_term(0.5 * (sig[i] + sig[j]), float(np.sqrt(eps[i] * eps[j])), lam)
+        al = np.flatnonzero(alch)
+        for a in range(len(al)):
+            for b in range(a + 1, len(al)):
+                tot += pair_term(0.5 * (sig[al[a]] + sig[al[b]]), float(np.sqrt(eps[al[a]] * eps[al[b]])), 1.0)
+        ref = 2 * np.pi * N * N / V * tot / (0.5 * N * (N + 1))
+        assert _backend.alchemical_dispersion_correction(s, lam) == pytest.approx(ref, rel=1e-7, abs=1e-12)
+
+
 def test_splitting_grammar():
     assert mcmc.parse_splitting('V R O R V') == 'VRORV'
     assert mcmc.parse_splitting('O V R V O') == 'OVRVO'
