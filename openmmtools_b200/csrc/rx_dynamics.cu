@@ -763,7 +763,7 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {
         if (!h->state_moves.empty()) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: per-state moves are not provided for molecules");
         const uint2 mkey = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
-        k_propagate_mol<<<h->kloc, 32, ((const MolDev *)h->mol_dev)->dyn_shared_bytes, h->stream>>>(*(const MolDev *)h->mol_dev, p, (const StateDev *)h->d_states, (const int *)h->d_perm,
+        k_propagate_mol<<<h->kloc, 32 * MOL_WARPS, ((const MolDev *)h->mol_dev)->dyn_shared_bytes, h->stream>>>(*(const MolDev *)h->mol_dev, p, (const StateDev *)h->d_states, (const int *)h->d_perm,
                                                       (double *)h->d_pos, (double *)h->d_vel, h->k0, mkey, (uint32_t)iteration, reassign,
                                                       h->d_pot, h->d_kin, h->d_nan, d_only);
         RX_CHECK_CUDA(h, cudaGetLastError());

@@ -1,7 +1,8 @@
 // rx_mix.cu -- replica mixing (Gibbs / Metropolis state swaps) on the device.
 //
 // Replaces ReplicaExchangeSampler._mix_replicas (openmmtools/multistate/replicaexchange.py:255-292):
-//   swap-all       _mix_all_replicas_numba  (replicaexchange.py:294-349)  -> k_mix_walk_pow2 / k_mix_walk_serial
+//   swap-all       _mix_all_replicas_numba  (replicaexchange.py:294-349)  -> k_mix_walk2 / k_mix_walk_pow2 (K a power of two),
+//                                                                            k_mix_walk2c / k_mix_walk_any (any other K), k_mix_walk_serial
 //   swap-neighbors _mix_neighboring_replicas (replicaexchange.py:366-406) -> k_mix_neighbors
 // The results are bit-identical to the reference for the same MT19937 state: the random stream is numba's
 // (numba/_random.c:37-73; randint = low bit_length(K-1) bits of one word with rejection, rand = 53-bit double

@@ -173,9 +173,9 @@ __device__ double mol_atom(const MolShared &m, const double (*X)[3], int a, doub
 // All terms, each once (see MolTerms).  FS: float[n_slots][3] in shared memory.
 __device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned char *tb, const double (*X)[3], float (*FS)[3]) {
     const MolTerms *h = (const MolTerms *)tb;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x, nth = blockDim.x;   // (k_propagate_mol: all warps of the block; the other kernels: one warp)
     const TBond *B = (const TBond *)(tb + h->o_bond);
-    for (int t = lane; t < m.n_tb; t += 32) {
+    for (int t = lane; t < m.n_tb; t += nth) {
         const TBond b = B[t];
         const float d[3] = {(float)(X[b.i][0] - X[b.j][0]), (float)(X[b.i][1] - X[b.j][1]), (float)(X[b.i][2] - X[b.j][2])};
         const float r = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -183,7 +183,7 @@ __device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned
         for (int q = 0; q < 3; q++) { FS[b.si][q] = c * d[q]; FS[b.sj][q] = -c * d[q]; }
     }
     const TAngle *A = (const TAngle *)(tb + h->o_angle);
-    for (int t = lane; t < m.n_ta; t += 32) {
+    for (int t = lane; t < m.n_ta; t += nth) {
         const TAngle g = A[t];
         float u[3], v[3];
         for (int c = 0; c < 3; c++) { u[c] = (float)(X[g.i][c] - X[g.j][c]); v[c] = (float)(X[g.k][c] - X[g.j][c]); }
@@ -199,7 +199,7 @@ __device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned
         }
     }
     const TTors *T = (const TTors *)(tb + h->o_tors);
-    for (int t = lane; t < m.n_tt; t += 32) {
+    for (int t = lane; t < m.n_tt; t += nth) {
         const TTors w = T[t];
         float rij[3], rkj[3], rkl[3], mm[3], nn[3];
         for (int c = 0; c < 3; c++) { rij[c] = (float)(X[w.i][c] - X[w.j][c]); rkj[c] = (float)(X[w.k][c] - X[w.j][c]); rkl[c] = (float)(X[w.k][c] - X[w.l][c]); }
@@ -219,7 +219,7 @@ __device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned
         }
     }
     const TPair *P = (const TPair *)(tb + h->o_pair);
-    for (int t = lane; t < m.n_tp; t += 32) {
+    for (int t = lane; t < m.n_tp; t += nth) {
         const TPair p = P[t];
         const float d[3] = {(float)(X[p.i][0] - X[p.j][0]), (float)(X[p.i][1] - X[p.j][1]), (float)(X[p.i][2] - X[p.j][2])};
         const float ir2 = 1.f / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), ir = sqrtf(ir2);
@@ -232,9 +232,10 @@ __device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned
 // Copy the term tables into shared memory (all lanes of the warp; `buf` has room for mol_shared_bytes(m)).
 __device__ void mol_stage(const MolDev &m, unsigned char *buf, MolShared &s) {
     const int n = m.n, lane = threadIdx.x;
+    const size_t stride = (size_t)blockDim.x * 8;
     auto put = [&](const void *src, size_t bytes) {
         unsigned char *dst = buf;
-        for (size_t q = lane * 8; q < bytes; q += 32 * 8) *(unsigned long long *)(dst + q) = *(const unsigned long long *)((const unsigned char *)src + q);
+        for (size_t q = lane * 8; q < bytes; q += stride) *(unsigned long long *)(dst + q) = *(const unsigned long long *)((const unsigned char *)src + q);
         buf += (bytes + 15) & ~(size_t)15;
         return dst;
     };
@@ -249,7 +250,7 @@ __device__ void mol_stage(const MolDev &m, unsigned char *buf, MolShared &s) {
     s.charge = (const double *)put(m.charge, sizeof(double) * n); s.sigma = (const double *)put(m.sigma, sizeof(double) * n);
     s.seps = (const double *)put(m.seps, sizeof(double) * n);
     s.nb_mask = (const unsigned *)put(m.nb_mask, sizeof(unsigned) * (n + 1));
-    __syncwarp();
+    if (blockDim.x > 32) __syncthreads(); else __syncwarp();
 }
 
 // Constraints are solved per cluster (connected component of the constraint graph) by ONE lane.  Clusters of up to
@@ -427,8 +428,13 @@ __device__ __forceinline__ double mol_warp_sum(double v) {   // fixed tree: bit-
     return v;
 }
 
-// One warp per owned replica.  pos / vel: double[kloc][n][3].
-__global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, const StateDev *__restrict__ states,
+// One block of MOL_WARPS warps per owned replica.  Warp 0 integrates (one lane per atom, one lane per constraint cluster);
+// all warps evaluate the force terms (each term once, by whichever thread its index falls to, into its fixed slots: the
+// per-atom sums in slot order do not depend on the number of threads -- the same bits as with one warp), between two block
+// barriers per force evaluation.  Every warp runs the same control flow (steps, program, lazy force flag); warps 1.. only take
+// part in the force evaluations.  pos / vel: double[kloc][n][3].
+#define MOL_WARPS 4
+__global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynParams p, const StateDev *__restrict__ states,
                                                       const int *__restrict__ perm, double *__restrict__ pos,
                                                       double *__restrict__ vel, int k0, uint2 key, uint32_t iteration,
                                                       int reassign, double *__restrict__ pot, double *__restrict__ kin,
@@ -441,9 +447,9 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
     mol_stage(m, (unsigned char *)mol_tab, ms);
     // the dynamics' term tables and the slots of their force contributions, behind the other tables
     unsigned char *tb = (unsigned char *)mol_tab + m.shared_bytes;
-    for (int q = threadIdx.x * 8; q < m.terms_bytes; q += 32 * 8) *(unsigned long long *)(tb + q) = *(const unsigned long long *)((const unsigned char *)m.terms + q);
+    for (int q = threadIdx.x * 8; q < m.terms_bytes; q += 32 * MOL_WARPS * 8) *(unsigned long long *)(tb + q) = *(const unsigned long long *)((const unsigned char *)m.terms + q);
     float (*FS)[3] = (float (*)[3])(tb + ((m.terms_bytes + 15) & ~15));
-    __syncwarp();
+    __syncthreads();
     const int *g_off = (const int *)(tb + ((const MolTerms *)tb)->o_goff);
     const bool active = a < n;
     const StateDev st = states[perm[k]];
@@ -477,8 +483,9 @@ __global__ void __launch_bounds__(32) k_propagate_mol(MolDev m, DynParams p, con
             const char op = p.prog[q];
             if (op == 'V') {
                 if (!f_valid) {
+                    __syncthreads();   // warp 0's positions are in shared memory
                     mol_forces_terms(m, tb, X, FS);
-                    __syncwarp();
+                    __syncthreads();   // every term's contributions are in their slots
                     if (active) {   // this atom's slots, in slot order
                         float fx = 0.f, fy = 0.f, fz = 0.f;
                         for (int q = g_off[a]; q < g_off[a + 1]; q++) { fx += FS[q][0]; fy += FS[q][1]; fz += FS[q][2]; }

@@ -17,8 +17,8 @@
 // stride-2 masks (the bit between two grid positions of an F-run is filled so that the carry runs through).  A visited T
 // switches to the other grid; there the steady-state pattern holds from the entry position on unless the steady state
 // skips the entry position, in which case the pattern of the F-run that contains it is complemented.  One grid phase per
-// visited T (a uniform loop: all masks are warp-wide values); the window positions 28..31 end the round (a hop is at most
-// 4, so every chain visits one of them and the next round always starts inside the window).  tests/test_walk_cand_logic_model.py is the
+// visited T (a uniform loop: all masks are warp-wide values); a visited position whose hop would leave the window by more
+// than one position ends the round (a lane moves on by one window per round at most).  tests/test_walk_cand_logic_model.py is the
 // lane-level CPU model of this logic.
 #pragma once
 
@@ -172,7 +172,10 @@ __device__ __forceinline__ void w2c_chain(unsigned Gw, unsigned K1w, unsigned K2
         x = Xc; Xc = Xn; Xn = x;
         x = gc; gc = gn; gn = x;
     }
-    Cf = V & 0xF0000000u;   // a hop is at most 4: every chain visits one of the last four positions
+    // The next round has to start inside the window or right behind it (a lane moves on by one window per round at most): a
+    // visited position p ends the round if p + hop(p) > 32 -- position 31 always, 30 unless it hops 2, 29 if it hops 4.  The
+    // chain's last visited position either is such a position or hops to 32 exactly (then the whole window commits).
+    Cf = V & (0x80000000u | ((T | F) & 0x40000000u) | (F & 0x20000000u));
 }
 
 __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2c(const SlotRec2 *__restrict__ rec, const uint32_t *__restrict__ words,
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(W2_THREADS) k_mix_walk2c(const SlotRec2 *__res
                 unsigned earlier;   // bit 31-b: window position w-1-b is a visited state-changing swap
                 asm("shl.b32 %0, %1, %2;" : "=r"(earlier) : "r"(VA), "r"(32u - w));
                 const unsigned C = __ballot_sync(0xffffffffu, ((earlier & bmA) | und) != 0u);
-                Cw = (__funnelshift_r(C, C, r) | Cf) & V;   // never empty: Cf holds a visited position
+                Cw = (__funnelshift_r(C, C, r) | Cf) & V;   // empty: the whole window commits and the next round starts at 32
                 const unsigned low = Cw & (0u - Cw);
                 const unsigned below = low - 1u;
                 p_cm = V & below; p_below = below; p_chg = changes ? 0xffffffffu : 0u;

@@ -36,7 +36,7 @@ def chain(Gw, K1w, K2w):
         st = (t << 3) & M32
         if st == 0: break
         Vc, Xc, gc, Vn, Xn, gn = Vn, Xn, gn, Vc, Xc, gc
-    Cf = V & 0xF0000000
+    Cf = V & (0x80000000 | ((T | F) & 0x40000000) | (F & 0x20000000))   # positions whose hop ends beyond position 32
     return V, Cf
 
 
@@ -55,11 +55,10 @@ def test_chain_masks_reproduce_the_sequential_chain():
         while pos < 32:
             Vs |= 1 << pos
             pos += 2 if (G >> pos) & 1 else 2 + ((K1 >> pos) & 1) + 2 * ((K2 >> pos) & 1)
-        assert Cf != 0
-        low = Cf & -Cf
-        assert V & low                       # the forced stop is itself a visited position: the next round starts there
-        m = (low << 1) - 1
-        assert (V & m) == (Vs & m)
+        assert V == Vs
+        last = Vs.bit_length() - 1           # the chain's last visited position either is the forced stop or hops to 32 exactly
+        hop = 2 if (G >> last) & 1 else 2 + ((K1 >> last) & 1) + 2 * ((K2 >> last) & 1)
+        assert Cf == ((1 << last) if last + hop > 32 else 0)
 
 
 def run(K, nswap, model, seed):
@@ -106,9 +105,9 @@ def run(K, nswap, model, seed):
             earlier = (VA << (32 - w)) & M32 if w else 0
             if earlier & lanes[w]['bm']: C |= 1 << w
         Cw = (C | Cf) & V
-        assert Cw and not (Cw & 1)
+        assert not (Cw & 1)
         low = Cw & -Cw
-        below = low - 1
+        below = (low - 1) & M32              # Cw == 0: the whole window commits, the next round starts at position 32
         cm = V & below
         for w in range(32):
             if (cm >> w) & 1:

@@ -7,11 +7,13 @@ from energy_models import energies
 from openmmtools_b200 import testsystems, alchemy, states, mcmc, multistate, unit
 from openmmtools_b200._engine import Engine
 
-# mixing kernels: pow2 small, K=256 (row image, k_mix_walk2 + tail), K not a power of two (k_mix_walk_any + plain tail), neighbours
-for K, n in ((16, 4096), (256, 60000), (12, 1728), (100, 30000)):
+# mixing kernels: pow2 small, K=256 (row image, k_mix_walk2 + tail), K not a power of two (k_cand_* + k_mix_walk2c + plain tail;
+# above 256 k_words_build + k_mix_walk_any), neighbours
+for K, n in ((16, 4096), (256, 60000), (12, 1728), (100, 30000), (255, 20000), (300, 20000)):
     e = Engine(0, K, K)
     e.set_energies(energies('flat', K, 7)); e.set_replica_states(np.arange(K)); e.mix_seed(3, 0); e.mix_seed(4, 1)
     e.mix_swap_all(n); e.mix_swap_all(n); e.mix_swap_neighbors()
+    e.selftest_exp(np.linspace(-40.0, 0.0, 64))
     e.close()
 # sampler: LJ alchemical (propagate with Verlet list, energies) and harmonic oscillator
 fluid = testsystems.LennardJonesFluid(nparticles=128)
