@@ -423,6 +423,97 @@ __device__ __forceinline__ void mol_rattle_cluster(const MolDev &m, int c, const
     }
 }
 
+// --- k_propagate_mol's constraint path for clusters of up to three constraints (every H-bond cluster: XH, XH2, XH3) ----------
+// The RATTLE matrix A = coup o (r r^T) depends on the positions only, and positions change in the R operations only: its
+// inverse is formed ONCE per position update (closed form, one reciprocal) and serves the two to three velocity projections
+// that follow as a matrix-vector product -- no pivoting, no division on the step's critical path.  SHAKE iterates with the
+// same inverse (the Jacobian at the previous constrained positions, which is 2 A: a chord iteration; the bond vectors turn by
+// about 1e-2 per R operation, so every iteration gains ~1.5-2 digits), i.e. 3 dot products + a 3x3 product per iteration
+// instead of a Newton solve.  Clusters with fewer constraints are padded (zero vectors, unit diagonal): one instruction
+// stream for all lanes.  Same constrained point as mol_shake_n / the oracle's sweeps to the tolerance.
+struct MolCache {
+    double r[3][3];    // bond vectors at the last constrained positions
+    double Ai[3][3];   // inverse of coup o (r r^T)
+};
+
+__device__ __forceinline__ void mol_cache_invert(const MolCluster &k, MolCache &c) {
+    double A[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) A[a][b] = (a == b && a >= k.nc) ? 1.0 : k.coup[a][b] * mol_dot(c.r[a], c.r[b]);
+    const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1], c01 = A[1][0] * A[2][2] - A[1][2] * A[2][0],
+                 c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+    const double id = 1.0 / (A[0][0] * c00 - A[0][1] * c01 + A[0][2] * c02);
+    c.Ai[0][0] = c00 * id;
+    c.Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * id;
+    c.Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
+    c.Ai[1][0] = -c01 * id;
+    c.Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
+    c.Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
+    c.Ai[2][0] = c02 * id;
+    c.Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * id;
+    c.Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
+}
+
+__device__ __forceinline__ void mol_cache_build(const MolCluster &k, const double (*X)[3], MolCache &c) {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) c.r[a][q] = a < k.nc ? X[k.i[a]][q] - X[k.j[a]][q] : 0.0;
+    mol_cache_invert(k, c);
+}
+
+__device__ __forceinline__ void mol_rattle_cached(const MolCluster &k, const MolCache &c, double (*V)[3]) {
+    double g[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        double dv[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) dv[q] = V[k.i[a]][q] - V[k.j[a]][q];
+        g[a] = mol_dot(c.r[a], dv);   // (padded: r = 0)
+    }
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const double lam = c.Ai[b][0] * g[0] + c.Ai[b][1] * g[1] + c.Ai[b][2] * g[2];
+        if (b < k.nc) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) { V[k.i[b]][q] -= lam * k.wi[b] * c.r[b][q]; V[k.j[b]][q] += lam * k.wj[b] * c.r[b][q]; }
+        }
+    }
+}
+
+// positions X (moved from the constrained positions the cache was built at) back onto the constraints, along the cached bond
+// vectors; the cache is rebuilt at the result.
+__device__ __forceinline__ void mol_shake_cached(const MolDev &m, const MolCluster &k, MolCache &c, double (*X)[3]) {
+    double rc[3][3];
+    for (int it = 0; it < 60; it++) {
+        double g[3];
+        bool done = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) rc[a][q] = X[k.i[a]][q] - X[k.j[a]][q];
+            g[a] = a < k.nc ? k.d2[a] - mol_dot(rc[a], rc[a]) : 0.0;
+            if (fabs(g[a]) > m.tol * k.d2[a]) done = false;
+        }
+        if (done) break;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const double lam = 0.5 * (c.Ai[b][0] * g[0] + c.Ai[b][1] * g[1] + c.Ai[b][2] * g[2]);
+            if (b < k.nc) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) { X[k.i[b]][q] += lam * k.wi[b] * c.r[b][q]; X[k.j[b]][q] -= lam * k.wj[b] * c.r[b][q]; }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) c.r[a][q] = a < k.nc ? rc[a][q] : 0.0;
+    mol_cache_invert(k, c);
+}
+
 __device__ __forceinline__ double mol_warp_sum(double v) {   // fixed tree: bit-reproducible
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -454,7 +545,7 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
     const bool active = a < n;
     const StateDev st = states[perm[k]];
     const double mass = active ? m.mass[a] : 1.0, sg = sqrt(st.kT / mass);
-    double mt = mol_warp_sum(active ? mass : 0.0);
+    const double inv_mt = 1.0 / mol_warp_sum(active ? mass : 0.0);
     if (active) {
         for (int c = 0; c < 3; c++) { X[a][c] = pos[((size_t)r * n + a) * 3 + c]; V[a][c] = vel[((size_t)r * n + a) * 3 + c]; }
         if (reassign) {   // context.setVelocitiesToTemperature, mcmc.py:711
@@ -464,10 +555,17 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
     }
     MolCluster kc;
     kc.nc = 0;
-    if (a < m.n_clusters) mol_load_cluster(m, a, kc);
+    const bool has_c = a < m.n_clusters;
+    if (has_c) mol_load_cluster(m, a, kc);
+    // every cluster small enough for the cached path?  (warp-uniform; warps 1.. have no clusters and never look at it)
+    const bool cached = !__any_sync(0xffffffffu, has_c && kc.nc > 3);
+    MolCache cc;
     __syncwarp();
-    if (a < m.n_clusters) mol_rattle_cluster(m, a, kc, X, V);   // incoming velocities obey the constraints
+    if (has_c && cached) mol_cache_build(kc, X, cc);
+    // incoming velocities obey the constraints
+    if (has_c) { if (cached) mol_rattle_cached(kc, cc, V); else mol_rattle_cluster(m, a, kc, X, V); }
     __syncwarp();
+    const double inv_mass = 1.0 / mass;
     int nV = p.nV, nR = p.nR;
     double f[3] = {0, 0, 0};
     bool f_valid = false;
@@ -476,7 +574,7 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
         if (m.remove_cm) {
             double px = mol_warp_sum(active ? mass * V[a][0] : 0.0), py = mol_warp_sum(active ? mass * V[a][1] : 0.0),
                    pz = mol_warp_sum(active ? mass * V[a][2] : 0.0);
-            if (active) { V[a][0] -= px / mt; V[a][1] -= py / mt; V[a][2] -= pz / mt; }
+            if (active) { V[a][0] -= px * inv_mt; V[a][1] -= py * inv_mt; V[a][2] -= pz * inv_mt; }
             __syncwarp();
         }
         for (int q = 0; q < p.n_prog; q++) {
@@ -494,22 +592,22 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
                     __syncwarp();
                     f_valid = true;
                 }
-                const double h = (double)p.dt_d / nV;
-                if (active) for (int c = 0; c < 3; c++) V[a][c] += h * f[c] / mass;
+                const double hm = (double)p.dt_d / nV * inv_mass;
+                if (active) for (int c = 0; c < 3; c++) V[a][c] += hm * f[c];
                 __syncwarp();
-                if (a < m.n_clusters) mol_rattle_cluster(m, a, kc, X, V);
+                if (has_c) { if (cached) mol_rattle_cached(kc, cc, V); else mol_rattle_cluster(m, a, kc, X, V); }
                 __syncwarp();
             } else if (op == 'R') {
-                const double h = (double)p.dt_d / nR;
+                const double h = (double)p.dt_d / nR, inv_h = 1.0 / h;
                 double xu[3] = {0, 0, 0};
                 if (active) for (int c = 0; c < 3; c++) { XO[a][c] = X[a][c]; X[a][c] += h * V[a][c]; xu[c] = X[a][c]; }
                 __syncwarp();
                 if (m.n_clusters) {
-                    if (a < m.n_clusters) mol_shake_cluster(m, a, kc, XO, X);
+                    if (has_c) { if (cached) mol_shake_cached(m, kc, cc, X); else mol_shake_cluster(m, a, kc, XO, X); }
                     __syncwarp();
-                    if (active) for (int c = 0; c < 3; c++) V[a][c] += (X[a][c] - xu[c]) / h;
+                    if (active) for (int c = 0; c < 3; c++) V[a][c] += (X[a][c] - xu[c]) * inv_h;
                     __syncwarp();
-                    if (a < m.n_clusters) mol_rattle_cluster(m, a, kc, X, V);
+                    if (has_c) { if (cached) mol_rattle_cached(kc, cc, V); else mol_rattle_cluster(m, a, kc, X, V); }
                     __syncwarp();
                 }
                 f_valid = false;
@@ -522,7 +620,7 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
                 }
                 ocount++;
                 __syncwarp();
-                if (a < m.n_clusters) mol_rattle_cluster(m, a, kc, X, V);
+                if (has_c) { if (cached) mol_rattle_cached(kc, cc, V); else mol_rattle_cluster(m, a, kc, X, V); }
                 __syncwarp();
             }
         }
