@@ -763,9 +763,12 @@ int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign,
     if (h->cfg.system_kind == RX_SYSTEM_MOLECULE) {
         if (!h->state_moves.empty()) RX_FAIL(h, RX_ERR_UNSUPPORTED, "rx_propagate: per-state moves are not provided for molecules");
         const uint2 mkey = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
-        k_propagate_mol<<<h->kloc, 32 * MOL_WARPS, ((const MolDev *)h->mol_dev)->dyn_shared_bytes, h->stream>>>(*(const MolDev *)h->mol_dev, p, (const StateDev *)h->d_states, (const int *)h->d_perm,
-                                                      (double *)h->d_pos, (double *)h->d_vel, h->k0, mkey, (uint32_t)iteration, reassign,
-                                                      h->d_pot, h->d_kin, h->d_nan, d_only);
+        const MolDev *md = (const MolDev *)h->mol_dev;
+        const bool no_star = getenv("RX_MOL_NO_STAR") != nullptr;   // cross-check: the general cluster path for every molecule
+        auto kern = (md->max_cluster <= 3 && !no_star) ? k_propagate_mol<true> : k_propagate_mol<false>;
+        kern<<<h->kloc, 32 * MOL_WARPS, md->dyn_shared_bytes, h->stream>>>(*md, p, (const StateDev *)h->d_states, (const int *)h->d_perm, (double *)h->d_pos,
+                                                                           (double *)h->d_vel, h->k0, mkey, (uint32_t)iteration, reassign, h->d_pot,
+                                                                           h->d_kin, h->d_nan, d_only);
         RX_CHECK_CUDA(h, cudaGetLastError());
         (*launches)++;
         return RX_OK;
@@ -1169,6 +1172,7 @@ int rxi_set_molecule(rx_engine *h, const rx_molecule *mol) {
                                 up(sizeof(MolExc) * exc.size()) + 4 * up(sizeof(int) * (n + 2)) + 3 * up(sizeof(double) * n) + up(sizeof(unsigned) * (n + 1)) + 64);
     }
     m->n = n; m->n_clusters = (int)cl.size(); m->remove_cm = mol->remove_cm_motion ? 1 : 0;
+    for (auto &c : cl) m->max_cluster = std::max(m->max_cluster, (int)c.size());
     m->tol = mol->constraint_tolerance > 0 ? mol->constraint_tolerance : 1e-8;   // integrators.py constraint_tolerance default
     // ---- term tables of the dynamics (each term once) and the slots of their force contributions: atom by atom, in the
     // order bonds, angles, torsions, pairs, each in list order

@@ -37,7 +37,7 @@ struct MolTerms {      // one contiguous blob: header, then the arrays (offsets 
 };
 
 struct MolDev {
-    int n, n_clusters, remove_cm, pad;
+    int n, n_clusters, remove_cm, max_cluster;   // max_cluster: constraints in the largest cluster
     double tol;
     const double *mass, *charge, *sigma, *eps, *seps;
     const int *b_off, *a_off, *t_off, *x_off, *c_off;
@@ -423,95 +423,181 @@ __device__ __forceinline__ void mol_rattle_cluster(const MolDev &m, int c, const
     }
 }
 
-// --- k_propagate_mol's constraint path for clusters of up to three constraints (every H-bond cluster: XH, XH2, XH3) ----------
-// The RATTLE matrix A = coup o (r r^T) depends on the positions only, and positions change in the R operations only: its
-// inverse is formed ONCE per position update (closed form, one reciprocal) and serves the two to three velocity projections
-// that follow as a matrix-vector product -- no pivoting, no division on the step's critical path.  SHAKE iterates with the
-// same inverse (the Jacobian at the previous constrained positions, which is 2 A: a chord iteration; the bond vectors turn by
-// about 1e-2 per R operation, so every iteration gains ~1.5-2 digits), i.e. 3 dot products + a 3x3 product per iteration
-// instead of a Newton solve.  Clusters with fewer constraints are padded (zero vectors, unit diagonal): one instruction
-// stream for all lanes.  Same constrained point as mol_shake_n / the oracle's sweeps to the tolerance.
-struct MolCache {
-    double r[3][3];    // bond vectors at the last constrained positions
-    double Ai[3][3];   // inverse of coup o (r r^T)
+// --- k_propagate_mol's constraint path for clusters of up to three constraints (every H-bond cluster: XH, XH2, XH3; a rigid
+// water) ------------------------------------------------------------------------------------------------------------------
+// A connected cluster of nc <= 3 constraints has at most 4 atoms: the lane that owns the cluster works on register copies of
+// those atoms -- one load and one store per atom and call, nothing read back from shared memory in between (the coupled
+// updates of the shared heavy atom were three dependent read-modify-writes per component before).  The geometry is two small
+// coefficient tables: E[b][n] (+1, -1, 0: bond vector of constraint b = sum_n E x_n) and S[n][b] (+1/m_i, -1/m_j, 0: a unit
+// multiplier on constraint b moves atom n by S r_b).
+// The RATTLE matrix A = coup o (r r^T), coup = E S, depends on the positions only, and positions change in the R operations
+// only: its inverse is formed ONCE per position update (closed form, one reciprocal) and serves the two to three velocity
+// projections that follow as a matrix-vector product -- no pivoting, no division on the step's critical path.  SHAKE iterates
+// with the same inverse (the Jacobian at the previous constrained positions is 2 A: a chord iteration; the bond vectors turn
+// by about 1e-2 per R operation, so every iteration gains 1.5-2 digits), entirely in registers: 3 dot products and a 3x3
+// product per iteration instead of a Newton solve.  Clusters with fewer constraints / atoms are padded (zero coefficients,
+// unit diagonal): one instruction stream for all lanes.  Same constrained point as mol_shake_n / the oracle's sweeps to the
+// tolerance.
+struct MolStar {
+    int nc, na;
+    int idx[4];          // the cluster's atoms (padded with its first atom: read, never written)
+    double S[4][3];
+    float E[3][4];
+    double d2[3];
+    double coup[3][3];
+    double r[3][3];      // bond vectors at the last constrained positions
+    double Ai[3][3];     // inverse of coup o (r r^T)
 };
 
-__device__ __forceinline__ void mol_cache_invert(const MolCluster &k, MolCache &c) {
+__device__ __forceinline__ void mol_star_load(const MolDev &m, int c, MolStar &k) {
+    const int q0 = m.c_off[c];
+    k.nc = m.c_off[c + 1] - q0;
+    int ci[3], cj[3], at[4] = {-1, -1, -1, -1}, na = 0;
+    double wi[3], wj[3];
+    // (static indices only, so that the whole record lives in registers)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const bool on = a < k.nc;
+        const MolCons s = on ? m.cons[q0 + a] : MolCons{-1, -1, 1.0};
+        ci[a] = s.i; cj[a] = s.j; k.d2[a] = s.d * s.d;
+        wi[a] = on ? 1.0 / m.mass[s.i] : 0.0; wj[a] = on ? 1.0 / m.mass[s.j] : 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int atom = e ? cj[a] : ci[a];
+            bool found = atom < 0;
+#pragma unroll
+            for (int n = 0; n < 4; n++) found |= at[n] == atom;
+            if (!found) {
+#pragma unroll
+                for (int n = 0; n < 4; n++) if (n == na) at[n] = atom;
+                na++;
+            }
+        }
+    k.na = na;
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        k.idx[n] = n < na ? at[n] : at[0];
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const bool is_i = at[n] >= 0 && at[n] == ci[b], is_j = at[n] >= 0 && at[n] == cj[b];
+            k.S[n][b] = (is_i ? wi[b] : 0.0) - (is_j ? wj[b] : 0.0);
+            k.E[b][n] = (float)((int)is_i - (int)is_j);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            double v = 0.0;
+#pragma unroll
+            for (int n = 0; n < 4; n++) v += (double)k.E[a][n] * k.S[n][b];
+            k.coup[a][b] = v;
+        }
+}
+
+__device__ __forceinline__ void mol_star_invert(MolStar &k) {
     double A[3][3];
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
-        for (int b = 0; b < 3; b++) A[a][b] = (a == b && a >= k.nc) ? 1.0 : k.coup[a][b] * mol_dot(c.r[a], c.r[b]);
+        for (int b = 0; b < 3; b++) A[a][b] = (a == b && a >= k.nc) ? 1.0 : k.coup[a][b] * mol_dot(k.r[a], k.r[b]);
     const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1], c01 = A[1][0] * A[2][2] - A[1][2] * A[2][0],
                  c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
     const double id = 1.0 / (A[0][0] * c00 - A[0][1] * c01 + A[0][2] * c02);
-    c.Ai[0][0] = c00 * id;
-    c.Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * id;
-    c.Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
-    c.Ai[1][0] = -c01 * id;
-    c.Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
-    c.Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
-    c.Ai[2][0] = c02 * id;
-    c.Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * id;
-    c.Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
+    k.Ai[0][0] = c00 * id;
+    k.Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * id;
+    k.Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
+    k.Ai[1][0] = -c01 * id;
+    k.Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
+    k.Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
+    k.Ai[2][0] = c02 * id;
+    k.Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * id;
+    k.Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
 }
 
-__device__ __forceinline__ void mol_cache_build(const MolCluster &k, const double (*X)[3], MolCache &c) {
+// bond vectors of the cluster's constraints from register copies of its atoms
+__device__ __forceinline__ void mol_star_bonds(const MolStar &k, const double (*x)[3], double (*rb)[3]) {
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
-        for (int q = 0; q < 3; q++) c.r[a][q] = a < k.nc ? X[k.i[a]][q] - X[k.j[a]][q] : 0.0;
-    mol_cache_invert(k, c);
+        for (int q = 0; q < 3; q++) {
+            double v = 0.0;
+#pragma unroll
+            for (int n = 0; n < 4; n++) v += (double)k.E[a][n] * x[n][q];
+            rb[a][q] = v;
+        }
 }
 
-__device__ __forceinline__ void mol_rattle_cached(const MolCluster &k, const MolCache &c, double (*V)[3]) {
-    double g[3];
+__device__ __forceinline__ void mol_star_init(MolStar &k, const double (*X)[3]) {
+    double x[4][3];
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-        double dv[3];
+    for (int n = 0; n < 4; n++)
 #pragma unroll
-        for (int q = 0; q < 3; q++) dv[q] = V[k.i[a]][q] - V[k.j[a]][q];
-        g[a] = mol_dot(c.r[a], dv);   // (padded: r = 0)
-    }
+        for (int q = 0; q < 3; q++) x[n][q] = X[k.idx[n]][q];
+    mol_star_bonds(k, x, k.r);
+    mol_star_invert(k);
+}
+
+__device__ __forceinline__ void mol_star_rattle(const MolStar &k, double (*V)[3]) {
+    double v[4][3], dv[3][3], g[3], lam[3];
 #pragma unroll
-    for (int b = 0; b < 3; b++) {
-        const double lam = c.Ai[b][0] * g[0] + c.Ai[b][1] * g[1] + c.Ai[b][2] * g[2];
-        if (b < k.nc) {
+    for (int n = 0; n < 4; n++)
 #pragma unroll
-            for (int q = 0; q < 3; q++) { V[k.i[b]][q] -= lam * k.wi[b] * c.r[b][q]; V[k.j[b]][q] += lam * k.wj[b] * c.r[b][q]; }
+        for (int q = 0; q < 3; q++) v[n][q] = V[k.idx[n]][q];
+    mol_star_bonds(k, v, dv);
+#pragma unroll
+    for (int a = 0; a < 3; a++) g[a] = mol_dot(k.r[a], dv[a]);
+#pragma unroll
+    for (int b = 0; b < 3; b++) lam[b] = k.Ai[b][0] * g[0] + k.Ai[b][1] * g[1] + k.Ai[b][2] * g[2];
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+        if (n < k.na) {
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+                V[k.idx[n]][q] = v[n][q] - (k.S[n][0] * lam[0] * k.r[0][q] + k.S[n][1] * lam[1] * k.r[1][q] + k.S[n][2] * lam[2] * k.r[2][q]);
         }
-    }
 }
 
 // positions X (moved from the constrained positions the cache was built at) back onto the constraints, along the cached bond
 // vectors; the cache is rebuilt at the result.
-__device__ __forceinline__ void mol_shake_cached(const MolDev &m, const MolCluster &k, MolCache &c, double (*X)[3]) {
-    double rc[3][3];
+__device__ __forceinline__ void mol_star_shake(const MolDev &m, MolStar &k, double (*X)[3]) {
+    double x[4][3], rc[3][3];
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) x[n][q] = X[k.idx[n]][q];
     for (int it = 0; it < 60; it++) {
-        double g[3];
+        double g[3], lam[3];
         bool done = true;
+        mol_star_bonds(k, x, rc);
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-#pragma unroll
-            for (int q = 0; q < 3; q++) rc[a][q] = X[k.i[a]][q] - X[k.j[a]][q];
             g[a] = a < k.nc ? k.d2[a] - mol_dot(rc[a], rc[a]) : 0.0;
             if (fabs(g[a]) > m.tol * k.d2[a]) done = false;
         }
         if (done) break;
 #pragma unroll
-        for (int b = 0; b < 3; b++) {
-            const double lam = 0.5 * (c.Ai[b][0] * g[0] + c.Ai[b][1] * g[1] + c.Ai[b][2] * g[2]);
-            if (b < k.nc) {
+        for (int b = 0; b < 3; b++) lam[b] = 0.5 * (k.Ai[b][0] * g[0] + k.Ai[b][1] * g[1] + k.Ai[b][2] * g[2]);
 #pragma unroll
-                for (int q = 0; q < 3; q++) { X[k.i[b]][q] += lam * k.wi[b] * c.r[b][q]; X[k.j[b]][q] -= lam * k.wj[b] * c.r[b][q]; }
-            }
-        }
+        for (int n = 0; n < 4; n++)
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+                x[n][q] += k.S[n][0] * lam[0] * k.r[0][q] + k.S[n][1] * lam[1] * k.r[1][q] + k.S[n][2] * lam[2] * k.r[2][q];
     }
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+        if (n < k.na) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) X[k.idx[n]][q] = x[n][q];
+        }
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
-        for (int q = 0; q < 3; q++) c.r[a][q] = a < k.nc ? rc[a][q] : 0.0;
-    mol_cache_invert(k, c);
+        for (int q = 0; q < 3; q++) k.r[a][q] = rc[a][q];
+    mol_star_invert(k);
 }
 
 __device__ __forceinline__ double mol_warp_sum(double v) {   // fixed tree: bit-reproducible
@@ -525,6 +611,7 @@ __device__ __forceinline__ double mol_warp_sum(double v) {   // fixed tree: bit-
 // barriers per force evaluation.  Every warp runs the same control flow (steps, program, lazy force flag); warps 1.. only take
 // part in the force evaluations.  pos / vel: double[kloc][n][3].
 #define MOL_WARPS 4
+template <bool STAR>   // STAR: every constraint cluster has at most three constraints (MolDev::max_cluster): the MolStar path
 __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynParams p, const StateDev *__restrict__ states,
                                                       const int *__restrict__ perm, double *__restrict__ pos,
                                                       double *__restrict__ vel, int k0, uint2 key, uint32_t iteration,
@@ -554,16 +641,13 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
         }
     }
     MolCluster kc;
+    MolStar ks;
     kc.nc = 0;
     const bool has_c = a < m.n_clusters;
-    if (has_c) mol_load_cluster(m, a, kc);
-    // every cluster small enough for the cached path?  (warp-uniform; warps 1.. have no clusters and never look at it)
-    const bool cached = !__any_sync(0xffffffffu, has_c && kc.nc > 3);
-    MolCache cc;
+    if (has_c) { if (STAR) mol_star_load(m, a, ks); else mol_load_cluster(m, a, kc); }
     __syncwarp();
-    if (has_c && cached) mol_cache_build(kc, X, cc);
     // incoming velocities obey the constraints
-    if (has_c) { if (cached) mol_rattle_cached(kc, cc, V); else mol_rattle_cluster(m, a, kc, X, V); }
+    if (has_c) { if (STAR) { mol_star_init(ks, X); mol_star_rattle(ks, V); } else mol_rattle_cluster(m, a, kc, X, V); }
     __syncwarp();
     const double inv_mass = 1.0 / mass;
     int nV = p.nV, nR = p.nR;
@@ -595,7 +679,7 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
                 const double hm = (double)p.dt_d / nV * inv_mass;
                 if (active) for (int c = 0; c < 3; c++) V[a][c] += hm * f[c];
                 __syncwarp();
-                if (has_c) { if (cached) mol_rattle_cached(kc, cc, V); else mol_rattle_cluster(m, a, kc, X, V); }
+                if (has_c) { if (STAR) mol_star_rattle(ks, V); else mol_rattle_cluster(m, a, kc, X, V); }
                 __syncwarp();
             } else if (op == 'R') {
                 const double h = (double)p.dt_d / nR, inv_h = 1.0 / h;
@@ -603,11 +687,11 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
                 if (active) for (int c = 0; c < 3; c++) { XO[a][c] = X[a][c]; X[a][c] += h * V[a][c]; xu[c] = X[a][c]; }
                 __syncwarp();
                 if (m.n_clusters) {
-                    if (has_c) { if (cached) mol_shake_cached(m, kc, cc, X); else mol_shake_cluster(m, a, kc, XO, X); }
+                    if (has_c) { if (STAR) mol_star_shake(m, ks, X); else mol_shake_cluster(m, a, kc, XO, X); }
                     __syncwarp();
                     if (active) for (int c = 0; c < 3; c++) V[a][c] += (X[a][c] - xu[c]) * inv_h;
                     __syncwarp();
-                    if (has_c) { if (cached) mol_rattle_cached(kc, cc, V); else mol_rattle_cluster(m, a, kc, X, V); }
+                    if (has_c) { if (STAR) mol_star_rattle(ks, V); else mol_rattle_cluster(m, a, kc, X, V); }
                     __syncwarp();
                 }
                 f_valid = false;
@@ -620,7 +704,7 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
                 }
                 ocount++;
                 __syncwarp();
-                if (has_c) { if (cached) mol_rattle_cached(kc, cc, V); else mol_rattle_cluster(m, a, kc, X, V); }
+                if (has_c) { if (STAR) mol_star_rattle(ks, V); else mol_rattle_cluster(m, a, kc, X, V); }
                 __syncwarp();
             }
         }

@@ -107,6 +107,31 @@ def test_long_launch_keeps_constraints_and_is_reproducible():
     assert ka[-3:].mean() > ka[:3].mean()
 
 
+def test_register_resident_cluster_path_agrees_with_the_general_one(monkeypatch):
+    """k_propagate_mol<true> (clusters of <= 3 constraints on register copies, cached RATTLE inverse, chord SHAKE) against
+    k_propagate_mol<false> (Newton M-SHAKE / one solve per RATTLE, any cluster size; forced with RX_MOL_NO_STAR): the same
+    constrained trajectory to the constraint tolerance."""
+    a, x = aladip()
+    temps = np.linspace(300.0, 600.0, 6)
+    K = len(temps)
+    out = []
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv('RX_MOL_NO_STAR', '1')
+        e = make_engine(a.system, temps)
+        e.set_integrator(0.002, 5.0, 40, 'V R O R V')
+        e.set_positions(np.stack([x] * K)); e.randomize_velocities(5)
+        e.propagate(9, 3)
+        out.append((e.get_positions(), e.get_velocities()))
+        e.close()
+    (xs, vs), (xg, vg) = out
+    assert np.abs(xs - xg).max() < 1e-8 and np.abs(vs - vg).max() < 1e-5, (np.abs(xs - xg).max(), np.abs(vs - vg).max())
+    c = a.system.constraints
+    i, j = c[:, 0].astype(int), c[:, 1].astype(int)
+    for xx in (xs, xg):
+        assert np.abs(np.linalg.norm(xx[:, i] - xx[:, j], axis=2) - c[None, :, 2]).max() < 1e-10
+
+
 def test_parallel_tempering_on_alanine_dipeptide():
     """BASELINE config 4 at reduced size: 12 temperatures 300-600 K, 5 iterations of 100 steps."""
     from oracle import oracle
