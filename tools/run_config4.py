@@ -4,7 +4,15 @@ oracle.  usage: run_config4.py [iterations [K [n_steps]]]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import zlib
 import numpy as np
+rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+if world > 1:
+    import torch, torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    dist.init_process_group('nccl')
+if rank != 0:
+    sys.stdout = open(os.devnull, 'w')
 from openmmtools_b200 import testsystems, states, mcmc, multistate, unit
 from oracle import oracle
 
@@ -23,6 +31,9 @@ e = s._engine
 e.phase_times(reset=True)
 t0 = time.time(); s.run(n_it); dt = time.time() - t0
 pt = e.phase_times()
+print('%d GPU(s)  digest after %d iterations: replica states %08x  energy matrix %08x' % (
+    world, s._iteration, zlib.crc32(np.ascontiguousarray(s._replica_thermodynamic_states, np.int64).tobytes()),
+    zlib.crc32(np.ascontiguousarray(s._energy_thermodynamic_states, np.float64).tobytes())))
 print('config 4: K=%d, %d steps/iteration: %.2f ms per iteration (%.1f iterations/s); device phases per iteration: mix %.3f propagate %.3f '
       'energies %.3f ms' % (K, n_steps, 1e3 * dt / n_it, n_it / dt, pt['mix_ms'] / n_it, pt['propagate_ms'] / n_it, pt['energies_ms'] / n_it))
 e.phase_times(reset=True)
@@ -32,8 +43,8 @@ m = oracle.Molecule(a.system)
 T = np.array([st.temperature.value_in_unit(unit.kelvin) for st in s._thermodynamic_states])
 s._states_stale = True
 u = e.compute_energies()
-x = e.get_positions()
-err = max(np.abs(u[k] - m.energy(np.ascontiguousarray(x[k])) / (KB * T)).max() for k in range(K))
+x = e.get_positions()       # (this rank's replicas)
+err = max(np.abs(u[e.k0 + k] - m.energy(np.ascontiguousarray(x[k])) / (KB * T)).max() for k in range(len(x)))
 c = a.system.constraints
 i, j = c[:, 0].astype(int), c[:, 1].astype(int)
 print('max |u - oracle| %.2e   max constraint error %.2e nm   acceptance %.3f' % (
