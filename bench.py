@@ -42,6 +42,9 @@ def parse():
     ap.add_argument('--atoms', type=int, default=512)
     ap.add_argument('--md-steps', type=int, default=500)
     ap.add_argument('--mixing', default='swap-all', choices=['swap-all', 'swap-neighbors', 'none'])
+    ap.add_argument('--workload', default='lj', choices=['lj', 'config4'],
+                    help="lj: the BASELINE metric's alchemical LJ fluid (default); config4: BASELINE configs[3], T-REMD of "
+                         "AlanineDipeptideVacuum (128 temperatures 300-600 K, 1000 steps/iteration; --replicas/--md-steps override)")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -283,6 +286,188 @@ def state_digest(sampler, dist):
             'note': 'after warm-up + timed + end-to-end iterations; equal digests at every --gpus = the same trajectory'}
 
 
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs[3] with the same contract (not the default: the headline metric is the LJ fluid)
+C4_METRIC = 'replica-exchange iterations/sec, AlanineDipeptideVacuum T-REMD (BASELINE configs[3])'
+
+
+def config4_sizes(args):
+    K = 128 if args.replicas == 256 else args.replicas          # (256 / 500 are the LJ defaults of the flags)
+    n_steps = 1000 if args.md_steps == 500 else args.md_steps
+    return K, n_steps
+
+
+def config4_config(args, K, n_steps):
+    return {'workload': '%s: testsystems.AlanineDipeptideVacuum (22 atoms, HBonds constraints, no cutoff), ParallelTemperingSampler, %d '
+                        'temperatures 300-600 K, %d steps of 2 fs per iteration (V R O R V, 5/ps), swap-all'
+                        % ('configs[3]' if (K, n_steps) == (128, 1000) else 'non-BASELINE variant of configs[3]', K, n_steps),
+            'replicas': K, 'atoms': 22, 'md_steps': n_steps, 'mixing': 'swap-all',
+            'parallelism': 'replica-sharded x%d, NCCL allgather of energy rows, replicated mixing' % args.gpus,
+            'l2': 'no explicit flush: each iteration streams the RNG words and slot records of K^3 swap attempts (> 126 MB L2 '
+                  'from K = 128 on); the replica state (K x 22 atoms) is the resident working set by design'}
+
+
+def cpu_arm_config4(args, steps, warmup, full_line):
+    """The reference's CPU path for configs[3] restated (oracle/rx_oracle_mol.c + rx_oracle.c): constrained Langevin
+    dynamics per replica (one host thread per replica through a thread pool: the C calls release the GIL), K x K
+    reduced-potential matrix, numba-identical swap-all mixing on one thread."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    from openmmtools_b200 import testsystems, unit
+    K, n_steps = config4_sizes(args)
+    a = testsystems.AlanineDipeptideVacuum()
+    m = oracle.Molecule(a.system)
+    x0 = np.ascontiguousarray(a.positions.value_in_unit(unit.nanometer), np.float64)
+    T = np.logspace(np.log10(300.0), np.log10(600.0), num=K)      # paralleltempering.py:162
+    betas = 1.0 / (KB * T)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    rng = np.random.default_rng(2024)
+    xs = [x0.copy() for _ in range(K)]
+    vs = [np.ascontiguousarray(rng.normal(size=x0.shape) * np.sqrt(KB * 300.0 / m.mass)[:, None]) for _ in range(K)]
+    perm = np.arange(K, dtype=np.int64)
+    mt = oracle.MT(1234)
+    pool = ThreadPoolExecutor(max_workers=min(threads, K))
+
+    def energies():
+        U = np.array(list(pool.map(lambda k: m.energy(xs[k]), range(K))))
+        return np.ascontiguousarray(U[:, None] * betas[None, :])
+
+    def step_replica(k_it):
+        k, it = k_it
+        noise = np.random.default_rng(1000003 * it + k).normal(size=(n_steps, 22, 3))
+        m.langevin(xs[k], vs[k], noise, KB * T[perm[k]], 0.002, 5.0, n_steps, 'VRORV', tol=1e-8)
+
+    u = energies()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.time()
+        nacc = np.zeros((K, K), np.int64); nprop = np.zeros((K, K), np.int64)
+        oracle.mix_swap_all(mt, K ** 3, perm, u, nacc, nprop)
+        t1 = time.time()
+        list(pool.map(step_replica, [(k, it) for k in range(K)]))
+        t2 = time.time()
+        u = energies()
+        t3 = time.time()
+        if it >= warmup:
+            times.append((t3 - t0, t1 - t0, t2 - t1, t3 - t2))
+    pool.shutdown()
+    tt = np.array(times)
+    mean = tt[:, 0].mean()
+    base = {'value': 1.0 / mean, 'unit': 'iterations/s', 'cores': min(threads, K), 'kind': 'port',
+            'sample': '%d full iterations (K=%d, 22 atoms, %d constrained Langevin steps, swap-all): mixing single-threaded '
+                      '(serial chain), one replica per host thread on %d threads (noise drawn by numpy inside the timed region, '
+                      'as OpenMM draws its own); oracle/rx_oracle_mol.c + rx_oracle.c (OpenMM itself is not installable here)'
+                      % (steps, K, n_steps, min(threads, K)),
+            'phases_ms': {'mix': 1e3 * tt[:, 1].mean(), 'propagate': 1e3 * tt[:, 2].mean(), 'energies': 1e3 * tt[:, 3].mean()}}
+    if not full_line:
+        return base
+    return {'impl': 'reference', 'metric': C4_METRIC, 'value': 1.0 / mean, 'unit': 'iterations/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': 1e3 * mean, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config4_config(args, K, n_steps),
+            'cpu_baseline': base,
+            'e2e': {'value': 1.0 / mean, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+
+
+def main_config4(args, world, rank):
+    if args.impl == 'reference':
+        if rank == 0:
+            _emit(cpu_arm_config4(args, args.steps, max(args.warmup, 0), True))
+        return 0
+    if world != args.gpus and world > 1:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
+    dist = Dist(world)
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    os.environ['LOCAL_RANK'] = str(local_rank)
+    from openmmtools_b200 import testsystems, states, mcmc, multistate, unit
+    from openmmtools_b200._dist import TorchCommunicator
+    K, n_steps = config4_sizes(args)
+    a = testsystems.AlanineDipeptideVacuum()
+    ts = states.ThermodynamicState(a.system, 300.0 * unit.kelvin)
+    move = mcmc.LangevinSplittingDynamicsMove(timestep=2.0 * unit.femtosecond, collision_rate=5.0 / unit.picosecond, n_steps=n_steps)
+    comm = TorchCommunicator() if world > 1 else None
+    sampler = multistate.ParallelTemperingSampler(mcmc_moves=move, number_of_iterations=10 ** 9, seed=1234, communicator=comm)
+    sampler.create(ts, [states.SamplerState(a.positions)], storage=None, min_temperature=300.0 * unit.kelvin,
+                   max_temperature=600.0 * unit.kelvin, n_temperatures=K)
+    eng = sampler._engine
+    sampler._compute_energies()
+    eng.run_iterations(args.warmup, 'swap-all', sampler._seed, 1)
+    eng.phase_times(reset=True)
+    clocks = ClockSampler(local_rank) if (rank == 0 and not os.environ.get('RX_BENCH_NO_CLOCKS')) else None
+    dist.barrier()
+    eng.timer_mark(0)
+    t0 = time.time()
+    eng.run_iterations(args.steps, 'swap-all', sampler._seed, 1 + args.warmup)
+    eng.timer_mark(1)
+    ms = dist.max(eng.timer_elapsed_ms())
+    wall = time.time() - t0
+    dist.barrier()
+    ck = clocks.stop() if clocks else None
+    pt = eng.phase_times()
+    mstats = eng.mix_stats()
+    launches = dist.sum(pt['launches'])
+    ms_iter = ms / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    kloc = eng.k1 - eng.k0
+    b_prop = kloc * 22 * n_steps * 96.0          # x, v (f64) read + written per atom-step: the streaming model of SURVEY 8(d)
+    t_prop = pt['propagate_ms'] / args.steps * 1e-3
+    ach = b_prop / t_prop / 1e9 if t_prop > 0 else 0.0
+    roof = {'kernel': 'k_propagate_mol', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+            'traffic': 284416.0 * kloc / 128.0,
+            'traffic_source': 'dram__bytes_read+write of one launch in the committed ncu capture profiles/mol_r2c.summary.txt '
+                              '(128 replicas), scaled by replicas per GPU; NOT measured in this run',
+            'peak_source': 'MEASURED_PEAKS.json (of measured)' if peaks else 'fallback 6650 GB/s',
+            'algorithmic_bytes_per_launch': b_prop, 'share_of_step': pt['propagate_ms'] / args.steps / ms_iter,
+            'note': 'one block of four warps per replica, the state on chip for all steps: a latency chain of ~14 k cycles per '
+                    'constrained step (DESIGN.md 7, f-2), neither HBM nor FP throughput; the streaming-model figure is given '
+                    'for the contract only',
+            'dominant_kernel': {'name': 'k_mix_walk2 (+ k_mix_walk_pow2 tail)' if (K & (K - 1)) == 0 else 'k_mix_walk2c',
+                                'share_of_step': mstats['walker_ms'] / ms_iter,
+                                'bound': 'latency: one warp, one dependent chain per speculation round (exact swap-all chain)',
+                                'rounds': mstats['rounds'], 'ns_per_round': 1e6 * mstats['walker_ms'] / max(mstats['rounds'], 1),
+                                'attempts_per_round': (K ** 3) / max(mstats['rounds'], 1), 'mix_phase_ms': pt['mix_ms'] / args.steps}}
+    e2e = None
+    if not args.no_e2e:
+        sampler.host_resident_states = True
+        sampler._states_stale = True
+        sampler._sync_sampler_states()
+        sampler._iteration = 1 + args.warmup + args.steps
+        n_e2e = max(2, min(args.steps, 10))
+        sampler.run(1)
+        dist.barrier()
+        t0 = time.time()
+        sampler.run(n_e2e)
+        dt = dist.max(time.time() - t0)
+        dist.barrier()
+        h2d = kloc * 22 * 3 * 8 * 2
+        d2h = kloc * 22 * 3 * 8 * 2 + K * K * 8 + K * 8 + 2 * K * K * 8 + 2 * K * 8
+        e2e = {'value': n_e2e / dt, 'unit': 'iterations/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+               'iterations': n_e2e, 'api': 'ParallelTemperingSampler.run(host_resident_states=True)'}
+    digest = state_digest(sampler, dist)
+    if rank != 0:
+        return 0
+    line = {'metric': C4_METRIC, 'value': args.steps / (ms * 1e-3), 'unit': 'iterations/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_iter, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32 forces, f64 positions/velocities/constraints/energies/mixing', 'data': 'synthetic',
+            'config': config4_config(args, K, n_steps), 'roofline': roof,
+            'phases_ms': {'mix': pt['mix_ms'] / args.steps, 'propagate': pt['propagate_ms'] / args.steps,
+                          'energies_incl_allgather': pt['energies_ms'] / args.steps},
+            'mixing_stats': mstats, 'clocks': ck, 'e2e': e2e, 'gpu_launches': int(launches), 'state_digest': digest,
+            'host_wall_ms_per_step': 1e3 * wall / args.steps}
+    if not args.no_cpu_baseline:
+        try:
+            line['cpu_baseline'] = cpu_arm_config4(args, 2, 1, False)
+        except Exception as e:
+            line['cpu_baseline'] = {'error': repr(e)}
+    _emit(line)
+    return 0
+
+
 _REAL_STDOUT = sys.stdout
 
 
@@ -303,6 +488,8 @@ def main():
     args = parse()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
+    if args.workload == 'config4':
+        return main_config4(args, world, rank)
     if args.impl == 'reference':
         if rank != 0:
             return 0

@@ -36,3 +36,15 @@ def test_reference_arm_other_ranks_exit_silently():
     out = run_bench('--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0',
                     env={'RANK': '1', 'WORLD_SIZE': '2', 'LOCAL_RANK': '1'})
     assert out.strip() == ''
+
+
+def test_config4_reference_arm_keeps_the_contract():
+    """--workload config4 (BASELINE configs[3], AlanineDipeptideVacuum T-REMD): the same line, its own metric name."""
+    out = run_bench('--workload', 'config4', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--replicas', '4',
+                    '--md-steps', '20')
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, out
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and 'AlanineDipeptideVacuum' in d['metric'] and d['config']['atoms'] == 22
+    assert d['config']['replicas'] == 4 and d['config']['md_steps'] == 20 and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['e2e']['value'] == d['value']
