@@ -204,6 +204,32 @@ RX_API int rx_mix_stream_position(rx_engine *h, int32_t stream, uint64_t *words_
 RX_API int rx_run_iterations(rx_engine *h, int32_t n_iterations, int32_t mixing, uint64_t seed,
                       uint64_t first_iteration, int32_t reassign_velocities);
 
+/* Replaces SAMSSampler._mix_replicas (/root/reference/openmmtools/multistate/sams.py:395-437): the global state jump
+ * (_global_jump, :477-501), the stage schedule (_update_stage, :564-604), the online logZ update (_update_logZ_estimates,
+ * :606-681) and log_weights = log_target - logZ (:683-691) in ONE kernel on the resident K x M energy matrix; logZ, weights,
+ * state histogram, stage and t0 stay on the device between iterations.  The jump draws numpy RandomState.choice's uniform (one
+ * random_sample per replica) from the RX_STREAM_NUMPY stream (rx_mix_seed).
+ *   rx_sams_set   configuration + initial logZ [M], log target probabilities [M], state histogram [M] (NULL: zeros)
+ *   rx_sams_step  one jump for every replica (+ the weight update when update_weights != 0; sams.py:429-435 skips it during
+ *                 equilibration); histogram: the host's state histogram to use (NULL: the device's own count, which the kernel
+ *                 advances by the new states of every call); results through rx_sams_get
+ *   rx_sams_run_iterations  n x (jump + update -> propagate -> energies), no host round trip                             */
+typedef struct rx_sams_config {
+    double gamma0, flatness_threshold;
+    int32_t weight_update_method;   /* 0 'optimal', 1 'rao-blackwellized' */
+    int32_t two_stage;              /* update_stages == 'two-stage' */
+    int32_t flatness_criteria;      /* 0 'minimum-visits', 1 'histogram-flatness', 2 'logZ-flatness' */
+    int32_t stage;                  /* current stage (0 | 1) and t0, sams.py:318-328 */
+    int64_t t0;
+} rx_sams_config;
+RX_API int rx_sams_set(rx_engine *h, const rx_sams_config *config, const double *log_target_probabilities, const double *logZ,
+                       const int64_t *histogram);
+RX_API int rx_sams_step(rx_engine *h, int64_t iteration, int32_t update_weights, const int64_t *histogram);
+RX_API int rx_sams_get(rx_engine *h, double *logZ, double *log_weights, int64_t *histogram, int32_t *stage, int64_t *t0,
+                       double *gamma, int64_t *states /*[K]*/, int64_t *previous_states /*[K]*/);
+RX_API int rx_sams_run_iterations(rx_engine *h, int32_t n_iterations, uint64_t seed, uint64_t first_iteration,
+                                  int32_t reassign_velocities);
+
 /* Device-side phase timings (CUDA events) of the last rx_run_iterations / phase calls, in ms:
  * [0] mix, [1] propagate, [2] energies (incl. allgather), [3] rng-stream generation, accumulated;
  * counts[i] = number of launches of my kernels in phase i.                                                */

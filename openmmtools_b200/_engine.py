@@ -278,6 +278,36 @@ class Engine:
         self._check(self._lib.rx_run_iterations(self._h, int(n), code, int(seed), int(first_iteration),
                                                 int(bool(reassign_velocities))))
 
+    # ---- SAMS on the device (rx_sams.cuh; sams.py:395-437, 477-501, 564-691)
+    SAMS_METHODS = {'optimal': 0, 'rao-blackwellized': 1}
+    SAMS_CRITERIA = {'minimum-visits': 0, 'histogram-flatness': 1, 'logZ-flatness': 2}
+
+    def sams_set(self, log_target_probabilities, logZ, histogram=None, gamma0=1.0, flatness_threshold=0.2,
+                 weight_update_method='rao-blackwellized', update_stages='two-stage', flatness_criteria='logZ-flatness',
+                 stage=0, t0=0):
+        cfg = _lib.RxSamsConfig(float(gamma0), float(flatness_threshold), self.SAMS_METHODS[weight_update_method],
+                                1 if update_stages == 'two-stage' else 0, self.SAMS_CRITERIA[flatness_criteria], int(stage), int(t0))
+        lt = _c64(log_target_probabilities, (self.M,)); lz = _c64(logZ, (self.M,))
+        hh = None if histogram is None else np.ascontiguousarray(histogram, np.int64)
+        self._check(self._lib.rx_sams_set(self._h, C.byref(cfg), _ptr(lt), _ptr(lz), None if hh is None else _ptr(hh)))
+
+    def sams_step(self, iteration, update_weights=True, histogram=None):
+        hh = None if histogram is None else np.ascontiguousarray(histogram, np.int64)
+        self._check(self._lib.rx_sams_step(self._h, int(iteration), int(bool(update_weights)), None if hh is None else _ptr(hh)))
+
+    def sams_get(self):
+        """dict(logZ, log_weights, histogram, stage, t0, gamma, states, previous_states) of the device-resident SAMS state."""
+        logZ = np.zeros(self.M); lw = np.zeros(self.M); hist = np.zeros(self.M, np.int64)
+        st = np.zeros(self.K, np.int64); prev = np.zeros(self.K, np.int64)
+        stage = C.c_int32(); t0 = C.c_int64(); gamma = C.c_double()
+        self._check(self._lib.rx_sams_get(self._h, _ptr(logZ), _ptr(lw), _ptr(hist), C.byref(stage), C.byref(t0), C.byref(gamma),
+                                          _ptr(st), _ptr(prev)))
+        return dict(logZ=logZ, log_weights=lw, histogram=hist, stage=stage.value, t0=t0.value, gamma=gamma.value, states=st,
+                    previous_states=prev)
+
+    def sams_run_iterations(self, n, seed, first_iteration, reassign_velocities=False):
+        self._check(self._lib.rx_sams_run_iterations(self._h, int(n), int(seed), int(first_iteration), int(bool(reassign_velocities))))
+
     def phase_times(self, reset=False):
         ms = np.zeros(4); cnt = np.zeros(4, np.int64)
         self._check(self._lib.rx_get_phase_times(self._h, _ptr(ms), _ptr(cnt), int(reset)))

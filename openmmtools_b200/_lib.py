@@ -21,7 +21,7 @@ SYMBOLS = [
     'rx_get_replica_energies', 'rx_pin_host_memory', 'rx_unpin_host_memory', 'rx_randomize_velocities', 'rx_minimize', 'rx_set_replica_states', 'rx_get_replica_states',
     'rx_propagate', 'rx_propagate_retry', 'rx_compute_energies', 'rx_compute_energies_at', 'rx_set_energies', 'rx_get_energies', 'rx_mix_seed',
     'rx_mix_skip', 'rx_mix_swap_all', 'rx_mix_swap_neighbors', 'rx_get_mix_counts', 'rx_mix_stream_position',
-    'rx_run_iterations', 'rx_get_phase_times', 'rx_timer_mark', 'rx_timer_elapsed', 'rx_get_mix_stats', 'rx_selftest_exp', 'rx_comm_unique_id', 'rx_comm_init',
+    'rx_run_iterations', 'rx_sams_set', 'rx_sams_step', 'rx_sams_get', 'rx_sams_run_iterations', 'rx_get_phase_times', 'rx_timer_mark', 'rx_timer_elapsed', 'rx_get_mix_stats', 'rx_selftest_exp', 'rx_comm_unique_id', 'rx_comm_init',
 ]
 
 
@@ -37,6 +37,11 @@ class RxConfig(C.Structure):
 class RxStateParams(C.Structure):
     _fields_ = [('temperature', C.c_double), ('lambda_sterics', C.c_double), ('energy_offset', C.c_double),
                 ('ho_K', C.c_double), ('ho_x0', C.c_double * 3)]
+
+
+class RxSamsConfig(C.Structure):
+    _fields_ = [('gamma0', C.c_double), ('flatness_threshold', C.c_double), ('weight_update_method', C.c_int32),
+                ('two_stage', C.c_int32), ('flatness_criteria', C.c_int32), ('stage', C.c_int32), ('t0', C.c_int64)]
 
 
 class RxMolecule(C.Structure):
@@ -94,6 +99,10 @@ def load():
     lib.rx_get_mix_counts.argtypes = [vp, vp, vp]
     lib.rx_mix_stream_position.argtypes = [vp, i32, C.POINTER(u64)]
     lib.rx_run_iterations.argtypes = [vp, i32, i32, u64, u64, i32]
+    lib.rx_sams_set.argtypes = [vp, C.POINTER(RxSamsConfig), vp, vp, vp]
+    lib.rx_sams_step.argtypes = [vp, i64, i32, vp]
+    lib.rx_sams_get.argtypes = [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(dbl), vp, vp]
+    lib.rx_sams_run_iterations.argtypes = [vp, i32, u64, u64, i32]
     lib.rx_get_phase_times.argtypes = [vp, vp, vp, i32]
     lib.rx_timer_mark.argtypes = [vp, i32]
     lib.rx_timer_elapsed.argtypes = [vp, C.POINTER(dbl)]

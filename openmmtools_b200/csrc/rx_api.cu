@@ -118,6 +118,7 @@ extern "C" void rx_destroy(rx_engine *h) {
         destroy_t f = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");
         if (f) f(h->nccl_comm);
     }
+    rxi_sams_free(h);
     rxi_mix_free(h);
     cudaFree(h->d_atom); cudaFree(h->d_atom_d); cudaFree(h->d_alch_list); cudaFree(h->d_states);
     cudaFree(h->d_pos_snap); cudaFree(h->d_vel_snap); cudaFree(h->d_retry);
@@ -633,6 +634,70 @@ extern "C" int rx_run_iterations(rx_engine *h, int32_t n_iterations, int32_t mix
     RX_CHECK_CUDA(h, cudaMemcpy(f.data(), h->d_nan, sizeof(int) * K, cudaMemcpyDeviceToHost));
     for (int k = h->k0; k < h->k0 + h->kloc; k++)
         if (f[k]) RX_FAIL(h, RX_ERR_NAN, "rx_run_iterations: NaN encountered in a replica");
+    return RX_OK;
+}
+
+// ---- SAMS (rx_sams.cuh) ------------------------------------------------------------------------------------------------------
+extern "C" int rx_sams_set(rx_engine *h, const rx_sams_config *config, const double *log_target, const double *logZ,
+                           const int64_t *histogram) {
+    ENTER(h);
+    if (!config || !log_target || !logZ) RX_FAIL(h, RX_ERR_INVALID, "rx_sams_set: null argument");
+    return rxi_sams_set(h, config, log_target, logZ, histogram);
+}
+
+extern "C" int rx_sams_step(rx_engine *h, int64_t iteration, int32_t update_weights, const int64_t *histogram) {
+    ENTER(h);
+    int rc = check_ready(h, "rx_sams_step");
+    if (rc) return rc;
+    if (histogram && (rc = rxi_sams_set_histogram(h, histogram))) return rc;
+    int lm = 0;
+    PhaseTimer Tm(h, 0);
+    rc = rxi_sams_step(h, iteration, update_weights, &lm);
+    if (rc) return rc;
+    Tm.stop(lm);
+    RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+    Tm.accumulate();
+    return check_device_error(h);
+}
+
+extern "C" int rx_sams_get(rx_engine *h, double *logZ, double *log_weights, int64_t *histogram, int32_t *stage, int64_t *t0,
+                           double *gamma, int64_t *states, int64_t *previous_states) {
+    ENTER(h);
+    return rxi_sams_get(h, logZ, log_weights, histogram, stage, t0, gamma, states, previous_states);
+}
+
+extern "C" int rx_sams_run_iterations(rx_engine *h, int32_t n_iterations, uint64_t seed, uint64_t first_iteration, int32_t reassign) {
+    ENTER(h);
+    int rc = check_ready(h, "rx_sams_run_iterations");
+    if (rc) return rc;
+    if (!h->have_integrator) RX_FAIL(h, RX_ERR_INVALID, "rx_sams_run_iterations: rx_set_integrator must be called first");
+    const long long K = h->cfg.n_replicas;
+    for (int it = 0; it < n_iterations; it++) {
+        // multistatesampler.py:776-782 with sams.py:395-437 as the mixing: jump + weight update -> propagate -> energies
+        int lm = 0, lp = 0, le = 0;
+        PhaseTimer Tm(h, 0);
+        rc = rxi_sams_step(h, (long long)(first_iteration + it), first_iteration + it > 0 ? 1 : 0, &lm);
+        if (rc) return rc;
+        Tm.stop(lm);
+        PhaseTimer Tp(h, 1);
+        rc = rxi_propagate(h, seed, first_iteration + it, reassign, &lp);
+        if (rc) return rc;
+        Tp.stop(lp);
+        PhaseTimer Te(h, 2);
+        rc = rxi_compute_energy_rows(h, &le);
+        if (rc) return rc;
+        rc = rxi_allgather_energies(h);
+        if (rc) return rc;
+        Te.stop(le);
+        RX_CHECK_CUDA(h, cudaStreamSynchronize(h->stream));
+        Tm.accumulate(); Tp.accumulate(); Te.accumulate();
+    }
+    rc = check_device_error(h);
+    if (rc) return rc;
+    std::vector<int> f(K, 0);
+    RX_CHECK_CUDA(h, cudaMemcpy(f.data(), h->d_nan, sizeof(int) * K, cudaMemcpyDeviceToHost));
+    for (int k = h->k0; k < h->k0 + h->kloc; k++)
+        if (f[k]) RX_FAIL(h, RX_ERR_NAN, "rx_sams_run_iterations: NaN encountered in a replica");
     return RX_OK;
 }
 

@@ -116,6 +116,7 @@ struct rx_engine {
     size_t last_consumed = 0;     // words the previous swap-all call consumed (sizes the generate-ahead)
     size_t slots_for_avail = 0;   // S.avail the slot records were built for
     cudaEvent_t ev_prepared = nullptr, ev_consumed = nullptr;
+    void *sams = nullptr;         // SamsState (rx_sams.cuh): device-resident logZ / weights / histogram of a SAMSSampler
     // timing
     double phase_ms[4] = {0, 0, 0, 0};
     long long phase_launches[4] = {0, 0, 0, 0};
@@ -164,6 +165,12 @@ int rxi_selftest_exp(rx_engine *h, const double *x, double *y, int n);
 int rxi_mix_swap_all(rx_engine *h, long long nswap, int *launches);
 int rxi_mix_swap_neighbors(rx_engine *h, int *launches);
 void rxi_mix_free(rx_engine *h);
+int rxi_sams_set(rx_engine *h, const rx_sams_config *c, const double *log_target, const double *logZ, const int64_t *histogram);
+int rxi_sams_step(rx_engine *h, long long iteration, int update, int *launches);
+int rxi_sams_get(rx_engine *h, double *logZ, double *log_weights, int64_t *histogram, int32_t *stage, int64_t *t0, double *gamma,
+                 int64_t *states, int64_t *previous_states);
+int rxi_sams_set_histogram(rx_engine *h, const int64_t *histogram);
+void rxi_sams_free(rx_engine *h);
 
 // ---- implemented in rx_dynamics.cu ----
 int rxi_propagate(rx_engine *h, uint64_t seed, uint64_t iteration, int reassign, int *launches, const int *d_only = nullptr);

@@ -1090,3 +1090,5 @@ void rxi_mix_free(rx_engine *h) {
     cudaFree(h->d_filt_scale);
     cudaFree(h->d_ctl);
 }
+
+#include "rx_sams.cuh"

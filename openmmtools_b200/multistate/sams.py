@@ -10,6 +10,12 @@ not have to equal M states here).  The jump itself and the weight update are O(K
 reporter needs on the host anyway; they restate the reference line by line with numpy's legacy ``RandomState`` (the
 reference uses numpy's global generator, seeded or not), and are pinned to golden vectors lifted from the reference
 (tests/golden/make_sams_golden.py).
+
+``device_weight_update=True`` moves the jump and the weight update onto the GPU as well (``rx_sams_step``, csrc/rx_sams.cuh:
+one kernel on the resident energy matrix; logZ, weights, histogram, stage and t0 stay on the device), drawing the same
+uniforms from the engine's copy of the MT19937 stream; the host generator is advanced in lockstep, so checkpoints and a later
+switch back to the host path see the same stream.  The device arithmetic uses CUDA's exp/log, so logZ agrees with the host
+path to ~1e-13, not bitwise (tests/test_gpu_sams.py); ``run_fused(n)`` runs n whole iterations without a host round trip.
 """
 import numpy as np
 from scipy.special import logsumexp
@@ -21,13 +27,16 @@ class SAMSSampler(MultiStateSampler):
                        'class of openmmtools_b200.multistate on {}')
     _STORED_OPTIONS = MultiStateSampler._STORED_OPTIONS + (
         'state_update_scheme', 'update_stages', 'flatness_criteria', 'flatness_threshold', 'weight_update_method',
-        'adapt_target_probabilities', 'gamma0', 'log_target_probabilities')   # (a _StoredProperty in the reference, sams.py:281)
+        'adapt_target_probabilities', 'gamma0', 'log_target_probabilities', 'device_weight_update')   # (a _StoredProperty in the reference, sams.py:281)
 
     def __init__(self, number_of_iterations=1, log_target_probabilities=None, state_update_scheme='global-jump',
                  locality=5, update_stages='two-stage', flatness_criteria='logZ-flatness', flatness_threshold=0.2,
                  weight_update_method='rao-blackwellized', adapt_target_probabilities=False, gamma0=1.0,
-                 logZ_guess=None, **kwargs):
+                 logZ_guess=None, device_weight_update=False, **kwargs):
         super().__init__(number_of_iterations=number_of_iterations, **kwargs)
+        self.device_weight_update = bool(device_weight_update)
+        self._sams_on_device = False
+        self._sams_draws = 0          # uniforms drawn for jumps so far (either path): positions the device's stream copy
         self.log_target_probabilities = log_target_probabilities
         self.state_update_scheme = self._validate('state_update_scheme', state_update_scheme, ['global-jump'])
         self.locality = locality
@@ -81,7 +90,80 @@ class SAMSSampler(MultiStateSampler):
             return list(range(0, self.n_states))
         return list(range(max(0, state_index - self.locality), min(self.n_states, state_index + self.locality + 1)))
 
+    def _seed_mixing_streams(self):
+        super()._seed_mixing_streams()
+        from .. import _lib
+        # the engine's numpy-RandomState stream is a copy of self._rng's (same seed): rx_sams_step draws the jumps from it
+        self._engine.mix_seed((self._seed >> 8) & 0xFFFFFFFF, _lib.RX_STREAM_NUMPY)
+        self._sams_on_device = False
+
+    def _sams_device_init(self):
+        """Hand the host's SAMS state to the device (first device step, after a restore, after host-path iterations)."""
+        if self._sams_on_device:
+            return
+        from .. import _lib
+        e = self._engine
+        pos = e.mix_stream_position(_lib.RX_STREAM_NUMPY)
+        if pos > 2 * self._sams_draws:
+            raise RuntimeError('the device copy of the SAMS random stream is ahead of the host generator')
+        if pos < 2 * self._sams_draws:
+            e.mix_skip(2 * self._sams_draws - pos, _lib.RX_STREAM_NUMPY)
+        e.set_energies(self._energy_thermodynamic_states)
+        e.set_replica_states(self._replica_thermodynamic_states)
+        e.sams_set(self.log_target_probabilities, self._logZ, histogram=self._cached_state_histogram, gamma0=self.gamma0,
+                   flatness_threshold=self.flatness_threshold, weight_update_method=self.weight_update_method,
+                   update_stages=self.update_stages, flatness_criteria=self.flatness_criteria, stage=self._stage, t0=self._t0)
+        self._sams_on_device = True
+
+    def _mix_replicas_device(self):
+        """sams.py:395-437 in one kernel (rx_sams_step): jump of every replica, stage schedule, logZ and weight update."""
+        from .. import _lib
+        e = self._engine
+        K = self.n_replicas
+        self._sams_device_init()
+        update = self._iteration > 0          # not during equilibration (sams.py:429-435)
+        e.sams_step(self._iteration, update_weights=update, histogram=self._cached_state_histogram)
+        r = e.sams_get()
+        self._n_accepted_matrix[:, :] = 0
+        self._n_proposed_matrix[:, :] = 0
+        for cur, new in zip(r['previous_states'], r['states']):
+            self._n_proposed_matrix[cur, :] += 1
+            self._n_accepted_matrix[cur, new] += 1
+        self._replica_thermodynamic_states[:] = r['states']
+        if update:
+            self._logZ = r['logZ']
+            self.log_weights = r['log_weights']
+            self._stage, self._t0, self._last_gamma = int(r['stage']), int(r['t0']), float(r['gamma'])
+        self._rng.random_sample(K)            # the host generator stays in lockstep (checkpoints, switching paths)
+        self._sams_draws += K
+        return self._replica_thermodynamic_states
+
+    def run_fused(self, n_iterations):
+        """n whole SAMS iterations (jump + weight update -> propagate -> energies) on the device without a host round trip
+        (rx_sams_run_iterations); nothing is reported for them.  The sampler's host mirrors are refreshed at the end."""
+        from .. import _lib
+        e = self._engine
+        K = self.n_replicas
+        if not self.device_weight_update:
+            raise RuntimeError('run_fused needs device_weight_update=True')
+        self._sams_device_init()
+        e.sams_run_iterations(n_iterations, self._seed, self._iteration + 1)
+        self._iteration += n_iterations
+        r = e.sams_get()
+        self._replica_thermodynamic_states[:] = r['states']
+        self._logZ, self.log_weights = r['logZ'], r['log_weights']
+        self._stage, self._t0, self._last_gamma = int(r['stage']), int(r['t0']), float(r['gamma'])
+        self._cached_state_histogram[:] = r['histogram']
+        self._rng.random_sample(K * n_iterations)
+        self._sams_draws += K * n_iterations
+        self._energy_thermodynamic_states[:] = e.get_energies()
+        self._states_stale = True
+
     def _mix_replicas(self):
+        if self.device_weight_update and self._engine is not None:
+            return self._mix_replicas_device()
+        self._sams_on_device = False
+        self._sams_draws += self.n_replicas
         self._n_accepted_matrix[:, :] = 0
         self._n_proposed_matrix[:, :] = 0
         replicas_log_P_k = np.zeros([self.n_replicas, self.n_states], np.float64)
@@ -184,6 +266,7 @@ class SAMSSampler(MultiStateSampler):
         e = super()._checkpoint_extra()
         st = self._rng.get_state()
         e['sams_rng'] = [st[0], [int(x) for x in st[1]], int(st[2]), int(st[3]), float(st[4])]
+        e['sams_draws'] = int(self._sams_draws)
         return e
 
     def _restore_sampler_from_reporter(self, reporter):
@@ -203,3 +286,5 @@ class SAMSSampler(MultiStateSampler):
         self._rng = np.random.RandomState(0)
         r = extra['sams_rng']
         self._rng.set_state((r[0], np.array(r[1], dtype=np.uint32), r[2], r[3], r[4]))
+        self._sams_draws = int(extra.get('sams_draws', int(extra.get('mt_numpy_words', 0)) // 2))
+        self._sams_on_device = False
