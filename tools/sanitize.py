@@ -38,4 +38,9 @@ hs = multistate.ReplicaExchangeSampler(mcmc_moves=mcmc.LangevinSplittingDynamics
                                        replica_mixing_scheme='swap-neighbors')
 hs.create([states.ThermodynamicState(ho.system, T * unit.kelvin) for T in (300, 310, 320)], [states.SamplerState(ho.positions)])
 hs.run()
+# SAMS on the device (k_sams_step): 2 replicas over 3 oscillator states, per-iteration and fused
+ss_ = multistate.SAMSSampler(mcmc_moves=mcmc.LangevinSplittingDynamicsMove(n_steps=20), number_of_iterations=10 ** 6, seed=5,
+                             flatness_criteria='minimum-visits', device_weight_update=True)
+ss_.create([states.ThermodynamicState(ho.system, T * unit.kelvin) for T in (300, 310, 320)], [states.SamplerState(ho.positions)] * 2)
+ss_.run(6); ss_.run_fused(4)
 print('sanitize workload done')
