@@ -175,7 +175,9 @@ __device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned
     const MolTerms *h = (const MolTerms *)tb;
     const int lane = threadIdx.x, nth = blockDim.x;   // (k_propagate_mol: all warps of the block; the other kernels: one warp)
     const TBond *B = (const TBond *)(tb + h->o_bond);
-    for (int t = lane; t < m.n_tb; t += nth) {
+    // (which thread evaluates a term does not matter for the result -- fixed slots; the four kinds start at different threads so
+    // that no thread gets a torsion AND an angle AND two pairs: the evaluation is as long as its busiest thread)
+    for (int t = (lane + nth / 2) % nth; t < m.n_tb; t += nth) {
         const TBond b = B[t];
         const float d[3] = {(float)(X[b.i][0] - X[b.j][0]), (float)(X[b.i][1] - X[b.j][1]), (float)(X[b.i][2] - X[b.j][2])};
         const float r = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -183,7 +185,7 @@ __device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned
         for (int q = 0; q < 3; q++) { FS[b.si][q] = c * d[q]; FS[b.sj][q] = -c * d[q]; }
     }
     const TAngle *A = (const TAngle *)(tb + h->o_angle);
-    for (int t = lane; t < m.n_ta; t += nth) {
+    for (int t = nth - 1 - lane; t < m.n_ta; t += nth) {
         const TAngle g = A[t];
         float u[3], v[3];
         for (int c = 0; c < 3; c++) { u[c] = (float)(X[g.i][c] - X[g.j][c]); v[c] = (float)(X[g.k][c] - X[g.j][c]); }
@@ -219,7 +221,7 @@ __device__ __forceinline__ void mol_forces_terms(const MolDev &m, const unsigned
         }
     }
     const TPair *P = (const TPair *)(tb + h->o_pair);
-    for (int t = lane; t < m.n_tp; t += nth) {
+    for (int t = ((lane - m.n_tt) % nth + nth) % nth; t < m.n_tp; t += nth) {
         const TPair p = P[t];
         const float d[3] = {(float)(X[p.i][0] - X[p.j][0]), (float)(X[p.i][1] - X[p.j][1]), (float)(X[p.i][2] - X[p.j][2])};
         const float ir2 = 1.f / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), ir = sqrtf(ir2);
@@ -650,7 +652,8 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
     if (has_c) { if (STAR) { mol_star_init(ks, X); mol_star_rattle(ks, V); } else mol_rattle_cluster(m, a, kc, X, V); }
     __syncwarp();
     const double inv_mass = 1.0 / mass;
-    int nV = p.nV, nR = p.nR;
+    // (the program is interpreted, so the compiler does not hoist these out of the step loop: two f64 divisions per R)
+    const double hm = (double)p.dt_d / p.nV * inv_mass, h = (double)p.dt_d / p.nR, inv_h = 1.0 / h;
     double f[3] = {0, 0, 0};
     bool f_valid = false;
     uint32_t ocount = 0;
@@ -676,13 +679,11 @@ __global__ void __launch_bounds__(32 * MOL_WARPS) k_propagate_mol(MolDev m, DynP
                     __syncwarp();
                     f_valid = true;
                 }
-                const double hm = (double)p.dt_d / nV * inv_mass;
                 if (active) for (int c = 0; c < 3; c++) V[a][c] += hm * f[c];
                 __syncwarp();
                 if (has_c) { if (STAR) mol_star_rattle(ks, V); else mol_rattle_cluster(m, a, kc, X, V); }
                 __syncwarp();
             } else if (op == 'R') {
-                const double h = (double)p.dt_d / nR, inv_h = 1.0 / h;
                 double xu[3] = {0, 0, 0};
                 if (active) for (int c = 0; c < 3; c++) { XO[a][c] = X[a][c]; X[a][c] += h * V[a][c]; xu[c] = X[a][c]; }
                 __syncwarp();
