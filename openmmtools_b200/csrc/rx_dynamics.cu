@@ -269,6 +269,8 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
     const float m_dt = PS ? mv->dt : p.dt, m_a = PS ? mv->a : p.a, m_b = PS ? mv->b : p.b;
     const int m_steps = PS ? mv->n_steps : p.n_steps, m_nprog = PS ? mv->n_prog : p.n_prog, m_nV = PS ? mv->nV : p.nV,
               m_nR = PS ? mv->nR : p.nR;
+    // (the program is interpreted: the compiler does not hoist these divisions out of the step loop; same values, same bits)
+    const float h_V = m_dt / (float)m_nV, h_R = m_dt / (float)m_nR;
     if (PS) reassign = mv->reassign;
     float sig_i, se_i, inv_m, sigma_v;
     bool alch_i;
@@ -447,10 +449,10 @@ __global__ void __launch_bounds__(1024) k_propagate(DynParams p, const float4 *_
             const char op = PS ? mv->prog[q] : p.prog[q];
             if (op == 'V') {
                 if (!f_valid) { compute_forces(false, dummy); f_valid = true; }
-                const float h = m_dt / (float)m_nV;
+                const float h = h_V;
                 vx += h * fx * inv_m; vy += h * fy * inv_m; vz += h * fz * inv_m;
             } else if (op == 'R') {
-                const float h = m_dt / (float)m_nR;
+                const float h = h_R;
                 x += h * vx; y += h * vy; z += h * vz;
                 f_valid = false;
             } else {  // 'O'
