@@ -95,6 +95,77 @@ def test_two_gpus_reproduce_single_gpu(tmp_path):
         assert np.array_equal(d['x'], x1[k0:k0 + d['x'].shape[0]])
 
 
+def _two_devices():
+    import ctypes
+    try:
+        cuda = ctypes.CDLL('libcudart.so.12')
+    except OSError:
+        cuda = ctypes.CDLL('libcudart.so')
+    n = ctypes.c_int()
+    cuda.cudaGetDeviceCount(ctypes.byref(n))
+    return n.value >= 2
+
+
+WIDE_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+import numpy as np
+import torch.distributed as dist
+dist.init_process_group('gloo')
+from openmmtools_b200._dist import TorchCommunicator
+from test_multi_gpu import sams_run, tremd_run
+res = dict(sams_run(TorchCommunicator()))
+res.update(tremd_run(TorchCommunicator()))
+np.savez(%(out)r + '_%%d.npz' %% dist.get_rank(), **res)
+dist.barrier()
+'''
+
+
+def sams_run(communicator=None):
+    """SAMS with the device kernel: 4 replicas (2 per rank) over 5 oscillator states, per iteration and fused."""
+    from test_gpu_sams import make_sampler
+    s = make_sampler(True, n_replicas=4, flatness_criteria='minimum-visits', communicator=communicator)
+    s.run(12)
+    s.run_fused(6)
+    s.run(2)
+    return dict(sams_states=np.array(s._replica_thermodynamic_states), sams_logZ=s._logZ.copy(),
+                sams_u=s._energy_thermodynamic_states.copy(), sams_hist=np.array(s._state_histogram))
+
+
+def tremd_run(communicator=None):
+    """BASELINE configs[3] at reduced size: 8 temperatures of AlanineDipeptideVacuum (4 replicas per rank), 60 steps."""
+    from openmmtools_b200 import testsystems, states, mcmc, multistate, unit
+    a = testsystems.AlanineDipeptideVacuum()
+    move = mcmc.LangevinSplittingDynamicsMove(timestep=2.0 * unit.femtosecond, collision_rate=5.0 / unit.picosecond, n_steps=60)
+    s = multistate.ParallelTemperingSampler(mcmc_moves=move, number_of_iterations=10 ** 6, seed=77, communicator=communicator)
+    s.create(states.ThermodynamicState(a.system, 300.0 * unit.kelvin), [states.SamplerState(a.positions)], storage=None,
+             min_temperature=300.0 * unit.kelvin, max_temperature=600.0 * unit.kelvin, n_temperatures=8)
+    s.run(4)
+    return dict(pt_states=np.array(s._replica_thermodynamic_states), pt_u=s._energy_thermodynamic_states.copy())
+
+
+@pytest.mark.gpu
+def test_two_gpus_reproduce_single_gpu_for_sams_and_the_molecule_path(tmp_path):
+    """The widened rows shard like the headline path: device SAMS (replicated jump/update kernel on the all-gathered matrix)
+    and the constrained-molecule T-REMD give the same states and energies on two ranks as on one."""
+    if not _two_devices():
+        pytest.skip('needs 2 GPUs')
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    ref = dict(sams_run()); ref.update(tremd_run())
+    script = tmp_path / 'w2.py'
+    out = str(tmp_path / 'wide')
+    script.write_text(WIDE_WORKER % {'root': ROOT, 'out': out})
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29536', str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for rank in range(2):
+        d = np.load(out + '_%d.npz' % rank)
+        for key, v in ref.items():
+            assert np.array_equal(d[key], v), (rank, key)
+
+
 SOCKET_WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r)
