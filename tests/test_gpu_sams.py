@@ -167,3 +167,40 @@ def test_kernel_on_a_synthetic_matrix_at_the_size_of_config5(K, M, method, crite
             assert abs(r['gamma'] - gamma) <= 1e-13 * gamma
     assert e.mix_stream_position(_lib.RX_STREAM_NUMPY) == 2 * K * 30
     e.close()
+
+
+# ---- the kernel against the golden vectors lifted from the reference itself (tests/golden/make_sams_golden.py runs
+# /root/reference/openmmtools/multistate/sams.py's own _global_jump / _update_stage / _update_logZ_estimates) ------------------
+import os
+from test_sams import G, energies_for
+
+
+@pytest.mark.parametrize('tag', [str(t) for t in G['cases']])
+def test_kernel_reproduces_the_reference_goldens(tag):
+    _, K, M, s, stages, method, criteria = tag.split('_')
+    K, M, seed = int(K[1:]), int(M[1:]), int(s[1:])
+    e = gpu_engine(_lib.RX_SYSTEM_HARMONIC, K, M, 1)
+    e.set_particles(None, None, np.full(1, 12.0), None)
+    e.set_states(np.full(M, 300.0), ho_K=np.full(M, 100.0), ho_x0=np.zeros((M, 3)))
+    e.mix_seed(seed, _lib.RX_STREAM_NUMPY)                  # the reference draws from numpy's global RandomState
+    st0 = np.linspace(0, M - 1, K, dtype=int) if K > 1 else np.zeros(1, dtype=int)
+    e.set_replica_states(st0.astype(np.int64))
+    e.sams_set(np.zeros(M) - np.log(M), np.zeros(M), histogram=np.zeros(M, np.int64), gamma0=float(G[tag + '_gamma0']),
+               weight_update_method=method, update_stages=stages, flatness_criteria=criteria,
+               stage=1 if stages == 'one-stage' else 0, t0=0)
+    prev = st0
+    for it in range(1, 61):
+        e.set_energies(energies_for(it, K, M, seed + 17))
+        e.sams_step(it, update_weights=True)
+        r = e.sams_get()
+        i = it - 1
+        assert np.array_equal(r['previous_states'], prev) and np.array_equal(r['states'], G[tag + '_states'][i]), it
+        prev = r['states']
+        assert r['stage'] == G[tag + '_stage'][i] and r['t0'] == G[tag + '_t0'][i], it
+        np.testing.assert_allclose(r['logZ'], G[tag + '_logZ'][i], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(r['log_weights'], G[tag + '_log_weights'][i], rtol=1e-11, atol=1e-13)
+        nacc = np.zeros((M, M), np.int64); nprop = np.zeros((M, M), np.int64)
+        for c, n in zip(r['previous_states'], r['states']):
+            nprop[c, :] += 1; nacc[c, n] += 1
+        assert np.array_equal(nacc, G[tag + '_nacc'][i]) and np.array_equal(nprop, G[tag + '_nprop'][i])
+    e.close()
