@@ -8,11 +8,17 @@
 //   O  v = a v + b sqrt(kT/m) xi;  constrain velocities                                             (:1449-1460)
 // with the centre-of-mass velocity removed at the start of every step (CMMotionRemover through addUpdateContextState).
 //
-// One warp per replica, one lane per atom (N <= 32), everything in f64 (22 atoms: the step is a latency chain, not
-// arithmetic).  No atomics: a lane computes the force on ITS atom from the terms that contain it (per-atom term lists built
-// on the host; an angle is evaluated by its three lanes, a torsion by four), so results are bit-reproducible.  Constraints
-// are solved cluster by cluster (connected components of the constraint graph, e.g. a CH3 group), one lane per cluster,
-// Gauss-Seidel in list order -- the same arithmetic, in the same order, as oracle/rx_oracle_mol.c.
+// k_propagate_mol: one block of four warps per replica, the state (x, v in f64) on chip for all steps.  Warp 0 integrates --
+// one lane per atom (N <= 32), one lane per constraint cluster -- and all 128 threads evaluate the force terms in f32 on the
+// f64 positions: every bond / angle / torsion / pair ONCE, by whichever thread its index falls to, into fixed shared-memory
+// slots that each atom then adds up in slot order (no atomics: the same bits every run, whatever the thread count).
+// Constraints are solved cluster by cluster (connected components of the constraint graph, e.g. a CH3 group) by the lane that
+// owns the cluster.  Clusters of <= 3 constraints (every H-bond cluster) take the MolStar path: register copies of the
+// cluster's <= 4 atoms, the RATTLE matrix inverted once per position update in closed form, SHAKE as chord iterations on that
+// inverse (k_propagate_mol<true>); larger clusters a Newton M-SHAKE (<= 4 constraints) or Gauss-Seidel sweeps
+// (k_propagate_mol<false>).  All of them reach the constrained point of oracle/rx_oracle_mol.c's sweeps to the tolerance.
+// The energy kernel (k_energy_mol, f64) and the minimiser (k_minimize_mol) use one warp per replica and the per-atom term
+// lists (a lane computes the terms that contain its atom).
 #pragma once
 
 #define MOL_MAX_ATOMS 32
