@@ -204,3 +204,51 @@ def test_nan_restart_on_a_molecule_retries_only_the_failed_replica():
     for k in range(6):
         if k != 2:
             assert np.array_equal(xs[k], xc[k]), k
+
+
+@pytest.mark.xfail(strict=False, reason='open at the end of round 2: constraints hold on the device, the trajectory differs from the oracle')
+def test_rigid_waters_are_clusters_of_the_register_resident_path():
+    """Two rigid TIP3P waters in vacuum: three constraints over three atoms per molecule (a cycle; SETTLE's case in OpenMM)
+    through k_propagate_mol<true> and, forced, through the general path -- against the oracle with the same noise.
+    KNOWN OPEN ISSUE (not part of the green suite): in the single device run the round's GPU budget still allowed, every
+    constraint was kept to 1e-10 nm but the positions after 40 steps of 2 fs differed from the oracle's by up to 0.1 nm.  The
+    constraint algebra itself and the whole step sequence reproduce the oracle on the CPU (tests/test_molstar_logic_model.py,
+    1e-11 nm over the same 40 steps), so the difference is in the device implementation for this kind of system (six atoms,
+    no bonded terms, cyclic clusters, no centre-of-mass removal -- none of which AlanineDipeptideVacuum exercises); rigid
+    waters are therefore NOT claimed to work."""
+    import os
+    from oracle import oracle
+    from test_molstar_logic_model import water_dimer
+    s, x = water_dimer()
+    temps = np.array([300.0, 420.0])
+    K = len(temps)
+    m = oracle.Molecule(s)
+    rng = np.random.default_rng(2)
+    v0 = np.stack([rng.normal(size=x.shape) * np.sqrt(KB * T / m.mass)[:, None] for T in temps])
+    seed, it, n_steps, dt, gamma = 99, 3, 40, 0.002, 5.0
+    ref = []
+    for k in range(K):
+        xo, vo = x.copy(), np.ascontiguousarray(v0[k])
+        U = oracle_run(m, xo, vo, device_noise(seed, it, k, 6, n_steps), KB * temps[k], dt, gamma, n_steps, 'V R O R V')
+        ref.append((xo, vo, U))
+    for general in (False, True):
+        if general:
+            os.environ['RX_MOL_NO_STAR'] = '1'
+        try:
+            e = gpu_engine(_lib.RX_SYSTEM_MOLECULE, K, K, 6)
+            e.set_molecule(s, constraint_tolerance=1e-10)
+            e.set_states(temps, np.ones(K))
+            e.set_integrator(dt, gamma, n_steps, 'V R O R V')
+            e.set_positions(np.stack([x] * K)); e.set_velocities(v0)
+            e.propagate(seed, it)
+            xg, vg = e.get_positions(), e.get_velocities()
+            pg, _ = e.get_replica_energies()
+            e.close()
+        finally:
+            os.environ.pop('RX_MOL_NO_STAR', None)
+        c = s.constraints
+        i, j = c[:, 0].astype(int), c[:, 1].astype(int)
+        for k in range(K):
+            assert np.abs(np.linalg.norm(xg[k][i] - xg[k][j], axis=1) - c[:, 2]).max() < 1e-10
+            assert np.abs(xg[k] - ref[k][0]).max() < 3e-7 and np.abs(vg[k] - ref[k][1]).max() < 1e-4, (general, k)
+            assert abs(pg[k] - ref[k][2]) < 2e-3
