@@ -117,7 +117,6 @@ class SAMSSampler(MultiStateSampler):
 
     def _mix_replicas_device(self):
         """sams.py:395-437 in one kernel (rx_sams_step): jump of every replica, stage schedule, logZ and weight update."""
-        from .. import _lib
         e = self._engine
         K = self.n_replicas
         self._sams_device_init()
@@ -141,7 +140,6 @@ class SAMSSampler(MultiStateSampler):
     def run_fused(self, n_iterations):
         """n whole SAMS iterations (jump + weight update -> propagate -> energies) on the device without a host round trip
         (rx_sams_run_iterations); nothing is reported for them.  The sampler's host mirrors are refreshed at the end."""
-        from .. import _lib
         e = self._engine
         K = self.n_replicas
         if not self.device_weight_update:

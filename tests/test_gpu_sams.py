@@ -171,7 +171,6 @@ def test_kernel_on_a_synthetic_matrix_at_the_size_of_config5(K, M, method, crite
 
 # ---- the kernel against the golden vectors lifted from the reference itself (tests/golden/make_sams_golden.py runs
 # /root/reference/openmmtools/multistate/sams.py's own _global_jump / _update_stage / _update_logZ_estimates) ------------------
-import os
 from test_sams import G, energies_for
 
 
